@@ -1,0 +1,117 @@
+/* satmvs_b200.h — C ABI of the B200-native SatMVS plane-sweep path.
+ *
+ * The reference (WHU-GPCV/SatMVS) is 100 % Python and has no FFI; its "operator API" for this
+ * path is the set of Python call sites listed in SURVEY.md §8b.  Each entry point below names
+ * the reference function (file:line under /root/reference) it replaces.  The Python host side
+ * (satmvs_b200/*.py) binds these with ctypes and keeps the reference's signatures.
+ *
+ * Conventions
+ *  - every pointer documented "device" is a CUDA device pointer valid on the *current* device;
+ *    "host" pointers are plain CPU memory read before the call returns;
+ *  - tensors are dense, row-major (NCHW / NCDHW) fp32 unless stated otherwise;
+ *  - cameras are tiny (170 doubles / 16 doubles): they are passed as HOST pointers and travel to
+ *    the kernel by value in the launch parameters (constant bank), so calls are stateless and
+ *    re-entrant; one call handles one batch element's camera set — the `_batched` host loop lives
+ *    in the Python wrapper;
+ *  - the caller owns every buffer; nothing here allocates, frees or synchronises;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - return value 0 = ok, non-zero = error, text via satmvs_last_error() (thread-local).
+ */
+#ifndef SATMVS_B200_H
+#define SATMVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SATMVS_ABI_VERSION 1
+#define SATMVS_MAX_SRC_VIEWS 8
+#define SATMVS_RPC_LEN 170
+
+enum { SATMVS_OK = 0, SATMVS_EINVAL = 1, SATMVS_ECUDA = 2 };
+
+int satmvs_abi_version(void);
+const char* satmvs_last_error(void);
+
+/* ---- fused plane sweep: per-hypothesis geometry + bilinear gather + variance over views ----
+ * Replaces networks/casred.py:26-53 (== networks/casmvs.py:30-59; per-plane form casred.py:191-212)
+ * with rpc_warping (modules/warping.py:310-365) inlined for every source view.
+ *   ref_fea   device [C,H,W]           reference-view features of ONE batch element
+ *   src_feas  host array of n_src device pointers, each [C,H,W]
+ *   ref_rpc   host double[170]; src_rpcs host double[n_src*170]     (layout data_io.py:78-92)
+ *   depth     device; depth_per_pixel=0: [D] planes, =1: [D,H,W] per-pixel hypotheses
+ *   out_var   device [C,D,H,W]:  var = Q/V - (S/V)^2,  V = n_src+1
+ */
+int satmvs_cost_volume_rpc_fwd(const float* ref_fea, const float* const* src_feas, int n_src,
+                               const double* ref_rpc, const double* src_rpcs,
+                               const float* depth, int depth_per_pixel,
+                               int C, int D, int H, int W, float* out_var, void* stream);
+
+/* Same with the pin-hole homography of homo_warping (modules/warping.py:6-44).
+ *   ref_proj host double[16], src_projs host double[n_src*16]  (K·E, row-major 4x4) */
+int satmvs_cost_volume_homo_fwd(const float* ref_fea, const float* const* src_feas, int n_src,
+                                const double* ref_proj, const double* src_projs,
+                                const float* depth, int depth_per_pixel,
+                                int C, int D, int H, int W, float* out_var, void* stream);
+
+/* ---- single-view warps with the reference operator's meaning ----
+ * rpc_warping (modules/warping.py:310-365) / homo_warping (:6-44): out [C,D,H,W] warped volume. */
+int satmvs_rpc_warp_fwd(const float* src_fea, const double* src_rpc, const double* ref_rpc,
+                        const float* depth, int depth_per_pixel,
+                        int C, int D, int H, int W, float* out, void* stream);
+int satmvs_homo_warp_fwd(const float* src_fea, const double* src_proj, const double* ref_proj,
+                         const float* depth, int depth_per_pixel,
+                         int C, int D, int H, int W, float* out, void* stream);
+
+/* Backward of the two warps w.r.t. the source features only (the reference builds the grid
+ * under no_grad, warping.py:322-356): grad_src [C,H,W] += scatter of grad_out [C,D,H,W].
+ * grad_src must be zero-initialised by the caller. */
+int satmvs_rpc_warp_bwd(const float* grad_out, const double* src_rpc, const double* ref_rpc,
+                        const float* depth, int depth_per_pixel,
+                        int C, int D, int H, int W, float* grad_src, void* stream);
+int satmvs_homo_warp_bwd(const float* grad_out, const double* src_proj, const double* ref_proj,
+                         const float* depth, int depth_per_pixel,
+                         int C, int D, int H, int W, float* grad_src, void* stream);
+
+/* Backward of the fused variance volume: grad_var [C,D,H,W] -> grad_ref [C,H,W] and
+ * grad_srcs[v] [C,H,W] (zero-initialised by the caller; host array of n_src device pointers). */
+int satmvs_cost_volume_rpc_bwd(const float* grad_var, const float* ref_fea, const float* const* src_feas,
+                               int n_src, const double* ref_rpc, const double* src_rpcs,
+                               const float* depth, int depth_per_pixel, int C, int D, int H, int W,
+                               float* grad_ref, float* const* grad_srcs, void* stream);
+int satmvs_cost_volume_homo_bwd(const float* grad_var, const float* ref_fea, const float* const* src_feas,
+                                int n_src, const double* ref_proj, const double* src_projs,
+                                const float* depth, int depth_per_pixel, int C, int D, int H, int W,
+                                float* grad_ref, float* const* grad_srcs, void* stream);
+
+/* ---- RPC localisation / projection on flat fp64 point lists ----
+ * RPC_Photo2Obj (modules/warping.py:255-307) == RPCModelParameter.RPC_PHOTO2OBJ
+ * (tools/rpc_tensor.py:138-165); RPC_Obj2Photo (warping.py:218-252) == RPC_OBJ2PHOTO
+ * (rpc_tensor.py:109-136).  rpc host double[170]; all point arrays device double[n]. */
+int satmvs_rpc_localise(const double* rpc, const double* samp, const double* line, const double* hei,
+                        int64_t n, double* lat, double* lon, void* stream);
+int satmvs_rpc_project(const double* rpc, const double* lat, const double* lon, const double* hei,
+                       int64_t n, double* samp, double* line, void* stream);
+
+/* ---- soft-argmin heads ----
+ * mode 0: RED train head (networks/casred.py:58-62): softmax over D, depth = sum p*d, conf = max p.
+ * mode 1: CasMVS head (networks/casmvs.py:66-74): conf = sum of the 4 probabilities around the
+ *         regressed plane index.  logits device [D,H,W]; depth as above; out_* device [H,W]. */
+int satmvs_softargmin_fwd(const float* logits, const float* depth, int depth_per_pixel, int mode,
+                          int D, int H, int W, float* out_depth, float* out_conf, void* stream);
+
+/* Streaming fp64 head of the inference net (networks/casred.py:182-184, :218-236).
+ * state device double[3*H*W] = (exp_sum, depth_acc, max_e), zero-initialised by the caller.
+ * update: one plane, reg device [H,W], depth_plane device [H,W] (or [1] when depth_per_pixel=0).
+ * finish: depth = depth_acc/(exp_sum+1e-10), conf = max_e/(exp_sum+1e-10) -> fp32 [H,W]. */
+int satmvs_softargmin_stream_update(const float* reg, const float* depth_plane, int depth_per_pixel,
+                                    int H, int W, double* state, void* stream);
+int satmvs_softargmin_stream_finish(const double* state, int H, int W,
+                                    float* out_depth, float* out_conf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATMVS_B200_H */

@@ -142,8 +142,9 @@ def rpc_sweep_coords(ref_rpc: torch.Tensor, src_rpc: torch.Tensor, depth_values:
     (`modules/warping.py:322-341`).  Returns two [B, D, H, W] fp64 tensors."""
     B, D = depth_values.shape[:2]
     h = _expand_depth(depth_values, H, W).double().reshape(B, -1)
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64),
-                            torch.arange(W, dtype=torch.float64), indexing="ij")
+    dev = depth_values.device
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64, device=dev),
+                            torch.arange(W, dtype=torch.float64, device=dev), indexing="ij")
     x = xs.reshape(1, 1, H, W).expand(B, D, H, W).reshape(B, -1)
     y = ys.reshape(1, 1, H, W).expand(B, D, H, W).reshape(B, -1)
     lat, lon = rpc_localise(x, y, h, ref_rpc)
@@ -158,9 +159,10 @@ def homo_sweep_coords(ref_proj: torch.Tensor, src_proj: torch.Tensor, depth_valu
     B, D = depth_values.shape[:2]
     proj = torch.matmul(src_proj, torch.inverse(ref_proj))
     R, t = proj[:, :3, :3], proj[:, :3, 3:4]
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32),
-                            torch.arange(W, dtype=torch.float32), indexing="ij")
-    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(H * W))).double()   # [3, HW]
+    dev = depth_values.device
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=dev),
+                            torch.arange(W, dtype=torch.float32, device=dev), indexing="ij")
+    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(H * W, device=dev))).double()   # [3, HW]
     rot = torch.matmul(R, pix.unsqueeze(0).expand(B, 3, H * W))                       # [B, 3, HW]
     d = _expand_depth(depth_values, H, W).reshape(B, 1, D, H * W).double()
     p = rot.unsqueeze(2) * d + t.view(B, 3, 1, 1)                                     # [B, 3, D, HW]
@@ -168,39 +170,49 @@ def homo_sweep_coords(ref_proj: torch.Tensor, src_proj: torch.Tensor, depth_valu
     return uv[:, 0].reshape(B, D, H, W), uv[:, 1].reshape(B, D, H, W)
 
 
+def _fma32(a: torch.Tensor, b: torch.Tensor, c) -> torch.Tensor:
+    """fp32 fused multiply-add emulated through fp64 (the product of two fp32 is exact in fp64)."""
+    return (a.double() * b.double() + (c.double() if torch.is_tensor(c) else c)).float()
+
+
 def to_tap_coords(samp: torch.Tensor, line: torch.Tensor, H: int, W: int, *, rpc_style: bool):
     """fp64 source coords -> fp32 *pixel-space tap positions* as `F.grid_sample(align_corners=False)`
-    sees them.  RPC path casts to fp32 first and normalises in fp32 (`warping.py:347-351`);
-    the homography path normalises in fp64 and then casts (`warping.py:35-38`).  The un-normalise
-    step is the published grid_sampler formula `((g + 1) * size - 1) / 2`."""
+    sees them.  RPC path casts to fp32 first and normalises in fp32 with a true division
+    (`warping.py:347-351`); the homography path normalises in fp64 and then casts
+    (`warping.py:35-38`).  The un-normalise step is ATen-CPU's `(g + 1) * (size / 2) - 0.5`
+    evaluated as one fp32 add followed by one fused multiply-add (probed bit-exact against
+    `F.grid_sample` on 8e5 samples; the CUDA eager path's `((g + 1) * size - 1) / 2` differs
+    from it by <= 1 ulp)."""
     if rpc_style:
         gx = samp.float() / ((W - 1) / 2) - 1
         gy = line.float() / ((H - 1) / 2) - 1
     else:
         gx = (samp / ((W - 1) / 2) - 1).float()
         gy = (line / ((H - 1) / 2) - 1).float()
-    ix = ((gx + 1) * W - 1) / 2
-    iy = ((gy + 1) * H - 1) / 2
+    ix = _fma32(gx + 1, torch.tensor(W / 2, dtype=torch.float32, device=gx.device), -0.5)
+    iy = _fma32(gy + 1, torch.tensor(H / 2, dtype=torch.float32, device=gx.device), -0.5)
     return gx, gy, ix, iy
 
 
 def bilinear_sample_zeros(fea: torch.Tensor, ix: torch.Tensor, iy: torch.Tensor) -> torch.Tensor:
     """Explicit restatement of `grid_sampler_2d` (bilinear, zeros padding): fea [B, C, H, W],
     ix/iy [B, D, H, W] fp32 pixel positions -> [B, C, D, H, W].  Corner weights are the
-    products of differences used by ATen (nw = (x1-ix)(y1-iy), ...), out-of-range corners add 0."""
+    products of differences used by ATen (nw = (x1-ix)(y1-iy), ...); the four corners are
+    accumulated nw, ne, sw, se with fused multiply-adds; out-of-range corners add 0.
+    Bit-exact against ATen-CPU `F.grid_sample` (tests/test_oracle_golden.py)."""
     B, C, H, W = fea.shape
     shp = ix.shape
     ix, iy = ix.reshape(B, -1), iy.reshape(B, -1)
     x0, y0 = torch.floor(ix), torch.floor(iy)
     x1, y1 = x0 + 1, y0 + 1
     flat = fea.reshape(B, C, H * W)
-    out = torch.zeros(B, C, ix.shape[1], dtype=fea.dtype)
+    out = torch.zeros(B, C, ix.shape[1], dtype=fea.dtype, device=fea.device)
     for xc, yc, wgt in ((x0, y0, (x1 - ix) * (y1 - iy)), (x1, y0, (ix - x0) * (y1 - iy)),
                         (x0, y1, (x1 - ix) * (iy - y0)), (x1, y1, (ix - x0) * (iy - y0))):
         ok = (xc >= 0) & (xc <= W - 1) & (yc >= 0) & (yc <= H - 1)
         idx = (yc.clamp(0, H - 1) * W + xc.clamp(0, W - 1)).long()
         val = torch.gather(flat, 2, idx.unsqueeze(1).expand(B, C, -1))
-        out = out + val * (wgt * ok.to(wgt.dtype)).unsqueeze(1)
+        out = _fma32(val, torch.where(ok, wgt, torch.zeros_like(wgt)).unsqueeze(1), out)
     return out.view(B, C, *shp[1:])
 
 

@@ -24,7 +24,7 @@ def variance_cost_volume(features: list[torch.Tensor], cams: torch.Tensor, depth
     S = ref + sum warp_v, Q = ref^2 + sum warp_v^2, var = Q/V - (S/V)^2, evaluated in that order.
     """
     V = len(features)
-    cam = torch.unbind(cams, 1)
+    cam = torch.unbind(cams.to(features[0].device), 1)   # device-agnostic: the same code is the eager-GPU baseline
     D = depth_values.shape[1]
     ref = features[0].unsqueeze(2).repeat(1, 1, D, 1, 1)
     s, q = ref, ref ** 2

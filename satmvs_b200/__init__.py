@@ -1,0 +1,9 @@
+"""satmvs_b200 — B200-native (sm_100a) implementation of SatMVS's RPC plane-sweep hot path.
+
+Host code mirrors the reference's operator interface (`modules/warping.py`, `modules/module.py`,
+`modules/depth_range.py`); the arithmetic runs in hand-written CUDA kernels behind the C ABI of
+`include/satmvs_b200.h` (libsatmvs_b200.so, built in-tree by `satmvs_b200.build`).
+"""
+from .warping import rpc_warping, rpc_warping_enisum, homo_warping, build_cost_volume  # noqa: F401
+from .regress import softargmin, StreamingSoftArgmin  # noqa: F401
+from .rpc_tensor import RPCModelParameter  # noqa: F401

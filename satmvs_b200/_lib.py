@@ -1,0 +1,76 @@
+"""ctypes binding of libsatmvs_b200.so (include/satmvs_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is
+raised.  The product path never routes through torch ops or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsatmvs_b200.so")
+_lib = None
+
+_P, _I, _L = C.c_void_p, C.c_int, C.c_int64
+_SIGNATURES = {
+    "satmvs_abi_version": ([], _I),
+    "satmvs_last_error": ([], C.c_char_p),
+    "satmvs_cost_volume_rpc_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_cost_volume_homo_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_rpc_warp_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_homo_warp_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_rpc_warp_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_homo_warp_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_cost_volume_rpc_bwd": ([_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
+    "satmvs_cost_volume_homo_bwd": ([_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
+    "satmvs_rpc_localise": ([_P, _P, _P, _P, _L, _P, _P, _P], _I),
+    "satmvs_rpc_project": ([_P, _P, _P, _P, _L, _P, _P, _P], _I),
+    "satmvs_softargmin_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
+    "satmvs_softargmin_stream_update": ([_P, _P, _I, _I, _I, _P, _P], _I),
+    "satmvs_softargmin_stream_finish": ([_P, _I, _I, _P, _P, _P], _I),
+}
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python -m satmvs_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m satmvs_b200.build` "
+                               "(there is no non-CUDA fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes, fn.restype = argtypes, restype
+        if handle.satmvs_abi_version() != 1:
+            raise RuntimeError("libsatmvs_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {lib().satmvs_last_error().decode()}")
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: satmvs_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)

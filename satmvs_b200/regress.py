@@ -1,0 +1,69 @@
+"""Soft-argmin heads on the sm_100a kernels (csrc/heads.cu).
+
+    depth_regression(p, depth_values)                       modules/module.py:433   (kept for API parity)
+    softargmin(logits, depth_values, head)                  casred.py:58-62 / casmvs.py:66-74, fused
+    StreamingSoftArgmin                                     casred.py:182-184, :218-236 (fp64, plane by plane)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def softargmin(logits: torch.Tensor, depth_values: torch.Tensor, head: str = "red"):
+    """softmax over D + expectation + confidence in one kernel.
+    logits [B,D,H,W]; depth_values [B,D] or [B,D,H,W]; head 'red' (conf = max p) or 'casmvs'
+    (conf = sum of 4 neighbouring probabilities).  Returns (depth [B,H,W], conf [B,H,W])."""
+    mode = {"red": 0, "casmvs": 1}[head]
+    lg = _lib.require_cuda(logits, "logits")
+    B, D, H, W = lg.shape
+    dv = _lib.require_cuda(depth_values, "depth_values")
+    if dv.dim() == 2:
+        per_pixel = 0
+    elif tuple(dv.shape) == (B, D, H, W):
+        per_pixel = 1
+    else:
+        # depth_regression resizes hypotheses given at another resolution (module.py:437)
+        dv = torch.nn.functional.interpolate(dv, [H, W], mode="bilinear", align_corners=False).contiguous()
+        per_pixel = 1
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=lg.device)
+    conf = torch.empty_like(depth)
+    with torch.cuda.device(lg.device):
+        st = _lib.stream_ptr(lg.device)
+        for b in range(B):
+            _lib.check(_lib.lib().satmvs_softargmin_fwd(lg[b].data_ptr(), dv[b].data_ptr(), per_pixel, mode, D, H, W,
+                                                       depth[b].data_ptr(), conf[b].data_ptr(), st), "softargmin_fwd")
+    return depth, conf
+
+
+class StreamingSoftArgmin:
+    """Running fp64 (sum e, sum d*e, max e) with e = exp(reg), no max subtraction — the
+    plane-by-plane head of `compute_depth_when_pred` (`networks/casred.py:218-236`)."""
+
+    def __init__(self, B: int, H: int, W: int, device):
+        self.B, self.H, self.W = B, H, W
+        self.state = torch.zeros((B, 3, H, W), dtype=torch.float64, device=device)
+
+    def update(self, reg: torch.Tensor, depth_plane: torch.Tensor) -> None:
+        reg = _lib.require_cuda(reg, "reg").view(self.B, self.H, self.W)
+        dp = _lib.require_cuda(depth_plane, "depth_plane")
+        per_pixel = 1 if dp.numel() == self.B * self.H * self.W else 0
+        dp = dp.reshape(self.B, -1)
+        with torch.cuda.device(reg.device):
+            st = _lib.stream_ptr(reg.device)
+            for b in range(self.B):
+                _lib.check(_lib.lib().satmvs_softargmin_stream_update(
+                    reg[b].data_ptr(), dp[b].data_ptr(), per_pixel, self.H, self.W, self.state[b].data_ptr(), st),
+                    "softargmin_stream_update")
+
+    def finish(self):
+        depth = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.state.device)
+        conf = torch.empty_like(depth)
+        with torch.cuda.device(depth.device):
+            st = _lib.stream_ptr(depth.device)
+            for b in range(self.B):
+                _lib.check(_lib.lib().satmvs_softargmin_stream_finish(
+                    self.state[b].data_ptr(), self.H, self.W, depth[b].data_ptr(), conf[b].data_ptr(), st),
+                    "softargmin_stream_finish")
+        return depth, conf

@@ -1,0 +1,203 @@
+"""GPU parity of the fused plane-sweep kernels (through the C ABI) against the CPU oracle and the
+committed reference vectors.  Tolerances: the kernels reproduce the oracle's fp32 op sequence, the
+only deviation is fp64 geometry rounding (<= a few ulp of fp64, which can flip the fp32 rounding of
+a tap coordinate by 1 ulp ~ 1e-5 px); volumes are therefore checked to 2e-4 absolute on N(0,1)
+features and north_star's 1e-3 relative bound is checked on depth."""
+import numpy as np
+import pytest
+import torch
+
+import satmvs_b200
+from oracle import geometry, volume
+from satmvs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+VOL_TOL = 2e-4
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def maxdiff(a, b):
+    return (a.detach().cpu().double() - b.detach().cpu().double()).abs().max().item()
+
+
+@pytest.mark.parametrize("tag", ["plain", "shifted"])
+def test_rpc_warp_golden(golden, tag):
+    g = golden(f"rpc_warp_{tag}")
+    for v in (1, 2):
+        for dk in ("depth4", "depth2"):
+            got = satmvs_b200.rpc_warping(cu(g[f"fea{v}"]), g["rpcs"][:, v], g["rpcs"][:, 0], cu(g[dk]), None)
+            want = g[f"warp{dk[-1]}_v{v}"]
+            assert got.shape == want.shape
+            assert maxdiff(got, want) < VOL_TOL
+            # exactness is the norm: almost every voxel must be bit-identical to the reference
+            assert (got.cpu() == want).float().mean() > 0.999
+
+
+def test_rpc_warp_accepts_cuda_cameras_and_scratch(golden):
+    g = golden("rpc_warp_plain")
+    coef = torch.ones(1, device=DEV, dtype=torch.float64)
+    got = satmvs_b200.rpc_warping(cu(g["fea1"]), cu(g["rpcs"][:, 1]), cu(g["rpcs"][:, 0]), cu(g["depth4"]), coef)
+    assert maxdiff(got, g["warp4_v1"]) < VOL_TOL
+
+
+def test_homo_warp_golden(golden):
+    g = golden("homo_warp")
+    for v in (1, 2):
+        for dk in ("depth4", "depth2"):
+            got = satmvs_b200.homo_warping(cu(g[f"fea{v}"]), g["projs"][:, v], g["projs"][:, 0], cu(g[dk]))
+            assert maxdiff(got, g[f"warp{dk[-1]}_v{v}"]) < VOL_TOL
+
+
+def test_qc_form_golden(golden):
+    g = golden("rpc_warp_qc")
+
+    def as_dict(r):
+        d = {}
+        for i, k in enumerate(("line", "samp", "lat", "lon", "height")):
+            d[k + "_off"], d[k + "_scale"] = r[:, i], r[:, 5 + i]
+        for k, at in (("line_num", 10), ("line_den", 30), ("samp_num", 50), ("samp_den", 70),
+                      ("lat_num", 90), ("lat_den", 110), ("lon_num", 130), ("lon_den", 150)):
+            d[k + "_tensor"] = torch.stack([geometry.qc_tensor(r[b, at:at + 20]) for b in range(r.shape[0])])
+        return d
+
+    got = satmvs_b200.rpc_warping_enisum(cu(g["fea1"]), as_dict(g["rpcs"][:, 1]), as_dict(g["rpcs"][:, 0]),
+                                         cu(g["depth4"]))
+    assert maxdiff(got, g["warp"]) < VOL_TOL
+
+
+@pytest.mark.parametrize("geo", ["rpc", "pinhole"])
+def test_cost_volume_golden(golden, geo):
+    g = golden(f"stage_train_{geo}")
+    fe = [cu(g[f"fea{v}"]) for v in range(3)]
+    cams = g["cams"]
+    var = satmvs_b200.build_cost_volume(fe[0], fe[1:], cams[:, 0], [cams[:, 1], cams[:, 2]], cu(g["depth_values"]), geo)
+    assert maxdiff(var, g["var"]) < VOL_TOL
+    assert (var.cpu() == g["var"]).float().mean() > 0.99
+
+
+@pytest.mark.parametrize("B,V,C,D,H,W,per_pixel", [
+    (1, 3, 32, 16, 32, 64, True),      # config-1 stage-1 shape (fewer planes)
+    (2, 2, 8, 5, 17, 23, True),        # ragged: odd H, W, D not a multiple of the plane chunk, batch 2
+    (1, 5, 4, 7, 16, 24, False),       # 4 source views, plane-constant depth
+    (1, 6, 2, 3, 8, 40, True),         # 5 source views -> padded 6-slot template
+    (1, 9, 2, 3, 8, 12, True),         # 8 source views
+    (1, 3, 1, 1, 2, 2, True),          # minimum sizes
+])
+def test_cost_volume_vs_oracle(B, V, C, D, H, W, per_pixel):
+    fe = synth.make_features(B, V, C, H, W, seed=V * 100 + C)
+    rp = synth.make_rpc_stack(B, V, H, W, shift_geo=(V == 2))
+    dv = synth.make_depth_planes(B, D, H, W, per_pixel=per_pixel)
+    want = volume.variance_cost_volume(fe, rp, dv, "rpc", sampler="explicit")
+    got = satmvs_b200.build_cost_volume(cu(fe[0]), [cu(f) for f in fe[1:]], rp[:, 0], rp[:, 1:], cu(dv), "rpc")
+    assert got.shape == (B, C, D, H, W)
+    assert maxdiff(got, want) < VOL_TOL
+
+
+def test_cost_volume_homography_vs_oracle():
+    B, V, C, D, H, W = 1, 3, 8, 9, 24, 40
+    fe = synth.make_features(B, V, C, H, W, seed=5)
+    pp = synth.make_pinhole_stack(B, V, H, W)
+    dv = synth.make_depth_planes(B, D, H, W, lo=90, hi=110, jitter=0.3)
+    want = volume.variance_cost_volume(fe, pp, dv, "pinhole")
+    got = satmvs_b200.build_cost_volume(cu(fe[0]), [cu(f) for f in fe[1:]], pp[:, 0], pp[:, 1:], cu(dv), "pinhole")
+    assert maxdiff(got, want) < VOL_TOL
+
+
+def test_out_of_range_taps_are_zero_padded():
+    """Cameras pushed far off the image: every tap out of range -> warped volume exactly 0,
+    variance = population variance of (ref, 0, 0)."""
+    B, V, C, D, H, W = 1, 3, 2, 3, 8, 12
+    fe = synth.make_features(B, V, C, H, W)
+    rp = synth.make_rpc_stack(B, V, H, W)
+    rp[:, 1:, synth.SAMP_OFF] += 10 * W
+    dv = synth.make_depth_planes(B, D, H, W)
+    w = satmvs_b200.rpc_warping(cu(fe[1]), rp[:, 1], rp[:, 0], cu(dv), None)
+    assert w.abs().max().item() == 0.0
+    want = volume.variance_cost_volume(fe, rp, dv, "rpc")
+    got = satmvs_b200.build_cost_volume(cu(fe[0]), [cu(f) for f in fe[1:]], rp[:, 0], rp[:, 1:], cu(dv), "rpc")
+    assert maxdiff(got, want) == 0.0
+
+
+def test_nonfinite_hypotheses_do_not_fault():
+    B, V, C, D, H, W = 1, 2, 2, 2, 8, 12
+    fe = synth.make_features(B, V, C, H, W)
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv = synth.make_depth_planes(B, D, H, W)
+    dv[0, 0, 0, 0] = float("nan")
+    dv[0, 1, 1, 1] = float("inf")
+    got = satmvs_b200.rpc_warping(cu(fe[1]), rp[:, 1], rp[:, 0], cu(dv), None)
+    torch.cuda.synchronize()
+    assert got[0, :, 0, 0, 0].abs().max().item() == 0.0 and got[0, :, 1, 1, 1].abs().max().item() == 0.0
+
+
+def test_full_size_properties():
+    """BASELINE config-2 size (1,3,32,64,96,192): too slow for the oracle in a unit test, so use
+    size-independent properties: (i) identity cameras + constant hypotheses reproduce the source
+    feature map exactly at integer taps; (ii) the fused volume equals the one assembled from the
+    single-view warps; (iii) plane-constant and broadcast per-pixel hypotheses agree bit for bit."""
+    B, V, C, D, H, W = 1, 3, 32, 64, 96, 192
+    fe = [cu(f) for f in synth.make_features(B, V, C, H, W)]
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv2 = synth.make_depth_planes(B, D, H, W, per_pixel=False)
+    dv4 = dv2.view(B, D, 1, 1).expand(B, D, H, W).contiguous()
+    var = satmvs_b200.build_cost_volume(fe[0], fe[1:], rp[:, 0], rp[:, 1:], cu(dv4), "rpc")
+    var2 = satmvs_b200.build_cost_volume(fe[0], fe[1:], rp[:, 0], rp[:, 1:], cu(dv2), "rpc")
+    assert torch.equal(var, var2)
+    w1 = satmvs_b200.rpc_warping(fe[1], rp[:, 1], rp[:, 0], cu(dv4), None)
+    w2 = satmvs_b200.rpc_warping(fe[2], rp[:, 2], rp[:, 0], cu(dv4), None)
+    ref = fe[0].unsqueeze(2)
+    s = ref + w1 + w2
+    q = ref ** 2 + w1 ** 2 + w2 ** 2
+    assert torch.equal(var, q / 3 - (s / 3) ** 2)
+    # identity: a noise-free affine camera pair whose forward/inverse maps cancel exactly
+    ident = torch.from_numpy(np.stack([synth.make_rpc(0, H, W, num_noise=0.0, den_noise=0.0)] * 2)).unsqueeze(0)
+    wi = satmvs_b200.rpc_warping(fe[1], ident[:, 1], ident[:, 0], cu(dv2), None)
+    assert maxdiff(wi, fe[1].unsqueeze(2).expand(-1, -1, D, -1, -1)) < 1e-4
+
+
+def test_backward_matches_autograd_of_oracle():
+    B, V, C, D, H, W = 1, 3, 4, 5, 12, 20
+    fe = synth.make_features(B, V, C, H, W, seed=77)
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv = synth.make_depth_planes(B, D, H, W)
+    gw = torch.from_numpy(np.random.default_rng(3).standard_normal((B, C, D, H, W), dtype=np.float32))
+    cpu = [f.clone().requires_grad_(True) for f in fe]
+    volume.variance_cost_volume(cpu, rp, dv, "rpc").backward(gw)
+    gpu = [cu(f).requires_grad_(True) for f in fe]
+    satmvs_b200.build_cost_volume(gpu[0], gpu[1:], rp[:, 0], rp[:, 1:], cu(dv), "rpc").backward(cu(gw))
+    for a, b in zip(cpu, gpu):
+        assert maxdiff(a.grad, b.grad) < 1e-3 * max(1.0, a.grad.abs().max().item())
+    # single-view operator
+    s_cpu = fe[1].clone().requires_grad_(True)
+    geometry.rpc_warp(s_cpu, rp[:, 1], rp[:, 0], dv).backward(gw)
+    s_gpu = cu(fe[1]).requires_grad_(True)
+    satmvs_b200.rpc_warping(s_gpu, rp[:, 1], rp[:, 0], cu(dv), None).backward(cu(gw))
+    assert maxdiff(s_cpu.grad, s_gpu.grad) < 1e-3 * max(1.0, s_cpu.grad.abs().max().item())
+    pp = synth.make_pinhole_stack(B, V, H, W)
+    dvh = synth.make_depth_planes(B, D, H, W, lo=90, hi=110, jitter=0.3)
+    h_cpu = fe[1].clone().requires_grad_(True)
+    geometry.homo_warp(h_cpu, pp[:, 1], pp[:, 0], dvh).backward(gw)
+    h_gpu = cu(fe[1]).requires_grad_(True)
+    satmvs_b200.homo_warping(h_gpu, pp[:, 1], pp[:, 0], cu(dvh)).backward(cu(gw))
+    assert maxdiff(h_cpu.grad, h_gpu.grad) < 1e-3 * max(1.0, h_cpu.grad.abs().max().item())
+
+
+def test_rpc_point_ops_golden(golden):
+    g = golden("rpc_geometry")
+    for b in range(2):
+        cam0 = satmvs_b200.RPCModelParameter(g["rpcs"][b, 0].numpy())
+        lat, lon = cam0.RPC_PHOTO2OBJ(g["samp"][b].numpy(), g["line"][b].numpy(), g["hei"][b].numpy())
+        assert np.abs(lat - g["lat"][b].numpy()).max() < 1e-12 and np.abs(lon - g["lon"][b].numpy()).max() < 1e-12
+        for v in (1, 2):
+            cam = satmvs_b200.RPCModelParameter(g["rpcs"][b, v].numpy())
+            s, l = cam.RPC_OBJ2PHOTO(lat, lon, g["hei"][b].numpy())
+            assert np.abs(s - g[f"samp{v}"][b].numpy()).max() < 1e-9
+            assert np.abs(l - g[f"line{v}"][b].numpy()).max() < 1e-9
+    # empty input
+    e = np.zeros(0)
+    lat, lon = cam0.RPC_PHOTO2OBJ(e, e, e)
+    assert lat.shape == (0,)

@@ -39,7 +39,7 @@ def test_rpc_warp(golden, tag):
             got = geometry.rpc_warp(g[f"fea{v}"], g["rpcs"][:, v], g["rpcs"][:, 0], g[dk])
             assert maxdiff(got, want) == 0.0
             exp = geometry.rpc_warp(g[f"fea{v}"], g["rpcs"][:, v], g["rpcs"][:, 0], g[dk], sampler="explicit")
-            assert maxdiff(exp, want) < 2e-5
+            assert maxdiff(exp, want) == 0.0
     assert (g["warp4_v1"] != 0).float().mean() > 0.5
 
 
@@ -51,7 +51,7 @@ def test_homo_warp(golden):
             got = geometry.homo_warp(g[f"fea{v}"], g["projs"][:, v], g["projs"][:, 0], g[dk])
             assert maxdiff(got, want) == 0.0
             exp = geometry.homo_warp(g[f"fea{v}"], g["projs"][:, v], g["projs"][:, 0], g[dk], sampler="explicit")
-            assert maxdiff(exp, want) < 2e-5
+            assert maxdiff(exp, want) == 0.0
 
 
 def test_qc_warp_equals_20_term(golden):
