@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsatmvs_b200.so")
+LIB_PATH = os.environ.get("SATMVS_B200_LIB") or os.path.join(_HERE, "libsatmvs_b200.so")
 _lib = None
 
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64

@@ -28,6 +28,15 @@ def _headers_mtime() -> float:
     return max(os.path.getmtime(h) for h in hs)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experiment helper: a separately named library compiled with extra -D flags (selected at run
+    time with SATMVS_B200_LIB=<path>); never used by the default product path."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    out = os.path.join(HERE, f"libsatmvs_b200_{name}.so")
+    subprocess.check_call([nvcc, *ARCH, *CFLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", out, *sources()])
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a into one shared library; returns its path."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -104,6 +104,16 @@ inline RpcSrcPack make_rpc_src_pack(const double* s, const double* ref) {
   return p;
 }
 
+// x / b for a launch constant b, correctly rounded: q = RN(x*y), r = x - b*q (exact, fma),
+// q' = RN(q + r*y) with y = RN(1/b) from the host (Markstein).  3 instructions instead of the
+// ~12 + slow-path call of an IEEE fp32 division; equals torch's true division bit for bit
+// (checked exhaustively on 4e6 samples per divisor in DESIGN.md §numerics).
+__device__ __forceinline__ float div_const(float x, float b, float inv_b) {
+  float q = __fmul_rn(x, inv_b);
+  float r = __fmaf_rn(-b, q, x);
+  return __fmaf_rn(r, inv_b, q);
+}
+
 // num/den for two ratios with ONE reciprocal: a = an/ad, b = bn/bd
 __device__ __forceinline__ void ratio2(double an, double ad, double bn, double bd, double& a, double& b) {
   double r = fast_rcp(ad * bd);
@@ -117,6 +127,7 @@ struct RpcSweep {
   RpcRefPack ref;
   RpcSrcPack src[NSRC];
   float half_wm1, half_hm1;      // (W-1)/2, (H-1)/2 as fp32 (warping.py:350-351)
+  float inv_half_wm1, inv_half_hm1;
 
   struct Pixel { CubicH lat_num, lat_den, lon_num, lon_den; };
   struct Plane { double lat_n, lon_n, h; };
@@ -155,8 +166,8 @@ struct RpcSweep {
            poly20(s.line_num, L, P, H), poly20(s.line_den, L, P, H), sn, ln);
     float samp = (float)fma(sn, s.samp_scale, s.samp_off);
     float line = (float)fma(ln, s.line_scale, s.line_off);
-    gx = __fsub_rn(__fdiv_rn(samp, half_wm1), 1.0f);
-    gy = __fsub_rn(__fdiv_rn(line, half_hm1), 1.0f);
+    gx = __fsub_rn(div_const(samp, half_wm1, inv_half_wm1), 1.0f);
+    gy = __fsub_rn(div_const(line, half_hm1, inv_half_hm1), 1.0f);
   }
 };
 
@@ -264,9 +275,9 @@ __device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W, float 
 }
 
 // nw, ne, sw, se accumulated with fused multiply-adds, the order ATen uses
-__device__ __forceinline__ float tap_fetch(const float* __restrict__ f, const Tap& t, int W) {
-  const float* p = f + t.off;
-  float v00 = __ldg(p), v01 = __ldg(p + 1), v10 = __ldg(p + W), v11 = __ldg(p + W + 1);
+// f0 = channel plane, f1 = f0 + W (both warp-uniform), so the per-thread part of each address is t.off only
+__device__ __forceinline__ float tap_fetch(const float* __restrict__ f0, const float* __restrict__ f1, const Tap& t) {
+  float v00 = __ldg(f0 + t.off), v01 = __ldg(f0 + t.off + 1), v10 = __ldg(f1 + t.off), v11 = __ldg(f1 + t.off + 1);
   return __fmaf_rn(v11, t.w11, __fmaf_rn(v10, t.w10, __fmaf_rn(v01, t.w01, __fmul_rn(v00, t.w00))));
 }
 

@@ -16,6 +16,13 @@
 // coalesced and the gathers of a warp fall into 1-2 cache lines.
 #include "geometry.cuh"
 
+#ifndef SATMVS_DK2
+#define SATMVS_DK2 8     // planes per thread with <= 2 source views (tuning knob, see profiles/)
+#endif
+#ifndef SATMVS_MIN_BLOCKS
+#define SATMVS_MIN_BLOCKS 1
+#endif
+
 namespace satmvs {
 
 constexpr int kSweepThreads = 128;
@@ -30,12 +37,12 @@ struct SweepArgs {
   int depth_per_pixel;
   int n_src;                                  // live source views (<= Geo::kNumSrc; the rest carry zero weights)
   float half_w, half_h;                       // W/2, H/2 (ATen un-normalise)
-  float num_views;                            // V as fp32 (div_(num_views), casred.py:53)
+  float num_views, inv_num_views;             // V as fp32 (div_(num_views), casred.py:53) and RN(1/V)
   Geo geo;
 };
 
 template <class Geo, int DK, bool kVariance>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, SATMVS_MIN_BLOCKS)
 sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
   constexpr int NSRC = Geo::kNumSrc;
   const int HW = a.H * a.W;
@@ -75,7 +82,8 @@ sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
         float s = r, q = r2, val = 0.0f;
 #pragma unroll
         for (int v = 0; v < NSRC; ++v) {
-          val = tap_fetch(a.src_fea[v] + (size_t)c * HW, taps[k][v], a.W);
+          const float* f0 = a.src_fea[v] + (size_t)c * HW;
+          val = tap_fetch(f0, f0 + a.W, taps[k][v]);
           if (kVariance) {
             // volume_sum + warped ; volume_sq_sum + warped**2  (casred.py:47-48): separate roundings
             s = __fadd_rn(s, val);
@@ -85,8 +93,8 @@ sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
         float res = val;
         if (kVariance) {
           // volume_sq_sum.div_(V).sub_(volume_sum.div_(V).pow_(2))  (casred.py:53)
-          const float m = __fdiv_rn(s, a.num_views);
-          res = __fsub_rn(__fdiv_rn(q, a.num_views), __fmul_rn(m, m));
+          const float m = div_const(s, a.num_views, a.inv_num_views);
+          res = __fsub_rn(div_const(q, a.num_views, a.inv_num_views), __fmul_rn(m, m));
         }
         if (active) __stcs(outc + (size_t)k * plane_stride, res);
       }
@@ -113,7 +121,7 @@ struct SweepBwdArgs {
   int depth_per_pixel;
   int n_src;
   float half_w, half_h;
-  float num_views;
+  float num_views, inv_num_views;
   Geo geo;
 };
 
@@ -167,7 +175,8 @@ sweep_bwd_kernel(const __grid_constant__ SweepBwdArgs<Geo> a) {
           float s = r;
 #pragma unroll
           for (int v = 0; v < NSRC; ++v) {
-            vals[v] = tap_fetch(a.src_fea[v] + (size_t)c * HW, taps[k][v], a.W);
+            const float* f0 = a.src_fea[v] + (size_t)c * HW;
+            vals[v] = tap_fetch(f0, f0 + a.W, taps[k][v]);
             s += vals[v];
           }
           const float mean = s / a.num_views;
@@ -219,7 +228,7 @@ __global__ void rpc_project_kernel(const __grid_constant__ RpcSrcPack r, const d
 // ------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------
-template <int NSRC> struct PlanesPerThread { static constexpr int value = NSRC <= 2 ? 8 : (NSRC <= 4 ? 4 : 2); };
+template <int NSRC> struct PlanesPerThread { static constexpr int value = NSRC <= 2 ? SATMVS_DK2 : (NSRC <= 4 ? 4 : 2); };
 
 static int check_dims(int n_src, int C, int D, int H, int W) {
   SATMVS_REQUIRE(n_src >= 1 && n_src <= SATMVS_MAX_SRC_VIEWS);
@@ -250,6 +259,8 @@ static void fill_rpc_geo(RpcSweep<NSRC>& g, int n_src, const double* ref_rpc, co
   for (int v = 0; v < NSRC; ++v) g.src[v] = make_rpc_src_pack(src_rpcs + (size_t)(v < n_src ? v : 0) * SATMVS_RPC_LEN, ref_rpc);
   g.half_wm1 = (float)((W - 1) / 2.0);
   g.half_hm1 = (float)((H - 1) / 2.0);
+  g.inv_half_wm1 = 1.0f / g.half_wm1;
+  g.inv_half_hm1 = 1.0f / g.half_hm1;
 }
 
 template <int NSRC>
@@ -270,6 +281,7 @@ static void fill_common(Args& a, const float* depth, int depth_per_pixel, int n_
   a.C = C; a.D = D; a.H = H; a.W = W;
   a.half_w = (float)(W / 2.0); a.half_h = (float)(H / 2.0);
   a.num_views = (float)(n_src + 1);
+  a.inv_num_views = 1.0f / a.num_views;
 }
 
 // template slot count for a runtime number of source views

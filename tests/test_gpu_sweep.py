@@ -136,8 +136,7 @@ def test_nonfinite_hypotheses_do_not_fault():
 
 def test_full_size_properties():
     """BASELINE config-2 size (1,3,32,64,96,192): too slow for the oracle in a unit test, so use
-    size-independent properties: (i) identity cameras + constant hypotheses reproduce the source
-    feature map exactly at integer taps; (ii) the fused volume equals the one assembled from the
+    size-independent properties: (i) an identity camera pair reads a ramp image at x*W/(W-1)-0.5; (ii) the fused volume equals the one assembled from the
     single-view warps; (iii) plane-constant and broadcast per-pixel hypotheses agree bit for bit."""
     B, V, C, D, H, W = 1, 3, 32, 64, 96, 192
     fe = [cu(f) for f in synth.make_features(B, V, C, H, W)]
@@ -149,14 +148,20 @@ def test_full_size_properties():
     assert torch.equal(var, var2)
     w1 = satmvs_b200.rpc_warping(fe[1], rp[:, 1], rp[:, 0], cu(dv4), None)
     w2 = satmvs_b200.rpc_warping(fe[2], rp[:, 2], rp[:, 0], cu(dv4), None)
-    ref = fe[0].unsqueeze(2)
+    # assembled on the CPU: torch-CPU divides exactly (the CUDA eager path multiplies by 1/3)
+    ref, w1, w2 = fe[0].unsqueeze(2).cpu(), w1.cpu(), w2.cpu()
     s = ref + w1 + w2
     q = ref ** 2 + w1 ** 2 + w2 ** 2
-    assert torch.equal(var, q / 3 - (s / 3) ** 2)
-    # identity: a noise-free affine camera pair whose forward/inverse maps cancel exactly
+    assert torch.equal(var.cpu(), q / 3 - (s / 3) ** 2)
+    # identity camera pair + ramp image: the reference normalises by (W-1)/2 but samples with
+    # align_corners=False, so pixel x reads the source at x*W/(W-1) - 0.5 (SURVEY.md §7 "quirk")
     ident = torch.from_numpy(np.stack([synth.make_rpc(0, H, W, num_noise=0.0, den_noise=0.0)] * 2)).unsqueeze(0)
-    wi = satmvs_b200.rpc_warping(fe[1], ident[:, 1], ident[:, 0], cu(dv2), None)
-    assert maxdiff(wi, fe[1].unsqueeze(2).expand(-1, -1, D, -1, -1)) < 1e-4
+    ramp = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W).expand(1, 1, H, W).contiguous()
+    wi = satmvs_b200.rpc_warping(cu(ramp), ident[:, 1], ident[:, 0], cu(dv2), None).cpu()
+    xs = torch.arange(W, dtype=torch.float64)
+    want = (xs * W / (W - 1) - 0.5).float()
+    inner = slice(2, W - 2)
+    assert (wi[0, 0, :, 2:H - 2, inner] - want[inner]).abs().max().item() < 1e-3
 
 
 def test_backward_matches_autograd_of_oracle():
