@@ -122,14 +122,17 @@ def build_step(w, dev, fe, cams, dv):
         return step, w["B"]
     if w["stage"] == "red_train":
         from satmvs_b200 import synth
-        sd = {k: v.to(dev) for k, v in synth.make_red_weights(w["C"]).items()}
-        reg = satmvs_b200.RedRegulariser(sd)
+        reg = satmvs_b200.RED_Regularization(w["C"], 8)
+        reg.load_state_dict(synth.make_red_weights(w["C"]))
+        reg = reg.to(dev).eval()
         all_cams = cams
 
         def step():
-            out = satmvs_b200.stage_train_red(fe, all_cams, dv, reg, w["geo"])
+            with torch.no_grad():
+                out = satmvs_b200.stage_train_red(fe, all_cams, dv, reg, w["geo"])
             return out["depth"], out["photometric_confidence"]
-        return step, None
+        # launches per step: 1 sweep + 3 encoders + 8 x-halves + 4 per plane + 3 decoder + 1 head conv + 1 soft-argmin
+        return step, w["B"] * (1 + 3 + 8 + 4 * w["D"] + 3 + 1 + 1)
     raise ValueError(w["stage"])
 
 

@@ -20,6 +20,7 @@
 #ifndef SATMVS_B200_H
 #define SATMVS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -110,6 +111,38 @@ int satmvs_softargmin_stream_update(const float* reg, const float* depth_plane, 
                                     int H, int W, double* state, void* stream);
 int satmvs_softargmin_stream_finish(const double* state, int H, int W,
                                     float* out_depth, float* out_conf, void* stream);
+
+/* ---- RED regulariser: 2-D conv-GRU UNet recurring over depth planes ----
+ * RED_Regularization.forward (modules/module.py:614-649) with D planes, and, with D = 1 and explicit
+ * states, slice_RED_Regularization.forward (modules/module.py:672-693).  base_channels is 8 (hidden
+ * channels 8/16/32/64 are hard-coded in the reference, module.py:617-620).
+ * All pointers device fp32.  Weight fields carry the reference's state_dict names:
+ *   gate_w[l]  conv_gru{l+1}.gate_conv.weight   [2*ch, cx+ch, 3, 3]    gate_b[l]  .gate_conv.bias
+ *   out_w[l]   conv_gru{l+1}.output_conv.weight [ch, cx+ch, 3, 3]      out_b[l]   .output_conv.bias
+ *   rn_*, un_*, on_*  reset_gate_norm / update_gate_norm / output_norm  .weight / .bias   [ch]
+ *   conv_w[i]  conv{i+1}.conv.weight;  upconv_w[i]  upconv{i+1}.conv.weight  ([Cin, Cout, 3, 3])
+ *   upconv2d_w [8,1,3,3], upconv2d_b [1]
+ */
+typedef struct satmvs_red_weights {
+  const float* gate_w[4]; const float* gate_b[4]; const float* out_w[4]; const float* out_b[4];
+  const float* rn_w[4]; const float* rn_b[4]; const float* un_w[4]; const float* un_b[4];
+  const float* on_w[4]; const float* on_b[4];
+  const float* conv_w[3];
+  const float* upconv_w[3];
+  const float* upconv2d_w; const float* upconv2d_b;
+} satmvs_red_weights;
+
+/* bytes of caller-owned scratch satmvs_red_forward needs (0 if the shape is unsupported:
+ * H and W must be multiples of 8). */
+size_t satmvs_red_workspace_bytes(int C, int D, int H, int W);
+
+/*   volume   [C,D,H,W] variance cost volume of one batch element (the regulariser negates it itself)
+ *   state_in  host array of 4 device pointers [8,H,W] [16,H/2,W/2] [32,H/4,W/4] [64,H/8,W/8], or NULL /
+ *             NULL entries for zero initial states;  state_out likewise, receives the states after plane D-1
+ *   logits   [D,H,W] regularised cost (the reference's prob_volume before softmax) */
+int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, int D, int H, int W,
+                       const float* const* state_in, float* const* state_out, float* logits,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

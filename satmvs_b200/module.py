@@ -1,0 +1,166 @@
+"""Host-side mirror of the reference's regulariser modules (`modules/module.py`) on the sm_100a
+kernels of libsatmvs_b200.so.
+
+The classes keep the reference's constructor signatures, sub-module names and parameter shapes, so
+`load_state_dict` accepts a reference checkpoint unchanged (`train.py:216-219`); the sub-modules are
+parameter containers only — `forward` hands raw pointers to the C ABI and never calls a torch conv.
+
+    RED_Regularization(in_channels, base_channels=8).forward(volume)            modules/module.py:595-649
+    slice_RED_Regularization(...).forward(cost, s1, s2, s3, s4)                 modules/module.py:653-693
+    CostRegNet(in_channels, base_channels).forward(x)                           modules/module.py:546-577
+    depth_regression(p, depth_values)                                           modules/module.py:433-439
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_F = C.c_void_p
+
+
+class _RedWeights(C.Structure):
+    _fields_ = [(n, _F * 4) for n in ("gate_w", "gate_b", "out_w", "out_b", "rn_w", "rn_b", "un_w", "un_b", "on_w", "on_b")] + \
+               [("conv_w", _F * 3), ("upconv_w", _F * 3), ("upconv2d_w", _F), ("upconv2d_b", _F)]
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Caller-owned scratch for the C ABI, cached per device and grown on demand."""
+    key = (device.type, device.index)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+class ConvGRUCell2(nn.Module):
+    """Parameter container with the reference's names (`modules/module.py:6-22`)."""
+
+    def __init__(self, input_channel, output_channel, kernel_size):
+        super().__init__()
+        k = input_channel + output_channel
+        self.output_channel = output_channel
+        self.gate_conv = nn.Conv2d(k, output_channel * 2, kernel_size, padding=1)
+        self.reset_gate_norm = nn.GroupNorm(1, output_channel, 1e-5, True)
+        self.update_gate_norm = nn.GroupNorm(1, output_channel, 1e-5, True)
+        self.output_conv = nn.Conv2d(k, output_channel, kernel_size, padding=1)
+        self.output_norm = nn.GroupNorm(1, output_channel, 1e-5, True)
+
+
+class ConvReLU(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, pad=1):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=pad, bias=False)
+
+
+class ConvTransReLU(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, pad=1, output_pad=1):
+        super().__init__()
+        self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=pad,
+                                       output_padding=output_pad, bias=False)
+
+
+class _RedBase(nn.Module):
+    def __init__(self, in_channels, base_channels=8):
+        super().__init__()
+        if base_channels != 8:
+            # the reference hard-codes hidden states of 8/16/32/64 channels (module.py:617-620)
+            raise ValueError("RED regulariser: base_channels must be 8")
+        b = base_channels
+        self.in_channels = in_channels
+        self.base_channels = b
+        self.conv_gru1 = ConvGRUCell2(in_channels, b, 3)
+        self.conv_gru2 = ConvGRUCell2(b * 2, b * 2, 3)
+        self.conv_gru3 = ConvGRUCell2(b * 4, b * 4, 3)
+        self.conv_gru4 = ConvGRUCell2(b * 8, b * 8, 3)
+        self.conv1 = ConvReLU(in_channels, b * 2, 3, 2, 1)
+        self.conv2 = ConvReLU(b * 2, b * 4, 3, 2, 1)
+        self.conv3 = ConvReLU(b * 4, b * 8, 3, 2, 1)
+        self.upconv3 = ConvTransReLU(b * 8, b * 4, 3, 2, 1, 1)
+        self.upconv2 = ConvTransReLU(b * 4, b * 2, 3, 2, 1, 1)
+        self.upconv1 = ConvTransReLU(b * 2, b, 3, 2, 1, 1)
+        self.upconv2d = nn.ConvTranspose2d(b, 1, kernel_size=3, stride=1, padding=1, output_padding=0)
+
+    def _weights(self) -> _RedWeights:
+        w = _RedWeights()
+        keep = []
+
+        def ptr(t):
+            t = _lib.require_cuda(t.detach(), "parameter")
+            keep.append(t)
+            return t.data_ptr()
+
+        for i, g in enumerate((self.conv_gru1, self.conv_gru2, self.conv_gru3, self.conv_gru4)):
+            w.gate_w[i], w.gate_b[i] = ptr(g.gate_conv.weight), ptr(g.gate_conv.bias)
+            w.out_w[i], w.out_b[i] = ptr(g.output_conv.weight), ptr(g.output_conv.bias)
+            w.rn_w[i], w.rn_b[i] = ptr(g.reset_gate_norm.weight), ptr(g.reset_gate_norm.bias)
+            w.un_w[i], w.un_b[i] = ptr(g.update_gate_norm.weight), ptr(g.update_gate_norm.bias)
+            w.on_w[i], w.on_b[i] = ptr(g.output_norm.weight), ptr(g.output_norm.bias)
+        for i, m in enumerate((self.conv1, self.conv2, self.conv3)):
+            w.conv_w[i] = ptr(m.conv.weight)
+        for i, m in enumerate((self.upconv1, self.upconv2, self.upconv3)):
+            w.upconv_w[i] = ptr(m.conv.weight)
+        w.upconv2d_w, w.upconv2d_b = ptr(self.upconv2d.weight), ptr(self.upconv2d.bias)
+        w._keep = keep
+        return w
+
+    def _run(self, volume: torch.Tensor, states_in, want_states: bool):
+        """volume [B,C,D,H,W] -> logits [B,D,H,W] (+ final states)."""
+        vol = _lib.require_cuda(volume, "volume")
+        B, Cc, D, H, W = vol.shape
+        if Cc != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} channels, got {Cc}")
+        nbytes = _lib.lib().satmvs_red_workspace_bytes(Cc, D, H, W)
+        if nbytes == 0:
+            raise ValueError("RED regulariser needs H and W to be multiples of 8")
+        ws = _workspace(nbytes, vol.device)
+        w = self._weights()
+        logits = torch.empty((B, D, H, W), dtype=torch.float32, device=vol.device)
+        out_states = None
+        if want_states:
+            out_states = [torch.empty((B, c, H >> l, W >> l), dtype=torch.float32, device=vol.device)
+                          for l, c in enumerate((8, 16, 32, 64))]
+        if states_in is not None:
+            states_in = [_lib.require_cuda(s, "state") for s in states_in]
+        with torch.cuda.device(vol.device):
+            st = _lib.stream_ptr(vol.device)
+            for b in range(B):
+                sin = _lib.ptr_array([s[b].data_ptr() for s in states_in]) if states_in is not None else None
+                sout = _lib.ptr_array([s[b].data_ptr() for s in out_states]) if out_states is not None else None
+                _lib.check(_lib.lib().satmvs_red_forward(C.byref(w), vol[b].data_ptr(), Cc, D, H, W, sin, sout,
+                                                        logits[b].data_ptr(), ws.data_ptr(), ws.numel(), st), "red_forward")
+        return logits, out_states
+
+
+class RED_Regularization(_RedBase):
+    """`RED_Regularization` (`modules/module.py:595-649`): volume [B,C,D,H,W] -> [B,D,H,W]."""
+
+    def forward(self, volume_variance):
+        return self._run(volume_variance, None, False)[0]
+
+
+class slice_RED_Regularization(_RedBase):
+    """`slice_RED_Regularization` (`modules/module.py:653-693`): one depth slice with explicit states.
+    cost [B,C,H,W]; returns (reg [B,1,H,W], state1..state4)."""
+
+    def forward(self, cost, state1, state2, state3, state4):
+        logits, st = self._run(cost.unsqueeze(2), [state1, state2, state3, state4], True)
+        return (logits, *st)
+
+
+def depth_regression(p, depth_values):
+    """`depth_regression` (`modules/module.py:433-439`), kept for API parity: sum_d p*d on given
+    probabilities.  The fused softmax+regression kernel is `satmvs_b200.softargmin`."""
+    if depth_values.dim() <= 2:
+        depth_values = depth_values.view(*depth_values.shape, 1, 1)
+    else:
+        depth_values = torch.nn.functional.interpolate(depth_values, [p.shape[2], p.shape[3]], mode="bilinear",
+                                                       align_corners=False)
+    return torch.sum(p * depth_values, 1)

@@ -1,0 +1,56 @@
+"""One cascade stage on the GPU kernels: features in, depth + confidence out.
+
+Mirrors `compute_depth_when_train` (`networks/casred.py:10-64`), `compute_depth_when_pred`
+(`networks/casred.py:161-238`) and `DepthNet.forward` (`networks/casmvs.py:15-76`) from the feature
+maps onward; FeatureNet is outside the path.
+"""
+from __future__ import annotations
+
+import torch
+
+from .regress import StreamingSoftArgmin, softargmin
+from .warping import build_cost_volume
+
+
+def _split(features, cams):
+    if len(features) != cams.shape[1]:
+        raise AssertionError("Different number of images and projection matrices")      # casred.py:15
+    return features[0], list(features[1:]), cams[:, 0], [cams[:, v] for v in range(1, cams.shape[1])]
+
+
+def stage_train_red(features, cams, depth_values, regulariser, geo_model="rpc"):
+    """Whole-volume stage: fused sweep -> RED regulariser over D -> softmax/expectation/max-prob.
+    features: V x [B,C,H,W] CUDA; cams [B,V,170] or [B,V,4,4] f64 (host preferred); depth_values
+    [B,D] or [B,D,H,W]; regulariser: `satmvs_b200.module.RED_Regularization`."""
+    ref, srcs, ref_cam, src_cams = _split(features, cams)
+    var = build_cost_volume(ref, srcs, ref_cam, src_cams, depth_values, geo_model)
+    logits = regulariser(var)
+    depth, conf = softargmin(logits, depth_values, "red")
+    return {"depth": depth, "photometric_confidence": conf}
+
+
+def stage_casmvs(features, cams, depth_values, regulariser, geo_model="rpc"):
+    """CasMVSNet stage: fused sweep -> CostRegNet -> softmax/expectation/4-neighbour confidence."""
+    ref, srcs, ref_cam, src_cams = _split(features, cams)
+    var = build_cost_volume(ref, srcs, ref_cam, src_cams, depth_values, geo_model)
+    logits = regulariser(var).squeeze(1)
+    depth, conf = softargmin(logits, depth_values, "casmvs")
+    return {"depth": depth, "photometric_confidence": conf}
+
+
+def stage_pred_red(features, cams, depth_values, regulariser, geo_model="rpc"):
+    """Plane-streaming stage of the inference net: per plane, sweep one hypothesis, one recurrent
+    regulariser step (states carried), streaming fp64 soft-argmin.  O(H*W) memory.
+    regulariser: `satmvs_b200.module.slice_RED_Regularization`."""
+    ref, srcs, ref_cam, src_cams = _split(features, cams)
+    B, _, H, W = ref.shape
+    dev = ref.device
+    states = [torch.zeros((B, c, H >> l, W >> l), dtype=torch.float32, device=dev) for l, c in enumerate((8, 16, 32, 64))]
+    head = StreamingSoftArgmin(B, H, W, dev)
+    for d in range(depth_values.shape[1]):
+        plane = depth_values[:, d:d + 1].contiguous()
+        var = build_cost_volume(ref, srcs, ref_cam, src_cams, plane, geo_model)
+        reg, *states = regulariser(var.squeeze(2), *states)
+        head.update(reg, plane)
+    depth, conf = head.finish()
+    return {"depth": depth, "photometric_confidence": conf}

@@ -1,0 +1,87 @@
+"""GPU parity of the RED regulariser (conv engine + GRU kernels through the C ABI) against the
+committed reference vectors and the CPU oracle.  fp32 convolutions with a different summation
+order than oneDNN's: logits are checked to 2e-4 of their range, depth to north_star's 1e-3
+relative L-inf (measured values are ~1e-6, asserted at 1e-4)."""
+import pytest
+import torch
+
+import satmvs_b200
+from oracle import regnets, stages
+from satmvs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def maxdiff(a, b):
+    return (a.detach().cpu().double() - b.detach().cpu().double()).abs().max().item()
+
+
+def make_reg(cls, C, seed=13):
+    m = cls(C, 8)
+    m.load_state_dict(synth.make_red_weights(C, seed=seed))
+    return m.to(DEV).eval()
+
+
+def test_slice_golden(golden):
+    g = golden("red_slice")
+    m = make_reg(satmvs_b200.slice_RED_Regularization, 8)
+    out = m(g["cost"].to(DEV), *[g[k].to(DEV) for k in ("s1", "s2", "s3", "s4")])
+    errs = {key: maxdiff(got, g[key]) / max(1.0, g[key].abs().max().item())
+            for got, key in zip(out, ("reg", "n1", "n2", "n3", "n4"))}
+    assert all(got.shape == g[key].shape for got, key in zip(out, ("reg", "n1", "n2", "n3", "n4")))
+    assert max(errs.values()) < 2e-4, errs
+
+
+@pytest.mark.parametrize("geo", ["rpc", "pinhole"])
+def test_volume_golden(golden, geo):
+    g = golden(f"stage_train_{geo}")
+    m = make_reg(satmvs_b200.RED_Regularization, 8)
+    logits = m(g["var"].to(DEV))
+    assert logits.shape == g["logits"].shape
+    assert maxdiff(logits, g["logits"]) < 2e-4 * max(1.0, g["logits"].abs().max().item())
+    fe = [g[f"fea{v}"].to(DEV) for v in range(3)]
+    out = satmvs_b200.stage_train_red(fe, g["cams"], g["depth_values"].to(DEV), m, geo)
+    rel = maxdiff(out["depth"], g["depth"]) / g["depth"].abs().max().item()
+    assert rel < 1e-4, rel
+    assert maxdiff(out["photometric_confidence"], g["conf"]) < 1e-4
+
+
+@pytest.mark.parametrize("C,D,H,W", [(32, 12, 32, 64), (16, 3, 16, 24), (8, 1, 8, 8)])
+def test_volume_vs_oracle(C, D, H, W):
+    sd = synth.make_red_weights(C, seed=5)
+    m = satmvs_b200.RED_Regularization(C, 8)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    x = synth.make_features(1, 1, C * D, H, W, seed=9)[0].view(1, C, D, H, W).abs()
+    want = regnets.red_regularization(x, sd)
+    got = m(x.to(DEV))
+    assert maxdiff(got, want) < 2e-4 * max(1.0, want.abs().max().item())
+
+
+def test_pred_stage_equals_train_stage():
+    """Plane-streaming inference form == whole-volume form (the reference's two nets agree to
+    1.7e-5 relative)."""
+    B, V, C, D, H, W = 1, 3, 8, 6, 16, 24
+    fe = [f.to(DEV) for f in synth.make_features(B, V, C, H, W, seed=2)]
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv = synth.make_depth_planes(B, D, H, W).to(DEV)
+    sd = synth.make_red_weights(C)
+    a = make_reg(satmvs_b200.RED_Regularization, C)
+    b = make_reg(satmvs_b200.slice_RED_Regularization, C)
+    ta = satmvs_b200.stage_train_red(fe, rp, dv, a, "rpc")
+    tb = satmvs_b200.stage_pred_red(fe, rp, dv, b, "rpc")
+    scale = ta["depth"].abs().max().item()
+    assert maxdiff(ta["depth"], tb["depth"]) < 1e-4 * scale
+    want = stages.stage_pred_red([f.cpu() for f in fe], rp, dv.cpu(), sd, "rpc")
+    assert maxdiff(tb["depth"], want["depth"]) < 1e-4 * scale
+    assert maxdiff(tb["photometric_confidence"], want["photometric_confidence"]) < 1e-4
+
+
+def test_reference_checkpoint_keys():
+    """state_dict keys/shapes are the reference's (`train.py:216-219` checkpoints must load)."""
+    m = satmvs_b200.RED_Regularization(32, 8)
+    want = synth.make_red_weights(32)
+    have = m.state_dict()
+    assert set(have) == set(want)
+    assert all(have[k].shape == want[k].shape for k in want)
