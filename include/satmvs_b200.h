@@ -112,6 +112,15 @@ int satmvs_softargmin_stream_update(const float* reg, const float* depth_plane, 
 int satmvs_softargmin_stream_finish(const double* state, int H, int W,
                                     float* out_depth, float* out_conf, void* stream);
 
+/* ---- depth hypotheses + cascade resampling ----
+ * get_depth_range_samples (modules/depth_range.py:4-42) fused with the bilinear up-sampling of the
+ * previous stage's depth and the trilinear resize to the stage grid (networks/casred.py:132-145).
+ *   prev_depth device [hp,wp] previous-stage depth, or NULL for the first stage, in which case
+ *   depth_range device [n_range] gives the range (planes from [0] to [n_range-1] inclusive);
+ *   out device [D,h,w] hypotheses on the stage grid (h = Himg/scale, w = Wimg/scale). */
+int satmvs_depth_hypotheses(const float* prev_depth, int hp, int wp, const float* depth_range, int n_range,
+                            int D, float interval, int Himg, int Wimg, int h, int w, float* out, void* stream);
+
 /* ---- RED regulariser: 2-D conv-GRU UNet recurring over depth planes ----
  * RED_Regularization.forward (modules/module.py:614-649) with D planes, and, with D = 1 and explicit
  * states, slice_RED_Regularization.forward (modules/module.py:672-693).  base_channels is 8 (hidden
@@ -143,6 +152,24 @@ size_t satmvs_red_workspace_bytes(int C, int D, int H, int W);
 int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, int D, int H, int W,
                        const float* const* state_in, float* const* state_out, float* logits,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- CostRegNet: 3-D conv UNet regulariser (CasMVSNet / UCS-Net) ----
+ * CostRegNet.forward (modules/module.py:546-577), inference-mode BatchNorm.
+ *   conv_w[0..6]  conv0..conv6 .conv.weight [Cout,Cin,3,3,3];  conv_w[7..9]  conv7, conv9, conv11
+ *                 .conv.weight (ConvTranspose3d layout [Cin,Cout,3,3,3])
+ *   bn_scale[i] = bn.weight / sqrt(bn.running_var + eps),  bn_shift[i] = bn.bias - bn.running_mean * bn_scale[i]
+ *   prob_w        prob.weight [1,base,3,3,3]
+ *   x [Cin,D,H,W] -> out [D,H,W] (the reference's [1,D,H,W]); D, H, W multiples of 8. */
+typedef struct satmvs_costreg_weights {
+  const float* conv_w[10];
+  const float* bn_scale[10];
+  const float* bn_shift[10];
+  const float* prob_w;
+} satmvs_costreg_weights;
+
+size_t satmvs_costreg_workspace_bytes(int base_channels, int D, int H, int W);
+int satmvs_costreg_forward(const satmvs_costreg_weights* w, const float* x, int Cin, int base_channels,
+                           int D, int H, int W, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,136 @@
+// costreg.cu — CostRegNet, the 3-D conv UNet regulariser of CasMVSNet / UCS-Net, on the conv engine.
+//
+// Reference: CostRegNet.forward (modules/module.py:546-577) with blocks Conv3d (:324-366) and
+// Deconv3d (:369-410): every block is conv(bias=False) + BatchNorm3d + ReLU; the three transposed
+// blocks add a skip tensor AFTER the ReLU (x = conv4 + conv7(x), module.py:573-575); `prob` is a bare
+// 3x3x3 conv to one channel.  BatchNorm is applied in inference form (running statistics) folded to
+// a per-channel scale/shift by the host wrapper.
+//
+// 11 launches: 7 dense 27-tap convs (3 of them stride 2), 3 transposed convs (each one grouped launch
+// of its 8 output-parity classes, so no multiply ever touches a structural zero), 1 head conv.
+#include "conv_engine.cuh"
+
+namespace satmvs {
+
+static ConvProblem conv3d_problem(const float* in, int Cin, int Di, int Hi, int Wi, const float* w,
+                                  float* out, int Cout, int stride) {
+  ConvProblem p;
+  conv_problem_defaults(p);
+  p.in = in; p.w = w; p.out = out;
+  p.Cin = Cin; p.Cout = Cout;
+  p.Di = Di; p.Hi = Hi; p.Wi = Wi;
+  p.Do = Di / stride; p.Ho = Hi / stride; p.Wo = Wi / stride;
+  p.Qd = p.Do; p.Qh = p.Ho; p.Qw = p.Wo;
+  p.w_co_stride = (long long)Cin * 27; p.w_ci_stride = 27;          // nn.Conv3d weight [Cout][Cin][3][3][3]
+  for (int i = 0; i < 3; ++i) { p.q2i_mul[i] = stride; p.q2i_add[i] = -1; }
+  conv_taps_dense(p, true);
+  p.relu = 1;
+  return p;
+}
+
+template <class T>
+static int run_conv(ConvProblem p, cudaStream_t st, const char* what) {
+  conv_finalize(p);
+  ConvGroup g{};
+  g.p[0] = p; g.n = 1;
+  return conv_launch<T>(g, st, what);
+}
+
+static int run_by_cout(const ConvProblem& p, cudaStream_t st, const char* what) {
+  if (p.Cout >= 64) return run_conv<Tile64>(p, st, what);
+  if (p.Cout >= 32) return run_conv<Tile32>(p, st, what);
+  if (p.Cout >= 16) return run_conv<Tile16>(p, st, what);
+  return run_conv<Tile8>(p, st, what);
+}
+
+// ConvTranspose3d(k=3, stride 2, padding 1, output_padding 1): 8 parity classes in one launch
+static int run_deconv3d(const float* in, int Cin, int Di, int Hi, int Wi, const float* w, const float* scale,
+                        const float* shift, const float* skip, float* out, int Cout, cudaStream_t st) {
+  ConvGroup g{};
+  int n = 0;
+  for (int pz = 0; pz < 2; ++pz)
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        ConvProblem p;
+        conv_problem_defaults(p);
+        p.in = in; p.w = w; p.out = out;
+        p.Cin = Cin; p.Cout = Cout;
+        p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
+        p.Qd = Di; p.Qh = Hi; p.Qw = Wi;
+        p.w_ci_stride = (long long)Cout * 27; p.w_co_stride = 27;   // nn.ConvTranspose3d weight [Cin][Cout][3][3][3]
+        for (int i = 0; i < 3; ++i) p.q2o_mul[i] = 2;
+        p.q2o_add[0] = pz; p.q2o_add[1] = py; p.q2o_add[2] = px;
+        conv_taps_deconv_class(p, true, pz, py, px);
+        p.scale = scale; p.shift = shift; p.relu = 1; p.post_add = skip;
+        conv_finalize(p);
+        g.p[n++] = p;
+      }
+  g.n = n;
+  if (Cout >= 32) return conv_launch<Tile32>(g, st, "costreg deconv");
+  if (Cout >= 16) return conv_launch<Tile16>(g, st, "costreg deconv");
+  return conv_launch<Tile8>(g, st, "costreg deconv");
+}
+
+struct CostRegPlan { float* c[7]; float* x7; float* x9; float* x11; size_t bytes; };
+
+static CostRegPlan costreg_plan(int base, int D, int H, int W, char* mem) {
+  CostRegPlan p{};
+  size_t off = 0;
+  auto take = [&](size_t n) { float* r = reinterpret_cast<float*>(mem + off); off += (n * 4 + 255) / 256 * 256; return r; };
+  const size_t v0 = (size_t)D * H * W, v1 = v0 / 8, v2 = v1 / 8, v3 = v2 / 8;
+  p.c[0] = take(base * v0);
+  p.c[1] = take(2 * base * v1); p.c[2] = take(2 * base * v1);
+  p.c[3] = take(4 * base * v2); p.c[4] = take(4 * base * v2);
+  p.c[5] = take(8 * base * v3); p.c[6] = take(8 * base * v3);
+  p.x7 = take(4 * base * v2); p.x9 = take(2 * base * v1); p.x11 = take(base * v0);
+  p.bytes = off;
+  return p;
+}
+
+}  // namespace satmvs
+
+using namespace satmvs;
+
+extern "C" {
+
+size_t satmvs_costreg_workspace_bytes(int base, int D, int H, int W) {
+  if (base < 1 || D < 8 || H < 8 || W < 8 || (D % 8) || (H % 8) || (W % 8)) return 0;
+  return costreg_plan(base, D, H, W, nullptr).bytes;
+}
+
+int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int Cin, int base, int D, int H, int W,
+                           float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  SATMVS_REQUIRE(wt && x && out && workspace);
+  SATMVS_REQUIRE(Cin >= 1 && base >= 1 && D >= 8 && H >= 8 && W >= 8 && D % 8 == 0 && H % 8 == 0 && W % 8 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  CostRegPlan P = costreg_plan(base, D, H, W, reinterpret_cast<char*>(workspace));
+  SATMVS_REQUIRE(workspace_bytes >= P.bytes);
+  int rc;
+#define RUN(e) do { rc = (e); if (rc) return rc; } while (0)
+  // conv0..conv6 (module.py:569-572): channel and stride schedule
+  const int cin[7] = {Cin, base, 2 * base, 2 * base, 4 * base, 4 * base, 8 * base};
+  const int cout[7] = {base, 2 * base, 2 * base, 4 * base, 4 * base, 8 * base, 8 * base};
+  const int stride[7] = {1, 2, 1, 2, 1, 2, 1};
+  const float* cur = x;
+  int d = D, h = H, w = W;
+  for (int i = 0; i < 7; ++i) {
+    ConvProblem p = conv3d_problem(cur, cin[i], d, h, w, wt->conv_w[i], P.c[i], cout[i], stride[i]);
+    p.scale = wt->bn_scale[i]; p.shift = wt->bn_shift[i];
+    RUN(run_by_cout(p, st, "costreg conv"));
+    cur = P.c[i];
+    d /= stride[i]; h /= stride[i]; w /= stride[i];
+  }
+  // conv7 / conv9 / conv11: transposed, BN + ReLU, then + skip (module.py:573-575)
+  RUN(run_deconv3d(P.c[6], 8 * base, d, h, w, wt->conv_w[7], wt->bn_scale[7], wt->bn_shift[7], P.c[4], P.x7, 4 * base, st));
+  RUN(run_deconv3d(P.x7, 4 * base, 2 * d, 2 * h, 2 * w, wt->conv_w[8], wt->bn_scale[8], wt->bn_shift[8], P.c[2], P.x9, 2 * base, st));
+  RUN(run_deconv3d(P.x9, 2 * base, 4 * d, 4 * h, 4 * w, wt->conv_w[9], wt->bn_scale[9], wt->bn_shift[9], P.c[0], P.x11, base, st));
+  {  // prob: bare Conv3d(base, 1, 3, padding=1, bias=False) (module.py:566, :576)
+    ConvProblem p = conv3d_problem(P.x11, base, D, H, W, wt->prob_w, out, 1, 1);
+    p.relu = 0;
+    RUN(run_conv<Tile8>(p, st, "costreg prob"));
+  }
+#undef RUN
+  return SATMVS_OK;
+}
+
+}  // extern "C"

@@ -81,15 +81,18 @@ struct GruLevelArgs {
   const float *rn_w, *rn_b, *un_w, *un_b, *on_w, *on_b;
   const double* stats;   // [3][2] of this (plane, level): r, u, o
   long long gcs, ocs, scs;
+  double inv_n;          // 1 / (ch * px)
   int ch, px;
   int begin;             // first flat element index of this level in the launch
 };
 struct GruArgs { GruLevelArgs l[4]; int total; };
 
-__device__ __forceinline__ void gn_coeff(const double* st, double n, float gamma, float beta, float& a, float& b) {
-  const double mean = st[0] / n;
-  const double var = fmax(st[1] / n - mean * mean, 0.0);
-  const float rstd = (float)(1.0 / sqrt(var + (double)kGnEps));
+// y = (x - mean) * rstd * gamma + beta = x*a + b.  Sums are fp64; mean/var formed in fp64 (no
+// cancellation problem), rstd in fp32 like ATen's GroupNorm.
+__device__ __forceinline__ void gn_coeff(const double* st, double inv_n, float gamma, float beta, float& a, float& b) {
+  const double mean = st[0] * inv_n;
+  const float var = (float)fmax(st[1] * inv_n - mean * mean, 0.0);
+  const float rstd = rsqrtf(var + kGnEps);
   a = gamma * rstd;
   b = beta - (float)mean * a;
 }
@@ -105,7 +108,7 @@ __global__ void gru_reset_kernel(const __grid_constant__ GruArgs a) {
   const GruLevelArgs& L = a.l[li];
   const int e = i - L.begin, c = e / L.px, p = e - c * L.px;
   float ga, gb;
-  gn_coeff(L.stats, (double)L.ch * L.px, __ldg(L.rn_w + c), __ldg(L.rn_b + c), ga, gb);
+  gn_coeff(L.stats, L.inv_n, __ldg(L.rn_w + c), __ldg(L.rn_b + c), ga, gb);
   const float r = sigmoidf_(fmaf(__ldg(L.g + c * L.gcs + p), ga, gb));
   L.rh[e] = r * __ldg(L.hprev + c * L.scs + p);
 }
@@ -118,14 +121,251 @@ __global__ void gru_update_kernel(const __grid_constant__ GruArgs a) {
   for (int k = 1; k < 4; ++k) if (i >= a.l[k].begin) li = k;
   const GruLevelArgs& L = a.l[li];
   const int e = i - L.begin, c = e / L.px, p = e - c * L.px;
-  const double n = (double)L.ch * L.px;
   float ua, ub, oa, ob;
-  gn_coeff(L.stats + 2, n, __ldg(L.un_w + c), __ldg(L.un_b + c), ua, ub);
-  gn_coeff(L.stats + 4, n, __ldg(L.on_w + c), __ldg(L.on_b + c), oa, ob);
+  gn_coeff(L.stats + 2, L.inv_n, __ldg(L.un_w + c), __ldg(L.un_b + c), ua, ub);
+  gn_coeff(L.stats + 4, L.inv_n, __ldg(L.on_w + c), __ldg(L.on_b + c), oa, ob);
   const float u = sigmoidf_(fmaf(__ldg(L.g + (c + L.ch) * L.gcs + p), ua, ub));
   const float y = tanhf(fmaf(__ldg(L.o + c * L.ocs + p), oa, ob));
   const float h = __ldg(L.hprev + c * L.scs + p);
   L.hnext[c * L.scs + p] = u * h + (1.0f - u) * y;       // module.py:57
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// recurrent step convolution: out[co, p] = pre[co, p] + sum_{ci, 3x3} w[co, ci, tap] * in[ci, p + tap]
+// for the hidden-state halves of the four GRUs in ONE launch.  These problems are tiny (21 M MAC per
+// level) and latency-bound, so the decomposition maximises resident warps instead of tile reuse:
+// one warp = 8 output channels x 128 pixels (4 per lane) x 8 (16 at Cin 64) input channels; the
+// warps that share an output tile reduce through shared memory in a fixed order (deterministic).
+// Every CTA has 4 busy warps whatever the level: 4 tiles x 1 k-part (Cin 8) ... 1 tile x 4 k-parts
+// (Cin >= 32), two CTAs per SM, and the whole step fits one wave (264 CTAs at 96x192).
+// ---------------------------------------------------------------------------------------------
+struct GruConvLevel {
+  const float* in;  long long in_cs;        // [cin] planes of h*w
+  const float* w;   long long w_co;         // w[co * w_co + ci * 9 + tap]   (h-half of the conv weight)
+  const float* pre; float* out; long long out_cs;
+  double* stats;                            // (sum, sum^2) per group of stats_group output channels
+  int cin, cout, h, w_, stats_group;
+  int ksplit;                               // warps sharing one output tile: min(cin / 8, 4)
+  int ci_per_warp;                          // cin / ksplit (8 or 16)
+  int px_groups;                            // CTAs per output-channel chunk
+  int cta_begin;
+};
+struct GruConvArgs { GruConvLevel l[4]; };
+
+constexpr int kGcWarps = 4, kGcCo = 8, kGcPx = 4, kGcTilePx = 32 * kGcPx, kGcCi = 8;
+
+// kAligned: every level's width is a multiple of 4, so a lane's 4 pixels sit in one row at a
+// 16-byte aligned address: 3 vector + 6 scalar loads per input channel instead of 36 predicated ones.
+template <bool kAligned>
+__global__ void __launch_bounds__(kGcWarps * 32)
+gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
+  __shared__ __align__(16) float wsm[64 * 9 * kGcCo];                    // [ci][tap][co]  (<= 18 KB)
+  __shared__ __align__(16) float part[kGcWarps][kGcCo][kGcTilePx];      // 16 KB
+  __shared__ double red[2][kGcWarps];
+  int li = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) if ((int)blockIdx.x >= a.l[k].cta_begin) li = k;
+  const GruConvLevel& L = a.l[li];
+  const int cta = blockIdx.x - L.cta_begin;
+  const int co0 = (cta / L.px_groups) * kGcCo;
+  const int tiles_per_cta = kGcWarps / L.ksplit;
+  const int tile0 = (cta % L.px_groups) * tiles_per_cta;
+  const int npx = L.h * L.w_;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // weights of this CTA's 8 output channels -> smem [ci][tap][co].  All loads are issued before the
+  // first store (one round trip to L2 instead of one per loop iteration).
+  {
+    const int kr = L.cin * 9;                                   // contiguous run per output channel
+    const int per_co = (kr + kGcWarps * 32 - 1) / (kGcWarps * 32);   // <= 5 (cin 64)
+    constexpr int kMaxPerCo = (64 * 9 + kGcWarps * 32 - 1) / (kGcWarps * 32);
+    float t[kGcCo][kMaxPerCo];
+#pragma unroll
+    for (int co = 0; co < kGcCo; ++co) {
+      const float* wp = L.w + (long long)(co0 + co) * L.w_co;
+#pragma unroll
+      for (int k = 0; k < kMaxPerCo; ++k) {
+        const int r = tid + k * (kGcWarps * 32);
+        t[co][k] = (k < per_co && r < kr) ? __ldg(wp + r) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < kGcCo; ++co)
+#pragma unroll
+      for (int k = 0; k < kMaxPerCo; ++k) {
+        const int r = tid + k * (kGcWarps * 32);
+        if (k < per_co && r < kr) wsm[r * kGcCo + co] = t[co][k];
+      }
+  }
+
+  const int tile = tile0 + warp / L.ksplit, kpart = warp % L.ksplit;
+  int base[kGcPx]; unsigned mask[kGcPx];
+#pragma unroll
+  for (int j = 0; j < kGcPx; ++j) {
+    const int p = tile * kGcTilePx + lane * kGcPx + j;
+    const bool ok = p < npx;
+    const int y = ok ? p / L.w_ : 0, x = ok ? p - y * L.w_ : 0;
+    base[j] = y * L.w_ + x;
+    unsigned m = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
+      if (ok && (unsigned)iy < (unsigned)L.h && (unsigned)ix < (unsigned)L.w_) m |= 1u << t;
+    }
+    mask[j] = m;
+  }
+  float acc[kGcCo][kGcPx];
+#pragma unroll
+  for (int i = 0; i < kGcCo; ++i)
+#pragma unroll
+    for (int j = 0; j < kGcPx; ++j) acc[i][j] = 0.0f;
+  __syncthreads();
+
+  // input taps of one input channel for this lane's 4 pixels (predicated: zero padding)
+  auto load_taps = [&](int ci, float (&v)[kGcPx][9]) {
+    const float* ip = L.in + ci * L.in_cs;
+#pragma unroll
+    for (int j = 0; j < kGcPx; ++j)
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        v[j][t] = ((mask[j] >> t) & 1u) ? __ldg(ip + base[j] + (t / 3 - 1) * L.w_ + (t % 3 - 1)) : 0.0f;
+  };
+  auto fma_taps = [&](int ci, const float (&v)[kGcPx][9]) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&wsm[(ci * 9 + t) * kGcCo]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&wsm[(ci * 9 + t) * kGcCo + 4]);
+      const float wv[kGcCo] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < kGcCo; ++i)
+#pragma unroll
+        for (int j = 0; j < kGcPx; ++j) acc[i][j] = fmaf(wv[i], v[j][t], acc[i][j]);
+    }
+  };
+  if constexpr (kAligned) {
+    const int pl = tile * kGcTilePx + lane * kGcPx;
+    const bool ok = pl < npx;
+    const int y = ok ? pl / L.w_ : 0, x = ok ? pl - y * L.w_ : 0;
+    const bool rowok[3] = {ok && y > 0, ok, ok && y + 1 < L.h};
+    const bool lok = x > 0, rok = x + kGcPx < L.w_;
+    const int ci0 = kpart * L.ci_per_warp;
+    // rows[dy][0..5] = in[y+dy-1][x-1 .. x+4]
+    auto load_rows = [&](int ci, float (&r)[3][6]) {
+      const float* ip = L.in + ci * L.in_cs + (y - 1) * L.w_ + x;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const float* rp = ip + dy * L.w_;
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        float lft = 0.f, rgt = 0.f;
+        if (rowok[dy]) {
+          m = __ldg(reinterpret_cast<const float4*>(rp));
+          if (lok) lft = __ldg(rp - 1);
+          if (rok) rgt = __ldg(rp + kGcPx);
+        }
+        r[dy][0] = lft; r[dy][1] = m.x; r[dy][2] = m.y; r[dy][3] = m.z; r[dy][4] = m.w; r[dy][5] = rgt;
+      }
+    };
+    auto fma_rows = [&](int ci, const float (&r)[3][6]) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[(ci * 9 + t) * kGcCo]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[(ci * 9 + t) * kGcCo + 4]);
+        const float wv[kGcCo] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < kGcCo; ++i)
+#pragma unroll
+          for (int j = 0; j < kGcPx; ++j) acc[i][j] = fmaf(wv[i], r[t / 3][j + t % 3], acc[i][j]);
+      }
+    };
+    float ra[3][6], rb[3][6];
+    load_rows(ci0, ra);
+    for (int c = 0; c < L.ci_per_warp; c += 2) {
+      load_rows(ci0 + c + 1, rb);
+      fma_rows(ci0 + c, ra);
+      if (c + 2 < L.ci_per_warp) load_rows(ci0 + c + 2, ra);
+      fma_rows(ci0 + c + 1, rb);
+    }
+  } else {
+  // two input channels per iteration, ping-pong registers: the next channel's taps are in flight
+  // while the current channel's 288 FMAs issue
+  float va[kGcPx][9], vb[kGcPx][9];
+  const int ci0 = kpart * L.ci_per_warp;
+  load_taps(ci0, va);
+  for (int c = 0; c < L.ci_per_warp; c += 2) {
+    load_taps(ci0 + c + 1, vb);
+    fma_taps(ci0 + c, va);
+    if (c + 2 < L.ci_per_warp) load_taps(ci0 + c + 2, va);
+    fma_taps(ci0 + c + 1, vb);
+  }
+  }
+
+  // this thread's share of the CTA's outputs: fetch the addends now, so the loads fly during the
+  // partial-sum exchange
+  constexpr int kMaxOut = kGcCo * kGcTilePx / 32;          // 32 outputs per thread when ksplit == 1
+  const int outs = tiles_per_cta * kGcCo * kGcTilePx;
+  float pre[kMaxOut];
+#pragma unroll
+  for (int r = 0; r < kMaxOut; ++r) {
+    const int o = tid + r * (kGcWarps * 32);
+    pre[r] = 0.0f;
+    if (o < outs) {
+      const int ts = o / (kGcCo * kGcTilePx), q = o - ts * (kGcCo * kGcTilePx);
+      const int i = q / kGcTilePx, p = (tile0 + ts) * kGcTilePx + (q - i * kGcTilePx);
+      if (p < npx) pre[r] = __ldg(L.pre + (long long)(co0 + i) * L.out_cs + p);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kGcCo; ++i)
+    *reinterpret_cast<float4*>(&part[warp][i][lane * kGcPx]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+
+  // fixed-order reduction over the k-parts, epilogue, GroupNorm sums
+  float ssum = 0.0f, ssq = 0.0f;
+#pragma unroll
+  for (int r = 0; r < kMaxOut; ++r) {
+    const int o = tid + r * (kGcWarps * 32);
+    if (o >= outs) break;
+    const int ts = o / (kGcCo * kGcTilePx), q = o - ts * (kGcCo * kGcTilePx);
+    const int i = q / kGcTilePx, px = q - i * kGcTilePx;
+    const int p = (tile0 + ts) * kGcTilePx + px;
+    if (p >= npx) continue;
+    float sum = 0.0f;
+    for (int kp = 0; kp < L.ksplit; ++kp) sum += part[ts * L.ksplit + kp][i][px];
+    const float val = sum + pre[r];
+    L.out[(long long)(co0 + i) * L.out_cs + p] = val;
+    ssum += val; ssq += val * val;
+  }
+  double ds = ssum, dq = ssq;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, off); dq += __shfl_xor_sync(0xffffffffu, dq, off); }
+  if (lane == 0) { red[0][warp] = ds; red[1][warp] = dq; }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < kGcWarps; ++i) { s += red[0][i]; q += red[1][i]; }
+    const int grp = co0 / L.stats_group;
+    atomicAdd(L.stats + 2 * grp, s);
+    atomicAdd(L.stats + 2 * grp + 1, q);
+  }
+}
+
+static int gru_conv_launch(const GruConvArgs& c, int ctas, cudaStream_t st, const char* what) {
+  bool aligned = true;
+  for (int l = 0; l < 4; ++l) aligned = aligned && (c.l[l].w_ % kGcPx == 0);
+  if (aligned) gru_conv_kernel<true><<<ctas, kGcWarps * 32, 0, st>>>(c);
+  else gru_conv_kernel<false><<<ctas, kGcWarps * 32, 0, st>>>(c);
+  return check_launch(what);
+}
+
+static int gru_conv_fill(GruConvLevel& g, int cta_begin) {
+  g.ksplit = g.cin / kGcCi < kGcWarps ? g.cin / kGcCi : kGcWarps;
+  g.ci_per_warp = g.cin / g.ksplit;
+  const int tiles = (g.h * g.w_ + kGcTilePx - 1) / kGcTilePx;
+  const int tiles_per_cta = kGcWarps / g.ksplit;
+  g.px_groups = (tiles + tiles_per_cta - 1) / tiles_per_cta;
+  g.cta_begin = cta_begin;
+  return cta_begin + g.px_groups * (g.cout / kGcCo);
 }
 
 // conv problem over [Cin][Di][Hi][Wi] -> [Cout][Do][Ho][Wo], 2-D 3x3 taps applied per plane
@@ -218,32 +458,30 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
 
   // ---- B. recurrence over planes ----
   for (int d = 0; d < D; ++d) {
-    ConvGroup g1{}, g2{};
+    GruConvArgs c1{}, c2{};
     GruArgs ga{};
-    int total = 0;
+    int total = 0, ctas1 = 0, ctas2 = 0;
     for (int l = 0; l < 4; ++l) {
       RedLevel& L = P.lv[l];
       const size_t px = (size_t)L.h * L.w;
       const long long kin = (long long)(L.cx + L.ch) * 9;
       double* stats = P.stats + ((size_t)d * 4 + l) * 6;
-      // P1: gates += conv(h_prev; h-half of gate_conv.weight)
-      ConvProblem a = plane_conv(L.s, L.ch, D + 1, L.h, L.w, wt->gate_w[l] + (size_t)L.cx * 9, kin, 9,
-                                 L.gx, 2 * L.ch, D, L.h, L.w, 1);
-      a.Qd = 1; a.Qh = L.h; a.Qw = L.w;
-      a.q2i_add[0] = d; a.q2o_add[0] = d;
-      a.pre_add = L.gx;
+      // P1: gates[d] += conv(h_prev; h-half of gate_conv.weight), GroupNorm sums of the r and u halves
+      GruConvLevel& a = c1.l[l];
+      a.in = L.s + (size_t)d * px; a.in_cs = (long long)(D + 1) * px;
+      a.w = wt->gate_w[l] + (size_t)L.cx * 9; a.w_co = kin;
+      a.pre = a.out = L.gx + (size_t)d * px; a.out_cs = (long long)D * px;
       a.stats = stats; a.stats_group = L.ch;
-      conv_finalize(a);
-      g1.p[l] = a;
-      // P2: out += conv(r*h; h-half of output_conv.weight)
-      ConvProblem b = plane_conv(L.rh, L.ch, 1, L.h, L.w, wt->out_w[l] + (size_t)L.cx * 9, kin, 9,
-                                 L.ox, L.ch, D, L.h, L.w, 1);
-      b.Qd = 1; b.Qh = L.h; b.Qw = L.w;
-      b.q2o_add[0] = d;
-      b.pre_add = L.ox;
+      a.cin = L.ch; a.cout = 2 * L.ch; a.h = L.h; a.w_ = L.w;
+      ctas1 = gru_conv_fill(a, ctas1);
+      // P2: out[d] += conv(r*h; h-half of output_conv.weight), GroupNorm sums
+      GruConvLevel& b = c2.l[l];
+      b.in = L.rh; b.in_cs = (long long)px;
+      b.w = wt->out_w[l] + (size_t)L.cx * 9; b.w_co = kin;
+      b.pre = b.out = L.ox + (size_t)d * px; b.out_cs = (long long)D * px;
       b.stats = stats + 4; b.stats_group = L.ch;
-      conv_finalize(b);
-      g2.p[l] = b;
+      b.cin = L.ch; b.cout = L.ch; b.h = L.h; b.w_ = L.w;
+      ctas2 = gru_conv_fill(b, ctas2);
       GruLevelArgs& e = ga.l[l];
       e.g = L.gx + (size_t)d * px; e.gcs = (long long)D * px;
       e.o = L.ox + (size_t)d * px; e.ocs = (long long)D * px;
@@ -251,14 +489,14 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       e.rh = L.rh;
       e.rn_w = wt->rn_w[l]; e.rn_b = wt->rn_b[l]; e.un_w = wt->un_w[l]; e.un_b = wt->un_b[l];
       e.on_w = wt->on_w[l]; e.on_b = wt->on_b[l];
-      e.stats = stats; e.ch = L.ch; e.px = (int)px; e.begin = total;
+      e.stats = stats; e.ch = L.ch; e.px = (int)px; e.begin = total; e.inv_n = 1.0 / ((double)L.ch * (double)px);
       total += L.ch * (int)px;
     }
-    g1.n = g2.n = 4; ga.total = total;
-    RUN(conv_launch<Tile8s>(g1, st, "red gate h-half"));
+    ga.total = total;
+    RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)"));
     gru_reset_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
     RUN(check_launch("gru_reset_kernel"));
-    RUN(conv_launch<Tile8s>(g2, st, "red output h-half"));
+    RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output)"));
     gru_update_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
     RUN(check_launch("gru_update_kernel"));
   }

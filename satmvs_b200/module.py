@@ -155,6 +155,95 @@ class slice_RED_Regularization(_RedBase):
         return (logits, *st)
 
 
+class _CostRegWeights(C.Structure):
+    _fields_ = [("conv_w", _F * 10), ("bn_scale", _F * 10), ("bn_shift", _F * 10), ("prob_w", _F)]
+
+
+class Conv3d(nn.Module):
+    """Parameter container for the reference's `Conv3d` block (`modules/module.py:324-366`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        assert stride in [1, 2] and bn and relu
+        self.out_channels, self.kernel_size, self.stride, self.relu = out_channels, kernel_size, stride, relu
+        self.conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride=stride, bias=False, **kwargs)
+        self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum)
+
+
+class Deconv3d(nn.Module):
+    """Parameter container for the reference's `Deconv3d` block (`modules/module.py:369-410`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        assert stride in [1, 2] and bn and relu
+        self.out_channels, self.stride, self.relu = out_channels, stride, relu
+        self.conv = nn.ConvTranspose3d(in_channels, out_channels, kernel_size, stride=stride, bias=False, **kwargs)
+        self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum)
+
+
+class CostRegNet(nn.Module):
+    """`CostRegNet` (`modules/module.py:546-577`): x [B,Cin,D,H,W] -> [B,1,D,H,W].
+    Inference-mode BatchNorm (running statistics); calling it in training mode raises."""
+
+    _BLOCKS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11")
+
+    def __init__(self, in_channels, base_channels):
+        super().__init__()
+        b = base_channels
+        self.in_channels, self.base_channels = in_channels, b
+        self.conv0 = Conv3d(in_channels, b, padding=1)
+        self.conv1 = Conv3d(b, b * 2, stride=2, padding=1)
+        self.conv2 = Conv3d(b * 2, b * 2, padding=1)
+        self.conv3 = Conv3d(b * 2, b * 4, stride=2, padding=1)
+        self.conv4 = Conv3d(b * 4, b * 4, padding=1)
+        self.conv5 = Conv3d(b * 4, b * 8, stride=2, padding=1)
+        self.conv6 = Conv3d(b * 8, b * 8, padding=1)
+        self.conv7 = Deconv3d(b * 8, b * 4, stride=2, padding=1, output_padding=1)
+        self.conv9 = Deconv3d(b * 4, b * 2, stride=2, padding=1, output_padding=1)
+        self.conv11 = Deconv3d(b * 2, b * 1, stride=2, padding=1, output_padding=1)
+        self.prob = nn.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
+
+    def _weights(self) -> _CostRegWeights:
+        w = _CostRegWeights()
+        keep = []
+
+        def ptr(t):
+            t = _lib.require_cuda(t.detach(), "parameter")
+            keep.append(t)
+            return t.data_ptr()
+
+        for i, name in enumerate(self._BLOCKS):
+            blk = getattr(self, name)
+            scale = blk.bn.weight.detach() * torch.rsqrt(blk.bn.running_var + blk.bn.eps)
+            shift = blk.bn.bias.detach() - blk.bn.running_mean * scale
+            w.conv_w[i], w.bn_scale[i], w.bn_shift[i] = ptr(blk.conv.weight), ptr(scale), ptr(shift)
+        w.prob_w = ptr(self.prob.weight)
+        w._keep = keep
+        return w
+
+    def forward(self, x):
+        if self.training:
+            raise RuntimeError("satmvs_b200.CostRegNet implements inference-mode BatchNorm only; call .eval()")
+        x = _lib.require_cuda(x, "x")
+        B, Cc, D, H, W = x.shape
+        if Cc != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} channels, got {Cc}")
+        nbytes = _lib.lib().satmvs_costreg_workspace_bytes(self.base_channels, D, H, W)
+        if nbytes == 0:
+            raise ValueError("CostRegNet needs D, H and W to be multiples of 8")
+        ws = _workspace(nbytes, x.device)
+        w = self._weights()
+        out = torch.empty((B, 1, D, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            st = _lib.stream_ptr(x.device)
+            for b in range(B):
+                _lib.check(_lib.lib().satmvs_costreg_forward(C.byref(w), x[b].data_ptr(), Cc, self.base_channels, D, H, W,
+                                                            out[b].data_ptr(), ws.data_ptr(), ws.numel(), st), "costreg_forward")
+        return out
+
+
 def depth_regression(p, depth_values):
     """`depth_regression` (`modules/module.py:433-439`), kept for API parity: sum_d p*d on given
     probabilities.  The fused softmax+regression kernel is `satmvs_b200.softargmin`."""

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import torch
 
+from .depth_range import stage_depth_hypotheses
 from .regress import StreamingSoftArgmin, softargmin
 from .warping import build_cost_volume
 
@@ -54,3 +55,22 @@ def stage_pred_red(features, cams, depth_values, regulariser, geo_model="rpc"):
         head.update(reg, plane)
     depth, conf = head.finish()
     return {"depth": depth, "photometric_confidence": conf}
+
+
+_STAGE_FNS = {"red_train": stage_train_red, "red_pred": stage_pred_red, "casmvs": stage_casmvs}
+
+
+def cascade(features_per_stage, cams_per_stage, depth_values, regularisers, *, img_hw, ndepths=(48, 32, 8),
+            depth_interals_ratio=(4, 2, 1), min_interval=2.5, scales=(4, 2, 1), geo_model="rpc", head="red_train"):
+    """The stage loop of `CascadeREDNet.forward` (`networks/casred.py:125-154`), `Infer_CascadeREDNet.forward`
+    (`:296-331`) and `CascadeMVSNet.forward` (`networks/casmvs.py:138-168`) from per-stage feature maps on.
+    Returns {"stage1": {...}, ..., "depth", "photometric_confidence"} like the reference."""
+    fn = _STAGE_FNS[head]
+    outputs, depth, out = {}, None, None
+    for s, nd in enumerate(ndepths):
+        dv = stage_depth_hypotheses(depth, depth_values, nd, depth_interals_ratio[s] * min_interval, img_hw, scales[s])
+        out = fn(features_per_stage[s], cams_per_stage[s], dv, regularisers[s], geo_model)
+        depth = out["depth"]
+        outputs[f"stage{s + 1}"] = out
+    outputs.update(out)
+    return outputs
