@@ -3,16 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A step is one pass of the hot path over one synthetic 3-view 768x384 stack at BASELINE.json
-configs[1] (cost-volume resolution 96x192, C=32, 64 planes).  With N>1 (torchrun, one rank per GPU)
-every rank sweeps its own stack: independent units, no data-path collective, weak scaling.
+Default workload = BASELINE.json configs[1]: one synthetic 3-view 768x384 stack, casred stage 1
+(cost-volume grid 96x192, C=32, 64 per-pixel hypothesis planes): fused RPC sweep -> variance volume ->
+RED regulariser over the 64 planes -> softmax / expectation / confidence.  A step is one such pass.
+With N>1 (torchrun, one rank per GPU) every rank processes its own stack: independent units, no
+data-path collective, weak scaling.  `--workload cfg4_sharded192` is the depth-sharded 192-plane sweep
+(strong scaling, slabs reassembled with `--gather nccl|fused|none`).
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) between
-iterations outside the timed region, barrier + synchronize on both sides, max over ranks.
+iterations outside the timed events, barrier + synchronize on both sides, max over ranks.
 `e2e` repeats the measurement through the public operator API with pinned HOST inputs, the
-host->device copies and the device->host read of the result inside the timed region.
-`--impl reference` times the CPU oracle (a port of the reference's torch-CPU path; the reference is
-pure Python and cannot travel to the GPU box) on a bounded sample of the same workload.
+host->device copies and the device->host read of the result inside the timed events.
+`roofline`/`kernels` come from a separate instrumented pass (CUDA events around every launch inside
+the library, `satmvs_profile_begin/end`).  `--impl reference` times the CPU oracle (a port of the
+reference's torch-CPU path; the reference is pure Python and does not exist on the GPU box) on a
+bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -32,13 +37,16 @@ sys.path.insert(0, ROOT)
 METRIC = "depth-hypothesis-voxels/sec (BxVxDxHxW)"
 UNIT = "voxels/s"
 WORKLOADS = {
-    # BASELINE.json configs[1]: 3-view 768x384 image, casred stage 1 (scale 4 -> 96x192 features, C=32), 64 planes
-    "cfg2_build": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="rpc", stage="build",
-                       desc="3-view 768x384, 64 planes, casred stage-1 cost-volume build (fused RPC warp + variance)"),
     "cfg2_stage1": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="rpc", stage="red_train",
-                        desc="3-view 768x384, 64 planes, casred stage-1 only: cost volume + RED regulariser + soft-argmin"),
+                        desc="3-view 768x384, 64 planes, casred stage-1 only: fused RPC cost volume + RED regulariser + soft-argmin"),
+    "cfg2_build": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="rpc", stage="build",
+                       desc="3-view 768x384, 64 planes, casred stage-1 cost-volume build only (fused RPC warp + variance)"),
+    "cfg2_casmvs": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="rpc", stage="casmvs",
+                        desc="3-view 768x384, 64 planes, stage 1 with the CostRegNet (3-D UNet) regulariser"),
     "cfg5_build": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="pinhole", stage="build",
                        desc="pin-hole homography sweep 3-view 768x384, 64 planes, cost-volume build"),
+    "cfg4_sharded192": dict(B=1, V=5, C=32, D=192, H=192, W=384, geo="rpc", stage="sharded",
+                            desc="5-view 1536x768, 192 planes single-stage, cost-volume build depth-sharded across ranks"),
 }
 
 
@@ -47,8 +55,8 @@ def peaks():
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 def make_inputs(w, seed=0):
@@ -63,9 +71,24 @@ def make_inputs(w, seed=0):
     return fe, cams, dv
 
 
-def algorithmic_bytes_per_cell(w):
+def sweep_bytes_per_cell(w):
     # variance write 4C + per-pixel hypothesis read 4 + compulsory feature reads 4·C·V/D
     return 4 * w["C"] + 4 + 4.0 * w["C"] * w["V"] / w["D"]
+
+
+def red_flops(w):
+    """Algorithmic FLOPs of RED_Regularization at this size, split like the kernels
+    (2 * Cin * Cout * 9 per output pixel; transposed convs counted on input pixels)."""
+    C, D, H, W = w["C"], w["D"], w["H"], w["W"]
+    px = [H * W >> (2 * l) for l in range(4)]
+    ch = [8, 16, 32, 64]
+    cx = [C, 16, 32, 64]
+    enc = 18 * (C * 16 * px[1] + 16 * 32 * px[2] + 32 * 64 * px[3])
+    xhalf = sum(18 * cx[l] * 3 * ch[l] * px[l] for l in range(4))
+    gate = sum(18 * ch[l] * 2 * ch[l] * px[l] for l in range(4))
+    outp = sum(18 * ch[l] * ch[l] * px[l] for l in range(4))
+    dec = 18 * (64 * 32 * px[3] + 32 * 16 * px[2] + 16 * 8 * px[1] + 8 * px[0])
+    return {"conv_batched": (enc + xhalf) * D, "gru_gate_conv": gate * D, "gru_output_conv": outp * D, "red_decoder": dec * D}
 
 
 class ClockSampler:
@@ -80,10 +103,11 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            time.sleep(0.2)
         except OSError:
             self.proc = None
         return self
@@ -111,28 +135,42 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_step(w, dev, fe, cams, dv):
-    """Returns (step_fn() -> result tensors, kernel launches per step, name of the dominant kernel)."""
+def make_step(w, dev, args):
+    """Returns step(features, cams, depth) -> tuple of result tensors, through the public operator API."""
     import satmvs_b200
-    ref, srcs = fe[0], fe[1:]
-    ref_cam, src_cams = cams[:, 0], [cams[:, v] for v in range(1, w["V"])]
+    from satmvs_b200 import synth
+    V = w["V"]
     if w["stage"] == "build":
-        def step():
-            return (satmvs_b200.build_cost_volume(ref, srcs, ref_cam, src_cams, dv, w["geo"]),)
-        return step, w["B"]
+        def step(fe, cams, dv):
+            return (satmvs_b200.build_cost_volume(fe[0], fe[1:], cams[:, 0], [cams[:, v] for v in range(1, V)], dv, w["geo"]),)
+        return step
+    if w["stage"] == "sharded":
+        from satmvs_b200 import sharded
+
+        def step(fe, cams, dv):
+            return (sharded.build_cost_volume_sharded(fe[0], fe[1:], cams[:, 0], [cams[:, v] for v in range(1, V)], dv,
+                                                      w["geo"], mode=args.gather),)
+        return step
     if w["stage"] == "red_train":
-        from satmvs_b200 import synth
         reg = satmvs_b200.RED_Regularization(w["C"], 8)
         reg.load_state_dict(synth.make_red_weights(w["C"]))
         reg = reg.to(dev).eval()
-        all_cams = cams
 
-        def step():
+        def step(fe, cams, dv):
             with torch.no_grad():
-                out = satmvs_b200.stage_train_red(fe, all_cams, dv, reg, w["geo"])
+                out = satmvs_b200.stage_train_red(fe, cams, dv, reg, w["geo"])
             return out["depth"], out["photometric_confidence"]
-        # launches per step: 1 sweep + 3 encoders + 8 x-halves + 4 per plane + 3 decoder + 1 head conv + 1 soft-argmin
-        return step, w["B"] * (1 + 3 + 8 + 4 * w["D"] + 3 + 1 + 1)
+        return step
+    if w["stage"] == "casmvs":
+        reg = satmvs_b200.CostRegNet(w["C"], 8)
+        reg.load_state_dict(synth.make_costregnet_weights(w["C"]))
+        reg = reg.to(dev).eval()
+
+        def step(fe, cams, dv):
+            with torch.no_grad():
+                out = satmvs_b200.stage_casmvs(fe, cams, dv, reg, w["geo"])
+            return out["depth"], out["photometric_confidence"]
+        return step
     raise ValueError(w["stage"])
 
 
@@ -154,18 +192,22 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    fe_h, cams, dv_h = make_inputs(w, seed=rank)
+    sharded_run = w["stage"] == "sharded"
+    fe_h, cams, dv_h = make_inputs(w, seed=0 if sharded_run else rank)
     fe = [f.to(dev) for f in fe_h]
     dv = dv_h.to(dev)
-    step, launches = build_step(w, dev, fe, cams, dv)
+    step = make_step(w, dev, args)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     voxels = w["B"] * w["V"] * w["D"] * w["H"] * w["W"]
     cells = w["B"] * w["D"] * w["H"] * w["W"]
+    units = 1 if sharded_run else world          # stacks processed per step by the whole job
 
     def timed(fn, n):
         evs = []
         for _ in range(n):
             flush.zero_()                       # evict L2 between iterations (outside the timed events)
+            if sharded_run:
+                barrier()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             fn()
@@ -174,12 +216,13 @@ def run_ours(args, w):
         torch.cuda.synchronize()
         return [s.elapsed_time(e) for s, e in evs]
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         flush.zero_()
-        step()
+        step(fe, cams, dv)
     barrier()
     with ClockSampler(local) as clk:
-        times = timed(step, args.steps)
+        times = timed(lambda: step(fe, cams, dv), args.steps)
         barrier()
     total_ms = sum(times)
 
@@ -187,16 +230,14 @@ def run_ours(args, w):
     fe_p = [f.pin_memory() for f in fe_h]
     dv_p = dv_h.pin_memory()
     h2d = sum(f.numel() * 4 for f in fe_p) + dv_p.numel() * 4 + cams.numel() * 8
-    outs_host = None
+    outs_host = []
 
     def e2e_step():
-        nonlocal outs_host
         f_d = [f.to(dev, non_blocking=True) for f in fe_p]
         d_d = dv_p.to(dev, non_blocking=True)
-        st, _ = build_step(w, dev, f_d, cams, d_d)
-        res = st()
-        if outs_host is None:
-            outs_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
+        res = step(f_d, cams, d_d)
+        if not outs_host:
+            outs_host.extend(torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res)
         for h, r in zip(outs_host, res):
             h.copy_(r, non_blocking=True)
 
@@ -208,33 +249,69 @@ def run_ours(args, w):
     e2e_ms = sum(e2e_times)
     d2h = sum(h.numel() * h.element_size() for h in outs_host)
 
+    # instrumented pass: device time and launch count per kernel class (events inside the library)
+    prof_steps = min(args.steps, 10)
+    barrier()
+    with _lib.profile() as prof:
+        for _ in range(prof_steps):
+            flush.zero_()
+            step(fe, cams, dv)
+    barrier()
+
     if world > 1:
         t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = t.tolist()
 
     if rank == 0:
-        hbm, peak_src = peaks()
+        hbm, bf16, peak_src = peaks()
         ms = total_ms / args.steps
         line = {
-            "metric": METRIC, "value": voxels * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (geometry f64)", "data": "synthetic",
+            "metric": METRIC, "value": voxels * units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if sharded_run else "weak", "vs_baseline": None, "dtype": "f32 (camera geometry f64)",
+            "data": "synthetic",
             "config": {"workload": w["desc"], "name": args.workload, "B": w["B"], "V": w["V"], "C": w["C"], "D": w["D"],
                        "H": w["H"], "W": w["W"], "geo_model": w["geo"], "hypotheses": "per-pixel [B,D,H,W]",
-                       "l2": "flushed (256 MiB write) between timed iterations", "sharding": "one stack per rank"},
+                       "l2": "flushed (256 MiB write) between timed iterations",
+                       "sharding": (f"depth planes split over ranks, gather={args.gather}" if sharded_run else "one stack per rank")},
             "clocks": clk.summary(),
-            "e2e": {"value": voxels * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+            "e2e": {"value": voxels * units / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": (launches if launches is not None else getattr(sys.modules["satmvs_b200"], "last_launch_count", lambda: 0)()) * args.steps,
+            "gpu_launches": int(sum(prof.launches.values()) / prof_steps * args.steps),
         }
-        if w["stage"] == "build":
-            bpc = algorithmic_bytes_per_cell(w)
-            ach = cells * bpc / (ms * 1e-3) / 1e9
-            line["roofline"] = {"kernel": "sweep_fwd_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                                "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
-                                "algorithmic_bytes_per_launch": cells * bpc, "bytes_per_cell": bpc,
-                                "avg_launch_us": ms * 1e3}
+        # per kernel class: share of the step, achieved rate against the bound that applies
+        flops = red_flops(w) if w["stage"] == "red_train" else {}
+        kernels, tot_prof = [], sum(prof.ms.values()) or 1.0
+        for name in _lib.PROFILE_CLASSES:
+            n, t_ms = prof.launches[name], prof.ms[name]
+            if n == 0:
+                continue
+            k = {"class": name, "launches_per_step": n / prof_steps, "ms_per_step": t_ms / prof_steps,
+                 "share": t_ms / tot_prof, "avg_launch_us": 1e3 * t_ms / n}
+            if name == "sweep":
+                planes = w["D"] / world if sharded_run else w["D"]
+                bpc = sweep_bytes_per_cell(dict(w, D=planes))
+                by = cells / (world if sharded_run else 1) * bpc
+                ach = by / (t_ms / n * 1e-3) / 1e9
+                k["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                                 "traffic": None, "algorithmic_bytes_per_launch": by, "bytes_per_cell": bpc}
+            elif name in flops:
+                ach = flops[name] / (t_ms / prof_steps * 1e-3) / 1e12
+                k["roofline"] = {"bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
+                                 "traffic": None, "algorithmic_flops_per_step": flops[name],
+                                 "note": "fp32 FFMA kernels measured against the bf16 tensor peak"}
+            kernels.append(k)
+        kernels.sort(key=lambda k: -k["share"])
+        line["kernels"] = kernels
+        dom = next((k for k in kernels if "roofline" in k), None)
+        if dom is not None:
+            line["roofline"] = dict(dom["roofline"], kernel=dom["class"], share_of_step=dom["share"],
+                                    avg_launch_us=dom["avg_launch_us"], peak_source=peak_src)
+        sw = next((k for k in kernels if k["class"] == "sweep"), None)
+        if sw is not None and dom is not sw:
+            line["roofline_sweep"] = dict(sw["roofline"], kernel="sweep", share_of_step=sw["share"],
+                                          avg_launch_us=sw["avg_launch_us"], peak_source=peak_src)
         if world == 1 and not args.no_cpu_baseline:
             line["gpu_eager_baseline"] = gpu_eager_baseline(w, dev, fe, cams, dv)
             line["cpu_baseline"] = cpu_baseline(w, budget_s=20.0)
@@ -246,48 +323,96 @@ def run_ours(args, w):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's torch-CPU path
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(w, planes):
-    """One bounded sample: the same workload restricted to `planes` depth planes."""
-    from oracle import volume
+def red_on_device(var, sd, device, regnets):
+    B, _, D, H, W = var.shape
+    states = [s.to(device) for s in regnets.red_initial_states(B, H, W)]
+    out = []
+    for d in range(D):
+        reg, *states = regnets.red_slice(var[:, :, d], *states, sd)
+        out.append(reg)
+    return torch.stack(out, dim=1).squeeze(2)
+
+
+def oracle_step(w, planes, device="cpu"):
+    """One bounded sample of the workload on `planes` depth planes with the oracle (a restatement of
+    networks/casred.py:10-64 + modules/*): returns (callable, voxels processed)."""
+    from oracle import regnets, regress, stages, volume
+    from satmvs_b200 import synth
     ws = dict(w, D=planes)
     fe, cams, dv = make_inputs(ws)
+    fe, dv, cams = [f.to(device) for f in fe], dv.to(device), cams.to(device)
+    vox = ws["B"] * ws["V"] * ws["D"] * ws["H"] * ws["W"]
+    if w["stage"] == "red_train":
+        sd = {k: v.to(device) for k, v in synth.make_red_weights(w["C"]).items()}
 
-    def run():
-        with torch.no_grad():
-            return volume.variance_cost_volume(fe, cams, dv, w["geo"])
-    return run, ws["B"] * ws["V"] * ws["D"] * ws["H"] * ws["W"]
+        def run():
+            with torch.no_grad():
+                var = volume.variance_cost_volume(fe, cams, dv, w["geo"])
+                logits = red_on_device(var, sd, device, regnets)
+                return regress.softargmin_red(logits, dv)
+    elif w["stage"] == "casmvs":
+        sd = {k: v.to(device) for k, v in synth.make_costregnet_weights(w["C"]).items()}
+
+        def run():
+            with torch.no_grad():
+                return stages.stage_casmvs(fe, cams, dv, sd, w["geo"])
+    else:
+        def run():
+            with torch.no_grad():
+                return volume.variance_cost_volume(fe, cams, dv, w["geo"])
+    return run, vox
 
 
 def gpu_eager_baseline(w, dev, fe, cams, dv):
-    """The reference's GPU eager path for the cost-volume build (north_star's >=10x denominator):
-    the oracle restates `networks/casred.py:26-53` op for op, so running it on CUDA tensors launches
-    the same ATen kernel chain the reference does.  Reported, never shipped."""
+    """The reference's GPU eager path (north_star's >=10x denominator for the cost-volume build): the
+    oracle restates the reference op for op, so on CUDA tensors it launches the same ATen / cuDNN kernel
+    chain the reference does.  Reported, never shipped."""
     from oracle import volume
-    cams_d = cams.to(dev)
+    out = {}
     try:
+        cams_d = cams.to(dev)
         with torch.no_grad():
+            def build():
+                return volume.variance_cost_volume(fe, cams_d, dv, w["geo"])
             for _ in range(3):
-                volume.variance_cost_volume(fe, cams_d, dv, w["geo"])
+                build()
             torch.cuda.synchronize()
             torch.cuda.reset_peak_memory_stats(dev)
             best = float("inf")
             for _ in range(10):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                volume.variance_cost_volume(fe, cams_d, dv, w["geo"])
+                build()
                 e.record()
                 torch.cuda.synchronize()
                 best = min(best, s.elapsed_time(e))
         vox = w["B"] * w["V"] * w["D"] * w["H"] * w["W"]
-        return {"value": vox / (best * 1e-3), "unit": UNIT, "ms": best, "kind": "port of networks/casred.py:26-53 on CUDA tensors "
-                "(ATen eager, best of 10)", "peak_alloc_bytes": torch.cuda.max_memory_allocated(dev)}
+        out["cost_volume_build"] = {"value": vox / (best * 1e-3), "unit": UNIT, "ms": best,
+                                    "kind": "port of networks/casred.py:26-53 on CUDA tensors (ATen eager, best of 10)",
+                                    "peak_alloc_bytes": torch.cuda.max_memory_allocated(dev)}
+        if w["stage"] in ("red_train", "casmvs"):
+            run, vox = oracle_step(w, w["D"], device=dev)
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            best = float("inf")
+            for _ in range(3):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                run()
+                e.record()
+                torch.cuda.synchronize()
+                best = min(best, s.elapsed_time(e))
+            out["stage"] = {"value": vox / (best * 1e-3), "unit": UNIT, "ms": best,
+                            "kind": "port of the whole stage on CUDA tensors (ATen/cuDNN eager, best of 3)"}
     except Exception as ex:  # an OOM in the baseline must not lose the bench line
-        return {"unavailable": repr(ex)[:200]}
+        out["unavailable"] = repr(ex)[:200]
+    return out
 
 
 def cpu_baseline(w, budget_s=20.0):
     planes = min(w["D"], 16)
-    run, vox = cpu_sample(w, planes)
+    run, vox = oracle_step(w, planes)
     run()
     ts = []
     t_end = time.perf_counter() + budget_s
@@ -297,9 +422,9 @@ def cpu_baseline(w, budget_s=20.0):
         ts.append(time.perf_counter() - t0)
     best = min(ts)
     return {"value": vox / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle.volume.variance_cost_volume (restatement of networks/casred.py:26-53 + modules/warping.py:310-365) "
-                      f"on the first {planes} of {w['D']} planes of the same stack, best of {len(ts)}, torch-CPU "
-                      f"{torch.get_num_threads()} threads of {os.cpu_count()} logical cores",
+            "sample": f"oracle (restatement of networks/casred.py:10-64 + modules/warping.py, module.py) on the first {planes} of "
+                      f"{w['D']} planes of the same stack, best of {len(ts)}, torch-CPU {torch.get_num_threads()} threads of "
+                      f"{os.cpu_count()} logical cores",
             "seconds_per_sample": best}
 
 
@@ -308,7 +433,7 @@ def run_reference(args, w):
     if rank != 0:
         return
     planes = min(w["D"], 16)
-    run, vox = cpu_sample(w, planes)
+    run, vox = oracle_step(w, planes)
     for _ in range(min(args.warmup, 2)):
         run()
     t0 = time.perf_counter()
@@ -321,7 +446,7 @@ def run_reference(args, w):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (geometry f64)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (camera geometry f64)", "data": "synthetic",
         "config": {"workload": w["desc"], "name": args.workload, "B": w["B"], "V": w["V"], "C": w["C"], "D": w["D"],
                    "H": w["H"], "W": w["W"], "geo_model": w["geo"]},
         "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -331,10 +456,11 @@ def run_reference(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2_build", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2_stage1", choices=sorted(WORKLOADS))
+    ap.add_argument("--gather", default="nccl", choices=["none", "nccl", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -29,12 +29,21 @@ extern "C" {
 
 #define SATMVS_ABI_VERSION 1
 #define SATMVS_MAX_SRC_VIEWS 8
+#define SATMVS_MAX_PEERS 8
 #define SATMVS_RPC_LEN 170
 
 enum { SATMVS_OK = 0, SATMVS_EINVAL = 1, SATMVS_ECUDA = 2 };
 
 int satmvs_abi_version(void);
 const char* satmvs_last_error(void);
+
+/* Measurement aid (bench.py): between begin and end every kernel launch of the calling thread is
+ * bracketed by CUDA events on its stream; end synchronises the device and returns, per kernel class,
+ * the summed device time [ms] and the launch count.  Classes: 0 sweep, 1 batched convs (conv engine),
+ * 2 GRU gate conv, 3 GRU output conv, 4 GRU pointwise, 5 RED decoder, 6 CostRegNet, 7 heads. */
+#define SATMVS_PROFILE_CLASSES 8
+int satmvs_profile_begin(void);
+int satmvs_profile_end(float* ms_by_class, int* launches_by_class);
 
 /* ---- fused plane sweep: per-hypothesis geometry + bilinear gather + variance over views ----
  * Replaces networks/casred.py:26-53 (== networks/casmvs.py:30-59; per-plane form casred.py:191-212)
@@ -56,6 +65,24 @@ int satmvs_cost_volume_homo_fwd(const float* ref_fea, const float* const* src_fe
                                 const double* ref_proj, const double* src_projs,
                                 const float* depth, int depth_per_pixel,
                                 int C, int D, int H, int W, float* out_var, void* stream);
+
+/* ---- depth-sharded sweep (multi-GPU) ----
+ * Same kernels, sweeping only D planes (hypotheses `depth` = the shard's [D] / [D,H,W]) and writing them
+ * at plane offset d0 of output volumes that hold D_total planes ([C,D_total,H,W]).  With n_outs == 1
+ * this fills one rank's slab of a shared layout; with n_outs == world size and `outs` = the peer-mapped
+ * pointers of every rank's volume (CUDA IPC / symmetric memory), the store loop IS the all-gather:
+ * each value is written once per peer over NVLink while the sweep is still computing, and the slab
+ * never makes a second trip through HBM.  The caller provides the cross-rank barrier afterwards. */
+int satmvs_cost_volume_rpc_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
+                                       const double* ref_rpc, const double* src_rpcs,
+                                       const float* depth, int depth_per_pixel,
+                                       int C, int D, int H, int W, int d0, int D_total,
+                                       float* const* outs, int n_outs, void* stream);
+int satmvs_cost_volume_homo_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
+                                        const double* ref_proj, const double* src_projs,
+                                        const float* depth, int depth_per_pixel,
+                                        int C, int D, int H, int W, int d0, int D_total,
+                                        float* const* outs, int n_outs, void* stream);
 
 /* ---- single-view warps with the reference operator's meaning ----
  * rpc_warping (modules/warping.py:310-365) / homo_warping (:6-44): out [C,D,H,W] warped volume. */

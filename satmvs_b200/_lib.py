@@ -18,8 +18,12 @@ _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 _SIGNATURES = {
     "satmvs_abi_version": ([], _I),
     "satmvs_last_error": ([], C.c_char_p),
+    "satmvs_profile_begin": ([], _I),
+    "satmvs_profile_end": ([_P, _P], _I),
     "satmvs_cost_volume_rpc_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_cost_volume_homo_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_cost_volume_rpc_fwd_sharded": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P], _I),
+    "satmvs_cost_volume_homo_fwd_sharded": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P], _I),
     "satmvs_rpc_warp_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_homo_warp_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_rpc_warp_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
@@ -58,6 +62,25 @@ def lib():
             raise RuntimeError("libsatmvs_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib
+
+
+PROFILE_CLASSES = ("sweep", "conv_batched", "gru_gate_conv", "gru_output_conv", "gru_pointwise", "red_decoder",
+                   "costreg", "heads")
+
+
+class profile:
+    """Context manager around satmvs_profile_begin/end: per-kernel-class device time inside the library."""
+
+    def __enter__(self):
+        lib().satmvs_profile_begin()
+        return self
+
+    def __exit__(self, *a):
+        ms = (C.c_float * len(PROFILE_CLASSES))()
+        n = (C.c_int * len(PROFILE_CLASSES))()
+        lib().satmvs_profile_end(ms, n)
+        self.ms = dict(zip(PROFILE_CLASSES, list(ms)))
+        self.launches = dict(zip(PROFILE_CLASSES, list(n)))
 
 
 def check(rc: int, what: str) -> None:

@@ -1,5 +1,6 @@
 // abi.cu — version and thread-local error text of libsatmvs_b200.so
 #include "common.cuh"
+#include "prof.cuh"
 #include <cstring>
 
 namespace satmvs {
@@ -11,9 +12,39 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
+ProfState& prof_state() {
+  static thread_local ProfState s;
+  return s;
+}
 }  // namespace satmvs
 
 extern "C" {
+int satmvs_profile_begin(void) {
+  satmvs::ProfState& s = satmvs::prof_state();
+  for (auto& v : s.ev) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }
+  s.on = true;
+  return SATMVS_OK;
+}
+
+int satmvs_profile_end(float* ms_by_class, int* launches_by_class) {
+  satmvs::ProfState& s = satmvs::prof_state();
+  s.on = false;
+  cudaDeviceSynchronize();
+  for (int p = 0; p < satmvs::kProfCount; ++p) {
+    float tot = 0.0f;
+    for (size_t i = 0; i + 1 < s.ev[p].size(); i += 2) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, s.ev[p][i], s.ev[p][i + 1]);
+      tot += ms;
+    }
+    if (ms_by_class) ms_by_class[p] = tot;
+    if (launches_by_class) launches_by_class[p] = (int)(s.ev[p].size() / 2);
+    for (cudaEvent_t e : s.ev[p]) cudaEventDestroy(e);
+    s.ev[p].clear();
+  }
+  return SATMVS_OK;
+}
+
 int satmvs_abi_version(void) { return SATMVS_ABI_VERSION; }
 const char* satmvs_last_error(void) { return satmvs::g_error; }
 }

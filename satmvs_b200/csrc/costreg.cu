@@ -9,6 +9,7 @@
 // 11 launches: 7 dense 27-tap convs (3 of them stride 2), 3 transposed convs (each one grouped launch
 // of its 8 output-parity classes, so no multiply ever touches a structural zero), 1 head conv.
 #include "conv_engine.cuh"
+#include "prof.cuh"
 
 namespace satmvs {
 
@@ -106,6 +107,7 @@ int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int
   CostRegPlan P = costreg_plan(base, D, H, W, reinterpret_cast<char*>(workspace));
   SATMVS_REQUIRE(workspace_bytes >= P.bytes);
   int rc;
+  ProfScope prof(kProfCostReg, st);
 #define RUN(e) do { rc = (e); if (rc) return rc; } while (0)
   // conv0..conv6 (module.py:569-572): channel and stride schedule
   const int cin[7] = {Cin, base, 2 * base, 2 * base, 4 * base, 4 * base, 8 * base};

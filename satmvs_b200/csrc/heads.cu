@@ -8,6 +8,7 @@
 // One thread per pixel, planes strided by H*W so every load is 128-byte coalesced across the warp.
 // HBM-bound: (4 + 4) bytes per (plane, pixel) read once (logits are re-read from L2 for the second pass).
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace satmvs {
 
@@ -76,6 +77,7 @@ int satmvs_softargmin_fwd(const float* logits, const float* depth, int depth_per
   SATMVS_REQUIRE(logits && depth && out_depth && out_conf);
   SATMVS_REQUIRE(D >= 1 && H >= 1 && W >= 1 && (mode == 0 || mode == 1));
   const int HW = H * W;
+  ProfScope prof(kProfHead, (cudaStream_t)stream);
   softargmin_kernel<<<ceil_div(HW, 128), 128, 0, (cudaStream_t)stream>>>(logits, depth, depth_per_pixel, mode, D, HW,
                                                                          out_depth, out_conf);
   return check_launch("softargmin_kernel");

@@ -18,6 +18,7 @@
 //                  conv with bias) over the stored states of all planes.
 // Only B is sequential in D: 4 launches per plane instead of ~70.
 #include "conv_engine.cuh"
+#include "prof.cuh"
 
 namespace satmvs {
 
@@ -439,7 +440,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     p.Qd = D; p.Qh = H >> (i + 1); p.Qw = W >> (i + 1);
     p.relu = 1;
     p.acc_scale = (i == 0) ? -1.0f : 1.0f;
-    RUN(launch_by_cout(p, st, "red encoder"));
+    { ProfScope prof(kProfConvBatched, st); RUN(launch_by_cout(p, st, "red encoder")); }
   }
   for (int l = 0; l < 4; ++l) {   // x-halves of the GRU convolutions, bias folded in (module.py:29-30, :44-45)
     RedLevel& L = P.lv[l];
@@ -448,12 +449,12 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     g.Qd = D; g.Qh = L.h; g.Qw = L.w;
     g.shift = wt->gate_b[l];
     g.acc_scale = (l == 0) ? -1.0f : 1.0f;
-    RUN(launch_by_cout(g, st, "red gate x-half"));
+    { ProfScope prof(kProfConvBatched, st); RUN(launch_by_cout(g, st, "red gate x-half")); }
     ConvProblem o = plane_conv(xin[l], L.cx, D, L.h, L.w, wt->out_w[l], kin, 9, L.ox, L.ch, D, L.h, L.w, 1);
     o.Qd = D; o.Qh = L.h; o.Qw = L.w;
     o.shift = wt->out_b[l];
     o.acc_scale = (l == 0) ? -1.0f : 1.0f;
-    RUN(launch_by_cout(o, st, "red output x-half"));
+    { ProfScope prof(kProfConvBatched, st); RUN(launch_by_cout(o, st, "red output x-half")); }
   }
 
   // ---- B. recurrence over planes ----
@@ -493,12 +494,14 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       total += L.ch * (int)px;
     }
     ga.total = total;
-    RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)"));
-    gru_reset_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
-    RUN(check_launch("gru_reset_kernel"));
-    RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output)"));
-    gru_update_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
-    RUN(check_launch("gru_update_kernel"));
+    { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)")); }
+    { ProfScope prof(kProfGruPointwise, st);
+      gru_reset_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
+      RUN(check_launch("gru_reset_kernel")); }
+    { ProfScope prof(kProfGruOutput, st); RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output)")); }
+    { ProfScope prof(kProfGruPointwise, st);
+      gru_update_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
+      RUN(check_launch("gru_update_kernel")); }
   }
 
   // ---- C. decoder over all planes: U_l = relu(convT_s2(U_{l+1})) + S_l  (module.py:633-642) ----
@@ -526,8 +529,11 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
         g.p[n++] = p;
       }
     g.n = n;
-    if (L.ch >= 32) RUN(conv_launch<Tile32>(g, st, "red upconv")); else if (L.ch >= 16) RUN(conv_launch<Tile16>(g, st, "red upconv"));
-    else RUN(conv_launch<Tile8>(g, st, "red upconv"));
+    {
+      ProfScope prof(kProfDecoder, st);
+      if (L.ch >= 32) RUN(conv_launch<Tile32>(g, st, "red upconv")); else if (L.ch >= 16) RUN(conv_launch<Tile16>(g, st, "red upconv"));
+      else RUN(conv_launch<Tile8>(g, st, "red upconv"));
+    }
     up_in = P.u[l];
   }
   {  // upconv2d: ConvTranspose2d(8, 1, k3, stride 1, pad 1) with bias (module.py:610, :643): out[o] = sum_k in[o+1-k] w[k]
@@ -544,7 +550,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       for (int kx = 0; kx < 3; ++kx) { p.tap_dz[n] = 0; p.tap_dy[n] = 1 - ky; p.tap_dx[n] = 1 - kx; p.tap_w[n] = ky * 3 + kx; ++n; }
     p.ntaps = n;
     p.shift = wt->upconv2d_b;
-    RUN(launch_one<Tile8>(p, st, "red upconv2d"));
+    { ProfScope prof(kProfDecoder, st); RUN(launch_one<Tile8>(p, st, "red upconv2d")); }
   }
   if (state_out)
     for (int l = 0; l < 4; ++l)

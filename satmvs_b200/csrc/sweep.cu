@@ -15,6 +15,7 @@
 // Lanes map to consecutive pixels (row-major over H*W), so ref loads and volume stores are 128-byte
 // coalesced and the gathers of a warp fall into 1-2 cache lines.
 #include "geometry.cuh"
+#include "prof.cuh"
 
 #ifndef SATMVS_DK2
 #define SATMVS_DK2 8     // planes per thread with <= 2 source views (tuning knob, see profiles/)
@@ -32,8 +33,10 @@ struct SweepArgs {
   const float* ref_fea;                       // [C,H,W] (variance mode) or nullptr
   const float* src_fea[Geo::kNumSrc];         // each [C,H,W]
   const float* depth;                         // [D] or [D,H,W]
-  float* out;                                 // [C,D,H,W]
-  int C, D, H, W;
+  float* out[SATMVS_MAX_PEERS];               // each [C,out_D,H,W]; every buffer receives the same planes
+  int n_out;                                  // 1, or the number of peer GPUs written over NVLink (fused all-gather)
+  int out_D, out_d0;                          // planes of the output tensor, first plane written by this launch
+  int C, D, H, W;                             // D = planes swept by this launch
   int depth_per_pixel;
   int n_src;                                  // live source views (<= Geo::kNumSrc; the rest carry zero weights)
   float half_w, half_h;                       // W/2, H/2 (ATen un-normalise)
@@ -75,7 +78,7 @@ sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
     float r = 0.0f;
     if (kVariance) r = __ldg(a.ref_fea + (size_t)c * HW + pixc);
     const float r2 = __fmul_rn(r, r);
-    float* outc = a.out + ((size_t)c * a.D + d0) * plane_stride + pix;
+    const size_t oidx = ((size_t)c * a.out_D + a.out_d0 + d0) * plane_stride + pix;
 #pragma unroll
     for (int k = 0; k < DK; ++k) {
       if (d0 + k < a.D) {
@@ -96,7 +99,10 @@ sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
           const float m = div_const(s, a.num_views, a.inv_num_views);
           res = __fsub_rn(div_const(q, a.num_views, a.inv_num_views), __fmul_rn(m, m));
         }
-        if (active) __stcs(outc + (size_t)k * plane_stride, res);
+        if (active) {
+          // one store per destination: the local volume, or every peer's volume (NVLink posted writes)
+          for (int o = 0; o < a.n_out; ++o) __stcs(a.out[o] + oidx + (size_t)k * plane_stride, res);
+        }
       }
     }
   }
@@ -241,6 +247,7 @@ template <class Geo, bool kVariance>
 static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
   constexpr int DK = PlanesPerThread<Geo::kNumSrc>::value;
   dim3 grid(ceil_div((int64_t)a.H * a.W, kSweepThreads), ceil_div(a.D, DK));
+  ProfScope prof(kProfSweep, st);
   sweep_fwd_kernel<Geo, DK, kVariance><<<grid, kSweepThreads, 0, st>>>(a);
   return check_launch("sweep_fwd_kernel");
 }
@@ -307,12 +314,26 @@ int satmvs_cost_volume_rpc_fwd(const float* ref_fea, const float* const* src_fea
                                const double* ref_rpc, const double* src_rpcs,
                                const float* depth, int depth_per_pixel,
                                int C, int D, int H, int W, float* out_var, void* stream) {
+  float* outs[1] = {out_var};
+  return satmvs_cost_volume_rpc_fwd_sharded(ref_fea, src_feas, n_src, ref_rpc, src_rpcs, depth, depth_per_pixel,
+                                            C, D, H, W, 0, D, outs, 1, stream);
+}
+
+int satmvs_cost_volume_rpc_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
+                                       const double* ref_rpc, const double* src_rpcs,
+                                       const float* depth, int depth_per_pixel,
+                                       int C, int D, int H, int W, int d0, int D_total,
+                                       float* const* outs, int n_outs, void* stream) {
   if (int e = check_dims(n_src, C, D, H, W)) return e;
-  SATMVS_REQUIRE(ref_fea && src_feas && ref_rpc && src_rpcs && depth && out_var);
+  SATMVS_REQUIRE(ref_fea && src_feas && ref_rpc && src_rpcs && depth && outs);
+  SATMVS_REQUIRE(n_outs >= 1 && n_outs <= SATMVS_MAX_PEERS && d0 >= 0 && d0 + D <= D_total);
+  for (int o = 0; o < n_outs; ++o) SATMVS_REQUIRE(outs[o] != nullptr);
   SATMVS_DISPATCH_NSRC(n_src, {
     SweepArgs<RpcSweep<NSRC>> a{};
     fill_common(a, depth, depth_per_pixel, n_src, C, D, H, W);
-    a.ref_fea = ref_fea; a.out = out_var;
+    a.ref_fea = ref_fea;
+    for (int o = 0; o < n_outs; ++o) a.out[o] = outs[o];
+    a.n_out = n_outs; a.out_D = D_total; a.out_d0 = d0;
     for (int v = 0; v < NSRC; ++v) a.src_fea[v] = src_feas[v < n_src ? v : 0];
     fill_rpc_geo(a.geo, n_src, ref_rpc, src_rpcs, H, W);
     return launch_fwd<RpcSweep<NSRC>, true>(a, (cudaStream_t)stream);
@@ -324,12 +345,26 @@ int satmvs_cost_volume_homo_fwd(const float* ref_fea, const float* const* src_fe
                                 const double* ref_proj, const double* src_projs,
                                 const float* depth, int depth_per_pixel,
                                 int C, int D, int H, int W, float* out_var, void* stream) {
+  float* outs[1] = {out_var};
+  return satmvs_cost_volume_homo_fwd_sharded(ref_fea, src_feas, n_src, ref_proj, src_projs, depth, depth_per_pixel,
+                                             C, D, H, W, 0, D, outs, 1, stream);
+}
+
+int satmvs_cost_volume_homo_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
+                                        const double* ref_proj, const double* src_projs,
+                                        const float* depth, int depth_per_pixel,
+                                        int C, int D, int H, int W, int d0, int D_total,
+                                        float* const* outs, int n_outs, void* stream) {
   if (int e = check_dims(n_src, C, D, H, W)) return e;
-  SATMVS_REQUIRE(ref_fea && src_feas && ref_proj && src_projs && depth && out_var);
+  SATMVS_REQUIRE(ref_fea && src_feas && ref_proj && src_projs && depth && outs);
+  SATMVS_REQUIRE(n_outs >= 1 && n_outs <= SATMVS_MAX_PEERS && d0 >= 0 && d0 + D <= D_total);
+  for (int o = 0; o < n_outs; ++o) SATMVS_REQUIRE(outs[o] != nullptr);
   SATMVS_DISPATCH_NSRC(n_src, {
     SweepArgs<HomoSweep<NSRC>> a{};
     fill_common(a, depth, depth_per_pixel, n_src, C, D, H, W);
-    a.ref_fea = ref_fea; a.out = out_var;
+    a.ref_fea = ref_fea;
+    for (int o = 0; o < n_outs; ++o) a.out[o] = outs[o];
+    a.n_out = n_outs; a.out_D = D_total; a.out_d0 = d0;
     for (int v = 0; v < NSRC; ++v) a.src_fea[v] = src_feas[v < n_src ? v : 0];
     if (int e = fill_homo_geo(a.geo, n_src, ref_proj, src_projs, H, W)) return e;
     return launch_fwd<HomoSweep<NSRC>, true>(a, (cudaStream_t)stream);
@@ -344,7 +379,7 @@ int satmvs_rpc_warp_fwd(const float* src_fea, const double* src_rpc, const doubl
   SATMVS_REQUIRE(src_fea && src_rpc && ref_rpc && depth && out);
   SweepArgs<RpcSweep<1>> a{};
   fill_common(a, depth, depth_per_pixel, 1, C, D, H, W);
-  a.ref_fea = nullptr; a.out = out; a.src_fea[0] = src_fea;
+  a.ref_fea = nullptr; a.out[0] = out; a.n_out = 1; a.out_D = D; a.out_d0 = 0; a.src_fea[0] = src_fea;
   fill_rpc_geo(a.geo, 1, ref_rpc, src_rpc, H, W);
   return launch_fwd<RpcSweep<1>, false>(a, (cudaStream_t)stream);
 }
@@ -356,7 +391,7 @@ int satmvs_homo_warp_fwd(const float* src_fea, const double* src_proj, const dou
   SATMVS_REQUIRE(src_fea && src_proj && ref_proj && depth && out);
   SweepArgs<HomoSweep<1>> a{};
   fill_common(a, depth, depth_per_pixel, 1, C, D, H, W);
-  a.ref_fea = nullptr; a.out = out; a.src_fea[0] = src_fea;
+  a.ref_fea = nullptr; a.out[0] = out; a.n_out = 1; a.out_D = D; a.out_d0 = 0; a.src_fea[0] = src_fea;
   if (int e = fill_homo_geo(a.geo, 1, ref_proj, src_proj, H, W)) return e;
   return launch_fwd<HomoSweep<1>, false>(a, (cudaStream_t)stream);
 }
