@@ -72,17 +72,23 @@ int satmvs_cost_volume_homo_fwd(const float* ref_fea, const float* const* src_fe
  * this fills one rank's slab of a shared layout; with n_outs == world size and `outs` = the peer-mapped
  * pointers of every rank's volume (CUDA IPC / symmetric memory), the store loop IS the all-gather:
  * each value is written once per peer over NVLink while the sweep is still computing, and the slab
- * never makes a second trip through HBM.  The caller provides the cross-rank barrier afterwards. */
+ * never makes a second trip through HBM.  The caller provides the cross-rank barrier afterwards.
+ * workspace: optional caller-owned scratch of n_src*C*H*W*4 bytes (16-byte aligned).  When given and C is
+ * a multiple of 4, the source features are re-packed to 4-channel words and the vectorised kernel runs
+ * (same results); with NULL the scalar kernel runs.  satmvs_cost_volume_*_fwd == this with d0 = 0,
+ * D_total = D, one output and no workspace. */
 int satmvs_cost_volume_rpc_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
                                        const double* ref_rpc, const double* src_rpcs,
                                        const float* depth, int depth_per_pixel,
                                        int C, int D, int H, int W, int d0, int D_total,
-                                       float* const* outs, int n_outs, void* stream);
+                                       float* const* outs, int n_outs,
+                                       void* workspace, size_t workspace_bytes, void* stream);
 int satmvs_cost_volume_homo_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
                                         const double* ref_proj, const double* src_projs,
                                         const float* depth, int depth_per_pixel,
                                         int C, int D, int H, int W, int d0, int D_total,
-                                        float* const* outs, int n_outs, void* stream);
+                                        float* const* outs, int n_outs,
+                                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- single-view warps with the reference operator's meaning ----
  * rpc_warping (modules/warping.py:310-365) / homo_warping (:6-44): out [C,D,H,W] warped volume. */

@@ -22,8 +22,8 @@ _SIGNATURES = {
     "satmvs_profile_end": ([_P, _P], _I),
     "satmvs_cost_volume_rpc_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_cost_volume_homo_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
-    "satmvs_cost_volume_rpc_fwd_sharded": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P], _I),
-    "satmvs_cost_volume_homo_fwd_sharded": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P], _I),
+    "satmvs_cost_volume_rpc_fwd_sharded": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, C.c_size_t, _P], _I),
+    "satmvs_cost_volume_homo_fwd_sharded": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, C.c_size_t, _P], _I),
     "satmvs_rpc_warp_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_homo_warp_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_rpc_warp_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),

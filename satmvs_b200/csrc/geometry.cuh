@@ -47,6 +47,49 @@ __host__ __device__ __forceinline__ double poly20(const Poly20& q, double L, dou
   return eval_h(collapse_lp(q, L, P), H);   // 19 FMAs, no monomial table
 }
 
+// The same 19-FMA nesting evaluated for N hypothesis planes in lock step: each coefficient is fetched
+// from the constant bank once and used N times, and the N chains are independent (ILP).
+template <int N>
+__device__ __forceinline__ void poly20_many(const Poly20& q, const double (&L)[N], const double (&P)[N],
+                                            const double (&H)[N], double (&out)[N]) {
+  const double* c = q.c;
+  double a0[N], a1[N], a2[N], t[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) a0[k] = fma(L[k], c[11], c[7]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) a0[k] = fma(L[k], a0[k], c[1]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) a0[k] = fma(L[k], a0[k], c[0]);               // p0
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] = fma(L[k], c[14], c[4]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] = fma(L[k], t[k], c[2]);                 // p1
+#pragma unroll
+  for (int k = 0; k < N; ++k) a1[k] = fma(L[k], c[12], c[8]);               // p2
+#pragma unroll
+  for (int k = 0; k < N; ++k) a1[k] = fma(P[k], c[15], a1[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) a1[k] = fma(P[k], a1[k], t[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) a0[k] = fma(P[k], a1[k], a0[k]);              // H^0 term
+#pragma unroll
+  for (int k = 0; k < N; ++k) a1[k] = fma(L[k], c[17], c[5]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) a1[k] = fma(L[k], a1[k], c[3]);               // q0
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] = fma(L[k], c[10], c[6]);                // q1
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] = fma(P[k], c[18], t[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) a1[k] = fma(P[k], t[k], a1[k]);               // H^1 term
+#pragma unroll
+  for (int k = 0; k < N; ++k) a2[k] = fma(L[k], c[13], c[9]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) a2[k] = fma(P[k], c[16], a2[k]);              // H^2 term
+#pragma unroll
+  for (int k = 0; k < N; ++k) out[k] = fma(H[k], fma(H[k], fma(H[k], c[19], a2[k]), a1[k]), a0[k]);
+}
+
 // 1/x to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps.  The reference divides with
 // IEEE fp64; the difference (<= ~2 ulp of fp64) is 9 orders below the fp32 tap-coordinate ulp.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -169,6 +212,42 @@ struct RpcSweep {
     gx = __fsub_rn(div_const(samp, half_wm1, inv_half_wm1), 1.0f);
     gy = __fsub_rn(div_const(line, half_hm1, inv_half_hm1), 1.0f);
   }
+
+  // grid coordinates of N planes x all source views for one reference pixel (same arithmetic as
+  // pixel/plane/project, planes innermost so every constant-bank coefficient is fetched once per N)
+  template <int N, class Emit>
+  __device__ __forceinline__ void grid_coords(const Pixel& px, const float (&h32)[N], Emit&& emit) const {
+    double latn[N], lonn[N], hh[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const Plane pl = plane(px, h32[k]);
+      latn[k] = pl.lat_n; lonn[k] = pl.lon_n; hh[k] = pl.h;
+    }
+#pragma unroll 1          // one copy of the 4 x 19 x N FMA body in the instruction cache, views iterate over it
+    for (int v = 0; v < NSRC; ++v) {
+      const RpcSrcPack& s = src[v];
+      double P[N], L[N], H[N], sn[N], sd[N], ln[N], ld[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        P[k] = fma(latn[k], s.p_a, s.p_b);
+        L[k] = fma(lonn[k], s.l_a, s.l_b);
+        H[k] = fma(hh[k], s.h_a, s.h_b);
+      }
+      poly20_many<N>(s.samp_num, L, P, H, sn);
+      poly20_many<N>(s.samp_den, L, P, H, sd);
+      poly20_many<N>(s.line_num, L, P, H, ln);
+      poly20_many<N>(s.line_den, L, P, H, ld);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        double a, b;
+        ratio2(sn[k], sd[k], ln[k], ld[k], a, b);
+        const float samp = (float)fma(a, s.samp_scale, s.samp_off);
+        const float line = (float)fma(b, s.line_scale, s.line_off);
+        emit(k, v, __fsub_rn(div_const(samp, half_wm1, inv_half_wm1), 1.0f),
+             __fsub_rn(div_const(line, half_hm1, inv_half_hm1), 1.0f));
+      }
+    }
+  }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -241,6 +320,20 @@ struct HomoSweep {
     double iz = fast_rcp(Z);             // Z == 0 -> NaN coordinates -> every tap out of range -> 0, like the reference's inf
     gx = (float)(X * iz * inv_half_wm1 - 1.0);
     gy = (float)(Y * iz * inv_half_hm1 - 1.0);
+  }
+
+  template <int N, class Emit>
+  __device__ __forceinline__ void grid_coords(const Pixel& px, const float (&d32)[N], Emit&& emit) const {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const Plane pl = plane(px, d32[k]);
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        float gx, gy;
+        project(v, px, pl, gx, gy);
+        emit(k, v, gx, gy);
+      }
+    }
   }
 };
 

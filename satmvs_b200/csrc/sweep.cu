@@ -23,6 +23,15 @@
 #ifndef SATMVS_MIN_BLOCKS
 #define SATMVS_MIN_BLOCKS 1
 #endif
+#ifndef SATMVS_SWEEP_V
+#define SATMVS_SWEEP_V 3  // 2 = scalar-arithmetic vec4 kernel, 3 = shared-memory records + packed f32x2 arithmetic
+#endif
+#ifndef SATMVS_NP
+#define SATMVS_NP 4       // hypothesis planes evaluated in lock step in the v3 geometry phase
+#endif
+#ifndef SATMVS_CH
+#define SATMVS_CH 16      // channels carried per gather pass in the v3 kernel
+#endif
 
 namespace satmvs {
 
@@ -32,6 +41,7 @@ template <class Geo>
 struct SweepArgs {
   const float* ref_fea;                       // [C,H,W] (variance mode) or nullptr
   const float* src_fea[Geo::kNumSrc];         // each [C,H,W]
+  const float4* src_v4[Geo::kNumSrc];         // each [C/4,H,W] of float4 (4 consecutive channels per pixel), or null
   const float* depth;                         // [D] or [D,H,W]
   float* out[SATMVS_MAX_PEERS];               // each [C,out_D,H,W]; every buffer receives the same planes
   int n_out;                                  // 1, or the number of peer GPUs written over NVLink (fused all-gather)
@@ -102,6 +112,280 @@ sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
         if (active) {
           // one store per destination: the local volume, or every peer's volume (NVLink posted writes)
           for (int o = 0; o < a.n_out; ++o) __stcs(a.out[o] + oidx + (size_t)k * plane_stride, res);
+        }
+      }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// v2 of the forward sweep: source features re-packed once per call to [C/4][H][W] float4 (four
+// consecutive channels of a pixel in one 16-byte word, pack_vec4_kernel).  A tap is then ONE
+// 128-bit load per 4 channels, lanes of a warp read consecutive pixels = consecutive 16-byte words
+// (full 128-byte lines, no partial sectors), and the channel loop runs over C/4 quads:
+// 4x fewer load instructions, 4 channels of S / Q / variance per iteration.  Geometry phase,
+// tap records, op order and therefore results are identical to sweep_fwd_kernel.
+// ------------------------------------------------------------------------------------------
+struct PackArgs { const float* in[SATMVS_MAX_SRC_VIEWS]; float4* out[SATMVS_MAX_SRC_VIEWS]; int HW; };
+
+__global__ void pack_vec4_kernel(const __grid_constant__ PackArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel
+  const int q = blockIdx.y;                               // channel quad
+  const int HW = a.HW;
+  if (i >= HW) return;
+  const float* p = a.in[blockIdx.z] + (size_t)(4 * q) * HW + i;   // blockIdx.z = source view
+  a.out[blockIdx.z][(size_t)q * HW + i] = make_float4(__ldg(p), __ldg(p + HW), __ldg(p + 2 * (size_t)HW), __ldg(p + 3 * (size_t)HW));
+}
+
+__device__ __forceinline__ float4 tap_fetch4(const float4* __restrict__ f0, const float4* __restrict__ f1, const Tap& t) {
+  const float4 a = __ldg(f0 + t.off), b = __ldg(f0 + t.off + 1), c = __ldg(f1 + t.off), d = __ldg(f1 + t.off + 1);
+  float4 r;
+  r.x = __fmaf_rn(d.x, t.w11, __fmaf_rn(c.x, t.w10, __fmaf_rn(b.x, t.w01, __fmul_rn(a.x, t.w00))));
+  r.y = __fmaf_rn(d.y, t.w11, __fmaf_rn(c.y, t.w10, __fmaf_rn(b.y, t.w01, __fmul_rn(a.y, t.w00))));
+  r.z = __fmaf_rn(d.z, t.w11, __fmaf_rn(c.z, t.w10, __fmaf_rn(b.z, t.w01, __fmul_rn(a.z, t.w00))));
+  r.w = __fmaf_rn(d.w, t.w11, __fmaf_rn(c.w, t.w10, __fmaf_rn(b.w, t.w01, __fmul_rn(a.w, t.w00))));
+  return r;
+}
+
+template <class Geo, int DK, bool kVariance>
+__global__ void __launch_bounds__(kSweepThreads, SATMVS_MIN_BLOCKS)
+sweep_fwd_vec4_kernel(const __grid_constant__ SweepArgs<Geo> a) {
+  constexpr int NSRC = Geo::kNumSrc;
+  const int HW = a.H * a.W;
+  const int pix = blockIdx.x * kSweepThreads + threadIdx.x;
+  const bool active = pix < HW;
+  const int pixc = active ? pix : HW - 1;
+  const int y = pixc / a.W, x = pixc - y * a.W;
+  const int d0 = blockIdx.y * DK;
+
+  Tap taps[DK][NSRC];
+  {
+    const typename Geo::Pixel px = a.geo.pixel(x, y);
+#pragma unroll
+    for (int k = 0; k < DK; ++k) {
+      const int d = min(d0 + k, a.D - 1);
+      const float h = a.depth_per_pixel ? __ldg(a.depth + (size_t)d * HW + pixc) : __ldg(a.depth + d);
+      const typename Geo::Plane pl = a.geo.plane(px, h);
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        float gx, gy;
+        a.geo.project(v, px, pl, gx, gy);
+        taps[k][v] = make_tap(gx, gy, a.H, a.W, a.half_w, a.half_h);
+        if (v >= a.n_src) { taps[k][v].w00 = taps[k][v].w01 = taps[k][v].w10 = taps[k][v].w11 = 0.0f; taps[k][v].off = 0; }
+      }
+    }
+  }
+
+  const size_t plane_stride = (size_t)HW;
+  const int C4 = a.C >> 2;
+  for (int q = 0; q < C4; ++q) {
+    float r[4] = {0.f, 0.f, 0.f, 0.f}, r2[4];
+    if (kVariance) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = __ldg(a.ref_fea + (size_t)(4 * q + j) * HW + pixc);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r2[j] = __fmul_rn(r[j], r[j]);
+    const size_t oidx = ((size_t)(4 * q) * a.out_D + a.out_d0 + d0) * plane_stride + pix;
+#pragma unroll
+    for (int k = 0; k < DK; ++k) {
+      if (d0 + k < a.D) {
+        float s[4] = {r[0], r[1], r[2], r[3]}, qq[4] = {r2[0], r2[1], r2[2], r2[3]};
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < NSRC; ++v) {
+          const float4* f0 = a.src_v4[v] + (size_t)q * HW;
+          val = tap_fetch4(f0, f0 + a.W, taps[k][v]);
+          if (kVariance) {
+            const float vv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              s[j] = __fadd_rn(s[j], vv[j]);
+              qq[j] = __fadd_rn(qq[j], __fmul_rn(vv[j], vv[j]));
+            }
+          }
+        }
+        float res[4] = {val.x, val.y, val.z, val.w};
+        if (kVariance) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float m = div_const(s[j], a.num_views, a.inv_num_views);
+            res[j] = __fsub_rn(div_const(qq[j], a.num_views, a.inv_num_views), __fmul_rn(m, m));
+          }
+        }
+        if (active) {
+          for (int o = 0; o < a.n_out; ++o) {
+            float* op = a.out[o] + oidx + (size_t)k * plane_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) __stcs(op + (size_t)j * a.out_D * plane_stride, res[j]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// v3 of the forward sweep (the default when a workspace is given and C % 4 == 0).
+//   phase A  geometry for the CTA's 128 pixels x DK planes, hypothesis planes evaluated in lock step
+//            (poly20_many: one constant-bank fetch per coefficient per 4 planes); tap records go to
+//            shared memory, so the fp64 state is dead before the gather starts.
+//   phase B  gather: for every (plane, view) the record is read back once and its weights duplicated
+//            into 2-lane operands; the channel loop issues one LDG.128 per tap per 4 channels from the
+//            [C/4][H][W] float4 re-pack and does ALL fp32 arithmetic with Blackwell's packed
+//            fma/mul/add.f32x2 (two IEEE-rounded results per instruction, so the op sequence and the
+//            bits are those of the scalar kernels).  CH channels (16) are carried per pass to keep
+//            ~20 warps resident.
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+#ifndef SATMVS_PACKED_MASK
+#define SATMVS_PACKED_MASK 15   // debug knob: bit0 fma2, bit1 mul2, bit2 add2, bit3 sub2 use the packed instruction
+#endif
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  if (SATMVS_PACKED_MASK & 1) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+  float a0, a1, b0, b1, c0, c1; upk(a, a0, a1); upk(b, b0, b1); upk(c, c0, c1);
+  return pk(__fmaf_rn(a0, b0, c0), __fmaf_rn(a1, b1, c1));
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  if (SATMVS_PACKED_MASK & 2) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+  float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1);
+  return pk(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  if (SATMVS_PACKED_MASK & 4) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+  float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1);
+  return pk(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  if (SATMVS_PACKED_MASK & 8) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+  float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1);
+  return pk(__fsub_rn(a0, b0), __fsub_rn(a1, b1));
+}
+// A product that feeds an add/sub and must be rounded on its own.  ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2
+// into one FFMA2 even with explicit .rn (and folds fma(a,b,-0) back to a multiply first), which shows up as
+// 1-ulp differences against the scalar kernels (profiles/r01_sweep_v3_notes.md).  Two scalar FMULs cannot be
+// merged into a packed add, so these few products stay scalar.
+__device__ __forceinline__ u64 mul2_rounded(u64 a, u64 b) {
+  float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1);
+  return pk(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+}
+
+struct __align__(16) TapW { float w00, w01, w10, w11; };
+
+template <class Geo, int DK, int CH, bool kVariance, bool kMultiOut>
+__global__ void __launch_bounds__(kSweepThreads, SATMVS_MIN_BLOCKS)
+sweep_fwd_v3_kernel(const __grid_constant__ SweepArgs<Geo> a) {
+  constexpr int NSRC = Geo::kNumSrc;
+  constexpr int NP = DK < SATMVS_NP ? DK : SATMVS_NP;   // planes evaluated in lock step
+  __shared__ int rec_off[DK * NSRC][kSweepThreads];
+  __shared__ TapW rec_w[DK * NSRC][kSweepThreads];
+
+  const int HW = a.H * a.W;
+  const int tid = threadIdx.x;
+  const int pix = blockIdx.x * kSweepThreads + tid;
+  const bool active = pix < HW;
+  const int pixc = active ? pix : HW - 1;
+  const int d0 = blockIdx.y * DK;
+
+  {  // ---- phase A ----
+    const int y = pixc / a.W, x = pixc - y * a.W;
+    const typename Geo::Pixel px = a.geo.pixel(x, y);
+#pragma unroll 1
+    for (int g = 0; g < DK; g += NP) {
+      float h[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        const int d = min(d0 + g + k, a.D - 1);
+        h[k] = a.depth_per_pixel ? __ldg(a.depth + (size_t)d * HW + pixc) : __ldg(a.depth + d);
+      }
+      a.geo.template grid_coords<NP>(px, h, [&](int k, int v, float gx, float gy) {
+        Tap t = make_tap(gx, gy, a.H, a.W, a.half_w, a.half_h);
+        if (v >= a.n_src) { t.w00 = t.w01 = t.w10 = t.w11 = 0.0f; t.off = 0; }
+        rec_off[(g + k) * NSRC + v][tid] = t.off;
+        rec_w[(g + k) * NSRC + v][tid] = TapW{t.w00, t.w01, t.w10, t.w11};
+      });
+    }
+  }
+  // each thread only reads back its own records: no barrier needed
+
+  // ---- phase B ----
+  // addresses = warp-uniform 64-bit base + 32-bit per-thread byte offset: no per-thread 64-bit arithmetic
+  const unsigned upix = (unsigned)pix * 4u;
+  const size_t quad_bytes = (size_t)HW * sizeof(float4);
+  const size_t row_bytes = (size_t)a.W * sizeof(float4);
+  const size_t plane_bytes = (size_t)HW * sizeof(float);
+  const u64 vinv = pk(a.inv_num_views, a.inv_num_views), vneg = pk(-a.num_views, -a.num_views);
+  for (int c0 = 0; c0 < a.C; c0 += CH) {
+    u64 r[CH / 2];
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) {
+      float lo = 0.f, hi = 0.f;
+      if (kVariance) {
+        const char* rb = reinterpret_cast<const char*>(a.ref_fea) + (size_t)(c0 + 2 * j) * plane_bytes;
+        lo = __ldg(reinterpret_cast<const float*>(rb + (unsigned)pixc * 4u));
+        hi = __ldg(reinterpret_cast<const float*>(rb + plane_bytes + (unsigned)pixc * 4u));
+      }
+      r[j] = pk(lo, hi);
+    }
+#pragma unroll 1
+    for (int k = 0; k < DK; ++k) {
+      if (d0 + k >= a.D) break;
+      u64 s[CH / 2], q[CH / 2];
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) { s[j] = r[j]; q[j] = mul2_rounded(r[j], r[j]); }
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        const unsigned offb = (unsigned)rec_off[k * NSRC + v][tid] * (unsigned)sizeof(float4);
+        const TapW w = rec_w[k * NSRC + v][tid];
+        const u64 w00 = pk(w.w00, w.w00), w01 = pk(w.w01, w.w01), w10 = pk(w.w10, w.w10), w11 = pk(w.w11, w.w11);
+        const char* vb = reinterpret_cast<const char*>(a.src_v4[v]) + (size_t)(c0 >> 2) * quad_bytes;
+#pragma unroll
+        for (int qd = 0; qd < CH / 4; ++qd) {
+          const char* b0 = vb + (size_t)qd * quad_bytes;          // uniform
+          const char* b1 = b0 + row_bytes;                         // uniform
+          const float4 A = __ldg(reinterpret_cast<const float4*>(b0 + offb));
+          const float4 B = __ldg(reinterpret_cast<const float4*>(b0 + offb + 16u));
+          const float4 Cc = __ldg(reinterpret_cast<const float4*>(b1 + offb));
+          const float4 Dd = __ldg(reinterpret_cast<const float4*>(b1 + offb + 16u));
+          // nw, ne, sw, se accumulated with FMAs (ATen order), two channels per instruction
+          u64 lo = fma2(pk(Dd.x, Dd.y), w11, fma2(pk(Cc.x, Cc.y), w10, fma2(pk(B.x, B.y), w01, mul2(pk(A.x, A.y), w00))));
+          u64 hi = fma2(pk(Dd.z, Dd.w), w11, fma2(pk(Cc.z, Cc.w), w10, fma2(pk(B.z, B.w), w01, mul2(pk(A.z, A.w), w00))));
+          if (kVariance) {
+            s[2 * qd] = add2(s[2 * qd], lo);         q[2 * qd] = add2(q[2 * qd], mul2_rounded(lo, lo));
+            s[2 * qd + 1] = add2(s[2 * qd + 1], hi); q[2 * qd + 1] = add2(q[2 * qd + 1], mul2_rounded(hi, hi));
+          } else {
+            s[2 * qd] = lo; s[2 * qd + 1] = hi;
+          }
+        }
+      }
+      const size_t obase = ((size_t)c0 * a.out_D + a.out_d0 + d0 + k) * plane_bytes;      // uniform
+      const size_t ostride = (size_t)a.out_D * plane_bytes;                                 // uniform, per channel
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) {
+        u64 res = s[j];
+        if (kVariance) {
+          // x / V as a correctly rounded constant division (div_const), packed
+          u64 m = mul2(s[j], vinv);  m = fma2(fma2(vneg, m, s[j]), vinv, m);
+          u64 e = mul2(q[j], vinv);  e = fma2(fma2(vneg, e, q[j]), vinv, e);
+          res = sub2(e, mul2_rounded(m, m));
+        }
+        float lo, hi;
+        upk(res, lo, hi);
+        if (active) {
+          if (kMultiOut) {
+            for (int o = 0; o < a.n_out; ++o) {
+              char* ob = reinterpret_cast<char*>(a.out[o]) + obase + (size_t)(2 * j) * ostride;
+              __stcs(reinterpret_cast<float*>(ob + upix), lo);
+              __stcs(reinterpret_cast<float*>(ob + ostride + upix), hi);
+            }
+          } else {
+            char* ob = reinterpret_cast<char*>(a.out[0]) + obase + (size_t)(2 * j) * ostride;
+            __stcs(reinterpret_cast<float*>(ob + upix), lo);
+            __stcs(reinterpret_cast<float*>(ob + ostride + upix), hi);
+          }
         }
       }
     }
@@ -248,6 +532,17 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
   constexpr int DK = PlanesPerThread<Geo::kNumSrc>::value;
   dim3 grid(ceil_div((int64_t)a.H * a.W, kSweepThreads), ceil_div(a.D, DK));
   ProfScope prof(kProfSweep, st);
+  if (a.src_v4[0] != nullptr) {
+#if SATMVS_SWEEP_V == 2
+    sweep_fwd_vec4_kernel<Geo, DK, kVariance><<<grid, kSweepThreads, 0, st>>>(a);
+    return check_launch("sweep_fwd_vec4_kernel");
+#else
+    if (a.n_out > 1) sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
+    else if (a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
+    else sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
+    return check_launch("sweep_fwd_v3_kernel");
+#endif
+  }
   sweep_fwd_kernel<Geo, DK, kVariance><<<grid, kSweepThreads, 0, st>>>(a);
   return check_launch("sweep_fwd_kernel");
 }
@@ -291,6 +586,29 @@ static void fill_common(Args& a, const float* depth, int depth_per_pixel, int n_
   a.inv_num_views = 1.0f / a.num_views;
 }
 
+// Re-pack the source feature maps into the caller's workspace ([n_src][C/4][H][W] float4) and point the
+// kernel arguments at them.  Without a workspace (or when C is not a multiple of 4) the scalar path runs.
+template <class Args>
+static int pack_sources(Args& a, const float* const* src_feas, int n_src, int nslots, void* workspace, size_t workspace_bytes,
+                        cudaStream_t st) {
+  for (int v = 0; v < nslots; ++v) a.src_v4[v] = nullptr;
+  const size_t per_view = (size_t)a.C * a.H * a.W * sizeof(float);
+  if (workspace == nullptr || (a.C & 3) || workspace_bytes < per_view * n_src ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15)) return SATMVS_OK;
+  const int HW = a.H * a.W;
+  ProfScope prof(kProfSweep, st);
+  PackArgs pa{};
+  pa.HW = HW;
+  for (int v = 0; v < n_src; ++v) {
+    float4* dst = reinterpret_cast<float4*>(static_cast<char*>(workspace) + per_view * v);
+    pa.in[v] = src_feas[v]; pa.out[v] = dst;
+    a.src_v4[v] = dst;
+  }
+  pack_vec4_kernel<<<dim3(ceil_div(HW, 256), a.C / 4, n_src), 256, 0, st>>>(pa);
+  for (int v = n_src; v < nslots; ++v) a.src_v4[v] = a.src_v4[0];
+  return check_launch("pack_vec4_kernel");
+}
+
 // template slot count for a runtime number of source views
 static int slot_for(int n_src) { return n_src <= 4 ? n_src : (n_src <= 6 ? 6 : 8); }
 
@@ -316,14 +634,14 @@ int satmvs_cost_volume_rpc_fwd(const float* ref_fea, const float* const* src_fea
                                int C, int D, int H, int W, float* out_var, void* stream) {
   float* outs[1] = {out_var};
   return satmvs_cost_volume_rpc_fwd_sharded(ref_fea, src_feas, n_src, ref_rpc, src_rpcs, depth, depth_per_pixel,
-                                            C, D, H, W, 0, D, outs, 1, stream);
+                                            C, D, H, W, 0, D, outs, 1, nullptr, 0, stream);
 }
 
 int satmvs_cost_volume_rpc_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
                                        const double* ref_rpc, const double* src_rpcs,
                                        const float* depth, int depth_per_pixel,
                                        int C, int D, int H, int W, int d0, int D_total,
-                                       float* const* outs, int n_outs, void* stream) {
+                                       float* const* outs, int n_outs, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_dims(n_src, C, D, H, W)) return e;
   SATMVS_REQUIRE(ref_fea && src_feas && ref_rpc && src_rpcs && depth && outs);
   SATMVS_REQUIRE(n_outs >= 1 && n_outs <= SATMVS_MAX_PEERS && d0 >= 0 && d0 + D <= D_total);
@@ -335,6 +653,7 @@ int satmvs_cost_volume_rpc_fwd_sharded(const float* ref_fea, const float* const*
     for (int o = 0; o < n_outs; ++o) a.out[o] = outs[o];
     a.n_out = n_outs; a.out_D = D_total; a.out_d0 = d0;
     for (int v = 0; v < NSRC; ++v) a.src_fea[v] = src_feas[v < n_src ? v : 0];
+    if (int e = pack_sources(a, src_feas, n_src, NSRC, workspace, workspace_bytes, (cudaStream_t)stream)) return e;
     fill_rpc_geo(a.geo, n_src, ref_rpc, src_rpcs, H, W);
     return launch_fwd<RpcSweep<NSRC>, true>(a, (cudaStream_t)stream);
   })
@@ -347,14 +666,14 @@ int satmvs_cost_volume_homo_fwd(const float* ref_fea, const float* const* src_fe
                                 int C, int D, int H, int W, float* out_var, void* stream) {
   float* outs[1] = {out_var};
   return satmvs_cost_volume_homo_fwd_sharded(ref_fea, src_feas, n_src, ref_proj, src_projs, depth, depth_per_pixel,
-                                             C, D, H, W, 0, D, outs, 1, stream);
+                                             C, D, H, W, 0, D, outs, 1, nullptr, 0, stream);
 }
 
 int satmvs_cost_volume_homo_fwd_sharded(const float* ref_fea, const float* const* src_feas, int n_src,
                                         const double* ref_proj, const double* src_projs,
                                         const float* depth, int depth_per_pixel,
                                         int C, int D, int H, int W, int d0, int D_total,
-                                        float* const* outs, int n_outs, void* stream) {
+                                        float* const* outs, int n_outs, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_dims(n_src, C, D, H, W)) return e;
   SATMVS_REQUIRE(ref_fea && src_feas && ref_proj && src_projs && depth && outs);
   SATMVS_REQUIRE(n_outs >= 1 && n_outs <= SATMVS_MAX_PEERS && d0 >= 0 && d0 + D <= D_total);
@@ -366,6 +685,7 @@ int satmvs_cost_volume_homo_fwd_sharded(const float* ref_fea, const float* const
     for (int o = 0; o < n_outs; ++o) a.out[o] = outs[o];
     a.n_out = n_outs; a.out_D = D_total; a.out_d0 = d0;
     for (int v = 0; v < NSRC; ++v) a.src_fea[v] = src_feas[v < n_src ? v : 0];
+    if (int e = pack_sources(a, src_feas, n_src, NSRC, workspace, workspace_bytes, (cudaStream_t)stream)) return e;
     if (int e = fill_homo_geo(a.geo, n_src, ref_proj, src_projs, H, W)) return e;
     return launch_fwd<HomoSweep<NSRC>, true>(a, (cudaStream_t)stream);
   })

@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .warping import _check_cam, _depth_arg, _dptr, build_cost_volume, host_f64
+from .warping import _check_cam, _depth_arg, _dptr, build_cost_volume, host_f64, sweep_workspace
 
 
 def plane_range(D: int, rank: int, world: int) -> tuple[int, int]:
@@ -89,6 +89,7 @@ def build_cost_volume_sharded(ref_fea, src_feas, ref_cam, src_cams, depth_values
     vol, peers, hdl = _symmetric_volume((B, C, D, H, W), ref.device, group)
     fn = _lib.lib().satmvs_cost_volume_rpc_fwd_sharded if geo_model == "rpc" else _lib.lib().satmvs_cost_volume_homo_fwd_sharded
     per_b = C * D * H * W * 4
+    ws = sweep_workspace(len(srcs) * C * H * W * 4, ref.device)
     hdl.barrier()                      # nobody is still reading the previous contents
     with torch.cuda.device(ref.device):
         st = _lib.stream_ptr(ref.device)
@@ -96,7 +97,8 @@ def build_cost_volume_sharded(ref_fea, src_feas, ref_cam, src_cams, depth_values
             outs = _lib.ptr_array([p + b * per_b for p in peers])
             cams = np.ascontiguousarray(s[:, b])
             _lib.check(fn(ref[b].data_ptr(), _lib.ptr_array([x[b].data_ptr() for x in srcs]), len(srcs), _dptr(r[b]),
-                          _dptr(cams), depth[b].data_ptr(), per_pixel, C, d1 - d0, H, W, d0, D, outs, len(peers), st),
+                          _dptr(cams), depth[b].data_ptr(), per_pixel, C, d1 - d0, H, W, d0, D, outs, len(peers),
+                          ws.data_ptr(), ws.numel(), st),
                        "cost_volume_fwd_sharded")
     hdl.barrier()                      # every rank's planes have landed everywhere
     return vol

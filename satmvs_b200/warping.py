@@ -24,6 +24,17 @@ import torch
 from . import _lib
 
 _HOST_CAM_CACHE: dict = {}
+_SWEEP_WS: dict = {}
+
+
+def sweep_workspace(nbytes: int, device) -> torch.Tensor:
+    """Caller-owned scratch of the sweep (re-packed source features), cached per device."""
+    key = (device.type, device.index)
+    ws = _SWEEP_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _SWEEP_WS[key] = ws
+    return ws
 
 
 def host_f64(cam: torch.Tensor) -> np.ndarray:
@@ -169,14 +180,17 @@ class _CostVolumeFn(torch.autograd.Function):
         D = depth.shape[1]
         n_src = len(srcs)
         out = torch.empty((B, Cc, D, H, W), dtype=torch.float32, device=ref.device)
-        fn = _lib.lib().satmvs_cost_volume_rpc_fwd if geo_model == "rpc" else _lib.lib().satmvs_cost_volume_homo_fwd
+        fn = (_lib.lib().satmvs_cost_volume_rpc_fwd_sharded if geo_model == "rpc"
+              else _lib.lib().satmvs_cost_volume_homo_fwd_sharded)
+        ws = sweep_workspace(n_src * Cc * H * W * 4, ref.device)
         with torch.cuda.device(ref.device):
             st = _lib.stream_ptr(ref.device)
             for b in range(B):
                 ptrs = _lib.ptr_array([s[b].data_ptr() for s in srcs])
                 cams = np.ascontiguousarray(src_cams[:, b])
                 _lib.check(fn(ref[b].data_ptr(), ptrs, n_src, _dptr(ref_cam[b]), _dptr(cams), depth[b].data_ptr(),
-                              per_pixel, Cc, D, H, W, out[b].data_ptr(), st), "cost_volume_fwd")
+                              per_pixel, Cc, D, H, W, 0, D, _lib.ptr_array([out[b].data_ptr()]), 1,
+                              ws.data_ptr(), ws.numel(), st), "cost_volume_fwd")
         ctx.save_for_backward(depth, ref, *srcs)
         ctx.meta = (ref_cam, src_cams, geo_model, per_pixel, (B, Cc, D, H, W))
         return out

@@ -206,3 +206,25 @@ def test_rpc_point_ops_golden(golden):
     e = np.zeros(0)
     lat, lon = cam0.RPC_PHOTO2OBJ(e, e, e)
     assert lat.shape == (0,)
+
+
+def test_vectorised_and_scalar_kernels_agree_bitwise():
+    """build_cost_volume uses the 4-channel-packed kernel; the plain C-ABI entry (no workspace) runs the
+    scalar kernel.  Same op order => identical bits."""
+    import ctypes as C
+    from satmvs_b200 import _lib
+    B, V, Cc, D, H, W = 1, 3, 16, 11, 24, 40
+    fe = [cu(f) for f in synth.make_features(B, V, Cc, H, W, seed=8)]
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv = cu(synth.make_depth_planes(B, D, H, W))
+    fast = satmvs_b200.build_cost_volume(fe[0], fe[1:], rp[:, 0], rp[:, 1:], dv, "rpc")
+    slow = torch.empty_like(fast)
+    ptrs = (C.c_void_p * 2)(fe[1][0].data_ptr(), fe[2][0].data_ptr())
+    ref_cam = np.ascontiguousarray(rp[0, 0].numpy())
+    src_cam = np.ascontiguousarray(rp[0, 1:].numpy())
+    rc = _lib.lib().satmvs_cost_volume_rpc_fwd(fe[0][0].data_ptr(), ptrs, 2, ref_cam.ctypes.data_as(C.c_void_p),
+                                               src_cam.ctypes.data_as(C.c_void_p), dv[0].data_ptr(), 1, Cc, D, H, W,
+                                               slow[0].data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(fast, slow)
