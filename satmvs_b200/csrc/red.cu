@@ -17,8 +17,11 @@
 //   C. batched:    the decoder (3 stride-2 transposed convs with skip adds, final 8->1 transposed
 //                  conv with bias) over the stored states of all planes.
 // Only B is sequential in D: 4 launches per plane instead of ~70.
+#include <cooperative_groups.h>
+#include <type_traits>
 #include "conv_engine.cuh"
 #include "prof.cuh"
+namespace cg = cooperative_groups;
 
 namespace satmvs {
 
@@ -67,7 +70,7 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
     p.u[i] = take((size_t)chs[i] * (D + 1) * (H >> i) * (W >> i));
   }
   p.stats = reinterpret_cast<double*>(base + off);
-  off += ((size_t)D * 4 * 3 * 2 * sizeof(double) + 255) / 256 * 256;
+  off += ((size_t)D * 4 * 3 * 2 * sizeof(double) + 64 * sizeof(double) + 255) / 256 * 256;   // + 64 debug counters
   p.bytes = off;
   return p;
 }
@@ -158,17 +161,24 @@ constexpr int kGcWarps = 4, kGcCo = 8, kGcPx = 4, kGcTilePx = 32 * kGcPx, kGcCi 
 
 // kAligned: every level's width is a multiple of 4, so a lane's 4 pixels sit in one row at a
 // 16-byte aligned address: 3 vector + 6 scalar loads per input channel instead of 36 predicated ones.
-template <bool kAligned>
-__global__ void __launch_bounds__(kGcWarps * 32)
-gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
-  __shared__ __align__(16) float wsm[64 * 9 * kGcCo];                    // [ci][tap][co]  (<= 18 KB)
-  __shared__ __align__(16) float part[kGcWarps][kGcCo][kGcTilePx];      // 16 KB
-  __shared__ double red[2][kGcWarps];
-  int li = 0;
-#pragma unroll
-  for (int k = 1; k < 4; ++k) if ((int)blockIdx.x >= a.l[k].cta_begin) li = k;
-  const GruConvLevel& L = a.l[li];
-  const int cta = blockIdx.x - L.cta_begin;
+// kCoherent: inputs / addends were written earlier in the SAME kernel by other CTAs (persistent
+// recurrence): they are read with ld.global.cg (L2, coherent) instead of the read-only path.
+template <bool kCoherent> __device__ __forceinline__ float ldf(const float* p) { return kCoherent ? __ldcg(p) : __ldg(p); }
+template <bool kCoherent> __device__ __forceinline__ float4 ldf4(const float4* p) { return kCoherent ? __ldcg(p) : __ldg(p); }
+
+template <bool kAligned, bool kCoherent>
+__device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, float* wsm,
+                                              float (*part)[kGcCo][kGcTilePx], double (*red)[kGcWarps], bool stage_weights,
+                                              unsigned long long* dbg = nullptr) {
+  unsigned long long t_prev = 0;
+  auto tick = [&](int slot) {
+    if (dbg && threadIdx.x == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      if (slot >= 0) dbg[slot] += t - t_prev;
+      t_prev = t;
+    }
+  };
+  tick(-1);
   const int co0 = (cta / L.px_groups) * kGcCo;
   const int tiles_per_cta = kGcWarps / L.ksplit;
   const int tile0 = (cta % L.px_groups) * tiles_per_cta;
@@ -177,7 +187,7 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
 
   // weights of this CTA's 8 output channels -> smem [ci][tap][co].  All loads are issued before the
   // first store (one round trip to L2 instead of one per loop iteration).
-  {
+  if (stage_weights) {
     const int kr = L.cin * 9;                                   // contiguous run per output channel
     const int per_co = (kr + kGcWarps * 32 - 1) / (kGcWarps * 32);   // <= 5 (cin 64)
     constexpr int kMaxPerCo = (64 * 9 + kGcWarps * 32 - 1) / (kGcWarps * 32);
@@ -222,6 +232,7 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
 #pragma unroll
     for (int j = 0; j < kGcPx; ++j) acc[i][j] = 0.0f;
   __syncthreads();
+  tick(0);
 
   // input taps of one input channel for this lane's 4 pixels (predicated: zero padding)
   auto load_taps = [&](int ci, float (&v)[kGcPx][9]) {
@@ -230,7 +241,7 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
     for (int j = 0; j < kGcPx; ++j)
 #pragma unroll
       for (int t = 0; t < 9; ++t)
-        v[j][t] = ((mask[j] >> t) & 1u) ? __ldg(ip + base[j] + (t / 3 - 1) * L.w_ + (t % 3 - 1)) : 0.0f;
+        v[j][t] = ((mask[j] >> t) & 1u) ? ldf<kCoherent>(ip + base[j] + (t / 3 - 1) * L.w_ + (t % 3 - 1)) : 0.0f;
   };
   auto fma_taps = [&](int ci, const float (&v)[kGcPx][9]) {
 #pragma unroll
@@ -260,9 +271,9 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
         float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
         float lft = 0.f, rgt = 0.f;
         if (rowok[dy]) {
-          m = __ldg(reinterpret_cast<const float4*>(rp));
-          if (lok) lft = __ldg(rp - 1);
-          if (rok) rgt = __ldg(rp + kGcPx);
+          m = ldf4<kCoherent>(reinterpret_cast<const float4*>(rp));
+          if (lok) lft = ldf<kCoherent>(rp - 1);
+          if (rok) rgt = ldf<kCoherent>(rp + kGcPx);
         }
         r[dy][0] = lft; r[dy][1] = m.x; r[dy][2] = m.y; r[dy][3] = m.z; r[dy][4] = m.w; r[dy][5] = rgt;
       }
@@ -279,13 +290,19 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
           for (int j = 0; j < kGcPx; ++j) acc[i][j] = fmaf(wv[i], r[t / 3][j + t % 3], acc[i][j]);
       }
     };
-    float ra[3][6], rb[3][6];
-    load_rows(ci0, ra);
-    for (int c = 0; c < L.ci_per_warp; c += 2) {
-      load_rows(ci0 + c + 1, rb);
-      fma_rows(ci0 + c, ra);
-      if (c + 2 < L.ci_per_warp) load_rows(ci0 + c + 2, ra);
-      fma_rows(ci0 + c + 1, rb);
+    // 4-slot register ring: the rows of channels c+1..c+3 are in flight while channel c's 288 FMAs issue
+    // (an L2 round trip is ~2 channels of arithmetic at 2 warps per scheduler)
+    float ring[4][3][6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c < L.ci_per_warp) load_rows(ci0 + c, ring[c]);
+#pragma unroll 1
+    for (int c = 0; c < L.ci_per_warp; c += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c + u + 3 < L.ci_per_warp) load_rows(ci0 + c + u + 3, ring[(u + 3) & 3]);
+        if (c + u < L.ci_per_warp) fma_rows(ci0 + c + u, ring[u]);
+      }
     }
   } else {
   // two input channels per iteration, ping-pong registers: the next channel's taps are in flight
@@ -301,42 +318,46 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
   }
   }
 
-  // this thread's share of the CTA's outputs: fetch the addends now, so the loads fly during the
-  // partial-sum exchange
-  constexpr int kMaxOut = kGcCo * kGcTilePx / 32;          // 32 outputs per thread when ksplit == 1
-  const int outs = tiles_per_cta * kGcCo * kGcTilePx;
+  tick(1);
+  // This thread's share of the CTA's outputs.  With 128 threads and 128-pixel tiles, output
+  // o = tid + 128 r is (tile-in-CTA r / 8, channel r % 8, pixel tid): the index math is compile time.
+  // The addends are fetched now, so the loads fly during the partial-sum exchange.
+  constexpr int kMaxOut = kGcCo * kGcWarps;                 // 32 outputs per thread when ksplit == 1
+  const int nout = tiles_per_cta * kGcCo;
   float pre[kMaxOut];
 #pragma unroll
   for (int r = 0; r < kMaxOut; ++r) {
-    const int o = tid + r * (kGcWarps * 32);
-    pre[r] = 0.0f;
-    if (o < outs) {
-      const int ts = o / (kGcCo * kGcTilePx), q = o - ts * (kGcCo * kGcTilePx);
-      const int i = q / kGcTilePx, p = (tile0 + ts) * kGcTilePx + (q - i * kGcTilePx);
-      if (p < npx) pre[r] = __ldg(L.pre + (long long)(co0 + i) * L.out_cs + p);
-    }
+    const int p = (tile0 + (r >> 3)) * kGcTilePx + tid;
+    pre[r] = (r < nout && p < npx) ? ldf<kCoherent>(L.pre + (long long)(co0 + (r & 7)) * L.out_cs + p) : 0.0f;
   }
 #pragma unroll
   for (int i = 0; i < kGcCo; ++i)
     *reinterpret_cast<float4*>(&part[warp][i][lane * kGcPx]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   __syncthreads();
 
+  tick(2);
   // fixed-order reduction over the k-parts, epilogue, GroupNorm sums
   float ssum = 0.0f, ssq = 0.0f;
+  auto epilogue = [&](auto ks_tag) {
+    constexpr int KS = decltype(ks_tag)::value;
 #pragma unroll
-  for (int r = 0; r < kMaxOut; ++r) {
-    const int o = tid + r * (kGcWarps * 32);
-    if (o >= outs) break;
-    const int ts = o / (kGcCo * kGcTilePx), q = o - ts * (kGcCo * kGcTilePx);
-    const int i = q / kGcTilePx, px = q - i * kGcTilePx;
-    const int p = (tile0 + ts) * kGcTilePx + px;
-    if (p >= npx) continue;
-    float sum = 0.0f;
-    for (int kp = 0; kp < L.ksplit; ++kp) sum += part[ts * L.ksplit + kp][i][px];
-    const float val = sum + pre[r];
-    L.out[(long long)(co0 + i) * L.out_cs + p] = val;
-    ssum += val; ssq += val * val;
-  }
+    for (int r = 0; r < kMaxOut / KS; ++r) {
+      const int ts = r >> 3, i = r & 7;
+      const int p = (tile0 + ts) * kGcTilePx + tid;
+      if (p < npx) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int kp = 0; kp < KS; ++kp) sum += part[ts * KS + kp][i][tid];
+        const float val = sum + pre[r];
+        L.out[(long long)(co0 + i) * L.out_cs + p] = val;
+        ssum += val; ssq += val * val;
+      }
+    }
+  };
+  if (L.ksplit == 1) epilogue(std::integral_constant<int, 1>{});
+  else if (L.ksplit == 2) epilogue(std::integral_constant<int, 2>{});
+  else epilogue(std::integral_constant<int, 4>{});
+  tick(3);
   double ds = ssum, dq = ssq;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, off); dq += __shfl_xor_sync(0xffffffffu, dq, off); }
@@ -349,6 +370,226 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
     atomicAdd(L.stats + 2 * grp, s);
     atomicAdd(L.stats + 2 * grp + 1, q);
   }
+  tick(4);
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kGcWarps * 32)
+gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
+  __shared__ __align__(16) float wsm[64 * 9 * kGcCo];                    // [ci][tap][co]  (<= 18 KB)
+  __shared__ __align__(16) float part[kGcWarps][kGcCo][kGcTilePx];      // 16 KB
+  __shared__ double red[2][kGcWarps];
+  int li = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) if ((int)blockIdx.x >= a.l[k].cta_begin) li = k;
+  gru_conv_unit<kAligned, false>(a.l[li], blockIdx.x - a.l[li].cta_begin, wsm, part, red, true);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Persistent recurrence: ONE cooperative launch runs phase B for all D planes.  Every CTA owns at most
+// one gate-conv unit and one output-conv unit for the whole sweep over depth, so their weights are
+// staged into shared memory once and stay resident; the four phases of a plane
+//     P1 gate conv (+GN sums) | E1 r*h | P2 output conv (+GN sums) | E2 state update
+// are separated by grid-wide barriers instead of kernel boundaries (no launch gaps, no cold restarts).
+// Tensors written inside the kernel are read back with ld.global.cg (coherent at L2).
+// ---------------------------------------------------------------------------------------------
+// out-of-line copy for the persistent kernel: its two call sites share one body and one register budget
+template <bool kAligned>
+__device__ __noinline__ void gru_conv_unit_coherent(const GruConvLevel& L, int cta, float* wsm,
+                                                    float (*part)[kGcCo][kGcTilePx], double (*red)[kGcWarps],
+                                                    bool stage_weights, unsigned long long* dbg) {
+  gru_conv_unit<kAligned, true>(L, cta, wsm, part, red, stage_weights, dbg);
+}
+
+struct RecLevel {
+  const float* s;  long long s_cs, s_ps;       // state history [ch][D+1][px]: channel stride, slot stride
+  float* gx;       long long g_cs;             // gates [2ch][D][px] (plane stride = px)
+  float* ox;       long long o_cs;             // output conv [ch][D][px]
+  float* rh;                                    // [ch][px]
+  const float* gate_w; const float* out_w; long long w_co;   // hidden-state halves of the conv weights
+  const float *rn_w, *rn_b, *un_w, *un_b, *on_w, *on_b;
+  double inv_n;
+  int ch, h, w, px;
+  int ksplit, ci_per_warp, px_groups1, px_groups2;
+  int p1_begin, p2_begin, e_begin;
+};
+struct RecArgs { RecLevel l[4]; double* stats; unsigned long long* dbg; int D; int p1_units, p2_units, e_total; };
+
+constexpr size_t kRecSmemBytes = (2 * 64 * 9 * kGcCo + kGcWarps * kGcCo * kGcTilePx) * sizeof(float);
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kGcWarps * 32, 2)
+red_recurrence_kernel(const __grid_constant__ RecArgs a) {
+  extern __shared__ __align__(16) float rec_smem[];
+  float* wsm1 = rec_smem;
+  float* wsm2 = rec_smem + 64 * 9 * kGcCo;
+  float (*part)[kGcCo][kGcTilePx] = reinterpret_cast<float (*)[kGcCo][kGcTilePx]>(rec_smem + 2 * 64 * 9 * kGcCo);
+  __shared__ double red[2][kGcWarps];
+  cg::grid_group grid = cg::this_grid();
+  const int G = gridDim.x, bid = blockIdx.x;
+  const bool resident = (a.p1_units <= G);           // one unit per CTA per phase: weights staged once
+
+  auto level_of = [&](int unit, bool p2) {
+    int li = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) if (unit >= (p2 ? a.l[k].p2_begin : a.l[k].p1_begin)) li = k;
+    return li;
+  };
+  auto conv_level = [&](int li, int d, bool p2) {
+    const RecLevel& R = a.l[li];
+    GruConvLevel L;
+    L.cin = R.ch; L.h = R.h; L.w_ = R.w; L.stats_group = R.ch;
+    L.ksplit = R.ksplit; L.ci_per_warp = R.ci_per_warp; L.w_co = R.w_co; L.cta_begin = 0;
+    double* st = a.stats + ((size_t)d * 4 + li) * 6;
+    if (!p2) {
+      L.in = R.s + (size_t)d * R.s_ps; L.in_cs = R.s_cs; L.w = R.gate_w;
+      L.pre = L.out = R.gx + (size_t)d * R.px; L.out_cs = R.g_cs; L.cout = 2 * R.ch;
+      L.stats = st; L.px_groups = R.px_groups1;
+    } else {
+      L.in = R.rh; L.in_cs = R.px; L.w = R.out_w;
+      L.pre = L.out = R.ox + (size_t)d * R.px; L.out_cs = R.o_cs; L.cout = R.ch;
+      L.stats = st + 4; L.px_groups = R.px_groups2;
+    }
+    return L;
+  };
+
+  unsigned long long tmark = 0, tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto mark = [&](int slot) {
+    if (a.dbg && bid == 0 && threadIdx.x == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      if (slot >= 0) tacc[slot] += t - tmark;
+      tmark = t;
+    }
+  };
+  mark(-1);
+  for (int d = 0; d < a.D; ++d) {
+    // ---- P1: gates[d] += conv(h[d]) ----
+    for (int u = bid; u < a.p1_units; u += G) {
+      const int li = level_of(u, false);
+      const GruConvLevel L = conv_level(li, d, false);
+      gru_conv_unit_coherent<kAligned>(L, u - a.l[li].p1_begin, wsm1, part, red, !resident || d == 0,
+                                       (a.dbg && bid == (int)(a.dbg[63] % gridDim.x)) ? a.dbg + 8 : nullptr);
+      if (!resident) __syncthreads();
+    }
+    mark(0);
+    grid.sync();
+    mark(1);
+    // ---- E1: rh = sigmoid(GN_r(G_r)) * h ----   (4 independent elements per iteration: loads first)
+    {
+      const int T = G * (kGcWarps * 32);
+      for (int i0 = bid * (kGcWarps * 32) + threadIdx.x; i0 < a.e_total; i0 += 4 * T) {
+        float gv[4], hv[4], ga[4], gb[4]; float* dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * T;
+          dst[u] = nullptr;
+          if (i < a.e_total) {
+            int li = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (i >= a.l[k].e_begin) li = k;
+            const RecLevel& R = a.l[li];
+            const int e = i - R.e_begin, c = e / R.px, p = e - c * R.px;
+            const double* st = a.stats + ((size_t)d * 4 + li) * 6;
+            const double mean = __ldcg(st) * R.inv_n;
+            const float rstd = rsqrtf((float)fmax(__ldcg(st + 1) * R.inv_n - mean * mean, 0.0) + kGnEps);
+            ga[u] = __ldg(R.rn_w + c) * rstd; gb[u] = __ldg(R.rn_b + c) - (float)mean * ga[u];
+            gv[u] = __ldcg(R.gx + (size_t)d * R.px + c * R.g_cs + p);
+            hv[u] = __ldcg(R.s + (size_t)d * R.s_ps + c * R.s_cs + p);
+            dst[u] = R.rh + e;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst[u]) *dst[u] = sigmoidf_(fmaf(gv[u], ga[u], gb[u])) * hv[u];
+      }
+    }
+    mark(2);
+    grid.sync();
+    mark(3);
+    // ---- P2: out[d] += conv(rh) ----
+    for (int u = bid; u < a.p2_units; u += G) {
+      const int li = level_of(u, true);
+      const GruConvLevel L = conv_level(li, d, true);
+      gru_conv_unit_coherent<kAligned>(L, u - a.l[li].p2_begin, wsm2, part, red, !resident || d == 0, nullptr);
+      if (!resident) __syncthreads();
+    }
+    mark(4);
+    grid.sync();
+    mark(5);
+    // ---- E2: h[d+1] = u*h + (1-u)*tanh(GN_o(O)) ----
+    {
+      const int T = G * (kGcWarps * 32);
+      for (int i0 = bid * (kGcWarps * 32) + threadIdx.x; i0 < a.e_total; i0 += 4 * T) {
+        float gv[4], ov[4], hv[4], ua[4], ub[4], oa[4], ob[4]; float* dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * T;
+          dst[u] = nullptr;
+          if (i < a.e_total) {
+            int li = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (i >= a.l[k].e_begin) li = k;
+            const RecLevel& R = a.l[li];
+            const int e = i - R.e_begin, c = e / R.px, p = e - c * R.px;
+            const double* st = a.stats + ((size_t)d * 4 + li) * 6;
+            const double um = __ldcg(st + 2) * R.inv_n, om = __ldcg(st + 4) * R.inv_n;
+            const float ur = rsqrtf((float)fmax(__ldcg(st + 3) * R.inv_n - um * um, 0.0) + kGnEps);
+            const float orr = rsqrtf((float)fmax(__ldcg(st + 5) * R.inv_n - om * om, 0.0) + kGnEps);
+            ua[u] = __ldg(R.un_w + c) * ur; ub[u] = __ldg(R.un_b + c) - (float)um * ua[u];
+            oa[u] = __ldg(R.on_w + c) * orr; ob[u] = __ldg(R.on_b + c) - (float)om * oa[u];
+            gv[u] = __ldcg(R.gx + (size_t)d * R.px + (c + R.ch) * R.g_cs + p);
+            ov[u] = __ldcg(R.ox + (size_t)d * R.px + c * R.o_cs + p);
+            hv[u] = __ldcg(R.s + (size_t)d * R.s_ps + c * R.s_cs + p);
+            dst[u] = const_cast<float*>(R.s) + (size_t)(d + 1) * R.s_ps + c * R.s_cs + p;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst[u]) {
+            const float uu = sigmoidf_(fmaf(gv[u], ua[u], ub[u]));
+            *dst[u] = uu * hv[u] + (1.0f - uu) * tanhf(fmaf(ov[u], oa[u], ob[u]));     // module.py:57
+          }
+      }
+    }
+    mark(6);
+    grid.sync();
+    mark(7);
+  }
+  if (a.dbg && bid == 0 && threadIdx.x == 0)
+    for (int i = 0; i < 8; ++i) a.dbg[i] = tacc[i];
+}
+
+// Launch the persistent recurrence if the device can keep enough CTAs co-resident; returns
+// SATMVS_OK + *launched = true on success, leaves *launched = false when the caller must fall back.
+static int red_recurrence_launch(RecArgs& ra, cudaStream_t st, bool* launched) {
+  *launched = false;
+  bool aligned = true;
+  for (int l = 0; l < 4; ++l) aligned = aligned && (ra.l[l].w % kGcPx == 0);
+  const void* fn = aligned ? (const void*)red_recurrence_kernel<true> : (const void*)red_recurrence_kernel<false>;
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!coop) return SATMVS_OK;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmemBytes) != cudaSuccess) {
+    cudaGetLastError();
+    return SATMVS_OK;
+  }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGcWarps * 32, kRecSmemBytes) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return SATMVS_OK;
+  }
+  int grid = per_sm * sms;
+  if (grid > ra.p1_units) grid = ra.p1_units;
+  void* params[] = {&ra};
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kGcWarps * 32), params, kRecSmemBytes, st);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return SATMVS_OK;     // fall back to per-plane launches
+  }
+  *launched = true;
+  return SATMVS_OK;
 }
 
 static int gru_conv_launch(const GruConvArgs& c, int ctas, cudaStream_t st, const char* what) {
@@ -458,7 +699,51 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
   }
 
   // ---- B. recurrence over planes ----
-  for (int d = 0; d < D; ++d) {
+  bool persistent = false;
+  {
+    RecArgs ra{};
+    ra.stats = P.stats; ra.D = D;
+    static const bool dbg_timers = getenv("SATMVS_RED_DEBUG_TIMERS") != nullptr;
+    ra.dbg = dbg_timers ? reinterpret_cast<unsigned long long*>(P.stats + (size_t)D * 4 * 3 * 2) : nullptr;
+    if (ra.dbg) {
+      static unsigned long long dbg_block;
+      dbg_block = getenv("SATMVS_RED_DEBUG_BLOCK") ? strtoull(getenv("SATMVS_RED_DEBUG_BLOCK"), nullptr, 10) : 0ULL;
+      cudaMemsetAsync(ra.dbg, 0, 64 * sizeof(double), st);
+      cudaMemcpyAsync(ra.dbg + 63, &dbg_block, sizeof(dbg_block), cudaMemcpyHostToDevice, st);
+    }
+    int u1 = 0, u2 = 0, et = 0;
+    for (int l = 0; l < 4; ++l) {
+      RedLevel& L = P.lv[l];
+      RecLevel& R = ra.l[l];
+      const long long px = (long long)L.h * L.w;
+      R.s = L.s; R.s_cs = (long long)(D + 1) * px; R.s_ps = px;
+      R.gx = L.gx; R.g_cs = (long long)D * px;
+      R.ox = L.ox; R.o_cs = (long long)D * px;
+      R.rh = L.rh;
+      R.gate_w = wt->gate_w[l] + (size_t)L.cx * 9; R.out_w = wt->out_w[l] + (size_t)L.cx * 9;
+      R.w_co = (long long)(L.cx + L.ch) * 9;
+      R.rn_w = wt->rn_w[l]; R.rn_b = wt->rn_b[l]; R.un_w = wt->un_w[l]; R.un_b = wt->un_b[l];
+      R.on_w = wt->on_w[l]; R.on_b = wt->on_b[l];
+      R.inv_n = 1.0 / ((double)L.ch * (double)px);
+      R.ch = L.ch; R.h = L.h; R.w = L.w; R.px = (int)px;
+      GruConvLevel t{};
+      t.cin = L.ch; t.h = L.h; t.w_ = L.w;
+      t.cout = 2 * L.ch; R.p1_begin = u1; u1 = gru_conv_fill(t, u1); R.px_groups1 = t.px_groups;
+      t.cout = L.ch;     R.p2_begin = u2; u2 = gru_conv_fill(t, u2); R.px_groups2 = t.px_groups;
+      R.ksplit = t.ksplit; R.ci_per_warp = t.ci_per_warp;
+      R.e_begin = et; et += L.ch * (int)px;
+    }
+    ra.p1_units = u1; ra.p2_units = u2; ra.e_total = et;
+    // Opt-in (SATMVS_RED_PERSISTENT=1): measured 50.8 us/plane against 48 us/plane for the four per-plane
+    // launches at 96x192 (profiles/r01_red_recurrence_notes.md): the L2-only coherent loads and the waits at
+    // the grid barriers (level-4 units carry twice the work) cost more than the launch gaps they remove.
+    static const bool use_persist = getenv("SATMVS_RED_PERSISTENT") != nullptr;
+    if (use_persist) {
+      ProfScope prof(kProfGruGate, st);     // profiled as one class: the persistent kernel has no per-phase boundary
+      RUN(red_recurrence_launch(ra, st, &persistent));
+    }
+  }
+  for (int d = 0; d < D && !persistent; ++d) {
     GruConvArgs c1{}, c2{};
     GruArgs ga{};
     int total = 0, ctas1 = 0, ctas2 = 0;
