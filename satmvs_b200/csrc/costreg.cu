@@ -9,6 +9,7 @@
 // 11 launches: 7 dense 27-tap convs (3 of them stride 2), 3 transposed convs (each one grouped launch
 // of its 8 output-parity classes, so no multiply ever touches a structural zero), 1 head conv.
 #include "conv_engine.cuh"
+#include "direct_conv.cuh"
 #include "prof.cuh"
 
 namespace satmvs {
@@ -38,6 +39,15 @@ static int run_conv(ConvProblem p, cudaStream_t st, const char* what) {
 }
 
 static int run_by_cout(const ConvProblem& p, cudaStream_t st, const char* what) {
+  {  // dense 3x3x3 layers: register-tiled direct kernel when rows are 16-byte aligned
+    DirectConv d{};
+    d.in = p.in; d.w = p.w; d.scale = p.scale; d.shift = p.shift; d.post_add = p.post_add; d.out = p.out;
+    d.Cin = p.Cin; d.Cout = p.Cout; d.Di = p.Di; d.Hi = p.Hi; d.Wi = p.Wi; d.Do = p.Do; d.Ho = p.Ho; d.Wo = p.Wo;
+    d.w_co = p.w_co_stride; d.w_ci = p.w_ci_stride; d.acc_scale = p.acc_scale; d.relu = p.relu;
+    const int stride = p.q2i_mul[0];
+    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+    if (!no_direct && p.ntaps == 27 && direct_conv_supported(d, 3, stride)) return direct_conv_launch(d, 3, stride, st, what);
+  }
   if (p.Cout >= 64) return run_conv<Tile64>(p, st, what);
   if (p.Cout >= 32) return run_conv<Tile32>(p, st, what);
   if (p.Cout >= 16) return run_conv<Tile16>(p, st, what);
@@ -129,7 +139,7 @@ int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int
   {  // prob: bare Conv3d(base, 1, 3, padding=1, bias=False) (module.py:566, :576)
     ConvProblem p = conv3d_problem(P.x11, base, D, H, W, wt->prob_w, out, 1, 1);
     p.relu = 0;
-    RUN(run_conv<Tile8>(p, st, "costreg prob"));
+    RUN(run_by_cout(p, st, "costreg prob"));
   }
 #undef RUN
   return SATMVS_OK;

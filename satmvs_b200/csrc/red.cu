@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 #include <type_traits>
 #include "conv_engine.cuh"
+#include "direct_conv.cuh"
 #include "prof.cuh"
 namespace cg = cooperative_groups;
 
@@ -633,11 +634,26 @@ static int launch_one(ConvProblem p, cudaStream_t st, const char* what) {
   return conv_launch<T>(g, st, what);
 }
 
+// Batched 2-D convs: the register-tiled direct kernel when rows are 16-byte aligned, else the engine.
+static int launch_plane_conv(const ConvProblem& p, int stride, cudaStream_t st, const char* what);
+
 static int launch_by_cout(ConvProblem p, cudaStream_t st, const char* what) {
   if (p.Cout >= 64) return launch_one<Tile64>(p, st, what);
   if (p.Cout >= 32) return launch_one<Tile32>(p, st, what);
   if (p.Cout >= 16) return launch_one<Tile16>(p, st, what);
   return launch_one<Tile8>(p, st, what);
+}
+
+static int launch_plane_conv(const ConvProblem& p, int stride, cudaStream_t st, const char* what) {
+  DirectConv d{};
+  d.in = p.in + (long long)p.in_c_off * p.Di * p.Hi * p.Wi; d.w = p.w; d.scale = p.scale; d.shift = p.shift;
+  d.post_add = p.post_add; d.out = p.out;
+  d.Cin = p.Cin; d.Cout = p.Cout; d.Di = p.Di; d.Hi = p.Hi; d.Wi = p.Wi; d.Do = p.Do; d.Ho = p.Ho; d.Wo = p.Wo;
+  d.w_co = p.w_co_stride; d.w_ci = p.w_ci_stride; d.acc_scale = p.acc_scale; d.relu = p.relu;
+  static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+  if (!no_direct && p.pre_add == nullptr && p.stats == nullptr && p.out_c_off == 0 && direct_conv_supported(d, 1, stride))
+    return direct_conv_launch(d, 1, stride, st, what);
+  return launch_by_cout(p, st, what);
 }
 
 }  // namespace satmvs
@@ -681,7 +697,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     p.Qd = D; p.Qh = H >> (i + 1); p.Qw = W >> (i + 1);
     p.relu = 1;
     p.acc_scale = (i == 0) ? -1.0f : 1.0f;
-    { ProfScope prof(kProfConvBatched, st); RUN(launch_by_cout(p, st, "red encoder")); }
+    { ProfScope prof(kProfConvBatched, st); RUN(launch_plane_conv(p, 2, st, "red encoder")); }
   }
   for (int l = 0; l < 4; ++l) {   // x-halves of the GRU convolutions, bias folded in (module.py:29-30, :44-45)
     RedLevel& L = P.lv[l];
@@ -690,12 +706,12 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     g.Qd = D; g.Qh = L.h; g.Qw = L.w;
     g.shift = wt->gate_b[l];
     g.acc_scale = (l == 0) ? -1.0f : 1.0f;
-    { ProfScope prof(kProfConvBatched, st); RUN(launch_by_cout(g, st, "red gate x-half")); }
+    { ProfScope prof(kProfConvBatched, st); RUN(launch_plane_conv(g, 1, st, "red gate x-half")); }
     ConvProblem o = plane_conv(xin[l], L.cx, D, L.h, L.w, wt->out_w[l], kin, 9, L.ox, L.ch, D, L.h, L.w, 1);
     o.Qd = D; o.Qh = L.h; o.Qw = L.w;
     o.shift = wt->out_b[l];
     o.acc_scale = (l == 0) ? -1.0f : 1.0f;
-    { ProfScope prof(kProfConvBatched, st); RUN(launch_by_cout(o, st, "red output x-half")); }
+    { ProfScope prof(kProfConvBatched, st); RUN(launch_plane_conv(o, 1, st, "red output x-half")); }
   }
 
   // ---- B. recurrence over planes ----
