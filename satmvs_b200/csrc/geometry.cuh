@@ -367,6 +367,19 @@ __device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W, float 
   return t;
 }
 
+// Same record with the clamped window origin kept as (x, y) and a flag telling whether any corner is in
+// range (used by the shared-memory-staged kernel to bound the source window of a CTA).
+struct TapXY { int xc, yc; float w00, w01, w10, w11; bool live; };
+
+__device__ __forceinline__ TapXY make_tap_xy(float gx, float gy, int H, int W, float half_w, float half_h) {
+  const Tap t = make_tap(gx, gy, H, W, half_w, half_h);
+  TapXY r;
+  r.yc = t.off / W; r.xc = t.off - r.yc * W;
+  r.w00 = t.w00; r.w01 = t.w01; r.w10 = t.w10; r.w11 = t.w11;
+  r.live = (t.w00 != 0.0f) || (t.w01 != 0.0f) || (t.w10 != 0.0f) || (t.w11 != 0.0f);
+  return r;
+}
+
 // nw, ne, sw, se accumulated with fused multiply-adds, the order ATen uses
 // f0 = channel plane, f1 = f0 + W (both warp-uniform), so the per-thread part of each address is t.off only
 __device__ __forceinline__ float tap_fetch(const float* __restrict__ f0, const float* __restrict__ f1, const Tap& t) {

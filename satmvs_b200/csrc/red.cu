@@ -140,10 +140,10 @@ __global__ void gru_update_kernel(const __grid_constant__ GruArgs a) {
 // recurrent step convolution: out[co, p] = pre[co, p] + sum_{ci, 3x3} w[co, ci, tap] * in[ci, p + tap]
 // for the hidden-state halves of the four GRUs in ONE launch.  These problems are tiny (21 M MAC per
 // level) and latency-bound, so the decomposition maximises resident warps instead of tile reuse:
-// one warp = 8 output channels x 128 pixels (4 per lane) x 8 (16 at Cin 64) input channels; the
+// one warp = 8 output channels x 128 pixels (4 per lane) x 4 (8 at Cin 64) input channels; the
 // warps that share an output tile reduce through shared memory in a fixed order (deterministic).
-// Every CTA has 4 busy warps whatever the level: 4 tiles x 1 k-part (Cin 8) ... 1 tile x 4 k-parts
-// (Cin >= 32), two CTAs per SM, and the whole step fits one wave (264 CTAs at 96x192).
+// Every CTA has 8 busy warps whatever the level: 4 tiles x 2 k-parts (Cin 8) ... 1 tile x 8 k-parts
+// (Cin >= 32); 264 CTAs x 8 warps at 96x192, one wave at two CTAs per SM.
 // ---------------------------------------------------------------------------------------------
 struct GruConvLevel {
   const float* in;  long long in_cs;        // [cin] planes of h*w
@@ -151,14 +151,15 @@ struct GruConvLevel {
   const float* pre; float* out; long long out_cs;
   double* stats;                            // (sum, sum^2) per group of stats_group output channels
   int cin, cout, h, w_, stats_group;
-  int ksplit;                               // warps sharing one output tile: min(cin / 8, 4)
-  int ci_per_warp;                          // cin / ksplit (8 or 16)
+  int ksplit;                               // warps sharing one output tile: min(cin / 4, 8)
+  int ci_per_warp;                          // cin / ksplit (4 or 8)
   int px_groups;                            // CTAs per output-channel chunk
   int cta_begin;
 };
 struct GruConvArgs { GruConvLevel l[4]; };
 
-constexpr int kGcWarps = 4, kGcCo = 8, kGcPx = 4, kGcTilePx = 32 * kGcPx, kGcCi = 8;
+constexpr int kGcWarps = 8, kGcCo = 8, kGcPx = 4, kGcTilePx = 32 * kGcPx, kGcCi = 4;
+constexpr int kGcThreads = kGcWarps * 32;
 
 // kAligned: every level's width is a multiple of 4, so a lane's 4 pixels sit in one row at a
 // 16-byte aligned address: 3 vector + 6 scalar loads per input channel instead of 36 predicated ones.
@@ -291,17 +292,16 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
           for (int j = 0; j < kGcPx; ++j) acc[i][j] = fmaf(wv[i], r[t / 3][j + t % 3], acc[i][j]);
       }
     };
-    // 4-slot register ring: the rows of channels c+1..c+3 are in flight while channel c's 288 FMAs issue
-    // (an L2 round trip is ~2 channels of arithmetic at 2 warps per scheduler)
-    float ring[4][3][6];
+    // 3-slot register ring: the rows of channels c+1, c+2 are in flight while channel c's 288 FMAs issue
+    float ring[3][3][6];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 2; ++c)
       if (c < L.ci_per_warp) load_rows(ci0 + c, ring[c]);
 #pragma unroll 1
-    for (int c = 0; c < L.ci_per_warp; c += 4) {
+    for (int c = 0; c < L.ci_per_warp; c += 3) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (c + u + 3 < L.ci_per_warp) load_rows(ci0 + c + u + 3, ring[(u + 3) & 3]);
+      for (int u = 0; u < 3; ++u) {
+        if (c + u + 2 < L.ci_per_warp) load_rows(ci0 + c + u + 2, ring[(u + 2) % 3]);
         if (c + u < L.ci_per_warp) fma_rows(ci0 + c + u, ring[u]);
       }
     }
@@ -320,16 +320,19 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
   }
 
   tick(1);
-  // This thread's share of the CTA's outputs.  With 128 threads and 128-pixel tiles, output
-  // o = tid + 128 r is (tile-in-CTA r / 8, channel r % 8, pixel tid): the index math is compile time.
+  // This thread's share of the CTA's outputs: output o = tid + NT*r is (tile-in-CTA q/8, channel q%8,
+  // pixel tid%128) with q = r*NT/128 + tid/128, so the index math is compile time up to tid.
   // The addends are fetched now, so the loads fly during the partial-sum exchange.
-  constexpr int kMaxOut = kGcCo * kGcWarps;                 // 32 outputs per thread when ksplit == 1
-  const int nout = tiles_per_cta * kGcCo;
-  float pre[kMaxOut];
+  constexpr int kRows = kGcThreads / kGcTilePx;              // (tile, channel) rows covered per pass: 2
+  constexpr int kMaxOut = kGcWarps * kGcCo / kRows;          // outputs per thread when ksplit == 1: 32
+  const int nrows = tiles_per_cta * kGcCo;
+  const int px_l = tid & (kGcTilePx - 1), row_l = tid / kGcTilePx;
+  float pre[kMaxOut / 2];                                     // ksplit >= 2 in every configuration
 #pragma unroll
-  for (int r = 0; r < kMaxOut; ++r) {
-    const int p = (tile0 + (r >> 3)) * kGcTilePx + tid;
-    pre[r] = (r < nout && p < npx) ? ldf<kCoherent>(L.pre + (long long)(co0 + (r & 7)) * L.out_cs + p) : 0.0f;
+  for (int r = 0; r < kMaxOut / 2; ++r) {
+    const int q = r * kRows + row_l;
+    const int p = (tile0 + (q >> 3)) * kGcTilePx + px_l;
+    pre[r] = (q < nrows && p < npx) ? ldf<kCoherent>(L.pre + (long long)(co0 + (q & 7)) * L.out_cs + p) : 0.0f;
   }
 #pragma unroll
   for (int i = 0; i < kGcCo; ++i)
@@ -343,21 +346,22 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
     constexpr int KS = decltype(ks_tag)::value;
 #pragma unroll
     for (int r = 0; r < kMaxOut / KS; ++r) {
-      const int ts = r >> 3, i = r & 7;
-      const int p = (tile0 + ts) * kGcTilePx + tid;
+      const int q = r * kRows + row_l;
+      const int ts = q >> 3, i = q & 7;
+      const int p = (tile0 + ts) * kGcTilePx + px_l;
       if (p < npx) {
         float sum = 0.0f;
 #pragma unroll
-        for (int kp = 0; kp < KS; ++kp) sum += part[ts * KS + kp][i][tid];
+        for (int kp = 0; kp < KS; ++kp) sum += part[ts * KS + kp][i][px_l];
         const float val = sum + pre[r];
         L.out[(long long)(co0 + i) * L.out_cs + p] = val;
         ssum += val; ssq += val * val;
       }
     }
   };
-  if (L.ksplit == 1) epilogue(std::integral_constant<int, 1>{});
-  else if (L.ksplit == 2) epilogue(std::integral_constant<int, 2>{});
-  else epilogue(std::integral_constant<int, 4>{});
+  if (L.ksplit == 2) epilogue(std::integral_constant<int, 2>{});
+  else if (L.ksplit == 4) epilogue(std::integral_constant<int, 4>{});
+  else epilogue(std::integral_constant<int, 8>{});
   tick(3);
   double ds = ssum, dq = ssq;
 #pragma unroll
@@ -375,10 +379,11 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
 }
 
 template <bool kAligned>
-__global__ void __launch_bounds__(kGcWarps * 32)
+__global__ void __launch_bounds__(kGcThreads, 2)
 gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
-  __shared__ __align__(16) float wsm[64 * 9 * kGcCo];                    // [ci][tap][co]  (<= 18 KB)
-  __shared__ __align__(16) float part[kGcWarps][kGcCo][kGcTilePx];      // 16 KB
+  extern __shared__ __align__(16) float gc_smem[];
+  float* wsm = gc_smem;                                                                  // [ci][tap][co]  (<= 18 KB)
+  float (*part)[kGcCo][kGcTilePx] = reinterpret_cast<float (*)[kGcCo][kGcTilePx]>(gc_smem + 64 * 9 * kGcCo);   // 32 KB
   __shared__ double red[2][kGcWarps];
   int li = 0;
 #pragma unroll
@@ -596,13 +601,22 @@ static int red_recurrence_launch(RecArgs& ra, cudaStream_t st, bool* launched) {
 static int gru_conv_launch(const GruConvArgs& c, int ctas, cudaStream_t st, const char* what) {
   bool aligned = true;
   for (int l = 0; l < 4; ++l) aligned = aligned && (c.l[l].w_ % kGcPx == 0);
-  if (aligned) gru_conv_kernel<true><<<ctas, kGcWarps * 32, 0, st>>>(c);
-  else gru_conv_kernel<false><<<ctas, kGcWarps * 32, 0, st>>>(c);
+  constexpr size_t smem = (64 * 9 * kGcCo + kGcWarps * kGcCo * kGcTilePx) * sizeof(float);
+  static thread_local int ready_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (ready_dev != dev) {
+    cudaFuncSetAttribute(gru_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ready_dev = dev;
+  }
+  if (aligned) gru_conv_kernel<true><<<ctas, kGcThreads, smem, st>>>(c);
+  else gru_conv_kernel<false><<<ctas, kGcThreads, smem, st>>>(c);
   return check_launch(what);
 }
 
 static int gru_conv_fill(GruConvLevel& g, int cta_begin) {
-  g.ksplit = g.cin / kGcCi < kGcWarps ? g.cin / kGcCi : kGcWarps;
+  g.ksplit = g.cin / kGcCi < kGcWarps ? g.cin / kGcCi : kGcWarps;   // cin 8 -> 2, 16 -> 4, >= 32 -> 8
   g.ci_per_warp = g.cin / g.ksplit;
   const int tiles = (g.h * g.w_ + kGcTilePx - 1) / kGcTilePx;
   const int tiles_per_cta = kGcWarps / g.ksplit;

@@ -24,7 +24,7 @@
 #define SATMVS_MIN_BLOCKS 1
 #endif
 #ifndef SATMVS_SWEEP_V
-#define SATMVS_SWEEP_V 3  // 2 = scalar-arithmetic vec4 kernel, 3 = shared-memory records + packed f32x2 arithmetic
+#define SATMVS_SWEEP_V 3  // 2 = scalar vec4 kernel, 3 = smem records + packed f32x2 (v4 = 3 + TMA staging is a run-time opt-in)
 #endif
 #ifndef SATMVS_NP
 #define SATMVS_NP 4       // hypothesis planes evaluated in lock step in the v3 geometry phase
@@ -393,6 +393,210 @@ sweep_fwd_v3_kernel(const __grid_constant__ SweepArgs<Geo> a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// v4 of the forward sweep: v3 + the source window of the CTA staged in shared memory by the TMA engine.
+// A CTA owns a segment of one reference row x DK planes.  After the geometry phase the CTA knows, per
+// source view, the bounding box of all its taps; for every pass over CH channels it copies that box
+// (rows of the [C/4][H][W] float4 re-pack are contiguous, so one cp.async.bulk per (view, quad, row),
+// completion counted on an mbarrier) and every tap of the pass becomes a shared-memory read with fixed
+// latency.  v3 re-read the same lines from L2 for every plane (L1 hit rate 54 %, long-scoreboard stalls
+// 46-60 %); here each source pixel crosses L2->SM once per CTA and pass.  If a view's box does not fit the
+// staging buffer (steep geometry) the CTA reads that pass straight from global memory through the same
+// generic-pointer code path.
+// ------------------------------------------------------------------------------------------
+constexpr int kWinPx = 384;                    // staging capacity per (view, quad) in pixels (6 KB)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy through the TMA engine (UBLKCP); bytes and both addresses multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class Geo, int DK, int CH, bool kVariance>
+__global__ void __launch_bounds__(kSweepThreads, SATMVS_MIN_BLOCKS)
+sweep_fwd_v4_kernel(const __grid_constant__ SweepArgs<Geo> a, int seg_w, int segs_per_row) {
+  constexpr int NSRC = Geo::kNumSrc;
+  constexpr int NP = DK < SATMVS_NP ? DK : SATMVS_NP;
+  constexpr int NQ = CH / 4;
+  extern __shared__ __align__(128) unsigned char v4_smem[];
+  float4* win = reinterpret_cast<float4*>(v4_smem);                                        // [NSRC][NQ][kWinPx]
+  int (*rec_xy)[kSweepThreads] = reinterpret_cast<int (*)[kSweepThreads]>(win + NSRC * NQ * kWinPx);
+  TapW (*rec_w)[kSweepThreads] = reinterpret_cast<TapW (*)[kSweepThreads]>(rec_xy + DK * NSRC);
+  __shared__ int bbox[NSRC][4];                 // xmin, xmax, ymin, ymax of the clamped tap origins
+  __shared__ __align__(8) unsigned long long mbar;
+
+  const int HW = a.H * a.W;
+  const int tid = threadIdx.x;
+  const int y = blockIdx.x / segs_per_row, x = (blockIdx.x % segs_per_row) * seg_w + tid;
+  const bool active = tid < seg_w && x < a.W;
+  const int xcl = min(x, a.W - 1);
+  const int pix = y * a.W + xcl;
+  const int d0 = blockIdx.y * DK;
+
+  if (tid < NSRC) { bbox[tid][0] = 1 << 30; bbox[tid][1] = -1; bbox[tid][2] = 1 << 30; bbox[tid][3] = -1; }
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+
+  {  // ---- phase A: geometry, records, bounding boxes ----
+    int bx0[NSRC], bx1[NSRC], by0[NSRC], by1[NSRC];
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) { bx0[v] = 1 << 30; bx1[v] = -1; by0[v] = 1 << 30; by1[v] = -1; }
+    const typename Geo::Pixel px = a.geo.pixel(xcl, y);
+#pragma unroll 1
+    for (int g = 0; g < DK; g += NP) {
+      float h[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        const int d = min(d0 + g + k, a.D - 1);
+        h[k] = a.depth_per_pixel ? __ldg(a.depth + (size_t)d * HW + pix) : __ldg(a.depth + d);
+      }
+      a.geo.template grid_coords<NP>(px, h, [&](int k, int v, float gx, float gy) {
+        TapXY t = make_tap_xy(gx, gy, a.H, a.W, a.half_w, a.half_h);
+        if (v >= a.n_src || !active) { t.w00 = t.w01 = t.w10 = t.w11 = 0.0f; t.live = false; }
+        if (t.live) {
+#pragma unroll
+          for (int vv = 0; vv < NSRC; ++vv)
+            if (vv == v) { bx0[vv] = min(bx0[vv], t.xc); bx1[vv] = max(bx1[vv], t.xc); by0[vv] = min(by0[vv], t.yc); by1[vv] = max(by1[vv], t.yc); }
+        } else {
+          t.xc = -1; t.yc = -1;            // resolved to the window origin below (weights are zero)
+        }
+        rec_xy[(g + k) * NSRC + v][tid] = (t.yc << 16) | (t.xc & 0xffff);
+        rec_w[(g + k) * NSRC + v][tid] = TapW{t.w00, t.w01, t.w10, t.w11};
+      });
+    }
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) {
+      const int m0 = __reduce_min_sync(0xffffffffu, bx0[v]), m1 = __reduce_max_sync(0xffffffffu, bx1[v]);
+      const int m2 = __reduce_min_sync(0xffffffffu, by0[v]), m3 = __reduce_max_sync(0xffffffffu, by1[v]);
+      if ((tid & 31) == 0) { atomicMin(&bbox[v][0], m0); atomicMax(&bbox[v][1], m1); atomicMin(&bbox[v][2], m2); atomicMax(&bbox[v][3], m3); }
+    }
+  }
+  __syncthreads();
+
+  // window geometry per view (uniform): origin, pitch, rows; staged = fits the buffer
+  int xs[NSRC], ys[NSRC], wc[NSRC], rows[NSRC];
+  bool staged = true;
+#pragma unroll
+  for (int v = 0; v < NSRC; ++v) {
+    if (bbox[v][1] < 0) { xs[v] = 0; ys[v] = 0; wc[v] = 2; rows[v] = 2; }            // no live tap at all
+    else { xs[v] = bbox[v][0]; ys[v] = bbox[v][2]; wc[v] = bbox[v][1] - bbox[v][0] + 2; rows[v] = bbox[v][3] - bbox[v][2] + 2; }
+    staged = staged && (wc[v] * rows[v] <= kWinPx);
+  }
+
+  const unsigned upix = (unsigned)pix * 4u;
+  const size_t plane_bytes = (size_t)HW * sizeof(float);
+  const u64 vinv = pk(a.inv_num_views, a.inv_num_views), vneg = pk(-a.num_views, -a.num_views);
+  unsigned parity = 0;
+  for (int c0 = 0; c0 < a.C; c0 += CH) {
+    const int q0 = c0 >> 2;
+    if (staged) {
+      __syncthreads();                            // every thread is done reading the previous pass's window
+      if (tid == 0) {
+        unsigned total = 0;
+#pragma unroll
+        for (int v = 0; v < NSRC; ++v) total += (unsigned)(NQ * rows[v] * wc[v]) * 16u;
+        mbar_expect_tx(&mbar, total);             // armed before any copy is issued
+      }
+      __syncthreads();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads above -> async-proxy writes below
+      // one bulk copy per (view, quad, row), spread over the threads
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        const int n = NQ * rows[v];
+        for (int i = tid; i < n; i += (int)blockDim.x) {
+          const int qd = i / rows[v], r = i - qd * rows[v];
+          const float4* src = a.src_v4[v] + ((size_t)(q0 + qd) * a.H + ys[v] + r) * a.W + xs[v];
+          bulk_g2s(win + ((size_t)v * NQ + qd) * kWinPx + r * wc[v], src, (unsigned)wc[v] * 16u, &mbar);
+        }
+      }
+      mbar_wait(&mbar, parity);
+      parity ^= 1u;
+    }
+
+    u64 r[CH / 2];
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) {
+      float lo = 0.f, hi = 0.f;
+      if (kVariance) {
+        const char* rb = reinterpret_cast<const char*>(a.ref_fea) + (size_t)(c0 + 2 * j) * plane_bytes;
+        lo = __ldg(reinterpret_cast<const float*>(rb + upix));
+        hi = __ldg(reinterpret_cast<const float*>(rb + plane_bytes + upix));
+      }
+      r[j] = pk(lo, hi);
+    }
+#pragma unroll 1
+    for (int k = 0; k < DK; ++k) {
+      if (d0 + k >= a.D) break;
+      u64 s[CH / 2], q[CH / 2];
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) { s[j] = r[j]; q[j] = mul2_rounded(r[j], r[j]); }
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        const int xy = rec_xy[k * NSRC + v][tid];
+        const TapW w = rec_w[k * NSRC + v][tid];
+        int xc = (int)(short)(xy & 0xffff), yc = xy >> 16;
+        if (xc < 0) { xc = xs[v]; yc = ys[v]; }
+        const u64 w00 = pk(w.w00, w.w00), w01 = pk(w.w01, w.w01), w10 = pk(w.w10, w.w10), w11 = pk(w.w11, w.w11);
+        // generic pointers: the staged window or the global re-pack, same code
+        const float4* base; int pitch; size_t qstride;
+        if (staged) { base = win + (size_t)v * NQ * kWinPx + (yc - ys[v]) * wc[v] + (xc - xs[v]); pitch = wc[v]; qstride = kWinPx; }
+        else { base = a.src_v4[v] + (size_t)q0 * HW + (size_t)yc * a.W + xc; pitch = a.W; qstride = (size_t)HW; }
+#pragma unroll
+        for (int qd = 0; qd < NQ; ++qd) {
+          const float4* b0 = base + qd * qstride;
+          const float4 A = b0[0], B = b0[1], Cc = b0[pitch], Dd = b0[pitch + 1];
+          u64 lo = fma2(pk(Dd.x, Dd.y), w11, fma2(pk(Cc.x, Cc.y), w10, fma2(pk(B.x, B.y), w01, mul2(pk(A.x, A.y), w00))));
+          u64 hi = fma2(pk(Dd.z, Dd.w), w11, fma2(pk(Cc.z, Cc.w), w10, fma2(pk(B.z, B.w), w01, mul2(pk(A.z, A.w), w00))));
+          if (kVariance) {
+            s[2 * qd] = add2(s[2 * qd], lo);         q[2 * qd] = add2(q[2 * qd], mul2_rounded(lo, lo));
+            s[2 * qd + 1] = add2(s[2 * qd + 1], hi); q[2 * qd + 1] = add2(q[2 * qd + 1], mul2_rounded(hi, hi));
+          } else {
+            s[2 * qd] = lo; s[2 * qd + 1] = hi;
+          }
+        }
+      }
+      const size_t obase = ((size_t)c0 * a.out_D + a.out_d0 + d0 + k) * plane_bytes;
+      const size_t ostride = (size_t)a.out_D * plane_bytes;
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) {
+        u64 res = s[j];
+        if (kVariance) {
+          u64 m = mul2(s[j], vinv);  m = fma2(fma2(vneg, m, s[j]), vinv, m);
+          u64 e = mul2(q[j], vinv);  e = fma2(fma2(vneg, e, q[j]), vinv, e);
+          res = sub2(e, mul2_rounded(m, m));
+        }
+        float lo, hi;
+        upk(res, lo, hi);
+        if (active) {
+          char* ob = reinterpret_cast<char*>(a.out[0]) + obase + (size_t)(2 * j) * ostride;
+          __stcs(reinterpret_cast<float*>(ob + upix), lo);
+          __stcs(reinterpret_cast<float*>(ob + ostride + upix), hi);
+        }
+      }
+    }
+  }
+}
+
+template <int DK, int NSRC, int CH>
+constexpr size_t v4_smem_bytes() { return (size_t)NSRC * (CH / 4) * kWinPx * 16 + (size_t)DK * NSRC * kSweepThreads * (4 + 16); }
+
+// ------------------------------------------------------------------------------------------
 // backward: gradients reach the feature maps only (the grid is built under no_grad,
 // warping.py:322-356).  Same geometry, scatter with float atomics (RED.ADD.F32 in L2).
 //   warp  : grad_src[c, tap] += w_tap * g[c,d,pix]
@@ -537,6 +741,25 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
     sweep_fwd_vec4_kernel<Geo, DK, kVariance><<<grid, kSweepThreads, 0, st>>>(a);
     return check_launch("sweep_fwd_vec4_kernel");
 #else
+    // Opt-in (SATMVS_SWEEP_TMA=1): the TMA-staged variant is bit-identical but measured 161 us against 110 us for
+    // v3 at cfg-2 (single-buffered staging, 2 CTAs x 3 warps per SM): profiles/r01_sweep_v3_notes.md.
+    static const bool use_tma = getenv("SATMVS_SWEEP_TMA") != nullptr;
+    if (use_tma && a.n_out == 1 && a.C % SATMVS_CH == 0 && a.W < 32768 && a.H < 32768) {
+      constexpr int NS = Geo::kNumSrc;
+      constexpr size_t smem = v4_smem_bytes<DK, NS, SATMVS_CH>();
+      if (smem <= 200 * 1024) {
+        auto kern = sweep_fwd_v4_kernel<Geo, DK, SATMVS_CH, kVariance>;
+        static thread_local int ready_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (ready_dev != dev) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ready_dev = dev; }
+        const int segs = ceil_div(a.W, kSweepThreads);
+        const int seg_w = ((ceil_div(a.W, segs) + 31) / 32) * 32;
+        dim3 g4(a.H * segs, ceil_div(a.D, DK));
+        kern<<<g4, seg_w, smem, st>>>(a, seg_w, segs);
+        return check_launch("sweep_fwd_v4_kernel");
+      }
+    }
     if (a.n_out > 1) sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
     else if (a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
     else sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
