@@ -23,8 +23,10 @@ struct DirectConv {
   float* out;             // [Cout][Do][Ho][Wo]
   int Cin, Cout, Di, Hi, Wi, Do, Ho, Wo;
   long long w_co, w_ci;
+  long long in_cs;        // input channel stride in elements (0: Di*Hi*Wi)
   float acc_scale;
   int relu;
+  int flip;               // 1: taps mirrored (tap -> TAPS-1-tap): a stride-1 transposed conv as a correlation
 };
 
 constexpr int kDcWarps = 4, kDcCo = 8, kDcPx = 4, kDcCiChunk = 16;
@@ -37,14 +39,17 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
   __shared__ __align__(16) float wsm[kDcCiChunk * TAPS * kDcCo];     // [ci][tap][co]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int oz = blockIdx.z;
   const int co0 = blockIdx.y * kDcCo;
   const int npx = a.Ho * a.Wo;
-  const int p0 = (blockIdx.x * kDcWarps + warp) * (32 * kDcPx) + lane * kDcPx;   // first output pixel of this lane
-  const bool ok = p0 < npx;
-  const int oy = ok ? p0 / a.Wo : 0, ox = ok ? p0 - oy * a.Wo : 0;
+  // lanes enumerate groups of 4 output pixels over ALL output planes (no idle lanes on small planes);
+  // Wo % 4 == 0 keeps a group inside one row
+  const long long g0 = ((long long)blockIdx.x * kDcWarps + warp) * (32 * kDcPx) + lane * kDcPx;
+  const bool ok = g0 < (long long)npx * a.Do;
+  const int oz = ok ? (int)(g0 / npx) : 0;
+  const int p0 = ok ? (int)(g0 - (long long)oz * npx) : 0;                     // first output pixel of this lane
+  const int oy = p0 / a.Wo, ox = p0 - oy * a.Wo;
   const int iy0 = oy * S - 1, ix0 = ox * S;                                      // top row, first aligned column
-  const long long in_plane = (long long)a.Hi * a.Wi, in_cs = in_plane * a.Di;
+  const long long in_plane = (long long)a.Hi * a.Wi, in_cs = a.in_cs ? a.in_cs : in_plane * a.Di;
 
   // validity of the NZ x 3 rows and of the two edge columns
   bool zok[NZ], yok[3];
@@ -108,7 +113,8 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
         const int e = tid + k * (kDcWarps * 32);
         const int co = e / (kDcCiChunk * TAPS), rr = e - co * (kDcCiChunk * TAPS);
         const int ci = rr / TAPS, tp = rr - ci * TAPS;
-        t[k] = (co < kDcCo && ci < nci && co0 + co < a.Cout) ? __ldg(a.w + (long long)(co0 + co) * a.w_co + (long long)(c0 + ci) * a.w_ci + tp) : 0.0f;
+        t[k] = (co < kDcCo && ci < nci && co0 + co < a.Cout)
+                   ? __ldg(a.w + (long long)(co0 + co) * a.w_co + (long long)(c0 + ci) * a.w_ci + (a.flip ? TAPS - 1 - tp : tp)) : 0.0f;
       }
 #pragma unroll
       for (int k = 0; k < kPer; ++k) {
@@ -168,8 +174,15 @@ inline bool direct_conv_supported(const DirectConv& p, int NZ, int S) {
          (p.post_add == nullptr || reinterpret_cast<uintptr_t>(p.post_add) % 16 == 0);
 }
 
+inline int direct_conv_launch(const DirectConv& p, int NZ, int S, cudaStream_t st, const char* what);
+// 2-D stride-1 launch with an explicit input channel stride (input tensor with extra planes per channel)
+inline int direct_conv_launch_cs(DirectConv p, long long in_cs, cudaStream_t st, const char* what) {
+  p.in_cs = in_cs;
+  return direct_conv_launch(p, 1, 1, st, what);
+}
+
 inline int direct_conv_launch(const DirectConv& p, int NZ, int S, cudaStream_t st, const char* what) {
-  dim3 grid(ceil_div((long long)p.Ho * p.Wo, kDcWarps * 32 * kDcPx), ceil_div(p.Cout, kDcCo), p.Do);
+  dim3 grid(ceil_div((long long)p.Ho * p.Wo * p.Do, kDcWarps * 32 * kDcPx), ceil_div(p.Cout, kDcCo), 1);
   if (NZ == 1 && S == 1) direct_conv_kernel<1, 1><<<grid, kDcWarps * 32, 0, st>>>(p);
   else if (NZ == 1 && S == 2) direct_conv_kernel<1, 2><<<grid, kDcWarps * 32, 0, st>>>(p);
   else if (NZ == 3 && S == 1) direct_conv_kernel<3, 1><<<grid, kDcWarps * 32, 0, st>>>(p);

@@ -865,7 +865,20 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       for (int kx = 0; kx < 3; ++kx) { p.tap_dz[n] = 0; p.tap_dy[n] = 1 - ky; p.tap_dx[n] = 1 - kx; p.tap_w[n] = ky * 3 + kx; ++n; }
     p.ntaps = n;
     p.shift = wt->upconv2d_b;
-    { ProfScope prof(kProfDecoder, st); RUN(launch_one<Tile8>(p, st, "red upconv2d")); }
+    // out[o] = sum_k in[o+1-k] w[k] = sum_k' in[o-1+k'] w[8-k']: a 3x3 correlation with mirrored taps
+    DirectConv dc{};
+    dc.in = P.u[0] + (size_t)H * W;                 // slot 1 of the [8][D+1][H][W] decoder tensor
+    dc.w = wt->upconv2d_w; dc.shift = wt->upconv2d_b; dc.out = logits;
+    dc.Cin = 8; dc.Cout = 1; dc.Di = D; dc.Hi = H; dc.Wi = W; dc.Do = D; dc.Ho = H; dc.Wo = W;
+    dc.w_co = 9; dc.w_ci = 9; dc.acc_scale = 1.0f; dc.relu = 0; dc.flip = 1;
+    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+    ProfScope prof(kProfDecoder, st);
+    if (!no_direct && direct_conv_supported(dc, 1, 1)) {
+      // the input tensor has D+1 planes per channel: express it as Di = D with the channel stride of D+1 planes
+      RUN(direct_conv_launch_cs(dc, (long long)(D + 1) * H * W, st, "red upconv2d (direct)"));
+    } else {
+      RUN(launch_one<Tile8>(p, st, "red upconv2d"));
+    }
   }
   if (state_out)
     for (int l = 0; l < 4; ++l)

@@ -760,7 +760,8 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
         return check_launch("sweep_fwd_v4_kernel");
       }
     }
-    if (a.n_out > 1) sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
+    if (a.n_out > 1 && a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
+    else if (a.n_out > 1) sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
     else if (a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
     else sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
     return check_launch("sweep_fwd_v3_kernel");
