@@ -191,3 +191,141 @@ inline int direct_conv_launch(const DirectConv& p, int NZ, int S, cudaStream_t s
 }
 
 }  // namespace satmvs
+
+// ---------------------------------------------------------------------------------------------
+// Direct 2-D transposed convolution, k = 3, stride 2, padding 1, output_padding 1 (ConvTransReLU,
+// modules/module.py:208-215), applied to every plane of a [C,D,h,w] tensor.
+// One thread = 4 output channels x 4 input pixels of a row = a 2 x 8 output block; the 9 taps of every
+// input pixel are used exactly once (o = 2 i - 1 + k):
+//   O[2q  ][2x  ] = I[q][x] w11                    O[2q  ][2x+1] = I[q][x+1] w10 + I[q][x] w12
+//   O[2q+1][2x  ] = I[q+1][x] w01 + I[q][x] w21    O[2q+1][2x+1] = I[q+1][x+1] w00 + I[q+1][x] w02 + I[q][x+1] w20 + I[q][x] w22
+// Weights [Cin][Cout][3][3].  Epilogue: ReLU, then + skip tensor (indexed like the output).
+// ---------------------------------------------------------------------------------------------
+namespace satmvs {
+
+struct DirectDeconv {
+  const float* in;   long long in_cs;    // [Cin] channels of Dn planes of Hi x Wi; channel stride in elements
+  const float* w;                        // [Cin][Cout][9]
+  const float* post_add;                 // like out, or null
+  float* out;        long long out_cs;   // [Cout] channels of Dn planes of 2Hi x 2Wi
+  int Cin, Cout, Dn, Hi, Wi;
+  int relu;
+};
+
+constexpr int kDdCo = 4, kDdPx = 4, kDdThreads = 128, kDdCiChunk = 32;
+
+template <int kUnused>     // template only so the header can be included from several translation units
+__global__ void __launch_bounds__(kDdThreads)
+direct_deconv2x_kernel(const __grid_constant__ DirectDeconv a) {
+  __shared__ __align__(16) float wsm[kDdCiChunk * 9 * kDdCo];       // [ci][tap][co]
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.y * kDdCo;
+  const int npx = a.Hi * a.Wi;
+  const long long g0 = ((long long)blockIdx.x * kDdThreads + tid) * kDdPx;
+  const bool ok = g0 < (long long)npx * a.Dn;
+  const int z = ok ? (int)(g0 / npx) : 0;
+  const int p0 = ok ? (int)(g0 - (long long)z * npx) : 0;
+  const int q = p0 / a.Wi, x0 = p0 - q * a.Wi;
+  const bool row1 = ok && (q + 1 < a.Hi), rok = x0 + kDdPx < a.Wi;
+  const float* in0 = a.in + (long long)z * npx + p0;
+
+  float acc[kDdCo][2][2 * kDdPx];
+#pragma unroll
+  for (int i = 0; i < kDdCo; ++i)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < 2 * kDdPx; ++j) acc[i][r][j] = 0.0f;
+
+  for (int c0 = 0; c0 < a.Cin; c0 += kDdCiChunk) {
+    const int nci = min(kDdCiChunk, a.Cin - c0);
+    __syncthreads();
+    {
+      constexpr int kPer = (kDdCiChunk * 9 * kDdCo + kDdThreads - 1) / kDdThreads;   // 9
+      float t[kPer];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int e = tid + k * kDdThreads;                 // e = (ci * kDdCo + co) * 9 + tap : contiguous in global per ci
+        const int ci = e / (kDdCo * 9), rr = e - ci * (kDdCo * 9);
+        const int co = rr / 9;
+        t[k] = (ci < nci && co0 + co < a.Cout) ? __ldg(a.w + ((long long)(c0 + ci) * a.Cout + co0) * 9 + rr) : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int e = tid + k * kDdThreads;
+        const int ci = e / (kDdCo * 9), rr = e - ci * (kDdCo * 9);
+        const int co = rr / 9, tp = rr - co * 9;
+        if (ci < kDdCiChunk) wsm[(ci * 9 + tp) * kDdCo + co] = t[k];
+      }
+    }
+    __syncthreads();
+    for (int c = 0; c < nci; ++c) {
+      const float* rp = in0 + (long long)(c0 + c) * a.in_cs;
+      float r0[kDdPx + 1], r1[kDdPx + 1];
+      {
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f), n = m;
+        float e0 = 0.f, e1 = 0.f;
+        if (ok) {
+          m = __ldg(reinterpret_cast<const float4*>(rp));
+          if (rok) e0 = __ldg(rp + kDdPx);
+          if (row1) {
+            n = __ldg(reinterpret_cast<const float4*>(rp + a.Wi));
+            if (rok) e1 = __ldg(rp + a.Wi + kDdPx);
+          }
+        }
+        r0[0] = m.x; r0[1] = m.y; r0[2] = m.z; r0[3] = m.w; r0[4] = e0;
+        r1[0] = n.x; r1[1] = n.y; r1[2] = n.z; r1[3] = n.w; r1[4] = e1;
+      }
+      float wv[9][kDdCo];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&wsm[(c * 9 + t) * kDdCo]);
+        wv[t][0] = w4.x; wv[t][1] = w4.y; wv[t][2] = w4.z; wv[t][3] = w4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < kDdCo; ++i)
+#pragma unroll
+        for (int j = 0; j < kDdPx; ++j) {
+          acc[i][0][2 * j] = fmaf(r0[j], wv[4][i], acc[i][0][2 * j]);
+          acc[i][0][2 * j + 1] = fmaf(r0[j + 1], wv[3][i], fmaf(r0[j], wv[5][i], acc[i][0][2 * j + 1]));
+          acc[i][1][2 * j] = fmaf(r1[j], wv[1][i], fmaf(r0[j], wv[7][i], acc[i][1][2 * j]));
+          acc[i][1][2 * j + 1] = fmaf(r1[j + 1], wv[0][i], fmaf(r1[j], wv[2][i],
+                                 fmaf(r0[j + 1], wv[6][i], fmaf(r0[j], wv[8][i], acc[i][1][2 * j + 1]))));
+        }
+    }
+  }
+  if (!ok) return;
+  const int Wo = 2 * a.Wi;
+  const long long oplane = 4LL * npx;
+#pragma unroll
+  for (int i = 0; i < kDdCo; ++i) {
+    if (co0 + i >= a.Cout) break;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long idx = (long long)(co0 + i) * a.out_cs + (long long)z * oplane + (long long)(2 * q + r) * Wo + 2 * x0;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = a.relu ? fmaxf(acc[i][r][j], 0.0f) : acc[i][r][j];
+      if (a.post_add) {
+        const float4 p0v = __ldg(reinterpret_cast<const float4*>(a.post_add + idx));
+        const float4 p1v = __ldg(reinterpret_cast<const float4*>(a.post_add + idx + 4));
+        v[0] += p0v.x; v[1] += p0v.y; v[2] += p0v.z; v[3] += p0v.w; v[4] += p1v.x; v[5] += p1v.y; v[6] += p1v.z; v[7] += p1v.w;
+      }
+      *reinterpret_cast<float4*>(a.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(a.out + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+inline bool direct_deconv_supported(const DirectDeconv& p) {
+  return p.Wi % 4 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
+         (p.post_add == nullptr || reinterpret_cast<uintptr_t>(p.post_add) % 16 == 0) && p.in_cs % 4 == 0 && p.out_cs % 4 == 0;
+}
+
+inline int direct_deconv_launch(const DirectDeconv& p, cudaStream_t st, const char* what) {
+  dim3 grid(ceil_div((long long)p.Hi * p.Wi * p.Dn, kDdThreads * kDdPx), ceil_div(p.Cout, kDdCo), 1);
+  direct_deconv2x_kernel<0><<<grid, kDdThreads, 0, st>>>(p);
+  return check_launch(what);
+}
+
+}  // namespace satmvs

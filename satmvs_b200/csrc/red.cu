@@ -846,8 +846,19 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     g.n = n;
     {
       ProfScope prof(kProfDecoder, st);
-      if (L.ch >= 32) RUN(conv_launch<Tile32>(g, st, "red upconv")); else if (L.ch >= 16) RUN(conv_launch<Tile16>(g, st, "red upconv"));
-      else RUN(conv_launch<Tile8>(g, st, "red upconv"));
+      // slots 1..D of the [C][D+1][h][w] tensors are D contiguous planes starting one plane into each channel
+      DirectDeconv dd{};
+      const long long pin = (long long)Lin.h * Lin.w, pout = (long long)L.h * L.w;
+      dd.in = up_in + pin; dd.in_cs = (long long)(D + 1) * pin;
+      dd.w = wt->upconv_w[l]; dd.post_add = L.s + pout; dd.out = P.u[l] + pout; dd.out_cs = (long long)(D + 1) * pout;
+      dd.Cin = Lin.ch; dd.Cout = L.ch; dd.Dn = D; dd.Hi = Lin.h; dd.Wi = Lin.w; dd.relu = 1;
+      static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+      if (!no_direct && direct_deconv_supported(dd)) {
+        RUN(direct_deconv_launch(dd, st, "red upconv (direct)"));
+      } else {
+        if (L.ch >= 32) RUN(conv_launch<Tile32>(g, st, "red upconv")); else if (L.ch >= 16) RUN(conv_launch<Tile16>(g, st, "red upconv"));
+        else RUN(conv_launch<Tile8>(g, st, "red upconv"));
+      }
     }
     up_in = P.u[l];
   }
