@@ -11,6 +11,7 @@
 // (16-byte aligned rows); the caller falls back to the engine otherwise.
 #pragma once
 #include "common.cuh"
+#include "packed.cuh"
 
 namespace satmvs {
 
@@ -83,22 +84,29 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
     }
   };
 
-  float acc[kDcCo][kDcPx];
+  // accumulators as (co, co+1) pairs: one FFMA2 = 2 output channels x 1 pixel; the weight pairs come
+  // straight out of the 128-bit shared-memory loads, only the input value is duplicated (once per row value)
+  u64 acc[kDcCo / 2][kDcPx];
 #pragma unroll
-  for (int i = 0; i < kDcCo; ++i)
+  for (int i = 0; i < kDcCo / 2; ++i)
 #pragma unroll
-    for (int j = 0; j < kDcPx; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < kDcPx; ++j) acc[i][j] = 0ULL;
 
   auto fma_slice = [&](int cil, int kz, const float (&r)[3][RW]) {
+    u64 rr[3][RW];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int c = 0; c < RW; ++c) rr[ky][c] = pk(r[ky][c], r[ky][c]);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float* wp = &wsm[((cil * NZ + kz) * 9 + t) * kDcCo];
-      const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
-      const float wv[kDcCo] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wp), w1 = *reinterpret_cast<const ulonglong2*>(wp + 4);
+      const u64 wv[kDcCo / 2] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
-      for (int i = 0; i < kDcCo; ++i)
+      for (int i = 0; i < kDcCo / 2; ++i)
 #pragma unroll
-        for (int j = 0; j < kDcPx; ++j) acc[i][j] = fmaf(wv[i], r[t / 3][j * S + t % 3], acc[i][j]);
+        for (int j = 0; j < kDcPx; ++j) acc[i][j] = ffma2(wv[i], rr[t / 3][j * S + t % 3], acc[i][j]);
     }
   };
 
@@ -152,7 +160,9 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
     float v[kDcPx];
 #pragma unroll
     for (int j = 0; j < kDcPx; ++j) {
-      v[j] = acc[i][j] * a.acc_scale * sc + sh;
+      float alo, ahi;
+      upk(acc[i >> 1][j], alo, ahi);
+      v[j] = ((i & 1) ? ahi : alo) * a.acc_scale * sc + sh;
       if (a.relu) v[j] = fmaxf(v[j], 0.0f);
     }
     if (a.post_add) {

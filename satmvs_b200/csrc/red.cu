@@ -21,6 +21,7 @@
 #include <type_traits>
 #include "conv_engine.cuh"
 #include "direct_conv.cuh"
+#include "packed.cuh"
 #include "prof.cuh"
 namespace cg = cooperative_groups;
 
@@ -280,16 +281,27 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
         r[dy][0] = lft; r[dy][1] = m.x; r[dy][2] = m.y; r[dy][3] = m.z; r[dy][4] = m.w; r[dy][5] = rgt;
       }
     };
+    // packed accumulation: (co, co+1) pairs per FFMA2, weight pairs straight from the 128-bit smem loads
+    u64 acc2[kGcCo / 2][kGcPx];
+#pragma unroll
+    for (int i = 0; i < kGcCo / 2; ++i)
+#pragma unroll
+      for (int j = 0; j < kGcPx; ++j) acc2[i][j] = 0ULL;
     auto fma_rows = [&](int ci, const float (&r)[3][6]) {
+      u64 rr[3][6];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) rr[dy][c] = pk(r[dy][c], r[dy][c]);
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[(ci * 9 + t) * kGcCo]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[(ci * 9 + t) * kGcCo + 4]);
-        const float wv[kGcCo] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(&wsm[(ci * 9 + t) * kGcCo]);
+        const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(&wsm[(ci * 9 + t) * kGcCo + 4]);
+        const u64 wv[kGcCo / 2] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
-        for (int i = 0; i < kGcCo; ++i)
+        for (int i = 0; i < kGcCo / 2; ++i)
 #pragma unroll
-          for (int j = 0; j < kGcPx; ++j) acc[i][j] = fmaf(wv[i], r[t / 3][j + t % 3], acc[i][j]);
+          for (int j = 0; j < kGcPx; ++j) acc2[i][j] = ffma2(wv[i], rr[t / 3][j + t % 3], acc2[i][j]);
       }
     };
     // 3-slot register ring: the rows of channels c+1, c+2 are in flight while channel c's 288 FMAs issue
@@ -305,6 +317,10 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
         if (c + u < L.ci_per_warp) fma_rows(ci0 + c + u, ring[u]);
       }
     }
+#pragma unroll
+    for (int i = 0; i < kGcCo / 2; ++i)
+#pragma unroll
+      for (int j = 0; j < kGcPx; ++j) upk(acc2[i][j], acc[2 * i][j], acc[2 * i + 1][j]);
   } else {
   // two input channels per iteration, ping-pong registers: the next channel's taps are in flight
   // while the current channel's 288 FMAs issue

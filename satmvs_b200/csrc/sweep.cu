@@ -15,6 +15,7 @@
 // Lanes map to consecutive pixels (row-major over H*W), so ref loads and volume stores are 128-byte
 // coalesced and the gathers of a warp fall into 1-2 cache lines.
 #include "geometry.cuh"
+#include "packed.cuh"
 #include "prof.cuh"
 
 #ifndef SATMVS_DK2
@@ -238,9 +239,6 @@ sweep_fwd_vec4_kernel(const __grid_constant__ SweepArgs<Geo> a) {
 //            bits are those of the scalar kernels).  CH channels (16) are carried per pass to keep
 //            ~20 warps resident.
 // ------------------------------------------------------------------------------------------
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 #ifndef SATMVS_PACKED_MASK
 #define SATMVS_PACKED_MASK 15   // debug knob: bit0 fma2, bit1 mul2, bit2 add2, bit3 sub2 use the packed instruction
 #endif
