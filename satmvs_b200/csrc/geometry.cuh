@@ -345,8 +345,12 @@ struct Tap {
   float w00, w01, w10, w11;    // corner weights in window order; out-of-range corners carry 0
 };
 
+// Same record with the clamped window origin kept as (x, y) and a flag telling whether any corner carries
+// weight (used by the shared-memory-staged kernels to bound the source window of a CTA).
+struct TapXY { int xc, yc; float w00, w01, w10, w11; bool live; };
+
 // un-normalise exactly like ATen: (g + 1) rounded, then one fused multiply-add with size/2 and -0.5
-__device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W, float half_w, float half_h) {
+__device__ __forceinline__ TapXY make_tap_xy(float gx, float gy, int H, int W, float half_w, float half_h) {
   float ix = __fmaf_rn(__fadd_rn(gx, 1.0f), half_w, -0.5f);
   float iy = __fmaf_rn(__fadd_rn(gy, 1.0f), half_h, -0.5f);
   float x0f = floorf(ix), y0f = floorf(iy);
@@ -360,24 +364,20 @@ __device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W, float 
   float wxb = (X0 == xc) ? wx1 : ((X0 == xc + 1) ? wx0 : 0.0f);
   float wya = (Y0 == yc) ? wy0 : ((Y0 == yc - 1) ? wy1 : 0.0f);
   float wyb = (Y0 == yc) ? wy1 : ((Y0 == yc + 1) ? wy0 : 0.0f);
-  Tap t;
-  t.off = yc * W + xc;
+  TapXY t;
+  t.xc = xc; t.yc = yc;
   t.w00 = __fmul_rn(wxa, wya); t.w01 = __fmul_rn(wxb, wya);
   t.w10 = __fmul_rn(wxa, wyb); t.w11 = __fmul_rn(wxb, wyb);
+  t.live = (t.w00 != 0.0f) || (t.w01 != 0.0f) || (t.w10 != 0.0f) || (t.w11 != 0.0f);
   return t;
 }
 
-// Same record with the clamped window origin kept as (x, y) and a flag telling whether any corner is in
-// range (used by the shared-memory-staged kernel to bound the source window of a CTA).
-struct TapXY { int xc, yc; float w00, w01, w10, w11; bool live; };
-
-__device__ __forceinline__ TapXY make_tap_xy(float gx, float gy, int H, int W, float half_w, float half_h) {
-  const Tap t = make_tap(gx, gy, H, W, half_w, half_h);
-  TapXY r;
-  r.yc = t.off / W; r.xc = t.off - r.yc * W;
-  r.w00 = t.w00; r.w01 = t.w01; r.w10 = t.w10; r.w11 = t.w11;
-  r.live = (t.w00 != 0.0f) || (t.w01 != 0.0f) || (t.w10 != 0.0f) || (t.w11 != 0.0f);
-  return r;
+__device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W, float half_w, float half_h) {
+  const TapXY r = make_tap_xy(gx, gy, H, W, half_w, half_h);
+  Tap t;
+  t.off = r.yc * W + r.xc;
+  t.w00 = r.w00; t.w01 = r.w01; t.w10 = r.w10; t.w11 = r.w11;
+  return t;
 }
 
 // nw, ne, sw, se accumulated with fused multiply-adds, the order ATen uses

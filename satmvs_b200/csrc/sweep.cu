@@ -17,6 +17,8 @@
 #include "geometry.cuh"
 #include "packed.cuh"
 #include "prof.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 #ifndef SATMVS_DK2
 #define SATMVS_DK2 8     // planes per thread with <= 2 source views (tuning knob, see profiles/)
@@ -52,6 +54,8 @@ struct SweepArgs {
   int n_src;                                  // live source views (<= Geo::kNumSrc; the rest carry zero weights)
   float half_w, half_h;                       // W/2, H/2 (ATen un-normalise)
   float num_views, inv_num_views;             // V as fp32 (div_(num_views), casred.py:53) and RN(1/V)
+  float neg_zero;                             // -0.0f, opaque to the compiler: fma(x, x, neg_zero) == RN(x*x) as one instruction
+  int packed_now;                             // src_v4 was written by the launch directly in front of this one
   Geo geo;
 };
 
@@ -131,6 +135,7 @@ sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
 struct PackArgs { const float* in[SATMVS_MAX_SRC_VIEWS]; float4* out[SATMVS_MAX_SRC_VIEWS]; int HW; };
 
 __global__ void pack_vec4_kernel(const __grid_constant__ PackArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;");     // the sweep's geometry phase may start while this runs
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel
   const int q = blockIdx.y;                               // channel quad
   const int HW = a.HW;
@@ -595,6 +600,302 @@ template <int DK, int NSRC, int CH>
 constexpr size_t v4_smem_bytes() { return (size_t)NSRC * (CH / 4) * kWinPx * 16 + (size_t)DK * NSRC * kSweepThreads * (4 + 16); }
 
 // ------------------------------------------------------------------------------------------
+// v5 of the forward sweep (default): 2-D reference tiles + TMA-staged, double-buffered source windows.
+//   CTA      = 32 x TH reference pixels (one warp per tile row) x DK planes; 3-4 CTAs per SM.
+//   phase A  fp64 geometry (lock-step planes) -> tap records in shared memory + per-view bounding box
+//            of the clamped tap origins (packed u16x2 min/max, warp redux, shared atomics).
+//   fix-up   each thread rewrites its own records into window-relative offsets (or global offsets
+//            when a view's box does not fit the staging buffer: steep geometry falls back to L1/L2).
+//   phase B  passes of CH (8) channels.  Warp 0 issues one cp.async.bulk per (view, quad, row) of the
+//            [C/4][H][W] float4 re-pack into stage (p+1)&1 BEFORE the CTA gathers pass p from stage p&1
+//            (completion on one mbarrier per stage), so the copy latency hides under the gather.  The
+//            pitch is padded to 8 pixels so that row breaks inside a quarter-warp stay conflict-free;
+//            every tap is an LDS.128 at base + immediate (no per-load address arithmetic).
+// The kernel is launched as a programmatic dependent of pack_vec4_kernel: its geometry phase overlaps
+// the re-pack, griddepcontrol.wait sits in front of the first read of the packed features.
+// Arithmetic and op order are those of v1/v3: results are bit-identical.
+// ------------------------------------------------------------------------------------------
+#ifndef SATMVS_V5_KUNROLL
+#define SATMVS_V5_KUNROLL 2
+#endif
+constexpr int kV5PlaneUnroll = SATMVS_V5_KUNROLL;   // planes gathered in one loop body (ILP for the 4 warps of a CTA)
+
+template <int NSRC, int TH, int DK, int CH, int WINPX>
+constexpr size_t v5_smem_bytes() {
+  return (size_t)2 * NSRC * (CH / 4) * WINPX * 16 + (size_t)DK * NSRC * (TH * 32) * (4 + 16);
+}
+
+__device__ __forceinline__ unsigned min_u16x2(unsigned a, unsigned b) { unsigned r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ unsigned max_u16x2(unsigned a, unsigned b) { unsigned r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
+template <class Geo, int TH, int DK, int CH, int WINPX, int MINB, bool kVariance, bool kMultiOut>
+__global__ void __launch_bounds__(TH * 32, MINB)
+sweep_fwd_v5_kernel(const __grid_constant__ SweepArgs<Geo> a, int tiles_x) {
+  constexpr int NSRC = Geo::kNumSrc;
+  constexpr int NT = TH * 32;
+  constexpr int NP = DK < SATMVS_NP ? DK : SATMVS_NP;
+  constexpr int NQ = CH / 4;
+  constexpr int STAGE = NSRC * NQ * WINPX;                                                  // float4 per stage
+  extern __shared__ __align__(128) unsigned char v5_smem[];
+  float4* win = reinterpret_cast<float4*>(v5_smem);                                         // [2][NSRC][NQ][WINPX]
+  int (*rec_off)[NT] = reinterpret_cast<int (*)[NT]>(win + 2 * STAGE);                      // [DK*NSRC][NT]
+  TapW (*rec_w)[NT] = reinterpret_cast<TapW (*)[NT]>(rec_off + DK * NSRC);                  // [DK*NSRC][NT]
+  __shared__ int bbox[NSRC][4];                 // xmin, xmax, ymin, ymax of the clamped origins of live taps
+  __shared__ __align__(8) unsigned long long mbar[2];
+
+  const int HW = a.H * a.W;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int x = tx * 32 + lane, y = ty * TH + warp;
+  const bool active = x < a.W && y < a.H;
+  const int pix = min(y, a.H - 1) * a.W + min(x, a.W - 1);
+  const int d0 = blockIdx.y * DK;
+
+  if (tid < NSRC) { bbox[tid][0] = 1 << 30; bbox[tid][1] = -1; bbox[tid][2] = 1 << 30; bbox[tid][3] = -1; }
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+  __syncthreads();
+
+  {  // ---- phase A: geometry, records, bounding boxes ----
+    unsigned bmin[NSRC], bmax[NSRC];            // packed (y << 16 | x), reduced per 16-bit half
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) { bmin[v] = 0xffffffffu; bmax[v] = 0u; }
+    const typename Geo::Pixel px = a.geo.pixel(min(x, a.W - 1), min(y, a.H - 1));
+#pragma unroll 1
+    for (int g = 0; g < DK; g += NP) {
+      float h[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        const int d = min(d0 + g + k, a.D - 1);
+        h[k] = a.depth_per_pixel ? __ldg(a.depth + (size_t)d * HW + pix) : __ldg(a.depth + d);
+      }
+      a.geo.template grid_coords<NP>(px, h, [&](int k, int v, float gx, float gy) {
+        TapXY t = make_tap_xy(gx, gy, a.H, a.W, a.half_w, a.half_h);
+        const bool live = t.live && active && v < a.n_src && d0 + g + k < a.D;
+        if (!live) { t.w00 = t.w01 = t.w10 = t.w11 = 0.0f; }
+        const unsigned xy = ((unsigned)t.yc << 16) | (unsigned)t.xc;
+#pragma unroll
+        for (int vv = 0; vv < NSRC; ++vv)
+          if (vv == v) { bmin[vv] = min_u16x2(bmin[vv], live ? xy : 0xffffffffu); bmax[vv] = max_u16x2(bmax[vv], live ? xy : 0u); }
+        rec_off[(g + k) * NSRC + v][tid] = live ? (int)xy : -1;
+        rec_w[(g + k) * NSRC + v][tid] = TapW{t.w00, t.w01, t.w10, t.w11};
+      });
+    }
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) {
+      const unsigned x0 = __reduce_min_sync(0xffffffffu, bmin[v] & 0xffffu), y0 = __reduce_min_sync(0xffffffffu, bmin[v] >> 16);
+      const unsigned x1 = __reduce_max_sync(0xffffffffu, bmax[v] & 0xffffu), y1 = __reduce_max_sync(0xffffffffu, bmax[v] >> 16);
+      if (lane == 0 && x0 != 0xffffu) {         // this warp has at least one live tap in view v
+        atomicMin(&bbox[v][0], (int)x0); atomicMax(&bbox[v][1], (int)x1); atomicMin(&bbox[v][2], (int)y0); atomicMax(&bbox[v][3], (int)y1);
+      }
+    }
+  }
+  __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the packed features (previous kernel) are complete from here on
+
+  // window geometry per view (uniform): origin, copied width, padded pitch, rows
+  int xs[NSRC], ys[NSRC], wc[NSRC], pitch[NSRC], rows[NSRC];
+  bool staged = true;
+#pragma unroll
+  for (int v = 0; v < NSRC; ++v) {
+    if (bbox[v][1] < 0) { xs[v] = 0; ys[v] = 0; wc[v] = 2; rows[v] = 2; }             // no live tap at all
+    else { xs[v] = bbox[v][0]; ys[v] = bbox[v][2]; wc[v] = bbox[v][1] - bbox[v][0] + 2; rows[v] = bbox[v][3] - bbox[v][2] + 2; }
+    pitch[v] = (wc[v] + 7) & ~7;
+    staged = staged && (pitch[v] * rows[v] <= WINPX);
+  }
+
+  // one bulk copy per (view, quad, row) of pass p into stage p & 1, issued by warp 0
+  auto issue = [&](int p) {
+    if (warp == 0) {
+      unsigned long long* bar = &mbar[p & 1];
+      float4* dst0 = win + (p & 1) * STAGE;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this stage -> async-proxy writes
+      if (lane == 0) {
+        unsigned total = 0;
+#pragma unroll
+        for (int v = 0; v < NSRC; ++v) total += (unsigned)(NQ * rows[v] * wc[v]) * 16u;
+        mbar_expect_tx(bar, total);
+      }
+      __syncwarp();
+      const int q0 = p * NQ;
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        const int n = NQ * rows[v];
+        for (int i = lane; i < n; i += 32) {
+          const int qd = i / rows[v], r = i - qd * rows[v];
+          const float4* src = a.src_v4[v] + ((size_t)(q0 + qd) * a.H + ys[v] + r) * a.W + xs[v];
+          bulk_g2s(dst0 + (v * NQ + qd) * WINPX + r * pitch[v], src, (unsigned)wc[v] * 16u, bar);
+        }
+      }
+    }
+  };
+  const int P = a.C / CH;
+  if (staged) issue(0);
+
+  // fix-up: packed (y, x) -> float4 index relative to the view's window (staged) or to the quad plane (global)
+#pragma unroll
+  for (int k = 0; k < DK; ++k)
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) {
+      const int xy = rec_off[k * NSRC + v][tid];
+      const int xc = xy & 0xffff, yc = xy >> 16;
+      int off = 0;
+      if (xy >= 0) off = staged ? (yc - ys[v]) * pitch[v] + (xc - xs[v]) : yc * a.W + xc;
+      rec_off[k * NSRC + v][tid] = off;
+    }
+
+  const unsigned upix = (unsigned)pix * 4u;
+  const size_t plane_bytes = (size_t)HW * sizeof(float);
+  const size_t ostride = (size_t)a.out_D * plane_bytes;                                    // per channel
+  const u64 vinv = pk(a.inv_num_views, a.inv_num_views), vneg = pk(-a.num_views, -a.num_views);
+  // x*x rounded on its own as fma(x, x, -0): the addend arrives as a kernel argument, so ptxas can neither fold
+  // it away nor contract the product into the following add (profiles/r01_sweep_v3_notes.md)
+  const u64 nz = pk(a.neg_zero, a.neg_zero);
+#pragma unroll 1
+  for (int p = 0; p < P; ++p) {
+    const int c0 = p * CH;
+    if (staged && p + 1 < P) {
+      if (p >= 1) __syncthreads();                // every thread is done with pass p-1, whose stage is refilled now
+      issue(p + 1);
+    }
+    u64 r[CH / 2];
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) {
+      float lo = 0.f, hi = 0.f;
+      if (kVariance) {
+        const char* rb = reinterpret_cast<const char*>(a.ref_fea) + (size_t)(c0 + 2 * j) * plane_bytes;
+        lo = __ldg(reinterpret_cast<const float*>(rb + upix));
+        hi = __ldg(reinterpret_cast<const float*>(rb + plane_bytes + upix));
+      }
+      r[j] = pk(lo, hi);
+    }
+    u64 r2[CH / 2];
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) r2[j] = fma2(r[j], r[j], nz);
+    if (staged) mbar_wait(&mbar[p & 1], (unsigned)(p >> 1) & 1u);
+    const float4* wst = win + (p & 1) * STAGE;
+
+    // one plane: gather all views from `fetch`, then the variance epilogue.  Planes past D (last chunk) carry dead
+    // records (zero weights, offset 0) and are computed but not stored, so the loop body has no exits and the
+    // compiler can interleave consecutive planes.
+    auto plane = [&](int k, auto fetch) {
+      u64 s[CH / 2], q[CH / 2];
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        const int off = rec_off[k * NSRC + v][tid];
+        const TapW w = rec_w[k * NSRC + v][tid];
+        const u64 w00 = pk(w.w00, w.w00), w01 = pk(w.w01, w.w01), w10 = pk(w.w10, w.w10), w11 = pk(w.w11, w.w11);
+#pragma unroll
+        for (int qd = 0; qd < NQ; ++qd) {
+          float4 A, B, Cc, Dd;
+          fetch(v, qd, off, A, B, Cc, Dd);
+          // nw, ne, sw, se accumulated with FMAs (ATen order), two channels per instruction
+          u64 lo = fma2(pk(Dd.x, Dd.y), w11, fma2(pk(Cc.x, Cc.y), w10, fma2(pk(B.x, B.y), w01, mul2(pk(A.x, A.y), w00))));
+          u64 hi = fma2(pk(Dd.z, Dd.w), w11, fma2(pk(Cc.z, Cc.w), w10, fma2(pk(B.z, B.w), w01, mul2(pk(A.z, A.w), w00))));
+          if (kVariance) {
+            // the first view accumulates onto the reference terms directly (no per-plane copies of r / r2)
+            s[2 * qd] = add2(v == 0 ? r[2 * qd] : s[2 * qd], lo);
+            q[2 * qd] = add2(v == 0 ? r2[2 * qd] : q[2 * qd], fma2(lo, lo, nz));
+            s[2 * qd + 1] = add2(v == 0 ? r[2 * qd + 1] : s[2 * qd + 1], hi);
+            q[2 * qd + 1] = add2(v == 0 ? r2[2 * qd + 1] : q[2 * qd + 1], fma2(hi, hi, nz));
+          } else {
+            s[2 * qd] = lo; s[2 * qd + 1] = hi;
+          }
+        }
+      }
+      const bool store = active && d0 + k < a.D;
+      const size_t obase = ((size_t)c0 * a.out_D + a.out_d0 + d0 + k) * plane_bytes + upix;
+      char* op = reinterpret_cast<char*>(a.out[0]) + obase;
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) {
+        u64 res = s[j];
+        if (kVariance) {
+          // x / V as a correctly rounded constant division (div_const), packed
+          u64 m = mul2(s[j], vinv);  m = fma2(fma2(vneg, m, s[j]), vinv, m);
+          u64 e = mul2(q[j], vinv);  e = fma2(fma2(vneg, e, q[j]), vinv, e);
+          res = sub2(e, fma2(m, m, nz));
+        }
+        float lo, hi;
+        upk(res, lo, hi);
+        if (store) {
+          if (kMultiOut) {
+            for (int o = 0; o < a.n_out; ++o) {
+              char* ob = reinterpret_cast<char*>(a.out[o]) + obase + (size_t)(2 * j) * ostride;
+              __stcs(reinterpret_cast<float*>(ob), lo);
+              __stcs(reinterpret_cast<float*>(ob + ostride), hi);
+            }
+          } else {
+            __stcs(reinterpret_cast<float*>(op), lo);
+            __stcs(reinterpret_cast<float*>(op + ostride), hi);
+            op += 2 * ostride;
+          }
+        }
+      }
+    };
+    if (staged) {
+      int pt[NSRC];
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) pt[v] = pitch[v];
+      auto fetch = [&](int v, int qd, int off, float4& A, float4& B, float4& Cc, float4& Dd) {
+        const float4* b0 = wst + v * (NQ * WINPX) + qd * WINPX + off;      // shared: LDS.128 at base + immediate
+        A = b0[0]; B = b0[1]; Cc = b0[pt[v]]; Dd = b0[pt[v] + 1];
+      };
+#pragma unroll kV5PlaneUnroll
+      for (int k = 0; k < DK; ++k) plane(k, fetch);
+    } else {
+      auto fetch = [&](int v, int qd, int off, float4& A, float4& B, float4& Cc, float4& Dd) {
+        const float4* b0 = a.src_v4[v] + (size_t)(p * NQ + qd) * HW + off;
+        A = __ldg(b0); B = __ldg(b0 + 1); Cc = __ldg(b0 + a.W); Dd = __ldg(b0 + a.W + 1);
+      };
+#pragma unroll 1
+      for (int k = 0; k < DK; ++k) plane(k, fetch);
+    }
+  }
+}
+
+template <class Geo, int TH, int DK, int CH, int WINPX, int MINB, bool kVariance>
+static int launch_v5(const SweepArgs<Geo>& a, cudaStream_t st, bool after_pack) {
+  constexpr size_t smem = v5_smem_bytes<Geo::kNumSrc, TH, DK, CH, WINPX>();
+  static_assert(smem <= 220 * 1024, "v5 configuration exceeds shared memory");
+  const int tiles_x = ceil_div(a.W, 32), tiles_y = ceil_div(a.H, TH);
+  auto run = [&](auto kern) {
+    static thread_local int ready_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (ready_dev != dev) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ready_dev = dev; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles_x * tiles_y, ceil_div(a.D, DK));
+    cfg.blockDim = dim3(TH * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = after_pack ? 1 : 0;          // only directly behind pack_vec4_kernel (which waited for all earlier work)
+    cudaLaunchKernelEx(&cfg, kern, a, tiles_x);
+  };
+  if (a.n_out > 1) run(sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, true>);
+  else run(sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, false>);
+  return check_launch("sweep_fwd_v5_kernel");
+}
+
+// v5 applies to <= 2 source views (3-view stacks, every cascade stage).  With 4 source views the records and
+// windows leave 2 CTAs per SM and the L1-gather kernel (v3) is faster (2.2 ms against 1.97 ms at cfg-4):
+// profiles/r01_sweep_v5_notes.md.  Returns -1 when v5 does not apply.
+template <class Geo, bool kVariance>
+static int dispatch_v5(const SweepArgs<Geo>& a, cudaStream_t st, bool after_pack) {
+  constexpr int NS = Geo::kNumSrc;
+  if (a.W >= 32768 || a.H >= 32768 || (a.C & 7)) return -1;
+  if constexpr (NS <= 2) {
+    static const bool dk8 = getenv("SATMVS_SWEEP_DK8") != nullptr;     // tuning alternative: 8 planes per CTA, 3 CTAs per SM
+    if (dk8) return launch_v5<Geo, 4, 8, 8, 256, 3, kVariance>(a, st, after_pack);
+    return launch_v5<Geo, 4, 4, 8, 256, 4, kVariance>(a, st, after_pack);
+  } else {
+    return -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward: gradients reach the feature maps only (the grid is built under no_grad,
 // warping.py:322-356).  Same geometry, scatter with float atomics (RED.ADD.F32 in L2).
 //   warp  : grad_src[c, tap] += w_tap * g[c,d,pix]
@@ -734,6 +1035,7 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
   constexpr int DK = PlanesPerThread<Geo::kNumSrc>::value;
   dim3 grid(ceil_div((int64_t)a.H * a.W, kSweepThreads), ceil_div(a.D, DK));
   ProfScope prof(kProfSweep, st);
+  a.neg_zero = -0.0f;
   if (a.src_v4[0] != nullptr) {
 #if SATMVS_SWEEP_V == 2
     sweep_fwd_vec4_kernel<Geo, DK, kVariance><<<grid, kSweepThreads, 0, st>>>(a);
@@ -757,6 +1059,11 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
         kern<<<g4, seg_w, smem, st>>>(a, seg_w, segs);
         return check_launch("sweep_fwd_v4_kernel");
       }
+    }
+    static const bool no_v5 = getenv("SATMVS_SWEEP_V3") != nullptr;
+    if (!no_v5) {
+      const int rc = dispatch_v5<Geo, kVariance>(a, st, a.packed_now != 0 && !prof_state().on);
+      if (rc >= 0) return rc;
     }
     if (a.n_out > 1 && a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
     else if (a.n_out > 1) sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
@@ -827,6 +1134,7 @@ static int pack_sources(Args& a, const float* const* src_feas, int n_src, int ns
     a.src_v4[v] = dst;
   }
   pack_vec4_kernel<<<dim3(ceil_div(HW, 256), a.C / 4, n_src), 256, 0, st>>>(pa);
+  a.packed_now = 1;
   for (int v = n_src; v < nslots; ++v) a.src_v4[v] = a.src_v4[0];
   return check_launch("pack_vec4_kernel");
 }

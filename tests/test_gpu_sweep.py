@@ -208,23 +208,34 @@ def test_rpc_point_ops_golden(golden):
     assert lat.shape == (0,)
 
 
-def test_vectorised_and_scalar_kernels_agree_bitwise():
-    """build_cost_volume uses the 4-channel-packed kernel; the plain C-ABI entry (no workspace) runs the
-    scalar kernel.  Same op order => identical bits."""
+@pytest.mark.parametrize("V,Cc,D,H,W,stretch", [
+    (3, 16, 11, 24, 40, 1.0),      # partial tiles in x and y, D not a multiple of the plane chunk
+    (3, 32, 8, 32, 64, 1.0),       # full tiles, two double-buffered passes per stage pair
+    (2, 8, 5, 17, 23, 1.0),        # one source view, one pass
+    (3, 16, 6, 24, 96, 3.0),       # source 3x coarser: the tap window of a tile exceeds the staging buffer -> L1/L2 fallback
+    (5, 8, 7, 16, 24, 1.0),        # 4 source views: the L1-gather kernel (v3)
+])
+def test_vectorised_and_scalar_kernels_agree_bitwise(V, Cc, D, H, W, stretch):
+    """build_cost_volume runs the packed kernels (v5: TMA-staged windows for <= 2 source views, v3 otherwise);
+    the plain C-ABI entry (no workspace) runs the scalar kernel.  Same op order => identical bits."""
     import ctypes as C
     from satmvs_b200 import _lib
-    B, V, Cc, D, H, W = 1, 3, 16, 11, 24, 40
+    B = 1
     fe = [cu(f) for f in synth.make_features(B, V, Cc, H, W, seed=8)]
     rp = synth.make_rpc_stack(B, V, H, W)
+    if stretch != 1.0:
+        rp[:, 1:, 6] *= stretch          # SAMP_SCALE of the source views (dataset/data_io.py:78-92)
+        rp[:, 1:, 5] *= 0.5 * stretch    # LINE_SCALE
     dv = cu(synth.make_depth_planes(B, D, H, W))
     fast = satmvs_b200.build_cost_volume(fe[0], fe[1:], rp[:, 0], rp[:, 1:], dv, "rpc")
     slow = torch.empty_like(fast)
-    ptrs = (C.c_void_p * 2)(fe[1][0].data_ptr(), fe[2][0].data_ptr())
+    ptrs = (C.c_void_p * (V - 1))(*[f[0].data_ptr() for f in fe[1:]])
     ref_cam = np.ascontiguousarray(rp[0, 0].numpy())
     src_cam = np.ascontiguousarray(rp[0, 1:].numpy())
-    rc = _lib.lib().satmvs_cost_volume_rpc_fwd(fe[0][0].data_ptr(), ptrs, 2, ref_cam.ctypes.data_as(C.c_void_p),
+    rc = _lib.lib().satmvs_cost_volume_rpc_fwd(fe[0][0].data_ptr(), ptrs, V - 1, ref_cam.ctypes.data_as(C.c_void_p),
                                                src_cam.ctypes.data_as(C.c_void_p), dv[0].data_ptr(), 1, Cc, D, H, W,
                                                slow[0].data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
+    assert fast.abs().max().item() > 0.0
     assert torch.equal(fast, slow)
