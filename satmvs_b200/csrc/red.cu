@@ -29,6 +29,25 @@ namespace satmvs {
 
 constexpr float kGnEps = 1e-5f;   // nn.GroupNorm(1, C, 1e-5, True), modules/module.py:15-20
 
+// Programmatic dependent launch for the per-plane chain P1 -> E1 -> P2 -> E2 -> P1 ...: every kernel of the chain
+// releases its successor at entry (griddepcontrol.launch_dependents), does the work that does not depend on its
+// predecessor (staging the conv weights, index arithmetic) and only then waits for the predecessor's memory
+// (griddepcontrol.wait).  Launch latency and the weight staging of kernel n+1 hide under kernel n.  Completion stays
+// serial, so every kernel still sees the results of all earlier ones after its wait.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class Kern, class... Args>
+static void launch_chain(Kern kern, int grid, int block, size_t smem, cudaStream_t st, bool pdl, const Args&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 struct RedLevel {
   int ch, h, w;          // hidden channels, spatial size
   int cx;                // channels of the x input of this level's GRU
@@ -106,7 +125,9 @@ __device__ __forceinline__ void gn_coeff(const double* st, double inv_n, float g
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void gru_reset_kernel(const __grid_constant__ GruArgs a) {
+  pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
   if (i >= a.total) return;
   int li = 0;
 #pragma unroll
@@ -115,12 +136,16 @@ __global__ void gru_reset_kernel(const __grid_constant__ GruArgs a) {
   const int e = i - L.begin, c = e / L.px, p = e - c * L.px;
   float ga, gb;
   gn_coeff(L.stats, L.inv_n, __ldg(L.rn_w + c), __ldg(L.rn_b + c), ga, gb);
+  // read-only path is safe here: nothing reads gates / states through L1 before their final value is written
+  // (the conv kernels, which update gates in place, use L2-coherent loads: see gru_conv_kernel)
   const float r = sigmoidf_(fmaf(__ldg(L.g + c * L.gcs + p), ga, gb));
   L.rh[e] = r * __ldg(L.hprev + c * L.scs + p);
 }
 
 __global__ void gru_update_kernel(const __grid_constant__ GruArgs a) {
+  pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
   if (i >= a.total) return;
   int li = 0;
 #pragma unroll
@@ -234,6 +259,7 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
   for (int i = 0; i < kGcCo; ++i)
 #pragma unroll
     for (int j = 0; j < kGcPx; ++j) acc[i][j] = 0.0f;
+  pdl_wait();                 // inputs, addends and GroupNorm sums of the predecessor kernel are visible from here on
   __syncthreads();
   tick(0);
 
@@ -401,10 +427,15 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
   float* wsm = gc_smem;                                                                  // [ci][tap][co]  (<= 18 KB)
   float (*part)[kGcCo][kGcTilePx] = reinterpret_cast<float (*)[kGcCo][kGcTilePx]>(gc_smem + 64 * 9 * kGcCo);   // 32 KB
   __shared__ double red[2][kGcWarps];
+  pdl_release();
   int li = 0;
 #pragma unroll
   for (int k = 1; k < 4; ++k) if ((int)blockIdx.x >= a.l[k].cta_begin) li = k;
-  gru_conv_unit<kAligned, false>(a.l[li], blockIdx.x - a.l[li].cta_begin, wsm, part, red, true);
+  // Coherent (L2) loads for everything the predecessor kernel wrote: under programmatic dependent launch this
+  // kernel's CTAs become resident (L1 invalidated) BEFORE the predecessor finishes, and the predecessor's own
+  // read-then-overwrite of the same addresses (gates / output conv are updated in place) can leave stale lines in
+  // the L1 of a shared SM, which ld.global.nc would hit after the wait.
+  gru_conv_unit<kAligned, true>(a.l[li], blockIdx.x - a.l[li].cta_begin, wsm, part, red, true);
 }
 
 
@@ -614,7 +645,7 @@ static int red_recurrence_launch(RecArgs& ra, cudaStream_t st, bool* launched) {
   return SATMVS_OK;
 }
 
-static int gru_conv_launch(const GruConvArgs& c, int ctas, cudaStream_t st, const char* what) {
+static int gru_conv_launch(const GruConvArgs& c, int ctas, cudaStream_t st, const char* what, bool pdl) {
   bool aligned = true;
   for (int l = 0; l < 4; ++l) aligned = aligned && (c.l[l].w_ % kGcPx == 0);
   constexpr size_t smem = (64 * 9 * kGcCo + kGcWarps * kGcCo * kGcTilePx) * sizeof(float);
@@ -626,8 +657,8 @@ static int gru_conv_launch(const GruConvArgs& c, int ctas, cudaStream_t st, cons
     cudaFuncSetAttribute(gru_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ready_dev = dev;
   }
-  if (aligned) gru_conv_kernel<true><<<ctas, kGcThreads, smem, st>>>(c);
-  else gru_conv_kernel<false><<<ctas, kGcThreads, smem, st>>>(c);
+  if (aligned) launch_chain(gru_conv_kernel<true>, ctas, kGcThreads, smem, st, pdl, c);
+  else launch_chain(gru_conv_kernel<false>, ctas, kGcThreads, smem, st, pdl, c);
   return check_launch(what);
 }
 
@@ -789,6 +820,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       RUN(red_recurrence_launch(ra, st, &persistent));
     }
   }
+  static const bool pdl = getenv("SATMVS_RED_NO_PDL") == nullptr;
   for (int d = 0; d < D && !persistent; ++d) {
     GruConvArgs c1{}, c2{};
     GruArgs ga{};
@@ -825,13 +857,14 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       total += L.ch * (int)px;
     }
     ga.total = total;
-    { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)")); }
+    // the first gate conv follows the batched launches (plain stream order); everything after it is chained
+    { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)", pdl && d > 0)); }
     { ProfScope prof(kProfGruPointwise, st);
-      gru_reset_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
+      launch_chain(gru_reset_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
       RUN(check_launch("gru_reset_kernel")); }
-    { ProfScope prof(kProfGruOutput, st); RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output)")); }
+    { ProfScope prof(kProfGruOutput, st); RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output)", pdl)); }
     { ProfScope prof(kProfGruPointwise, st);
-      gru_update_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ga);
+      launch_chain(gru_update_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
       RUN(check_launch("gru_update_kernel")); }
   }
 
