@@ -852,16 +852,21 @@ sweep_fwd_v5_kernel(const __grid_constant__ SweepArgs<Geo> a, int tiles_x) {
   }
 }
 
+// opt in to > 48 KB of dynamic shared memory once per (kernel, device, host thread)
+template <auto Kern>
+static void allow_dynamic_smem(size_t smem) {
+  static thread_local int ready_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (ready_dev != dev) { cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ready_dev = dev; }
+}
+
 template <class Geo, int TH, int DK, int CH, int WINPX, int MINB, bool kVariance>
 static int launch_v5(const SweepArgs<Geo>& a, cudaStream_t st, bool after_pack) {
   constexpr size_t smem = v5_smem_bytes<Geo::kNumSrc, TH, DK, CH, WINPX>();
   static_assert(smem <= 220 * 1024, "v5 configuration exceeds shared memory");
   const int tiles_x = ceil_div(a.W, 32), tiles_y = ceil_div(a.H, TH);
   auto run = [&](auto kern) {
-    static thread_local int ready_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (ready_dev != dev) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ready_dev = dev; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(tiles_x * tiles_y, ceil_div(a.D, DK));
     cfg.blockDim = dim3(TH * 32);
@@ -874,8 +879,14 @@ static int launch_v5(const SweepArgs<Geo>& a, cudaStream_t st, bool after_pack) 
     cfg.numAttrs = after_pack ? 1 : 0;          // only directly behind pack_vec4_kernel (which waited for all earlier work)
     cudaLaunchKernelEx(&cfg, kern, a, tiles_x);
   };
-  if (a.n_out > 1) run(sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, true>);
-  else run(sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, false>);
+  // (both instantiations have the same function type, so the opt-in is keyed on the kernel itself)
+  if (a.n_out > 1) {
+    allow_dynamic_smem<sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, true>>(smem);
+    run(sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, true>);
+  } else {
+    allow_dynamic_smem<sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, false>>(smem);
+    run(sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, false>);
+  }
   return check_launch("sweep_fwd_v5_kernel");
 }
 
