@@ -32,8 +32,14 @@ struct DirectConv {
 
 constexpr int kDcWarps = 4, kDcCo = 8, kDcPx = 4, kDcCiChunk = 16;
 
+#ifndef SATMVS_DC_MINB
+#define SATMVS_DC_MINB 4   // 16 warps per SM: measured 1.28 -> 0.99 ms on the batched RED convs against (1, ring 3)
+#endif
+#ifndef SATMVS_DC_RING
+#define SATMVS_DC_RING 2
+#endif
 template <int NZ, int S>
-__global__ void __launch_bounds__(kDcWarps * 32)
+__global__ void __launch_bounds__(kDcWarps * 32, SATMVS_DC_MINB)
 direct_conv_kernel(const __grid_constant__ DirectConv a) {
   constexpr int TAPS = NZ * 9;
   constexpr int RW = (S == 1) ? 6 : 9;                 // input values per row feeding 4 output pixels
@@ -134,16 +140,17 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
     __syncthreads();
     // slices s = (ci, kz) of this chunk through a 3-slot register ring: 2 slices in flight under the FMAs
     const int nsl = nci * NZ;
-    float ring[3][3][RW];
+    constexpr int RD = SATMVS_DC_RING;                 // ring slots: RD - 1 slices in flight under the FMAs
+    float ring[RD][3][RW];
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < RD - 1; ++s)
       if (s < nsl) load_slice(c0 + s / NZ, s % NZ, ring[s]);
 #pragma unroll 1
-    for (int s = 0; s < nsl; s += 3) {
+    for (int s = 0; s < nsl; s += RD) {
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int cur = s + u, nxt = cur + 2;
-        if (nxt < nsl) load_slice(c0 + nxt / NZ, nxt % NZ, ring[(u + 2) % 3]);
+      for (int u = 0; u < RD; ++u) {
+        const int cur = s + u, nxt = cur + RD - 1;
+        if (nxt < nsl) load_slice(c0 + nxt / NZ, nxt % NZ, ring[(u + RD - 1) % RD]);
         if (cur < nsl) fma_slice(cur / NZ, cur % NZ, ring[u]);
       }
     }
