@@ -71,6 +71,19 @@ def make_inputs(w, seed=0):
     return fe, cams, dv
 
 
+def ncu_traffic(kernel_class, w):
+    """DRAM bytes per launch of a kernel class from the committed `ncu --set full` capture of this workload shape
+    (profiles/ncu_traffic.json, written from profiles/*.txt), or None when no capture exists."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.isfile(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    key = "V{V}_C{C}_D{D}_{H}x{W}_{geo}".format(**w)
+    e = d.get(key, {}).get(kernel_class)
+    return None if e is None else e["dram_read_bytes"] + e["dram_write_bytes"]
+
+
 def sweep_bytes_per_cell(w):
     # SURVEY.md §8d: variance write 4C + per-pixel hypothesis read 4 + compulsory feature reads 4·C·V/D
     return 4 * w["C"] + 4 + 4.0 * w["C"] * w["V"] / w["D"]
@@ -296,7 +309,8 @@ def run_ours(args, w):
                 # one build = re-pack launch + sweep launch: the rate is taken over the whole class time of a step
                 ach = by / (t_ms / prof_steps * 1e-3) / 1e9
                 k["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                                 "traffic": None, "algorithmic_bytes_per_launch": by, "bytes_per_cell": bpc,
+                                 "traffic": None if sharded_run else ncu_traffic("sweep", w),
+                                 "algorithmic_bytes_per_launch": by, "bytes_per_cell": bpc,
                                  "note": "bytes of one cost-volume build / device time of its launches (re-pack + sweep)"}
             elif name in flops:
                 ach = flops[name] / (t_ms / prof_steps * 1e-3) / 1e12
