@@ -21,6 +21,7 @@
 #include <type_traits>
 #include "conv_engine.cuh"
 #include "direct_conv.cuh"
+#include "umma_conv.cuh"
 #include "packed.cuh"
 #include "prof.cuh"
 namespace cg = cooperative_groups;
@@ -63,6 +64,8 @@ struct RedPlan {
   float* u[3];           // U1 [8][D+1][H][W], U2 [16][D+1][H/2][W/2], U3 [32][D+1][H/4][W/4]
   RedLevel lv[4];
   double* stats;         // [D][4][3][2]
+  char* wpack[4]; size_t wpack_bytes[4];
+  int* umma_err;
   size_t bytes;
 };
 
@@ -92,6 +95,13 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   }
   p.stats = reinterpret_cast<double*>(base + off);
   off += ((size_t)D * 4 * 3 * 2 * sizeof(double) + 64 * sizeof(double) + 255) / 256 * 256;   // + 64 debug counters
+  for (int l = 0; l < 4; ++l) {   // packed (raw, lo) x-half weights of the tensor-core convs, per level
+    p.wpack[l] = base + off;
+    p.wpack_bytes[l] = (size_t)(p.lv[l].cx / 8 + 1) * 2 * 9 * 2 * ((3 * p.lv[l].ch + 15) / 16 * 16) * 16;
+    off += (p.wpack_bytes[l] + 255) / 256 * 256;
+  }
+  p.umma_err = reinterpret_cast<int*>(base + off);
+  off += 256;
   p.bytes = off;
   return p;
 }
@@ -760,9 +770,22 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     p.acc_scale = (i == 0) ? -1.0f : 1.0f;
     { ProfScope prof(kProfConvBatched, st); RUN(launch_plane_conv(p, 2, st, "red encoder")); }
   }
+  static const bool no_umma = getenv("SATMVS_NO_UMMA") != nullptr;
   for (int l = 0; l < 4; ++l) {   // x-halves of the GRU convolutions, bias folded in (module.py:29-30, :44-45)
     RedLevel& L = P.lv[l];
     const long long kin = (long long)(L.cx + L.ch) * 9;
+    if (!no_umma) {
+      // gate and output x-halves share their input: one tensor-core launch with two heads (umma_conv.cuh)
+      UmmaPackHead wh[2] = {{wt->gate_w[l], kin, 9, 2 * L.ch, 0}, {wt->out_w[l], kin, 9, L.ch, 0}};
+      const float sgn = (l == 0) ? -1.0f : 1.0f;
+      UmmaHead oh[2] = {{wt->gate_b[l], L.gx, 2 * L.ch, 0, sgn, 0}, {wt->out_b[l], L.ox, L.ch, 0, sgn, 0}};
+      UmmaConvPlan up;
+      if (umma_conv_plan(up, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 2, wh, oh, P.wpack[l], P.wpack_bytes[l])) {
+        ProfScope prof(kProfConvBatched, st);
+        RUN(umma_conv_launch(up, P.umma_err, st, "red gate/output x-halves (tcgen05)"));
+        continue;
+      }
+    }
     ConvProblem g = plane_conv(xin[l], L.cx, D, L.h, L.w, wt->gate_w[l], kin, 9, L.gx, 2 * L.ch, D, L.h, L.w, 1);
     g.Qd = D; g.Qh = L.h; g.Qw = L.w;
     g.shift = wt->gate_b[l];

@@ -1,0 +1,294 @@
+// umma_conv.cuh — 3x3 (stride 1, padding 1) plane convolution on the 5th-generation tensor cores (tcgen05),
+// fp32-faithful through a 3-way TF32 split, for the batched (all depth planes at once) layers of RED.
+//
+// Formulation.  A plane is addressed in PADDED-FLATTENED positions q = (y+1)*Wp + (x+1), Wp = W + 2, with zeros in the
+// halo.  For a run of consecutive output positions the input of tap (dy, dx) is the same run shifted by dy*Wp + dx, so
+// with the input window in shared memory as [channel quad][position] float4 (the sweep's re-pack layout, which IS the
+// SWIZZLE_NONE K-major canonical layout of tcgen05: 8 positions x 16 bytes per core matrix, SBO = 128 B between
+// 8-position groups, LBO = window pitch between channel quads) every tap is ONE shared-memory descriptor whose start
+// address is moved by the shift: no im2col copy, each input element is staged once per CTA.
+//   D[128 positions x N] += A_tap[128 x 8 channels] * W_tap[N x 8 channels]^T      (kind::tf32, M 128, K 8)
+// over 9 taps x Cin/8 k-steps.  N = all output channels that share the input (several "heads": GRU gate and output
+// convolutions of one level), padded to a multiple of 16; accumulators live in TMEM (MT tiles x N columns).
+//
+// Precision.  The tensor core TRUNCATES fp32 operands to TF32 (measured: tools/probes/umma_probe.cu), so the raw fp32
+// tile is the "hi" operand for free; lo = x - trunc(x) is exact in fp32 and is staged next to it.  Three MMAs per step
+// (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) leave ~2^-20 relative error per product, against 2^-11 for a
+// single TF32 pass: the logits stay within the parity bound of the fp32 FFMA path (tests/test_gpu_red.py).
+//
+// Pipeline per CTA (256 threads, 2 CTAs per SM so one stages while the other multiplies): for every chunk of 8 input
+// channels: wait for the previous chunk's MMAs (tcgen05.commit -> mbarrier), stage window + packed weights, proxy
+// fence + barrier, ONE thread issues MT x 9 x 3 tcgen05.mma; after the last chunk the accumulators are read back with
+// tcgen05.ld (32 lanes x 32 bit, one row = one position per thread) and the epilogue (scale, bias, ReLU) stores
+// coalesced rows of the NCDHW outputs.
+#pragma once
+#include "common.cuh"
+
+namespace satmvs {
+
+constexpr int kUcThreads = 256, kUcKC = 8, kUcMaxHeads = 3, kUcMaxMT = 4;
+
+struct UmmaHead {
+  const float* shift;      // [Cout] or null
+  float* out;              // [Cout][D][H][W]
+  int Cout;
+  int n0;                  // first column of this head in the fused N dimension
+  float acc_scale;
+  int relu;
+};
+
+struct UmmaConv2d {
+  const float* in;         // [Cin] channels of D planes of H x W
+  long long in_cs;         // input channel stride in elements
+  const float4* wpack;     // packed weights, see umma_pack_weights_kernel
+  int Cin, D, H, W;
+  int NP;                  // fused output channels, padded to a multiple of 16
+  int MT;                  // 128-position tiles per CTA
+  int PW;                  // window positions = 128*MT + 2*Wp + 2
+  int nheads;
+  UmmaHead head[kUcMaxHeads];
+};
+
+struct UmmaPackHead { const float* w; long long w_co, w_ci; int Cout, n0; };
+struct UmmaPack { UmmaPackHead head[kUcMaxHeads]; int nheads, Cin, NP; float4* out; };
+
+// Packed weights: [chunk = Cin/8][part: 0 raw, 1 lo][tap 9][kq 2][n NP] float4 (4 consecutive input channels).
+// Column n of the fused N dimension belongs to the head with n0 <= n < n0 + Cout; padding columns are zero.
+__global__ void umma_pack_weights_kernel(const __grid_constant__ UmmaPack a) {
+  const int total = (a.Cin / kUcKC) * 2 * 9 * 2 * a.NP;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i % a.NP;
+  int r = i / a.NP;
+  const int kq = r % 2; r /= 2;
+  const int tap = r % 9; r /= 9;
+  const int part = r % 2;
+  const int chunk = r / 2;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int h = 0; h < a.nheads; ++h) {
+    const UmmaPackHead& H = a.head[h];
+    if (n >= H.n0 && n < H.n0 + H.Cout) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ci = chunk * kUcKC + 4 * kq + j;
+        const float w = __ldg(H.w + (long long)(n - H.n0) * H.w_co + (long long)ci * H.w_ci + tap);
+        const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+        v[j] = part ? (w - hi) : w;
+      }
+    }
+  }
+  a.out[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__device__ __forceinline__ unsigned uc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// SWIZZLE_NONE K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 at bit 0,
+// leading (K-chunk) byte offset >> 4 at bit 16, stride (8-row group) byte offset >> 4 at bit 32, version 1 at bit 46
+__device__ __forceinline__ unsigned long long uc_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  return (unsigned long long)((saddr >> 4) & 0x3fffu) | ((unsigned long long)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((unsigned long long)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ULL << 46);
+}
+
+__device__ __forceinline__ void uc_mma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// bounded spin on an mbarrier phase; returns false on timeout (the kernel then skips its stores and flags the error)
+__device__ __forceinline__ bool uc_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  for (int it = 0; it < (1 << 22) && !ok; ++it)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(uc_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+__host__ __device__ constexpr int uc_tmem_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
+
+inline size_t umma_conv_smem_bytes(int NP, int PW) {
+  return (size_t)2 * 2 * PW * 16 + (size_t)2 * 9 * 2 * NP * 16;      // window (raw, lo) x 2 quads + packed weights of one chunk
+}
+
+__global__ void __launch_bounds__(kUcThreads, 2)
+umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
+  extern __shared__ __align__(128) unsigned char uc_smem[];
+  float4* win = reinterpret_cast<float4*>(uc_smem);                    // [part 2][kq 2][PW]
+  float4* wts = win + 4 * a.PW;                                        // [part 2][tap 9][kq 2][NP]
+  __shared__ unsigned tmem_base_s;
+  __shared__ __align__(8) unsigned long long bar;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Wp = a.W + 2, HW = a.H * a.W;
+  const int d = blockIdx.y;
+  const int q0 = Wp + blockIdx.x * (128 * a.MT);                       // first output position of this CTA (row y = 0 starts at Wp)
+  const int tmem_cols = uc_tmem_cols(a.MT * a.NP);
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(uc_smem_u32(&tmem_base_s)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+
+  // window positions owned by this thread (fixed over the chunks): source pixel offset or -1 for the zero halo
+  constexpr int kMaxPos = (128 * kUcMaxMT + 2 * 2050 + 2 + kUcThreads - 1) / kUcThreads;   // generous bound, loop is runtime
+  (void)kMaxPos;
+  const int npos = (a.PW + kUcThreads - 1) / kUcThreads;
+  // (kept in registers for up to 8 positions per thread; wider windows recompute)
+  int src_off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int p = tid + j * kUcThreads;
+    const int qin = q0 - Wp - 1 + p;
+    const int yy = qin / Wp, xx = qin - yy * Wp;
+    const bool ok = p < a.PW && qin >= 0 && yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
+    src_off[j] = ok ? (yy - 1) * a.W + (xx - 1) : -1;
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = tmem_base_s;
+  const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.NP >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+
+  const int nchunks = a.Cin / kUcKC;
+  const int wts_per_chunk = 2 * 9 * 2 * a.NP;                          // float4
+  bool alive = true;
+  for (int c = 0; c < nchunks; ++c) {
+    if (c > 0) alive = uc_wait(&bar, (unsigned)(c - 1) & 1u) && alive;   // previous chunk's MMAs have read the window and the weights
+    // packed weights of this chunk (contiguous block)
+    {
+      const float4* src = a.wpack + (size_t)c * wts_per_chunk;
+      for (int i = tid; i < wts_per_chunk; i += kUcThreads) wts[i] = __ldg(src + i);
+    }
+    // input window: 8 channels = 2 quads; raw value and low part (x - trunc_tf32(x))
+    {
+      const float* in_c = a.in + (long long)(c * kUcKC) * a.in_cs + (long long)d * HW;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < npos) {
+          const int p = tid + j * kUcThreads;
+          if (p < a.PW) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = src_off[j] >= 0 ? __ldg(in_c + k * a.in_cs + src_off[j]) : 0.0f;
+            float lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) lo[k] = v[k] - __uint_as_float(__float_as_uint(v[k]) & 0xffffe000u);
+            win[0 * a.PW + p] = make_float4(v[0], v[1], v[2], v[3]);
+            win[1 * a.PW + p] = make_float4(v[4], v[5], v[6], v[7]);
+            win[2 * a.PW + p] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            win[3 * a.PW + p] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> tensor-core (async proxy) reads
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned win_s = uc_smem_u32(win), wts_s = uc_smem_u32(wts);
+      const unsigned lbo_a = (unsigned)a.PW * 16u, lbo_b = (unsigned)a.NP * 16u;
+      for (int mt = 0; mt < a.MT; ++mt) {
+        const unsigned dcol = tmem + (unsigned)(mt * a.NP);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = 128 * mt + (tap / 3) * Wp + (tap % 3);     // (dy+1)*Wp + (dx+1)
+          const unsigned a_raw = win_s + (unsigned)shift * 16u, a_lo = a_raw + 2u * lbo_a;
+          const unsigned b_raw = wts_s + (unsigned)(tap * 2 * a.NP) * 16u, b_lo = b_raw + (unsigned)(9 * 2 * a.NP) * 16u;
+          const unsigned first = (c == 0 && tap == 0) ? 0u : 1u;
+          uc_mma_tf32(dcol, uc_desc(a_raw, lbo_a, 128), uc_desc(b_raw, lbo_b, 128), idesc, first);
+          uc_mma_tf32(dcol, uc_desc(a_raw, lbo_a, 128), uc_desc(b_lo, lbo_b, 128), idesc, 1u);
+          uc_mma_tf32(dcol, uc_desc(a_lo, lbo_a, 128), uc_desc(b_raw, lbo_b, 128), idesc, 1u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(uc_smem_u32(&bar)) : "memory");
+    }
+  }
+  alive = uc_wait(&bar, (unsigned)(nchunks - 1) & 1u) && alive;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!alive && tid == 0) atomicExch(error_flag, 1);
+
+  // epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (one output position per thread), tiles mt = w/4, w/4 + 2, ...
+  if (alive) {
+    const int quarter = warp & 3;
+    for (int mt = warp >> 2; mt < a.MT; mt += kUcThreads / 128) {
+      const int q = q0 + 128 * mt + 32 * quarter + lane;
+      const int yy = q / Wp, xx = q - yy * Wp;
+      const bool ok = yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
+      const long long opix = (long long)d * HW + (long long)(yy - 1) * a.W + (xx - 1);
+      for (int h = 0; h < a.nheads; ++h) {
+        const UmmaHead& Hd = a.head[h];
+        for (int c0 = 0; c0 < Hd.Cout; c0 += 8) {
+          unsigned r[8];
+          const unsigned taddr = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)(mt * a.NP + Hd.n0 + c0);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int co = c0 + j;
+              if (co < Hd.Cout) {
+                float v = __uint_as_float(r[j]) * Hd.acc_scale + (Hd.shift ? __ldg(Hd.shift + co) : 0.0f);
+                if (Hd.relu) v = fmaxf(v, 0.0f);
+                Hd.out[(long long)co * a.D * HW + opix] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+}
+
+// Plan + launch.  Returns -1 when the layer does not fit this kernel (the caller then uses the direct FFMA kernel).
+struct UmmaConvPlan { UmmaConv2d conv; UmmaPack pack; size_t smem; size_t wpack_bytes; dim3 grid; };
+
+inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, int Cin, int D, int H, int W,
+                           int nheads, const UmmaPackHead* wheads, const UmmaHead* oheads, void* wpack_buf, size_t wpack_cap) {
+  if (Cin % kUcKC || nheads < 1 || nheads > kUcMaxHeads) return false;
+  int n = 0;
+  P = UmmaConvPlan{};
+  for (int h = 0; h < nheads; ++h) {
+    P.pack.head[h] = wheads[h]; P.pack.head[h].n0 = n;
+    P.conv.head[h] = oheads[h]; P.conv.head[h].n0 = n;
+    if (wheads[h].Cout != oheads[h].Cout || wheads[h].Cout % 8) return false;
+    n += wheads[h].Cout;
+  }
+  const int NP = (n + 15) / 16 * 16;
+  if (NP > 256) return false;
+  const int Wp = W + 2;
+  int MT = kUcMaxMT;
+  while (MT > 1 && (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, 128 * MT + 2 * Wp + 2) > 100 * 1024)) MT >>= 1;
+  const int PW = 128 * MT + 2 * Wp + 2;
+  if (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, PW) > 100 * 1024) return false;   // 2 CTAs per SM or nothing
+  if (PW > 8 * kUcThreads || (size_t)PW * 16 >= (1u << 18)) return false;
+  P.wpack_bytes = (size_t)(Cin / kUcKC) * 2 * 9 * 2 * NP * 16;
+  if (wpack_buf == nullptr || wpack_cap < P.wpack_bytes || (reinterpret_cast<uintptr_t>(wpack_buf) & 15)) return false;
+  P.pack.nheads = nheads; P.pack.Cin = Cin; P.pack.NP = NP; P.pack.out = static_cast<float4*>(wpack_buf);
+  P.conv.in = in; P.conv.in_cs = in_cs; P.conv.wpack = static_cast<const float4*>(wpack_buf);
+  P.conv.Cin = Cin; P.conv.D = D; P.conv.H = H; P.conv.W = W; P.conv.NP = NP; P.conv.MT = MT; P.conv.PW = PW; P.conv.nheads = nheads;
+  P.smem = umma_conv_smem_bytes(NP, PW);
+  P.grid = dim3(ceil_div((long long)H * Wp, 128 * MT), D, 1);
+  return true;
+}
+
+inline int umma_conv_launch(const UmmaConvPlan& P, int* error_flag, cudaStream_t st, const char* what) {
+  const int total = (P.pack.Cin / kUcKC) * 2 * 9 * 2 * P.pack.NP;
+  umma_pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(P.pack);
+  static thread_local int ready_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (ready_dev != dev) { cudaFuncSetAttribute(umma_conv2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); ready_dev = dev; }
+  umma_conv2d_kernel<<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  return check_launch(what);
+}
+
+}  // namespace satmvs
