@@ -22,6 +22,7 @@
 // tcgen05.ld (32 lanes x 32 bit, one row = one position per thread) and the epilogue (scale, bias, ReLU) stores
 // coalesced rows of the NCDHW outputs.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace satmvs {
@@ -95,6 +96,12 @@ __device__ __forceinline__ void uc_mma_tf32(unsigned tmem_d, unsigned long long 
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ bool uc_elect_one() {
+  unsigned pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // bounded spin on an mbarrier phase; returns false on timeout (the kernel then skips its stores and flags the error)
 __device__ __forceinline__ bool uc_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok = 0;
@@ -110,13 +117,14 @@ inline size_t umma_conv_smem_bytes(int NP, int PW) {
   return (size_t)2 * 2 * PW * 16 + (size_t)2 * 9 * 2 * NP * 16;      // window (raw, lo) x 2 quads + packed weights of one chunk
 }
 
-__global__ void __launch_bounds__(kUcThreads, 2)
+template <int NPOS>      // window positions per thread: 4 (PW <= 1024, 3 CTAs per SM) or 8 (PW <= 2048, 2 CTAs per SM)
+__global__ void __launch_bounds__(kUcThreads, NPOS == 4 ? 3 : 2)
 umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
   extern __shared__ __align__(128) unsigned char uc_smem[];
   float4* win = reinterpret_cast<float4*>(uc_smem);                    // [part 2][kq 2][PW]
   float4* wts = win + 4 * a.PW;                                        // [part 2][tap 9][kq 2][NP]
   __shared__ unsigned tmem_base_s;
-  __shared__ __align__(8) unsigned long long bar;
+  __shared__ __align__(8) unsigned long long bar, wbar;                // MMAs of a chunk done / packed weights of a chunk landed
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Wp = a.W + 2, HW = a.H * a.W;
@@ -126,6 +134,7 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
 
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&wbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -133,20 +142,28 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
 
-  // window positions owned by this thread (fixed over the chunks): source pixel offset or -1 for the zero halo
-  constexpr int kMaxPos = (128 * kUcMaxMT + 2 * 2050 + 2 + kUcThreads - 1) / kUcThreads;   // generous bound, loop is runtime
-  (void)kMaxPos;
-  const int npos = (a.PW + kUcThreads - 1) / kUcThreads;
-  // (kept in registers for up to 8 positions per thread; wider windows recompute)
-  int src_off[8];
+  // window positions owned by this thread (fixed over the chunks): source pixel offset, or -1 for the zero halo
+  int src_off[NPOS];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NPOS; ++j) {
     const int p = tid + j * kUcThreads;
     const int qin = q0 - Wp - 1 + p;
     const int yy = qin / Wp, xx = qin - yy * Wp;
     const bool ok = p < a.PW && qin >= 0 && yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
     src_off[j] = ok ? (yy - 1) * a.W + (xx - 1) : -1;
   }
+  // 8 channels of a chunk for this thread's positions, global -> registers (all loads in flight together)
+  float v[NPOS][kUcKC];
+  auto load_chunk = [&](int c) {
+    const float* in_c = a.in + (long long)(c * kUcKC) * a.in_cs + (long long)d * HW;
+#pragma unroll
+    for (int k = 0; k < kUcKC; ++k) {
+      const float* in_k = in_c + k * a.in_cs;
+#pragma unroll
+      for (int j = 0; j < NPOS; ++j) v[j][k] = src_off[j] >= 0 ? __ldg(in_k + src_off[j]) : 0.0f;
+    }
+  };
+  load_chunk(0);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -155,73 +172,76 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
   const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.NP >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
 
   const int nchunks = a.Cin / kUcKC;
-  const int wts_per_chunk = 2 * 9 * 2 * a.NP;                          // float4
+  const unsigned wts_bytes = (unsigned)(2 * 9 * 2 * a.NP) * 16u;      // packed weights of one chunk
   bool alive = true;
   for (int c = 0; c < nchunks; ++c) {
     if (c > 0) alive = uc_wait(&bar, (unsigned)(c - 1) & 1u) && alive;   // previous chunk's MMAs have read the window and the weights
-    // packed weights of this chunk (contiguous block)
-    {
-      const float4* src = a.wpack + (size_t)c * wts_per_chunk;
-      for (int i = tid; i < wts_per_chunk; i += kUcThreads) wts[i] = __ldg(src + i);
+    if (tid == 0) {   // packed weights of this chunk: one TMA bulk copy (async proxy -> async proxy, no generic fence needed)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(uc_smem_u32(&wbar)), "r"(wts_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(uc_smem_u32(wts)), "l"(reinterpret_cast<const char*>(a.wpack) + (size_t)c * wts_bytes), "r"(wts_bytes),
+                     "r"(uc_smem_u32(&wbar)) : "memory");
     }
-    // input window: 8 channels = 2 quads; raw value and low part (x - trunc_tf32(x))
-    {
-      const float* in_c = a.in + (long long)(c * kUcKC) * a.in_cs + (long long)d * HW;
+    // window of this chunk: registers -> shared memory, raw value and low part (x - trunc_tf32(x))
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < npos) {
-          const int p = tid + j * kUcThreads;
-          if (p < a.PW) {
-            float v[8];
+    for (int j = 0; j < NPOS; ++j) {
+      const int p = tid + j * kUcThreads;
+      if (p < a.PW) {
+        float lo[kUcKC];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = src_off[j] >= 0 ? __ldg(in_c + k * a.in_cs + src_off[j]) : 0.0f;
-            float lo[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) lo[k] = v[k] - __uint_as_float(__float_as_uint(v[k]) & 0xffffe000u);
-            win[0 * a.PW + p] = make_float4(v[0], v[1], v[2], v[3]);
-            win[1 * a.PW + p] = make_float4(v[4], v[5], v[6], v[7]);
-            win[2 * a.PW + p] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            win[3 * a.PW + p] = make_float4(lo[4], lo[5], lo[6], lo[7]);
-          }
-        }
+        for (int k = 0; k < kUcKC; ++k) lo[k] = v[j][k] - __uint_as_float(__float_as_uint(v[j][k]) & 0xffffe000u);
+        win[0 * a.PW + p] = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+        win[1 * a.PW + p] = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
+        win[2 * a.PW + p] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        win[3 * a.PW + p] = make_float4(lo[4], lo[5], lo[6], lo[7]);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> tensor-core (async proxy) reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && uc_elect_one()) {   // one elected lane of a converged warp: the MMAs issue as straight uniform-datapath code
+      alive = uc_wait(&wbar, (unsigned)c & 1u) && alive;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned win_s = uc_smem_u32(win), wts_s = uc_smem_u32(wts);
+      // descriptors differ only in their start-address field (low word): one add per MMA
       const unsigned lbo_a = (unsigned)a.PW * 16u, lbo_b = (unsigned)a.NP * 16u;
+      const unsigned long long da0 = uc_desc(uc_smem_u32(win), lbo_a, 128), db0 = uc_desc(uc_smem_u32(wts), lbo_b, 128);
+      const unsigned a_lo_off = 2u * (unsigned)a.PW, b_lo_off = (unsigned)(9 * 2 * a.NP), b_tap = (unsigned)(2 * a.NP);   // 16-byte units
       for (int mt = 0; mt < a.MT; ++mt) {
         const unsigned dcol = tmem + (unsigned)(mt * a.NP);
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int shift = 128 * mt + (tap / 3) * Wp + (tap % 3);     // (dy+1)*Wp + (dx+1)
-          const unsigned a_raw = win_s + (unsigned)shift * 16u, a_lo = a_raw + 2u * lbo_a;
-          const unsigned b_raw = wts_s + (unsigned)(tap * 2 * a.NP) * 16u, b_lo = b_raw + (unsigned)(9 * 2 * a.NP) * 16u;
-          const unsigned first = (c == 0 && tap == 0) ? 0u : 1u;
-          uc_mma_tf32(dcol, uc_desc(a_raw, lbo_a, 128), uc_desc(b_raw, lbo_b, 128), idesc, first);
-          uc_mma_tf32(dcol, uc_desc(a_raw, lbo_a, 128), uc_desc(b_lo, lbo_b, 128), idesc, 1u);
-          uc_mma_tf32(dcol, uc_desc(a_lo, lbo_a, 128), uc_desc(b_raw, lbo_b, 128), idesc, 1u);
+          const unsigned shift = (unsigned)(128 * mt + (tap / 3) * Wp + (tap % 3));   // (dy+1)*Wp + (dx+1), 16-byte units
+          const unsigned long long a_raw = da0 + shift, a_lo = a_raw + a_lo_off;
+          const unsigned long long b_raw = db0 + (unsigned)tap * b_tap, b_lo = b_raw + b_lo_off;
+          uc_mma_tf32(dcol, a_raw, b_raw, idesc, (c == 0 && tap == 0) ? 0u : 1u);
+          uc_mma_tf32(dcol, a_raw, b_lo, idesc, 1u);
+          uc_mma_tf32(dcol, a_lo, b_raw, idesc, 1u);
         }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(uc_smem_u32(&bar)) : "memory");
     }
+    __syncwarp();
+    if (c + 1 < nchunks) load_chunk(c + 1);      // the next chunk's global loads fly while the tensor core works on this one
   }
   alive = uc_wait(&bar, (unsigned)(nchunks - 1) & 1u) && alive;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (!alive && tid == 0) atomicExch(error_flag, 1);
+  if (!alive) {            // a tensor-core completion never arrived: fail loudly (sticky CUDA error) instead of storing garbage
+    if (tid == 0) atomicExch(error_flag, 1);
+    __trap();
+  }
 
   // epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (one output position per thread), tiles mt = w/4, w/4 + 2, ...
-  if (alive) {
+  {
     const int quarter = warp & 3;
     for (int mt = warp >> 2; mt < a.MT; mt += kUcThreads / 128) {
       const int q = q0 + 128 * mt + 32 * quarter + lane;
       const int yy = q / Wp, xx = q - yy * Wp;
-      const bool ok = yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
+      const bool ok = alive && yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
       const long long opix = (long long)d * HW + (long long)(yy - 1) * a.W + (xx - 1);
       for (int h = 0; h < a.nheads; ++h) {
         const UmmaHead& Hd = a.head[h];
+        float* op = Hd.out + opix;
+        const long long ocs = (long long)a.D * HW;
         for (int c0 = 0; c0 < Hd.Cout; c0 += 8) {
           unsigned r[8];
           const unsigned taddr = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)(mt * a.NP + Hd.n0 + c0);
@@ -231,12 +251,9 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
           if (ok) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int co = c0 + j;
-              if (co < Hd.Cout) {
-                float v = __uint_as_float(r[j]) * Hd.acc_scale + (Hd.shift ? __ldg(Hd.shift + co) : 0.0f);
-                if (Hd.relu) v = fmaxf(v, 0.0f);
-                Hd.out[(long long)co * a.D * HW + opix] = v;
-              }
+              float val = __uint_as_float(r[j]) * Hd.acc_scale + (Hd.shift ? __ldg(Hd.shift + c0 + j) : 0.0f);
+              if (Hd.relu) val = fmaxf(val, 0.0f);
+              op[(long long)(c0 + j) * ocs] = val;
             }
           }
         }
@@ -265,8 +282,19 @@ inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, in
   const int NP = (n + 15) / 16 * 16;
   if (NP > 256) return false;
   const int Wp = W + 2;
-  int MT = kUcMaxMT;
-  while (MT > 1 && (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, 128 * MT + 2 * Wp + 2) > 100 * 1024)) MT >>= 1;
+  // prefer 3 CTAs per SM (<= 74 KB of shared memory, <= 128 TMEM columns, <= 1024 window positions): co-resident CTAs are
+  // what overlaps one CTA's staging with another's MMAs; else 2 CTAs per SM
+  static const int want3 = getenv("SATMVS_UMMA_2CTA") ? 0 : 1;
+  int MT = 0;
+  if (want3)
+    for (int m = kUcMaxMT; m >= 1 && MT == 0; --m) {
+      const int pw = 128 * m + 2 * Wp + 2;
+      if (uc_tmem_cols(m * NP) <= 128 && umma_conv_smem_bytes(NP, pw) <= 74 * 1024 && pw <= 4 * kUcThreads) MT = m;
+    }
+  if (MT == 0) {
+    MT = kUcMaxMT;
+    while (MT > 1 && (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, 128 * MT + 2 * Wp + 2) > 100 * 1024)) MT >>= 1;
+  }
   const int PW = 128 * MT + 2 * Wp + 2;
   if (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, PW) > 100 * 1024) return false;   // 2 CTAs per SM or nothing
   if (PW > 8 * kUcThreads || (size_t)PW * 16 >= (1u << 18)) return false;
@@ -286,8 +314,13 @@ inline int umma_conv_launch(const UmmaConvPlan& P, int* error_flag, cudaStream_t
   static thread_local int ready_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (ready_dev != dev) { cudaFuncSetAttribute(umma_conv2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); ready_dev = dev; }
-  umma_conv2d_kernel<<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  if (ready_dev != dev) {
+    cudaFuncSetAttribute(umma_conv2d_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(umma_conv2d_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    ready_dev = dev;
+  }
+  if (P.conv.PW <= 4 * kUcThreads) umma_conv2d_kernel<4><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  else umma_conv2d_kernel<8><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
   return check_launch(what);
 }
 
