@@ -66,6 +66,7 @@ struct RedPlan {
   double* stats;         // [D][4][3][2]
   char* wpack[4]; size_t wpack_bytes[4];
   int* umma_err;
+  int* fuse_cnt;
   size_t bytes;
 };
 
@@ -102,6 +103,8 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   }
   p.umma_err = reinterpret_cast<int*>(base + off);
   off += 256;
+  p.fuse_cnt = reinterpret_cast<int*>(base + off);           // [D][4][2] level-barrier counters of the fused pointwise tails
+  off += ((size_t)D * 4 * 2 * sizeof(int) + 255) / 256 * 256;
   p.bytes = off;
   return p;
 }
@@ -191,6 +194,19 @@ struct GruConvLevel {
   int ci_per_warp;                          // cin / ksplit (4 or 8)
   int px_groups;                            // CTAs per output-channel chunk
   int cta_begin;
+  // Fused pointwise tail (0 = none).  The GroupNorm that follows the conv needs the sums of the WHOLE level, so the
+  // CTAs of a level meet at a spin barrier in global memory (all CTAs of the launch are co-resident: checked by the
+  // host) and then apply the pointwise step to the outputs they still hold in registers:
+  //   1 (gate conv, r half only)  rh = sigmoid(GN_r(G_r)) * h                      (module.py:33-43)
+  //   2 (output conv)             h' = u*h + (1-u)*tanh(GN_o(O)), u = sigmoid(GN_u(G_u))   (module.py:46-57)
+  int fuse;
+  int* fuse_counter; int fuse_expected;
+  double fuse_inv_n;
+  const float *fuse_nw, *fuse_nb;           // GroupNorm affine of r (1) / o (2)
+  const float *fuse_uw, *fuse_ub;           // GroupNorm affine of u (2)
+  const float* fuse_h; long long fuse_h_cs; // current state
+  const float* fuse_gu; long long fuse_g_cs;// u-gate pre-activations of this plane (2)
+  float* fuse_dst; long long fuse_dst_cs;   // rh (1) / next state (2)
 };
 struct GruConvArgs { GruConvLevel l[4]; };
 
@@ -394,6 +410,7 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
   tick(2);
   // fixed-order reduction over the k-parts, epilogue, GroupNorm sums
   float ssum = 0.0f, ssq = 0.0f;
+  float vals[kMaxOut / 2];
   auto epilogue = [&](auto ks_tag) {
     constexpr int KS = decltype(ks_tag)::value;
 #pragma unroll
@@ -408,6 +425,7 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
         const float val = sum + pre[r];
         L.out[(long long)(co0 + i) * L.out_cs + p] = val;
         ssum += val; ssq += val * val;
+        vals[r] = val;
       }
     }
   };
@@ -428,6 +446,60 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
     atomicAdd(L.stats + 2 * grp + 1, q);
   }
   tick(4);
+
+  // ---- fused pointwise tail ----
+  if (L.fuse == 0 || (L.fuse == 1 && co0 >= L.stats_group)) return;      // the u half of the gates has no tail
+  // operands that do not depend on the level's sums: fetched before the barrier
+  const int KS = L.ksplit, nout = kMaxOut / KS;
+  float hv[kMaxOut / 2], gv[kMaxOut / 2];
+#pragma unroll
+  for (int r = 0; r < kMaxOut / 2; ++r) {
+    hv[r] = 0.0f; gv[r] = 0.0f;
+    if (r < nout) {
+      const int q = r * kRows + row_l;
+      const int p = (tile0 + (q >> 3)) * kGcTilePx + px_l;
+      if (p < npx) {
+        const int c = co0 + (q & 7);
+        hv[r] = __ldcg(L.fuse_h + (long long)c * L.fuse_h_cs + p);
+        if (L.fuse == 2) gv[r] = __ldcg(L.fuse_gu + (long long)c * L.fuse_g_cs + p);
+      }
+    }
+  }
+  if (tid == 0) {   // level barrier: this CTA's sums are published (fence) before it announces itself
+    __threadfence();
+    atomicAdd(L.fuse_counter, 1);
+    while (*reinterpret_cast<volatile int*>(L.fuse_counter) < L.fuse_expected) { }
+    __threadfence();
+  }
+  __syncthreads();
+  const double* st = L.stats;                                   // gate conv: r sums at +0; output conv: o sums (u sums at -2)
+  const double m0 = __ldcg(st) * L.fuse_inv_n;
+  const float rstd0 = rsqrtf((float)fmax(__ldcg(st + 1) * L.fuse_inv_n - m0 * m0, 0.0) + kGnEps);
+  double m1 = 0.0; float rstd1 = 0.0f;
+  if (L.fuse == 2) {
+    m1 = __ldcg(st - 2) * L.fuse_inv_n;
+    rstd1 = rsqrtf((float)fmax(__ldcg(st - 1) * L.fuse_inv_n - m1 * m1, 0.0) + kGnEps);
+  }
+#pragma unroll
+  for (int r = 0; r < kMaxOut / 2; ++r) {
+    if (r < nout) {
+      const int q = r * kRows + row_l;
+      const int p = (tile0 + (q >> 3)) * kGcTilePx + px_l;
+      if (p < npx) {
+        const int c = co0 + (q & 7);
+        const float a0 = __ldg(L.fuse_nw + c) * rstd0, b0 = __ldg(L.fuse_nb + c) - (float)m0 * a0;
+        float res;
+        if (L.fuse == 1) {
+          res = sigmoidf_(fmaf(vals[r], a0, b0)) * hv[r];
+        } else {
+          const float a1 = __ldg(L.fuse_uw + c) * rstd1, b1 = __ldg(L.fuse_ub + c) - (float)m1 * a1;
+          const float u = sigmoidf_(fmaf(gv[r], a1, b1));
+          res = u * hv[r] + (1.0f - u) * tanhf(fmaf(vals[r], a0, b0));       // module.py:57
+        }
+        L.fuse_dst[(long long)c * L.fuse_dst_cs + p] = res;
+      }
+    }
+  }
 }
 
 template <bool kAligned>
@@ -501,7 +573,7 @@ red_recurrence_kernel(const __grid_constant__ RecArgs a) {
   };
   auto conv_level = [&](int li, int d, bool p2) {
     const RecLevel& R = a.l[li];
-    GruConvLevel L;
+    GruConvLevel L{};
     L.cin = R.ch; L.h = R.h; L.w_ = R.w; L.stats_group = R.ch;
     L.ksplit = R.ksplit; L.ci_per_warp = R.ci_per_warp; L.w_co = R.w_co; L.cta_begin = 0;
     double* st = a.stats + ((size_t)d * 4 + li) * 6;
@@ -750,6 +822,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 
   cudaMemsetAsync(P.stats, 0, (size_t)D * 4 * 3 * 2 * sizeof(double), st);
+  cudaMemsetAsync(P.fuse_cnt, 0, (size_t)D * 4 * 2 * sizeof(int), st);
   for (int l = 0; l < 4; ++l) {   // slot 0 of the state history = the initial hidden state (zeros, module.py:617-620)
     RedLevel& L = P.lv[l];
     const size_t px = (size_t)L.h * L.w;
@@ -844,6 +917,25 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     }
   }
   static const bool pdl = getenv("SATMVS_RED_NO_PDL") == nullptr;
+  // Fused pointwise tails (opt-in, SATMVS_RED_FUSE=1) need every CTA of a launch co-resident: their level barrier spins in
+  // global memory.  Measured at cfg-2: 3.29 ms/step fused against 2.90 ms with the four-kernel PDL chain -- the conv CTAs
+  // (128 registers, 2 per SM) now live through the barrier and the tail, so the next conv's CTAs cannot become resident
+  // early and its weight staging is no longer hidden (profiles/r01_red_recurrence_notes.md).
+  static const bool want_fuse = getenv("SATMVS_RED_FUSE") != nullptr;
+  int resident_ctas = 0;
+  if (want_fuse) {
+    bool aligned = true;
+    for (int l = 0; l < 4; ++l) aligned = aligned && (P.lv[l].w % kGcPx == 0);
+    constexpr size_t smem = (64 * 9 * kGcCo + kGcWarps * kGcCo * kGcTilePx) * sizeof(float);
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(gru_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void* fn = aligned ? (const void*)gru_conv_kernel<true> : (const void*)gru_conv_kernel<false>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGcThreads, smem) == cudaSuccess) resident_ctas = per_sm * sms;
+    else cudaGetLastError();
+  }
   for (int d = 0; d < D && !persistent; ++d) {
     GruConvArgs c1{}, c2{};
     GruArgs ga{};
@@ -880,6 +972,29 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       total += L.ch * (int)px;
     }
     ga.total = total;
+    const bool fuse = want_fuse && ctas1 <= resident_ctas && ctas2 <= resident_ctas;
+    if (fuse) {
+      for (int l = 0; l < 4; ++l) {
+        RedLevel& L = P.lv[l];
+        const size_t px = (size_t)L.h * L.w;
+        GruConvLevel &a = c1.l[l], &b = c2.l[l];
+        a.fuse = 1; b.fuse = 2;
+        a.fuse_counter = P.fuse_cnt + ((size_t)d * 4 + l) * 2; b.fuse_counter = a.fuse_counter + 1;
+        a.fuse_expected = a.px_groups * (L.ch / kGcCo);      // the CTAs of the r half
+        b.fuse_expected = b.px_groups * (L.ch / kGcCo);
+        a.fuse_inv_n = b.fuse_inv_n = 1.0 / ((double)L.ch * (double)px);
+        a.fuse_nw = wt->rn_w[l]; a.fuse_nb = wt->rn_b[l];
+        b.fuse_nw = wt->on_w[l]; b.fuse_nb = wt->on_b[l]; b.fuse_uw = wt->un_w[l]; b.fuse_ub = wt->un_b[l];
+        a.fuse_h = b.fuse_h = L.s + (size_t)d * px; a.fuse_h_cs = b.fuse_h_cs = (long long)(D + 1) * px;
+        b.fuse_gu = L.gx + (size_t)d * px + (size_t)L.ch * D * px; b.fuse_g_cs = (long long)D * px;
+        a.fuse_dst = L.rh; a.fuse_dst_cs = (long long)px;
+        b.fuse_dst = L.s + (size_t)(d + 1) * px; b.fuse_dst_cs = (long long)(D + 1) * px;
+      }
+      // two launches per plane: gate conv + r*h, output conv + state update
+      { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates + reset)", pdl && d > 0)); }
+      { ProfScope prof(kProfGruOutput, st); RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output + update)", pdl)); }
+      continue;
+    }
     // the first gate conv follows the batched launches (plain stream order); everything after it is chained
     { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)", pdl && d > 0)); }
     { ProfScope prof(kProfGruPointwise, st);
