@@ -858,6 +858,17 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
         RUN(umma_conv_launch(up, P.umma_err, st, "red gate/output x-halves (tcgen05)"));
         continue;
       }
+      // the fused N does not fit (level 4: 192 columns of packed weights): one launch per head
+      UmmaConvPlan ug, uo;
+      const size_t half = (P.wpack_bytes[l] * 2 / 3 + 255) / 256 * 256;
+      if (umma_conv_plan(ug, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 1, wh, oh, P.wpack[l], half) &&
+          umma_conv_plan(uo, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 1, wh + 1, oh + 1, P.wpack[l] + half,
+                         P.wpack_bytes[l] - half)) {
+        ProfScope prof(kProfConvBatched, st);
+        RUN(umma_conv_launch(ug, P.umma_err, st, "red gate x-half (tcgen05)"));
+        RUN(umma_conv_launch(uo, P.umma_err, st, "red output x-half (tcgen05)"));
+        continue;
+      }
     }
     ConvProblem g = plane_conv(xin[l], L.cx, D, L.h, L.w, wt->gate_w[l], kin, 9, L.gx, 2 * L.ch, D, L.h, L.w, 1);
     g.Qd = D; g.Qh = L.h; g.Qw = L.w;
