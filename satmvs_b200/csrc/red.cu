@@ -98,7 +98,7 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   off += ((size_t)D * 4 * 3 * 2 * sizeof(double) + 64 * sizeof(double) + 255) / 256 * 256;   // + 64 debug counters
   for (int l = 0; l < 4; ++l) {   // packed (raw, lo) x-half weights of the tensor-core convs, per level
     p.wpack[l] = base + off;
-    p.wpack_bytes[l] = (size_t)(p.lv[l].cx / 8 + 1) * 2 * 9 * 2 * ((3 * p.lv[l].ch + 15) / 16 * 16) * 16;
+    p.wpack_bytes[l] = (size_t)(p.lv[l].cx / 8 + 1) * 2 * 9 * 2 * ((5 * p.lv[l].ch + 15) / 16 * 16) * 16;   // gates 2ch + output ch + encoder 2ch
     off += (p.wpack_bytes[l] + 255) / 256 * 256;
   }
   p.umma_err = reinterpret_cast<int*>(base + off);
@@ -835,24 +835,38 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
   // ---- A. batched over all planes ----
   const int ech[4] = {C, 16, 32, 64};
   const float* xin[4] = {volume, P.e[0], P.e[1], P.e[2]};
-  for (int i = 0; i < 3; ++i) {   // ConvReLU stride 2 (module.py:627-629); conv1 sees -cost
+  // encoder i: ConvReLU stride 2 (module.py:627-629); conv1 sees -cost.  Run by the direct kernel unless the level's
+  // tensor-core launch below takes it as a third head.
+  auto run_encoder = [&](int i) -> int {
     ConvProblem p = plane_conv(xin[i], ech[i], D, H >> i, W >> i, wt->conv_w[i], (long long)ech[i] * 9, 9,
                                P.e[i], ech[i + 1], D, H >> (i + 1), W >> (i + 1), 2);
     p.Qd = D; p.Qh = H >> (i + 1); p.Qw = W >> (i + 1);
     p.relu = 1;
     p.acc_scale = (i == 0) ? -1.0f : 1.0f;
-    { ProfScope prof(kProfConvBatched, st); RUN(launch_plane_conv(p, 2, st, "red encoder")); }
-  }
+    ProfScope prof(kProfConvBatched, st);
+    return launch_plane_conv(p, 2, st, "red encoder");
+  };
   static const bool no_umma = getenv("SATMVS_NO_UMMA") != nullptr;
   for (int l = 0; l < 4; ++l) {   // x-halves of the GRU convolutions, bias folded in (module.py:29-30, :44-45)
     RedLevel& L = P.lv[l];
     const long long kin = (long long)(L.cx + L.ch) * 9;
     if (!no_umma) {
-      // gate and output x-halves share their input: one tensor-core launch with two heads (umma_conv.cuh)
-      UmmaPackHead wh[2] = {{wt->gate_w[l], kin, 9, 2 * L.ch, 0}, {wt->out_w[l], kin, 9, L.ch, 0}};
+      // gate and output x-halves share their input (and so does the stride-2 encoder that feeds the next level):
+      // one tensor-core launch with two or three heads (umma_conv.cuh)
       const float sgn = (l == 0) ? -1.0f : 1.0f;
-      UmmaHead oh[2] = {{wt->gate_b[l], L.gx, 2 * L.ch, 0, sgn, 0}, {wt->out_b[l], L.ox, L.ch, 0, sgn, 0}};
+      UmmaPackHead wh[3] = {{wt->gate_w[l], kin, 9, 2 * L.ch, 0}, {wt->out_w[l], kin, 9, L.ch, 0}, {nullptr, 0, 0, 0, 0}};
+      UmmaHead oh[3] = {{wt->gate_b[l], L.gx, 2 * L.ch, 0, sgn, 0, 1}, {wt->out_b[l], L.ox, L.ch, 0, sgn, 0, 1}, {}};
       UmmaConvPlan up;
+      if (l < 3) {
+        wh[2] = UmmaPackHead{wt->conv_w[l], (long long)ech[l] * 9, 9, ech[l + 1], 0};
+        oh[2] = UmmaHead{nullptr, P.e[l], ech[l + 1], 0, sgn, 1, 2};
+        if (umma_conv_plan(up, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 3, wh, oh, P.wpack[l], P.wpack_bytes[l])) {
+          ProfScope prof(kProfConvBatched, st);
+          RUN(umma_conv_launch(up, P.umma_err, st, "red gate/output x-halves + encoder (tcgen05)"));
+          continue;
+        }
+        RUN(run_encoder(l));
+      }
       if (umma_conv_plan(up, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 2, wh, oh, P.wpack[l], P.wpack_bytes[l])) {
         ProfScope prof(kProfConvBatched, st);
         RUN(umma_conv_launch(up, P.umma_err, st, "red gate/output x-halves (tcgen05)"));
@@ -870,6 +884,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
         continue;
       }
     }
+    if (no_umma && l < 3) RUN(run_encoder(l));
     ConvProblem g = plane_conv(xin[l], L.cx, D, L.h, L.w, wt->gate_w[l], kin, 9, L.gx, 2 * L.ch, D, L.h, L.w, 1);
     g.Qd = D; g.Qh = L.h; g.Qw = L.w;
     g.shift = wt->gate_b[l];

@@ -36,6 +36,8 @@ struct UmmaHead {
   int n0;                  // first column of this head in the fused N dimension
   float acc_scale;
   int relu;
+  int stride;              // 1, or 2: only even (y, x) are stored, into a [Cout][D][H/2][W/2] tensor (a stride-2 conv shares
+                           // its input window with the stride-1 heads; the unused 3/4 of its columns cost no extra staging)
 };
 
 struct UmmaConv2d {
@@ -236,12 +238,15 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
     for (int mt = warp >> 2; mt < a.MT; mt += kUcThreads / 128) {
       const int q = q0 + 128 * mt + 32 * quarter + lane;
       const int yy = q / Wp, xx = q - yy * Wp;
-      const bool ok = alive && yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
-      const long long opix = (long long)d * HW + (long long)(yy - 1) * a.W + (xx - 1);
+      const bool ok1 = alive && yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
+      const long long opix1 = (long long)d * HW + (long long)(yy - 1) * a.W + (xx - 1);
+      const bool ok2 = ok1 && !((yy - 1) & 1) && !((xx - 1) & 1);
+      const long long opix2 = (long long)d * (HW >> 2) + (long long)((yy - 1) >> 1) * (a.W >> 1) + ((xx - 1) >> 1);
       for (int h = 0; h < a.nheads; ++h) {
         const UmmaHead& Hd = a.head[h];
-        float* op = Hd.out + opix;
-        const long long ocs = (long long)a.D * HW;
+        const bool ok = Hd.stride == 2 ? ok2 : ok1;
+        float* op = Hd.out + (Hd.stride == 2 ? opix2 : opix1);
+        const long long ocs = (long long)a.D * (Hd.stride == 2 ? (HW >> 2) : HW);
         for (int c0 = 0; c0 < Hd.Cout; c0 += 8) {
           unsigned r[8];
           const unsigned taddr = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)(mt * a.NP + Hd.n0 + c0);
