@@ -10,6 +10,7 @@
 // of its 8 output-parity classes, so no multiply ever touches a structural zero), 1 head conv.
 #include "conv_engine.cuh"
 #include "direct_conv.cuh"
+#include "umma_conv.cuh"
 #include "prof.cuh"
 
 namespace satmvs {
@@ -82,7 +83,12 @@ static int run_deconv3d(const float* in, int Cin, int Di, int Hi, int Wi, const 
   return conv_launch<Tile8>(g, st, "costreg deconv");
 }
 
-struct CostRegPlan { float* c[7]; float* x7; float* x9; float* x11; size_t bytes; };
+struct CostRegPlan {
+  float* c[7]; float* x7; float* x9; float* x11;
+  char* wpack[5]; size_t wpack_bytes[5];       // packed (raw, lo) weights of the tensor-core layers: conv0, conv2, conv4, conv6, prob
+  int* umma_err;
+  size_t bytes;
+};
 
 static CostRegPlan costreg_plan(int base, int D, int H, int W, char* mem) {
   CostRegPlan p{};
@@ -94,6 +100,15 @@ static CostRegPlan costreg_plan(int base, int D, int H, int W, char* mem) {
   p.c[3] = take(4 * base * v2); p.c[4] = take(4 * base * v2);
   p.c[5] = take(8 * base * v3); p.c[6] = take(8 * base * v3);
   p.x7 = take(4 * base * v2); p.x9 = take(2 * base * v1); p.x11 = take(base * v0);
+  // (Cin / 8) x 3 planes x (raw, lo) x 9 taps x 2 quads x N (padded to 16) float4; conv0's Cin is bounded by 64 here
+  const int wcin[5] = {64, 2 * base, 4 * base, 8 * base, base}, wn[5] = {base, 2 * base, 4 * base, 8 * base, 1};
+  for (int i = 0; i < 5; ++i) {
+    p.wpack_bytes[i] = (size_t)((wcin[i] + 7) / 8) * 3 * 2 * 9 * 2 * ((wn[i] + 15) / 16 * 16) * 16;
+    p.wpack[i] = mem + off;
+    off += (p.wpack_bytes[i] + 255) / 256 * 256;
+  }
+  p.umma_err = reinterpret_cast<int*>(mem + off);
+  off += 256;
   p.bytes = off;
   return p;
 }
@@ -125,7 +140,25 @@ int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int
   const int stride[7] = {1, 2, 1, 2, 1, 2, 1};
   const float* cur = x;
   int d = D, h = H, w = W;
+  static const bool no_umma = getenv("SATMVS_NO_UMMA") != nullptr;
+  // dense stride-1 3x3x3 layer on the tensor cores (umma_conv.cuh); false when the shape does not fit
+  auto try_umma = [&](int slot, const float* in, int ci, int dd, int hh, int ww, const float* wgt, const float* scale,
+                      const float* shift, int relu, float* o, int co) -> int {
+    // Small-N 27-tap layers (conv0: N 8, prob: N 1) are bound by the 27 x 3 re-reads of the A operand from shared memory
+    // (335 us against 284 us for the direct FFMA kernel at cfg-2): tensor cores only from 16 output channels up.
+    if (no_umma || co < 16) return -1;
+    UmmaPackHead wh{wgt, (long long)ci * 27, 27, co, 0};
+    UmmaHead oh{scale, shift, o, co, 0, 1.0f, relu, 1};
+    UmmaConvPlan up;
+    if (!umma_conv_plan(up, in, (long long)dd * hh * ww, ci, dd, hh, ww, 1, &wh, &oh, P.wpack[slot], P.wpack_bytes[slot], 3)) return -1;
+    return umma_conv_launch(up, P.umma_err, st, "costreg conv (tcgen05)");
+  };
   for (int i = 0; i < 7; ++i) {
+    if (stride[i] == 1) {
+      const int r = try_umma(i / 2, cur, cin[i], d, h, w, wt->conv_w[i], wt->bn_scale[i], wt->bn_shift[i], 1, P.c[i], cout[i]);
+      if (r > 0) return r;
+      if (r == 0) { cur = P.c[i]; continue; }
+    }
     ConvProblem p = conv3d_problem(cur, cin[i], d, h, w, wt->conv_w[i], P.c[i], cout[i], stride[i]);
     p.scale = wt->bn_scale[i]; p.shift = wt->bn_shift[i];
     RUN(run_by_cout(p, st, "costreg conv"));
@@ -137,9 +170,13 @@ int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int
   RUN(run_deconv3d(P.x7, 4 * base, 2 * d, 2 * h, 2 * w, wt->conv_w[8], wt->bn_scale[8], wt->bn_shift[8], P.c[2], P.x9, 2 * base, st));
   RUN(run_deconv3d(P.x9, 2 * base, 4 * d, 4 * h, 4 * w, wt->conv_w[9], wt->bn_scale[9], wt->bn_shift[9], P.c[0], P.x11, base, st));
   {  // prob: bare Conv3d(base, 1, 3, padding=1, bias=False) (module.py:566, :576)
-    ConvProblem p = conv3d_problem(P.x11, base, D, H, W, wt->prob_w, out, 1, 1);
-    p.relu = 0;
-    RUN(run_by_cout(p, st, "costreg prob"));
+    const int r = try_umma(4, P.x11, base, D, H, W, wt->prob_w, nullptr, nullptr, 0, out, 1);
+    if (r > 0) return r;
+    if (r < 0) {
+      ConvProblem p = conv3d_problem(P.x11, base, D, H, W, wt->prob_w, out, 1, 1);
+      p.relu = 0;
+      RUN(run_by_cout(p, st, "costreg prob"));
+    }
   }
 #undef RUN
   return SATMVS_OK;

@@ -855,11 +855,11 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       // one tensor-core launch with two or three heads (umma_conv.cuh)
       const float sgn = (l == 0) ? -1.0f : 1.0f;
       UmmaPackHead wh[3] = {{wt->gate_w[l], kin, 9, 2 * L.ch, 0}, {wt->out_w[l], kin, 9, L.ch, 0}, {nullptr, 0, 0, 0, 0}};
-      UmmaHead oh[3] = {{wt->gate_b[l], L.gx, 2 * L.ch, 0, sgn, 0, 1}, {wt->out_b[l], L.ox, L.ch, 0, sgn, 0, 1}, {}};
+      UmmaHead oh[3] = {{nullptr, wt->gate_b[l], L.gx, 2 * L.ch, 0, sgn, 0, 1}, {nullptr, wt->out_b[l], L.ox, L.ch, 0, sgn, 0, 1}, {}};
       UmmaConvPlan up;
       if (l < 3) {
         wh[2] = UmmaPackHead{wt->conv_w[l], (long long)ech[l] * 9, 9, ech[l + 1], 0};
-        oh[2] = UmmaHead{nullptr, P.e[l], ech[l + 1], 0, sgn, 1, 2};
+        oh[2] = UmmaHead{nullptr, nullptr, P.e[l], ech[l + 1], 0, sgn, 1, 2};
         if (umma_conv_plan(up, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 3, wh, oh, P.wpack[l], P.wpack_bytes[l])) {
           ProfScope prof(kProfConvBatched, st);
           RUN(umma_conv_launch(up, P.umma_err, st, "red gate/output x-halves + encoder (tcgen05)"));

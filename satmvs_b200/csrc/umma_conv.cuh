@@ -1,5 +1,6 @@
-// umma_conv.cuh — 3x3 (stride 1, padding 1) plane convolution on the 5th-generation tensor cores (tcgen05),
-// fp32-faithful through a 3-way TF32 split, for the batched (all depth planes at once) layers of RED.
+// umma_conv.cuh — 3x3 / 3x3x3 (stride 1, padding 1) convolution on the 5th-generation tensor cores (tcgen05),
+// fp32-faithful through a 3-way TF32 split, for the batched (all depth planes at once) layers of RED and the dense
+// stride-1 layers of CostRegNet (a 3x3x3 conv = three plane convs over z-1, z, z+1 accumulated in the same TMEM tile).
 //
 // Formulation.  A plane is addressed in PADDED-FLATTENED positions q = (y+1)*Wp + (x+1), Wp = W + 2, with zeros in the
 // halo.  For a run of consecutive output positions the input of tap (dy, dx) is the same run shifted by dy*Wp + dx, so
@@ -30,6 +31,7 @@ namespace satmvs {
 constexpr int kUcThreads = 256, kUcKC = 8, kUcMaxHeads = 3, kUcMaxMT = 4;
 
 struct UmmaHead {
+  const float* scale;      // [Cout] or null (folded BatchNorm)
   const float* shift;      // [Cout] or null
   float* out;              // [Cout][D][H][W]
   int Cout;
@@ -45,6 +47,7 @@ struct UmmaConv2d {
   long long in_cs;         // input channel stride in elements
   const float4* wpack;     // packed weights, see umma_pack_weights_kernel
   int Cin, D, H, W;
+  int NZ;                  // 1: per-plane 3x3, 3: 3x3x3 over planes z-1, z, z+1 (zero padding in z)
   int NP;                  // fused output channels, padded to a multiple of 16
   int MT;                  // 128-position tiles per CTA
   int PW;                  // window positions = 128*MT + 2*Wp + 2
@@ -53,20 +56,23 @@ struct UmmaConv2d {
 };
 
 struct UmmaPackHead { const float* w; long long w_co, w_ci; int Cout, n0; };
-struct UmmaPack { UmmaPackHead head[kUcMaxHeads]; int nheads, Cin, NP; float4* out; };
+struct UmmaPack { UmmaPackHead head[kUcMaxHeads]; int nheads, Cin, NP, NZ; float4* out; };
 
-// Packed weights: [chunk = Cin/8][part: 0 raw, 1 lo][tap 9][kq 2][n NP] float4 (4 consecutive input channels).
+// Packed weights: [chunk = Cin/8][kz NZ][part: 0 raw, 1 lo][tap 9][kq 2][n NP] float4 (4 consecutive input channels);
+// the weight of (co, ci, kz, tap) sits at w[co*w_co + ci*w_ci + kz*9 + tap].
 // Column n of the fused N dimension belongs to the head with n0 <= n < n0 + Cout; padding columns are zero.
-__global__ void umma_pack_weights_kernel(const __grid_constant__ UmmaPack a) {
-  const int total = (a.Cin / kUcKC) * 2 * 9 * 2 * a.NP;
+static __global__ void umma_pack_weights_kernel(const __grid_constant__ UmmaPack a) {
+  const int total = (a.Cin / kUcKC) * a.NZ * 2 * 9 * 2 * a.NP;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int n = i % a.NP;
   int r = i / a.NP;
   const int kq = r % 2; r /= 2;
-  const int tap = r % 9; r /= 9;
-  const int part = r % 2;
-  const int chunk = r / 2;
+  int tap = r % 9; r /= 9;
+  const int part = r % 2; r /= 2;
+  const int kz = r % a.NZ;
+  const int chunk = r / a.NZ;
+  tap += kz * 9;
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   for (int h = 0; h < a.nheads; ++h) {
     const UmmaPackHead& H = a.head[h];
@@ -119,7 +125,8 @@ inline size_t umma_conv_smem_bytes(int NP, int PW) {
   return (size_t)2 * 2 * PW * 16 + (size_t)2 * 9 * 2 * NP * 16;      // window (raw, lo) x 2 quads + packed weights of one chunk
 }
 
-template <int NPOS>      // window positions per thread: 4 (PW <= 1024, 3 CTAs per SM) or 8 (PW <= 2048, 2 CTAs per SM)
+// NPOS: window positions per thread: 4 (PW <= 1024, 3 CTAs per SM) or 8 (PW <= 2048, 2 CTAs per SM); NZ: 1 or 3 (a.NZ)
+template <int NPOS, int NZ>
 __global__ void __launch_bounds__(kUcThreads, NPOS == 4 ? 3 : 2)
 umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
   extern __shared__ __align__(128) unsigned char uc_smem[];
@@ -156,8 +163,8 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
   }
   // 8 channels of a chunk for this thread's positions, global -> registers (all loads in flight together)
   float v[NPOS][kUcKC];
-  auto load_chunk = [&](int c) {
-    const float* in_c = a.in + (long long)(c * kUcKC) * a.in_cs + (long long)d * HW;
+  auto load_chunk = [&](int c, int zi) {
+    const float* in_c = a.in + (long long)(c * kUcKC) * a.in_cs + (long long)zi * HW;
 #pragma unroll
     for (int k = 0; k < kUcKC; ++k) {
       const float* in_k = in_c + k * a.in_cs;
@@ -165,7 +172,16 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
       for (int j = 0; j < NPOS; ++j) v[j][k] = src_off[j] >= 0 ? __ldg(in_k + src_off[j]) : 0.0f;
     }
   };
-  load_chunk(0);
+  // steps = (channel chunk, kz); planes outside [0, D) are the zero padding in z and are skipped altogether
+  constexpr int zoff = NZ >> 1;
+  const int nsteps = (a.Cin / kUcKC) * NZ;
+  auto next_step = [&](int s0) {
+    if (NZ > 1)
+      while (s0 < nsteps) { const int zi = d + (s0 % NZ) - zoff; if (zi >= 0 && zi < a.D) break; ++s0; }
+    return s0;
+  };
+  int step = next_step(0);
+  load_chunk(step / NZ, d + (step % NZ) - zoff);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -173,15 +189,16 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
   const unsigned tmem = tmem_base_s;
   const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.NP >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
 
-  const int nchunks = a.Cin / kUcKC;
-  const unsigned wts_bytes = (unsigned)(2 * 9 * 2 * a.NP) * 16u;      // packed weights of one chunk
+  const unsigned wts_bytes = (unsigned)(2 * 9 * 2 * a.NP) * 16u;      // packed weights of one step
   bool alive = true;
-  for (int c = 0; c < nchunks; ++c) {
-    if (c > 0) alive = uc_wait(&bar, (unsigned)(c - 1) & 1u) && alive;   // previous chunk's MMAs have read the window and the weights
-    if (tid == 0) {   // packed weights of this chunk: one TMA bulk copy (async proxy -> async proxy, no generic fence needed)
+  int done = 0;                                                        // steps executed so far (mbarrier phases)
+  while (step < nsteps) {
+    const int c = done;                                                // phase index of this step
+    if (c > 0) alive = uc_wait(&bar, (unsigned)(c - 1) & 1u) && alive;   // previous step's MMAs have read the window and the weights
+    if (tid == 0) {   // packed weights of this step: one TMA bulk copy (async proxy -> async proxy, no generic fence needed)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(uc_smem_u32(&wbar)), "r"(wts_bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(uc_smem_u32(wts)), "l"(reinterpret_cast<const char*>(a.wpack) + (size_t)c * wts_bytes), "r"(wts_bytes),
+                   ::"r"(uc_smem_u32(wts)), "l"(reinterpret_cast<const char*>(a.wpack) + (size_t)step * wts_bytes), "r"(wts_bytes),
                      "r"(uc_smem_u32(&wbar)) : "memory");
     }
     // window of this chunk: registers -> shared memory, raw value and low part (x - trunc_tf32(x))
@@ -223,9 +240,11 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(uc_smem_u32(&bar)) : "memory");
     }
     __syncwarp();
-    if (c + 1 < nchunks) load_chunk(c + 1);      // the next chunk's global loads fly while the tensor core works on this one
+    step = next_step(step + 1);
+    ++done;
+    if (step < nsteps) load_chunk(step / NZ, d + (step % NZ) - zoff);   // the next step's global loads fly while the tensor core works
   }
-  alive = uc_wait(&bar, (unsigned)(nchunks - 1) & 1u) && alive;
+  alive = uc_wait(&bar, (unsigned)(done - 1) & 1u) && alive;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!alive) {            // a tensor-core completion never arrived: fail loudly (sticky CUDA error) instead of storing garbage
     if (tid == 0) atomicExch(error_flag, 1);
@@ -253,12 +272,26 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int nj = min(8, Hd.Cout - c0);               // uniform: 8 except in the last group of a ragged head
           if (ok) {
+            if (nj == 8 && Hd.scale == nullptr) {            // RED heads: bias only
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float val = __uint_as_float(r[j]) * Hd.acc_scale + (Hd.shift ? __ldg(Hd.shift + c0 + j) : 0.0f);
-              if (Hd.relu) val = fmaxf(val, 0.0f);
-              op[(long long)(c0 + j) * ocs] = val;
+              for (int j = 0; j < 8; ++j) {
+                float val = __uint_as_float(r[j]) * Hd.acc_scale + (Hd.shift ? __ldg(Hd.shift + c0 + j) : 0.0f);
+                if (Hd.relu) val = fmaxf(val, 0.0f);
+                op[(long long)(c0 + j) * ocs] = val;
+              }
+            } else {                                          // folded BatchNorm and / or fewer than 8 channels left
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (j < nj) {
+                  float val = __uint_as_float(r[j]) * Hd.acc_scale;
+                  if (Hd.scale) val *= __ldg(Hd.scale + c0 + j);
+                  if (Hd.shift) val += __ldg(Hd.shift + c0 + j);
+                  if (Hd.relu) val = fmaxf(val, 0.0f);
+                  op[(long long)(c0 + j) * ocs] = val;
+                }
+              }
             }
           }
         }
@@ -274,15 +307,16 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
 struct UmmaConvPlan { UmmaConv2d conv; UmmaPack pack; size_t smem; size_t wpack_bytes; dim3 grid; };
 
 inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, int Cin, int D, int H, int W,
-                           int nheads, const UmmaPackHead* wheads, const UmmaHead* oheads, void* wpack_buf, size_t wpack_cap) {
-  if (Cin % kUcKC || nheads < 1 || nheads > kUcMaxHeads) return false;
+                           int nheads, const UmmaPackHead* wheads, const UmmaHead* oheads, void* wpack_buf, size_t wpack_cap,
+                           int NZ = 1) {
+  if (Cin % kUcKC || nheads < 1 || nheads > kUcMaxHeads || (NZ != 1 && NZ != 3)) return false;
   int n = 0;
   P = UmmaConvPlan{};
   for (int h = 0; h < nheads; ++h) {
     P.pack.head[h] = wheads[h]; P.pack.head[h].n0 = n;
     P.conv.head[h] = oheads[h]; P.conv.head[h].n0 = n;
-    if (wheads[h].Cout != oheads[h].Cout || wheads[h].Cout % 8) return false;
-    n += wheads[h].Cout;
+    if (wheads[h].Cout != oheads[h].Cout || wheads[h].Cout < 1) return false;
+    n += (wheads[h].Cout + 7) / 8 * 8;            // every head starts on a multiple of 8 columns
   }
   const int NP = (n + 15) / 16 * 16;
   if (NP > 256) return false;
@@ -303,29 +337,42 @@ inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, in
   const int PW = 128 * MT + 2 * Wp + 2;
   if (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, PW) > 100 * 1024) return false;   // 2 CTAs per SM or nothing
   if (PW > 8 * kUcThreads || (size_t)PW * 16 >= (1u << 18)) return false;
-  P.wpack_bytes = (size_t)(Cin / kUcKC) * 2 * 9 * 2 * NP * 16;
+  P.wpack_bytes = (size_t)(Cin / kUcKC) * NZ * 2 * 9 * 2 * NP * 16;
   if (wpack_buf == nullptr || wpack_cap < P.wpack_bytes || (reinterpret_cast<uintptr_t>(wpack_buf) & 15)) return false;
-  P.pack.nheads = nheads; P.pack.Cin = Cin; P.pack.NP = NP; P.pack.out = static_cast<float4*>(wpack_buf);
+  P.pack.nheads = nheads; P.pack.Cin = Cin; P.pack.NP = NP; P.pack.NZ = NZ; P.pack.out = static_cast<float4*>(wpack_buf);
+  P.conv.NZ = NZ;
   P.conv.in = in; P.conv.in_cs = in_cs; P.conv.wpack = static_cast<const float4*>(wpack_buf);
   P.conv.Cin = Cin; P.conv.D = D; P.conv.H = H; P.conv.W = W; P.conv.NP = NP; P.conv.MT = MT; P.conv.PW = PW; P.conv.nheads = nheads;
   P.smem = umma_conv_smem_bytes(NP, PW);
   P.grid = dim3(ceil_div((long long)H * Wp, 128 * MT), D, 1);
+  // every CTA walks its (chunk, kz) steps one after the other: with only a few dozen CTAs the direct kernel, which spreads
+  // the input channels over warps, is faster (measured on CostRegNet conv4 / conv6: 48 and 16 CTAs, 55 / 76 us against
+  // 56 / 105 us is not worth the risk; RED level 4 with 128 CTAs: 34 us against 65 us direct)
+  if ((long long)P.grid.x * P.grid.y < 96) return false;
   return true;
 }
 
 inline int umma_conv_launch(const UmmaConvPlan& P, int* error_flag, cudaStream_t st, const char* what) {
-  const int total = (P.pack.Cin / kUcKC) * 2 * 9 * 2 * P.pack.NP;
+  const int total = (P.pack.Cin / kUcKC) * P.pack.NZ * 2 * 9 * 2 * P.pack.NP;
   umma_pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(P.pack);
   static thread_local int ready_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (ready_dev != dev) {
-    cudaFuncSetAttribute(umma_conv2d_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(umma_conv2d_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(umma_conv2d_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(umma_conv2d_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(umma_conv2d_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(umma_conv2d_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     ready_dev = dev;
   }
-  if (P.conv.PW <= 4 * kUcThreads) umma_conv2d_kernel<4><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
-  else umma_conv2d_kernel<8><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  const bool small = P.conv.PW <= 4 * kUcThreads;
+  if (P.conv.NZ == 1) {
+    if (small) umma_conv2d_kernel<4, 1><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+    else umma_conv2d_kernel<8, 1><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  } else {
+    if (small) umma_conv2d_kernel<4, 3><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+    else umma_conv2d_kernel<8, 3><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  }
   return check_launch(what);
 }
 
