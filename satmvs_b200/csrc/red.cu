@@ -155,6 +155,55 @@ __global__ void gru_reset_kernel(const __grid_constant__ GruArgs a) {
   L.rh[e] = r * __ldg(L.hprev + c * L.scs + p);
 }
 
+// Vectorised forms: one thread = 4 consecutive pixels of one channel (every level's plane size is a multiple of 4),
+// 128-bit loads and stores, a quarter of the CTAs.  `begin` / `total` are then counted in groups of 4.
+__global__ void gru_reset4_kernel(const __grid_constant__ GruArgs a) {
+  pdl_release();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  if (i >= a.total) return;
+  int li = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) if (i >= a.l[k].begin) li = k;
+  const GruLevelArgs& L = a.l[li];
+  const int px4 = L.px >> 2;
+  const int e = i - L.begin, c = e / px4, p = (e - c * px4) << 2;
+  float ga, gb;
+  gn_coeff(L.stats, L.inv_n, __ldg(L.rn_w + c), __ldg(L.rn_b + c), ga, gb);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(L.g + c * L.gcs + p));
+  const float4 h = __ldg(reinterpret_cast<const float4*>(L.hprev + c * L.scs + p));
+  float4 o;
+  o.x = sigmoidf_(fmaf(g.x, ga, gb)) * h.x; o.y = sigmoidf_(fmaf(g.y, ga, gb)) * h.y;
+  o.z = sigmoidf_(fmaf(g.z, ga, gb)) * h.z; o.w = sigmoidf_(fmaf(g.w, ga, gb)) * h.w;
+  *reinterpret_cast<float4*>(L.rh + (long long)c * L.px + p) = o;
+}
+
+__global__ void gru_update4_kernel(const __grid_constant__ GruArgs a) {
+  pdl_release();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  if (i >= a.total) return;
+  int li = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) if (i >= a.l[k].begin) li = k;
+  const GruLevelArgs& L = a.l[li];
+  const int px4 = L.px >> 2;
+  const int e = i - L.begin, c = e / px4, p = (e - c * px4) << 2;
+  float ua, ub, oa, ob;
+  gn_coeff(L.stats + 2, L.inv_n, __ldg(L.un_w + c), __ldg(L.un_b + c), ua, ub);
+  gn_coeff(L.stats + 4, L.inv_n, __ldg(L.on_w + c), __ldg(L.on_b + c), oa, ob);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(L.g + (c + L.ch) * L.gcs + p));
+  const float4 y = __ldg(reinterpret_cast<const float4*>(L.o + c * L.ocs + p));
+  const float4 h = __ldg(reinterpret_cast<const float4*>(L.hprev + c * L.scs + p));
+  auto upd = [&](float gv, float yv, float hv) {
+    const float u = sigmoidf_(fmaf(gv, ua, ub));
+    return u * hv + (1.0f - u) * tanhf(fmaf(yv, oa, ob));       // module.py:57
+  };
+  float4 o;
+  o.x = upd(g.x, y.x, h.x); o.y = upd(g.y, y.y, h.y); o.z = upd(g.z, y.z, h.z); o.w = upd(g.w, y.w, h.w);
+  *reinterpret_cast<float4*>(L.hnext + c * L.scs + p) = o;
+}
+
 __global__ void gru_update_kernel(const __grid_constant__ GruArgs a) {
   pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -998,6 +1047,24 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       total += L.ch * (int)px;
     }
     ga.total = total;
+    // vectorised pointwise kernels: 4 pixels per thread when every plane size is a multiple of 4 and the bases are 16-byte aligned
+    GruArgs ga4 = ga;
+    // opt-in (SATMVS_RED_VEC4=1): 0.87 against 1.06 ms per step when timed launch by launch, but the PDL chain as a whole is
+    // slower with them (2.86 against 2.79 ms/step, same box): profiles/r01_red_recurrence_notes.md
+    static const bool want_vec4 = getenv("SATMVS_RED_VEC4") != nullptr;
+    bool vec4 = want_vec4;
+    {
+      int t4 = 0;
+      for (int l = 0; l < 4; ++l) {
+        GruLevelArgs& e = ga4.l[l];
+        vec4 = vec4 && (e.px % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.g) | reinterpret_cast<uintptr_t>(e.o) |
+                                            reinterpret_cast<uintptr_t>(e.hprev) | reinterpret_cast<uintptr_t>(e.hnext) |
+                                            reinterpret_cast<uintptr_t>(e.rh)) % 16 == 0);
+        e.begin = t4;
+        t4 += e.ch * (e.px / 4);
+      }
+      ga4.total = t4;
+    }
     const bool fuse = want_fuse && ctas1 <= resident_ctas && ctas2 <= resident_ctas;
     if (fuse) {
       for (int l = 0; l < 4; ++l) {
@@ -1024,11 +1091,13 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     // the first gate conv follows the batched launches (plain stream order); everything after it is chained
     { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)", pdl && d > 0)); }
     { ProfScope prof(kProfGruPointwise, st);
-      launch_chain(gru_reset_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
+      if (vec4) launch_chain(gru_reset4_kernel, ceil_div(ga4.total, 256), 256, 0, st, pdl, ga4);
+      else launch_chain(gru_reset_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
       RUN(check_launch("gru_reset_kernel")); }
     { ProfScope prof(kProfGruOutput, st); RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output)", pdl)); }
     { ProfScope prof(kProfGruPointwise, st);
-      launch_chain(gru_update_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
+      if (vec4) launch_chain(gru_update4_kernel, ceil_div(ga4.total, 256), 256, 0, st, pdl, ga4);
+      else launch_chain(gru_update_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
       RUN(check_launch("gru_update_kernel")); }
   }
 
