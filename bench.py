@@ -45,6 +45,9 @@ WORKLOADS = {
                         desc="3-view 768x384, 64 planes, stage 1 with the CostRegNet (3-D UNet) regulariser"),
     "cfg5_build": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="pinhole", stage="build",
                        desc="pin-hole homography sweep 3-view 768x384, 64 planes, cost-volume build"),
+    "cfg3_cascade": dict(B=1, V=3, C=32, D=48, H=96, W=192, geo="rpc", stage="cascade",
+                         desc="3-view 768x384, cascade 48/32/8 planes, full casred (three stages: hypotheses, fused RPC cost "
+                              "volume, RED regulariser, soft-argmin), 1xB200"),
     "cfg4_sharded192": dict(B=1, V=5, C=32, D=192, H=192, W=384, geo="rpc", stage="sharded",
                             desc="5-view 1536x768, 192 planes single-stage, cost-volume build depth-sharded across ranks"),
 }
@@ -185,6 +188,121 @@ def make_step(w, dev, args):
             return out["depth"], out["photometric_confidence"]
         return step
     raise ValueError(w["stage"])
+
+
+def run_cascade(args, w):
+    """BASELINE config 3: the whole casred cascade (768x384 image; stages at scale 4/2/1 with C 32/16/8 and 48/32/8
+    planes, `networks/casred.py:125-154`) from per-stage feature maps to the final depth map.  One stack per rank."""
+    import satmvs_b200
+    from satmvs_b200 import _lib, synth
+    _lib.lib()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    img_hw, ndepths, chans, scales = (384, 768), (48, 32, 8), (32, 16, 8), (4, 2, 1)
+    V = w["V"]
+    feats_h = [synth.make_features(1, V, c, img_hw[0] // sc, img_hw[1] // sc, seed=rank * 10 + i)
+               for i, (c, sc) in enumerate(zip(chans, scales))]
+    cams = [synth.make_rpc_stack(1, V, img_hw[0] // sc, img_hw[1] // sc) for sc in scales]
+    drange = torch.tensor([[0.0, 1000.0]])
+    regs = []
+    for i, c in enumerate(chans):
+        m = satmvs_b200.RED_Regularization(c, 8)
+        m.load_state_dict(synth.make_red_weights(c, seed=100 + i))
+        regs.append(m.to(dev).eval())
+    feats = [[f.to(dev) for f in fs] for fs in feats_h]
+    dr = drange.to(dev)
+
+    def step(fs, dr_):
+        with torch.no_grad():
+            out = satmvs_b200.cascade(fs, cams, dr_, regs, img_hw=img_hw, ndepths=ndepths, head="red_train")
+        return out["depth"], out["photometric_confidence"]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    voxels = sum(V * d * (img_hw[0] // sc) * (img_hw[1] // sc) for d, sc in zip(ndepths, scales))
+
+    def timed(fn, n):
+        evs = []
+        for _ in range(n):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step(feats, dr)
+    barrier()
+    with ClockSampler(local) as clk:
+        total_ms = timed(lambda: step(feats, dr), args.steps)
+        barrier()
+    feats_p = [[f.pin_memory() for f in fs] for fs in feats_h]
+    dr_p = drange.pin_memory()
+    h2d = sum(f.numel() * 4 for fs in feats_p for f in fs) + dr_p.numel() * 4 + sum(c.numel() * 8 for c in cams)
+    outs_host = []
+
+    def e2e_step():
+        fs = [[f.to(dev, non_blocking=True) for f in fl] for fl in feats_p]
+        res = step(fs, dr_p.to(dev, non_blocking=True))
+        if not outs_host:
+            outs_host.extend(torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res)
+        for h, r in zip(outs_host, res):
+            h.copy_(r, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_ms = timed(e2e_step, args.steps)
+    barrier()
+    d2h = sum(h.numel() * h.element_size() for h in outs_host)
+    prof_steps = min(args.steps, 5)
+    with _lib.profile() as prof:
+        for _ in range(prof_steps):
+            flush.zero_()
+            step(feats, dr)
+    barrier()
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        hbm, _, peak_src = peaks()
+        ms = total_ms / args.steps
+        tot_prof = sum(prof.ms.values()) or 1.0
+        kernels = [{"class": n, "launches_per_step": prof.launches[n] / prof_steps, "ms_per_step": prof.ms[n] / prof_steps,
+                    "share": prof.ms[n] / tot_prof} for n in _lib.PROFILE_CLASSES if prof.launches[n]]
+        kernels.sort(key=lambda k: -k["share"])
+        sweep_bytes = sum(d * (img_hw[0] // sc) * (img_hw[1] // sc) * sweep_bytes_per_cell(dict(C=c, V=V, D=d))
+                          for d, sc, c in zip(ndepths, scales, chans))
+        sw = next(k for k in kernels if k["class"] == "sweep")
+        ach = sweep_bytes / (sw["ms_per_step"] * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": voxels * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (camera geometry f64)", "data": "synthetic",
+                "config": {"workload": w["desc"], "name": args.workload, "B": 1, "V": V, "C": list(chans), "D": list(ndepths),
+                           "image_hw": list(img_hw), "scales": list(scales), "geo_model": "rpc",
+                           "l2": "flushed (256 MiB write) between timed iterations", "sharding": "one stack per rank"},
+                "clocks": clk.summary(),
+                "e2e": {"value": voxels * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(sum(prof.launches.values()) / prof_steps * args.steps), "kernels": kernels,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                             "kernel": "sweep (three stages)", "algorithmic_bytes_per_step": sweep_bytes,
+                             "share_of_step": sw["share"], "peak_source": peak_src}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(args, w):
@@ -483,7 +601,11 @@ def main():
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
+        if w["stage"] == "cascade":   # the reference arm times one bounded stage-1 sample of the cascade's first stage
+            w = dict(WORKLOADS["cfg2_stage1"], D=48, desc=w["desc"] + " [reference arm: stage 1 only]")
         run_reference(args, w)
+    elif w["stage"] == "cascade":
+        run_cascade(args, w)
     else:
         run_ours(args, w)
 

@@ -257,7 +257,7 @@ struct GruConvLevel {
   const float* fuse_gu; long long fuse_g_cs;// u-gate pre-activations of this plane (2)
   float* fuse_dst; long long fuse_dst_cs;   // rh (1) / next state (2)
 };
-struct GruConvArgs { GruConvLevel l[4]; };
+struct GruConvArgs { GruConvLevel l[4]; int early_wait; };
 
 constexpr int kGcWarps = 8, kGcCo = 8, kGcPx = 4, kGcTilePx = 32 * kGcPx, kGcCi = 4;
 constexpr int kGcThreads = kGcWarps * 32;
@@ -559,6 +559,7 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
   float (*part)[kGcCo][kGcTilePx] = reinterpret_cast<float (*)[kGcCo][kGcTilePx]>(gc_smem + 64 * 9 * kGcCo);   // 32 KB
   __shared__ double red[2][kGcWarps];
   pdl_release();
+  if (a.early_wait) pdl_wait();          // experiment knob (SATMVS_RED_EARLY_WAIT): no weight staging under the predecessor
   int li = 0;
 #pragma unroll
   for (int k = 1; k < 4; ++k) if ((int)blockIdx.x >= a.l[k].cta_begin) li = k;
@@ -1013,6 +1014,8 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
   }
   for (int d = 0; d < D && !persistent; ++d) {
     GruConvArgs c1{}, c2{};
+    static const int early_wait = getenv("SATMVS_RED_EARLY_WAIT") ? atoi(getenv("SATMVS_RED_EARLY_WAIT")) : 0;
+    c1.early_wait = early_wait & 1; c2.early_wait = (early_wait >> 1) & 1;
     GruArgs ga{};
     int total = 0, ctas1 = 0, ctas2 = 0;
     for (int l = 0; l < 4; ++l) {

@@ -47,7 +47,9 @@ def test_volume_golden(golden, geo):
     assert maxdiff(out["photometric_confidence"], g["conf"]) < 1e-4
 
 
-@pytest.mark.parametrize("C,D,H,W", [(32, 12, 32, 64), (16, 3, 16, 24), (8, 1, 8, 8)])
+@pytest.mark.parametrize("C,D,H,W", [(32, 12, 32, 64), (16, 3, 16, 24), (8, 1, 8, 8),
+                                     (8, 2, 8, 512),      # wide planes: 8 window positions per thread in the tcgen05 conv
+                                     (16, 5, 24, 40)])    # ragged tiles, odd plane count
 def test_volume_vs_oracle(C, D, H, W):
     sd = synth.make_red_weights(C, seed=5)
     m = satmvs_b200.RED_Regularization(C, 8)
