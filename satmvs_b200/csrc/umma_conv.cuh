@@ -2,8 +2,10 @@
 // fp32-faithful through a 3-way TF32 split, for the batched (all depth planes at once) layers of RED and the dense
 // stride-1 layers of CostRegNet (a 3x3x3 conv = three plane convs over z-1, z, z+1 accumulated in the same TMEM tile).
 //
-// Formulation.  A plane is addressed in PADDED-FLATTENED positions q = (y+1)*Wp + (x+1), Wp = W + 2, with zeros in the
-// halo.  For a run of consecutive output positions the input of tap (dy, dx) is the same run shifted by dy*Wp + dx, so
+// Formulation.  A plane is cut into vertical strips of TW columns; a strip is addressed in PADDED-FLATTENED positions
+// q = ry*Wp + rx, Wp = TW + 2 (one halo column / row on every side: the neighbouring pixels, or zeros outside the image),
+// and a CTA owns a run of 128*MT consecutive output positions of its strip (runs need not start at a row boundary).
+// For such a run the input of tap (dy, dx) is the same run shifted by dy*Wp + dx, so
 // with the input window in shared memory as [channel quad][position] float4 (the sweep's re-pack layout, which IS the
 // SWIZZLE_NONE K-major canonical layout of tcgen05: 8 positions x 16 bytes per core matrix, SBO = 128 B between
 // 8-position groups, LBO = window pitch between channel quads) every tap is ONE shared-memory descriptor whose start
@@ -49,6 +51,8 @@ struct UmmaConv2d {
   int Cin, D, H, W;
   int NZ;                  // 1: per-plane 3x3, 3: 3x3x3 over planes z-1, z, z+1 (zero padding in z)
   int NP;                  // fused output channels, padded to a multiple of 16
+  int TW;                  // useful columns of a strip (window pitch Wp = TW + 2)
+  int strips;              // strips per plane: blockIdx.x = run * strips + strip
   int MT;                  // 128-position tiles per CTA
   int PW;                  // window positions = 128*MT + 2*Wp + 2
   int nheads;
@@ -136,9 +140,11 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
   __shared__ __align__(8) unsigned long long bar, wbar;                // MMAs of a chunk done / packed weights of a chunk landed
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Wp = a.W + 2, HW = a.H * a.W;
+  const int Wp = a.TW + 2, HW = a.H * a.W;
   const int d = blockIdx.y;
-  const int q0 = Wp + blockIdx.x * (128 * a.MT);                       // first output position of this CTA (row y = 0 starts at Wp)
+  const int run = blockIdx.x / a.strips, sx = blockIdx.x - run * a.strips;
+  const int x0 = sx * a.TW;                                            // first useful column of the strip
+  const int q0 = Wp + run * (128 * a.MT);                              // first output position of this CTA (row y = 0 starts at Wp)
   const int tmem_cols = uc_tmem_cols(a.MT * a.NP);
 
   if (tid == 0) {
@@ -156,10 +162,11 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
 #pragma unroll
   for (int j = 0; j < NPOS; ++j) {
     const int p = tid + j * kUcThreads;
-    const int qin = q0 - Wp - 1 + p;
-    const int yy = qin / Wp, xx = qin - yy * Wp;
-    const bool ok = p < a.PW && qin >= 0 && yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
-    src_off[j] = ok ? (yy - 1) * a.W + (xx - 1) : -1;
+    const int qs = q0 - Wp - 1 + p;                                    // strip-local flattened position of window index p
+    const int ry = qs / Wp, rx = qs - ry * Wp;
+    const int y = ry - 1, x = x0 - 1 + rx;
+    const bool ok = p < a.PW && qs >= 0 && y >= 0 && y < a.H && x >= 0 && x < a.W;
+    src_off[j] = ok ? y * a.W + x : -1;
   }
   // 8 channels of a chunk for this thread's positions, global -> registers (all loads in flight together)
   float v[NPOS][kUcKC];
@@ -256,11 +263,12 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
     const int quarter = warp & 3;
     for (int mt = warp >> 2; mt < a.MT; mt += kUcThreads / 128) {
       const int q = q0 + 128 * mt + 32 * quarter + lane;
-      const int yy = q / Wp, xx = q - yy * Wp;
-      const bool ok1 = alive && yy >= 1 && yy <= a.H && xx >= 1 && xx <= a.W;
-      const long long opix1 = (long long)d * HW + (long long)(yy - 1) * a.W + (xx - 1);
-      const bool ok2 = ok1 && !((yy - 1) & 1) && !((xx - 1) & 1);
-      const long long opix2 = (long long)d * (HW >> 2) + (long long)((yy - 1) >> 1) * (a.W >> 1) + ((xx - 1) >> 1);
+      const int ry = q / Wp, rx = q - ry * Wp;
+      const int y = ry - 1, x = x0 - 1 + rx;
+      const bool ok1 = alive && y < a.H && rx >= 1 && rx <= a.TW && x < a.W;
+      const long long opix1 = (long long)d * HW + (long long)y * a.W + x;
+      const bool ok2 = ok1 && !(y & 1) && !(x & 1);
+      const long long opix2 = (long long)d * (HW >> 2) + (long long)(y >> 1) * (a.W >> 1) + (x >> 1);
       for (int h = 0; h < a.nheads; ++h) {
         const UmmaHead& Hd = a.head[h];
         const bool ok = Hd.stride == 2 ? ok2 : ok1;
@@ -320,22 +328,30 @@ inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, in
   }
   const int NP = (n + 15) / 16 * 16;
   if (NP > 256) return false;
-  const int Wp = W + 2;
-  // prefer 3 CTAs per SM (<= 74 KB of shared memory, <= 128 TMEM columns, <= 1024 window positions): co-resident CTAs are
-  // what overlaps one CTA's staging with another's MMAs; else 2 CTAs per SM
+  // Tile search over (strips, MT).  The MMAs are shared-memory-read bound and cost ~7x a staged window position per row,
+  // so the cost is 7 * MMA rows issued + window positions staged, per plane.  Preference: 3 CTAs per SM (<= 74 KB of shared
+  // memory, <= 128 TMEM columns, <= 1024 window positions) -- co-resident CTAs are what overlaps one CTA's staging with
+  // another's MMAs -- then 2 CTAs per SM (<= 100 KB, <= 256 columns, <= 2048 positions).
   static const int want3 = getenv("SATMVS_UMMA_2CTA") ? 0 : 1;
-  int MT = 0;
-  if (want3)
-    for (int m = kUcMaxMT; m >= 1 && MT == 0; --m) {
-      const int pw = 128 * m + 2 * Wp + 2;
-      if (uc_tmem_cols(m * NP) <= 128 && umma_conv_smem_bytes(NP, pw) <= 74 * 1024 && pw <= 4 * kUcThreads) MT = m;
+  int TW = 0, MT = 0, PW = 0;
+  for (int pass = want3 ? 0 : 1; pass < 2 && TW == 0; ++pass) {
+    const int max_cols = pass == 0 ? 128 : 256, max_pos = (pass == 0 ? 4 : 8) * kUcThreads;
+    const size_t max_smem = (pass == 0 ? 74 : 100) * 1024;
+    double best = 1e30;
+    for (int nstr = 1; nstr <= 64; ++nstr) {
+      const int tw = (W + nstr - 1) / nstr, wp = tw + 2;
+      if (tw < 16 && nstr > 1) break;
+      for (int mt = 1; mt <= kUcMaxMT; ++mt) {
+        const int pw = 128 * mt + 2 * wp + 2;
+        if (uc_tmem_cols(mt * NP) > max_cols || pw > max_pos || umma_conv_smem_bytes(NP, pw) > max_smem) break;
+        const double runs = (double)((H * wp + 128 * mt - 1) / (128 * mt));
+        double cost = (7.0 * 128 * mt + pw) * runs * nstr;
+        if (tw < 32) cost *= 1.15;                    // rows shorter than a 128-byte line
+        if (cost < best) { best = cost; TW = tw; MT = mt; PW = pw; }
+      }
     }
-  if (MT == 0) {
-    MT = kUcMaxMT;
-    while (MT > 1 && (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, 128 * MT + 2 * Wp + 2) > 100 * 1024)) MT >>= 1;
   }
-  const int PW = 128 * MT + 2 * Wp + 2;
-  if (uc_tmem_cols(MT * NP) > 256 || umma_conv_smem_bytes(NP, PW) > 100 * 1024) return false;   // 2 CTAs per SM or nothing
+  if (TW == 0) return false;
   if (PW > 8 * kUcThreads || (size_t)PW * 16 >= (1u << 18)) return false;
   P.wpack_bytes = (size_t)(Cin / kUcKC) * NZ * 2 * 9 * 2 * NP * 16;
   if (wpack_buf == nullptr || wpack_cap < P.wpack_bytes || (reinterpret_cast<uintptr_t>(wpack_buf) & 15)) return false;
@@ -343,8 +359,9 @@ inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, in
   P.conv.NZ = NZ;
   P.conv.in = in; P.conv.in_cs = in_cs; P.conv.wpack = static_cast<const float4*>(wpack_buf);
   P.conv.Cin = Cin; P.conv.D = D; P.conv.H = H; P.conv.W = W; P.conv.NP = NP; P.conv.MT = MT; P.conv.PW = PW; P.conv.nheads = nheads;
+  P.conv.TW = TW; P.conv.strips = ceil_div(W, TW);
   P.smem = umma_conv_smem_bytes(NP, PW);
-  P.grid = dim3(ceil_div((long long)H * Wp, 128 * MT), D, 1);
+  P.grid = dim3(P.conv.strips * ceil_div((long long)H * (TW + 2), 128 * MT), D, 1);
   // every CTA walks its (chunk, kz) steps one after the other: with only a few dozen CTAs the direct kernel, which spreads
   // the input channels over warps, is faster (measured on CostRegNet conv4 / conv6: 48 and 16 CTAs, 55 / 76 us against
   // 56 / 105 us is not worth the risk; RED level 4 with 128 CTAs: 34 us against 65 us direct)
