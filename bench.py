@@ -546,7 +546,18 @@ def gpu_eager_baseline(w, dev, fe, cams, dv):
     return out
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(max(1, n))
+
+
 def cpu_baseline(w, budget_s=20.0):
+    use_all_host_threads()
     planes = min(w["D"], 16)
     run, vox = oracle_step(w, planes)
     run()
@@ -568,6 +579,7 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     planes = min(w["D"], 16)
     run, vox = oracle_step(w, planes)
     for _ in range(min(args.warmup, 2)):
