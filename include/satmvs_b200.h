@@ -186,6 +186,17 @@ int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, 
                        const float* const* state_in, float* const* state_out, float* logits,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- one convolution block of the regularisers ----
+ * ConvReLU (modules/module.py:178-186): 3x3 per depth plane (NZ = 1); Conv3d (modules/module.py:324-366): 3x3x3 (NZ = 3);
+ * padding 1, out = relu?( conv(in, w) * acc_scale * scale[co] + shift[co] ), scale / shift may be NULL.
+ *   in [Cin,D,H,W], w [Cout,Cin,(3,)3,3], out [Cout,Do,Ho,Wo]; stride 1 or 2 (NZ = 1 halves H, W; NZ = 3 halves D, H, W)
+ *   engine 0 automatic, 1 tcgen05 tensor cores (3xTF32 split; SATMVS_EINVAL when the shape does not fit), 2 fp32 FFMA kernels
+ *   workspace: satmvs_conv_workspace_bytes(Cin, Cout, NZ) bytes of device scratch (packed weights), may be NULL for engine 2 */
+size_t satmvs_conv_workspace_bytes(int Cin, int Cout, int NZ);
+int satmvs_conv_forward(const float* in, int Cin, int D, int H, int W, const float* w, const float* scale, const float* shift,
+                        int Cout, int NZ, int stride, int relu, float acc_scale, float* out, int engine,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- CostRegNet: 3-D conv UNet regulariser (CasMVSNet / UCS-Net) ----
  * CostRegNet.forward (modules/module.py:546-577), inference-mode BatchNorm.
  *   conv_w[0..6]  conv0..conv6 .conv.weight [Cout,Cin,3,3,3];  conv_w[7..9]  conv7, conv9, conv11

@@ -316,7 +316,7 @@ struct UmmaConvPlan { UmmaConv2d conv; UmmaPack pack; size_t smem; size_t wpack_
 
 inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, int Cin, int D, int H, int W,
                            int nheads, const UmmaPackHead* wheads, const UmmaHead* oheads, void* wpack_buf, size_t wpack_cap,
-                           int NZ = 1) {
+                           int NZ = 1, bool perf_rules = true) {
   if (Cin % kUcKC || nheads < 1 || nheads > kUcMaxHeads || (NZ != 1 && NZ != 3)) return false;
   int n = 0;
   P = UmmaConvPlan{};
@@ -365,7 +365,7 @@ inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, in
   // every CTA walks its (chunk, kz) steps one after the other: with only a few dozen CTAs the direct kernel, which spreads
   // the input channels over warps, is faster (measured on CostRegNet conv4 / conv6: 48 and 16 CTAs, 55 / 76 us against
   // 56 / 105 us is not worth the risk; RED level 4 with 128 CTAs: 34 us against 65 us direct)
-  if ((long long)P.grid.x * P.grid.y < 96) return false;
+  if (perf_rules && (long long)P.grid.x * P.grid.y < 96) return false;
   return true;
 }
 

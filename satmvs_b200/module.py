@@ -40,6 +40,44 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+_ENGINES = {"auto": 0, "tcgen05": 1, "ffma": 2}
+
+
+def conv_block(x, weight, scale=None, shift=None, *, stride=1, relu=False, acc_scale=1.0, engine="auto"):
+    """One convolution block of the regularisers on the library's kernels: `ConvReLU` (`modules/module.py:178-186`,
+    weight [Cout,Cin,3,3], applied to every depth plane of x [B,Cin,D,H,W] or to x [B,Cin,H,W]) or `Conv3d`
+    (`modules/module.py:324-366`, weight [Cout,Cin,3,3,3], x [B,Cin,D,H,W]); padding 1, per-channel scale / shift (folded
+    BatchNorm or bias) and optional ReLU.  engine: "auto", "tcgen05" (tensor cores, 3xTF32 split; raises when the shape
+    does not fit) or "ffma" (fp32 FFMA kernels).  Inference only (no autograd)."""
+    nz = 3 if weight.dim() == 5 else 1
+    squeeze = x.dim() == 4
+    if squeeze:
+        if nz == 3:
+            raise ValueError("a 3x3x3 weight needs a 5-D input")
+        x = x.unsqueeze(2)
+    x = _lib.require_cuda(x, "x")
+    w = _lib.require_cuda(weight, "weight")
+    B, Cin, D, H, W = x.shape
+    Cout = w.shape[0]
+    if w.shape[1] != Cin or tuple(w.shape[2:]) != (3,) * (3 if nz == 3 else 2):
+        want = "3, 3, 3" if nz == 3 else "3, 3"
+        raise ValueError(f"weight must be [Cout, {Cin}, {want}], got {tuple(w.shape)}")
+    sc = None if scale is None else _lib.require_cuda(scale, "scale")
+    sh = None if shift is None else _lib.require_cuda(shift, "shift")
+    Do = D // stride if nz == 3 else D
+    out = torch.empty((B, Cout, Do, H // stride, W // stride), dtype=torch.float32, device=x.device)
+    nbytes = _lib.lib().satmvs_conv_workspace_bytes(Cin, Cout, nz)
+    ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=x.device)   # not the shared cache: the packed weights live here
+    with torch.cuda.device(x.device):
+        st = _lib.stream_ptr(x.device)
+        for b in range(B):
+            _lib.check(_lib.lib().satmvs_conv_forward(
+                x[b].data_ptr(), Cin, D, H, W, w.data_ptr(), sc.data_ptr() if sc is not None else None,
+                sh.data_ptr() if sh is not None else None, Cout, nz, stride, int(bool(relu)), float(acc_scale), out[b].data_ptr(),
+                _ENGINES[engine], ws.data_ptr(), ws.numel(), st), "conv_forward")
+    return out.squeeze(2) if squeeze else out
+
+
 class ConvGRUCell2(nn.Module):
     """Parameter container with the reference's names (`modules/module.py:6-22`)."""
 
