@@ -190,7 +190,8 @@ int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, 
  * ConvReLU (modules/module.py:178-186): 3x3 per depth plane (NZ = 1); Conv3d (modules/module.py:324-366): 3x3x3 (NZ = 3);
  * padding 1, out = relu?( conv(in, w) * acc_scale * scale[co] + shift[co] ), scale / shift may be NULL.
  *   in [Cin,D,H,W], w [Cout,Cin,(3,)3,3], out [Cout,Do,Ho,Wo]; stride 1 or 2 (NZ = 1 halves H, W; NZ = 3 halves D, H, W)
- *   engine 0 automatic, 1 tcgen05 tensor cores (3xTF32 split; SATMVS_EINVAL when the shape does not fit), 2 fp32 FFMA kernels
+ *   engine 0 automatic, 1 tcgen05 tensor cores (3xTF32 split; SATMVS_EINVAL when the shape does not fit), 2 fp32 FFMA kernels,
+ *          3 tcgen05 with the nine in-plane taps in the N dimension (Cout <= 8, stride 1)
  *   workspace: satmvs_conv_workspace_bytes(Cin, Cout, NZ) bytes of device scratch (packed weights), may be NULL for engine 2 */
 size_t satmvs_conv_workspace_bytes(int Cin, int Cout, int NZ);
 int satmvs_conv_forward(const float* in, int Cin, int D, int H, int W, const float* w, const float* scale, const float* shift,

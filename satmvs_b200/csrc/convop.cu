@@ -11,7 +11,9 @@ extern "C" {
 
 size_t satmvs_conv_workspace_bytes(int Cin, int Cout, int NZ) {
   if (Cin < 1 || Cout < 1 || (NZ != 1 && NZ != 3)) return 0;
-  return (size_t)((Cin + 7) / 8) * NZ * 2 * 9 * 2 * ((Cout + 7) / 8 * 8 + 15) / 16 * 16 * 16 + 256;
+  const size_t shifted = (size_t)((Cin + 7) / 8) * NZ * 2 * 9 * 2 * (((Cout + 7) / 8 * 8 + 15) / 16 * 16) * 16;
+  const size_t taps_in_n = (size_t)((Cin + 7) / 8) * NZ * 2 * 2 * kTnNP * 16;
+  return (shifted > taps_in_n ? shifted : taps_in_n) + 256;
 }
 
 int satmvs_conv_forward(const float* in, int Cin, int D, int H, int W, const float* w, const float* scale, const float* shift,
@@ -19,10 +21,20 @@ int satmvs_conv_forward(const float* in, int Cin, int D, int H, int W, const flo
                         void* workspace, size_t workspace_bytes, void* stream) {
   SATMVS_REQUIRE(in && w && out);
   SATMVS_REQUIRE(Cin >= 1 && Cout >= 1 && D >= 1 && H >= 1 && W >= 1 && (NZ == 1 || NZ == 3) && (stride == 1 || stride == 2));
-  SATMVS_REQUIRE(engine >= 0 && engine <= 2);
+  SATMVS_REQUIRE(engine >= 0 && engine <= 3);
   if (stride == 2) SATMVS_REQUIRE(H % 2 == 0 && W % 2 == 0 && (NZ == 1 || D % 2 == 0));
   cudaStream_t st = (cudaStream_t)stream;
   const int taps = NZ * 9;
+  if ((engine == 3 || engine == 0) && workspace && stride == 1 && Cout <= kTnCo) {
+    // few output channels: the nine in-plane taps ride in the N dimension (one pass over the A operand)
+    char* ws = static_cast<char*>(workspace);
+    UmmaConvTnPlan tp;
+    const size_t cap = workspace_bytes > 256 ? workspace_bytes - 256 : 0;
+    if (umma_conv_tn_plan(tp, in, (long long)D * H * W, Cin, D, H, W, w, (long long)Cin * taps, taps, scale, shift, out, Cout, NZ,
+                          relu, acc_scale, ws + 256, cap) && (engine == 3 || (long long)tp.grid.x * tp.grid.y >= 96))
+      return umma_conv_tn_launch(tp, reinterpret_cast<int*>(ws), st, "satmvs_conv_forward (tcgen05, taps in N)");
+  }
+  if (engine == 3) return fail_invalid("shape does not fit the taps-in-N tcgen05 convolution (stride 1, Cout <= 8, Cin % 8) or no workspace");
   if (engine != 2 && workspace && (NZ == 1 || stride == 1)) {
     char* ws = static_cast<char*>(workspace);
     UmmaPackHead wh{w, (long long)Cin * taps, taps, Cout, 0};

@@ -144,9 +144,21 @@ int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int
   // dense stride-1 3x3x3 layer on the tensor cores (umma_conv.cuh); false when the shape does not fit
   auto try_umma = [&](int slot, const float* in, int ci, int dd, int hh, int ww, const float* wgt, const float* scale,
                       const float* shift, int relu, float* o, int co) -> int {
-    // Small-N 27-tap layers (conv0: N 8, prob: N 1) are bound by the 27 x 3 re-reads of the A operand from shared memory
-    // (335 us against 284 us for the direct FFMA kernel at cfg-2): tensor cores only from 16 output channels up.
-    if (no_umma || co < 16) return -1;
+    if (no_umma) return -1;
+    // Small-N 27-tap layers (conv0: N 8, prob: N 1): with shifted descriptors they are bound by the 27 x 3 re-reads of the
+    // A operand from shared memory (335 us against 284 us for the direct FFMA kernel at cfg-2), so their nine in-plane
+    // taps ride in the N dimension instead (umma_conv_tn_kernel: one pass over A, shifted row sum in the epilogue).
+    // Measured at cfg-2 (64 planes of 96x192): conv0 (Cin 32, Cout 8) 322 us against 453 us on the FFMA kernel; prob (Cin 8,
+    // Cout 1) 137 us against 115 us -- the fixed cost per CTA (TMEM allocation, nine-tap epilogue) needs >= 16 input channels
+    // to pay off (profiles/r01_umma_conv_notes.md).
+    if (co <= kTnCo) {
+      if (ci < 16) return -1;
+      UmmaConvTnPlan tp;
+      if (!umma_conv_tn_plan(tp, in, (long long)dd * hh * ww, ci, dd, hh, ww, wgt, (long long)ci * 27, 27, scale, shift, o, co, 3,
+                             relu, 1.0f, P.wpack[slot], P.wpack_bytes[slot]) || (long long)tp.grid.x * tp.grid.y < 96) return -1;
+      return umma_conv_tn_launch(tp, P.umma_err, st, "costreg conv (tcgen05, taps in N)");
+    }
+    if (co < 16) return -1;
     UmmaPackHead wh{wgt, (long long)ci * 27, 27, co, 0};
     UmmaHead oh{scale, shift, o, co, 0, 1.0f, relu, 1};
     UmmaConvPlan up;

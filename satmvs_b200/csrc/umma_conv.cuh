@@ -393,4 +393,309 @@ inline int umma_conv_launch(const UmmaConvPlan& P, int* error_flag, cudaStream_t
   return check_launch(what);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// "Taps in N" variant for layers with few output channels (Cout <= 8: CostRegNet conv0 and prob).
+// With N = Cout the shifted-descriptor kernel above re-reads the A operand from shared memory for every tap (27 x 3
+// MMAs per 8 channels).  Here the nine in-plane taps ride in the N dimension instead:
+//     D'[window position p][tap*8 + co] += A[p][8 ch] * W[(tap, co)][8 ch]^T          (N = 72 -> 80, ONE pass over A)
+// and the convolution is finished in the epilogue as a shifted row sum  out[q][co] = sum_tap D'[q + shift_tap][tap*8 + co],
+// staged through shared memory one tap (8 columns) at a time.  A CTA computes D' for R = 128*MT window positions of its
+// strip and emits the R - 2*Wp - 2 outputs whose nine rows all lie inside.  3 MMAs per (kz, chunk, tile) instead of 27.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTnNP = 80, kTnCo = 8;
+
+struct UmmaConvTn {
+  const float* in; long long in_cs;
+  const float4* wpack;     // [chunk][kz][part 2][kq KC/4][n 80] float4
+  const float* scale; const float* shift; float* out;
+  int Cin, Cout, D, H, W, NZ;
+  int TW, strips, MT, nout;   // nout = 128*MT - 2*(TW+2) - 2 outputs per CTA
+  int wts_resident;           // the packed weights of all steps fit in shared memory next to the window
+  float acc_scale; int relu;
+};
+
+struct UmmaPackTn { const float* w; long long w_co, w_ci; int Cin, Cout, NZ, KC; float4* out; };
+
+static __global__ void umma_pack_weights_tn_kernel(const __grid_constant__ UmmaPackTn a) {
+  const int nq = a.KC / 4;
+  const int total = (a.Cin / a.KC) * a.NZ * 2 * nq * kTnNP;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i % kTnNP;
+  int r = i / kTnNP;
+  const int kq = r % nq; r /= nq;
+  const int part = r % 2; r /= 2;
+  const int kz = r % a.NZ;
+  const int chunk = r / a.NZ;
+  const int tap = n / kTnCo, co = n - tap * kTnCo;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (tap < 9 && co < a.Cout) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = chunk * a.KC + 4 * kq + j;
+      const float w = __ldg(a.w + (long long)co * a.w_co + (long long)ci * a.w_ci + kz * 9 + tap);
+      const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+      v[j] = part ? (w - hi) : w;
+    }
+  }
+  a.out[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int NZ, int KC>      // KC input channels per step (8 or 16): fewer, fatter steps when Cin allows
+__global__ void __launch_bounds__(kUcThreads, 2)
+umma_conv_tn_kernel(const __grid_constant__ UmmaConvTn a, int* error_flag) {
+  constexpr int NQ = KC / 4;                                           // channel quads (16-byte K chunks) per step
+  extern __shared__ __align__(128) unsigned char uc_smem[];
+  const int PW = 128 * a.MT;                                           // window positions = MMA rows
+  float4* win = reinterpret_cast<float4*>(uc_smem);                    // [part 2][kq NQ][PW]; re-used as the epilogue stage [PW][8 floats]
+  float4* wts = win + 2 * NQ * PW;                                     // [part 2][kq NQ][80]
+  __shared__ unsigned tmem_base_s;
+  __shared__ __align__(8) unsigned long long bar, wbar;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Wp = a.TW + 2, HW = a.H * a.W;
+  const int d = blockIdx.y;
+  const int run = blockIdx.x / a.strips, sx = blockIdx.x - run * a.strips;
+  const int x0 = sx * a.TW;
+  const int q0 = Wp + run * a.nout;                                    // first output position (strip-local, row y = 0 starts at Wp)
+  const int w0 = q0 - Wp - 1;                                          // strip-local position of window index 0
+  const int tmem_cols = uc_tmem_cols(a.MT * kTnNP);
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&wbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(uc_smem_u32(&tmem_base_s)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  constexpr int NPOS = 2;                                              // PW <= 512
+  int src_off[NPOS];
+#pragma unroll
+  for (int j = 0; j < NPOS; ++j) {
+    const int p = tid + j * kUcThreads;
+    const int qs = w0 + p;
+    const int ry = qs / Wp, rx = qs - ry * Wp;
+    const int y = ry - 1, x = x0 - 1 + rx;
+    const bool ok = p < PW && qs >= 0 && y >= 0 && y < a.H && x >= 0 && x < a.W;
+    src_off[j] = ok ? y * a.W + x : -1;
+  }
+  float v[NPOS][KC];
+  auto load_chunk = [&](int c, int zi) {
+    const float* in_c = a.in + (long long)(c * KC) * a.in_cs + (long long)zi * HW;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const float* in_k = in_c + k * a.in_cs;
+#pragma unroll
+      for (int j = 0; j < NPOS; ++j) v[j][k] = src_off[j] >= 0 ? __ldg(in_k + src_off[j]) : 0.0f;
+    }
+  };
+  constexpr int zoff = NZ >> 1;
+  const int nsteps = (a.Cin / KC) * NZ;
+  auto next_step = [&](int s0) {
+    if (NZ > 1)
+      while (s0 < nsteps) { const int zi = d + (s0 % NZ) - zoff; if (zi >= 0 && zi < a.D) break; ++s0; }
+    return s0;
+  };
+  int step = next_step(0);
+  load_chunk(step / NZ, d + (step % NZ) - zoff);
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = tmem_base_s;
+  const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTnNP >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  const unsigned wts_bytes = (unsigned)(2 * NQ * kTnNP) * 16u;
+  bool alive = true;
+  int done = 0;
+  // Packed weights: all steps at once when they fit (one TMA bulk copy per CTA, no per-step wait), else step by step
+  const bool resident = a.wts_resident != 0;
+  if (resident && tid == 0) {
+    const unsigned all = wts_bytes * (unsigned)nsteps;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(uc_smem_u32(&wbar)), "r"(all) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(uc_smem_u32(wts)), "l"(reinterpret_cast<const char*>(a.wpack)), "r"(all), "r"(uc_smem_u32(&wbar)) : "memory");
+  }
+  while (step < nsteps) {
+    if (done > 0) alive = uc_wait(&bar, (unsigned)(done - 1) & 1u) && alive;   // previous step's MMAs have read the window (and the weights)
+    if (!resident && tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(uc_smem_u32(&wbar)), "r"(wts_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(uc_smem_u32(wts)), "l"(reinterpret_cast<const char*>(a.wpack) + (size_t)step * wts_bytes), "r"(wts_bytes),
+                     "r"(uc_smem_u32(&wbar)) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < NPOS; ++j) {
+      const int p = tid + j * kUcThreads;
+      if (p < PW) {
+        float lo[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) lo[k] = v[j][k] - __uint_as_float(__float_as_uint(v[j][k]) & 0xffffe000u);
+#pragma unroll
+        for (int qd = 0; qd < NQ; ++qd) {
+          win[qd * PW + p] = make_float4(v[j][4 * qd], v[j][4 * qd + 1], v[j][4 * qd + 2], v[j][4 * qd + 3]);
+          win[(NQ + qd) * PW + p] = make_float4(lo[4 * qd], lo[4 * qd + 1], lo[4 * qd + 2], lo[4 * qd + 3]);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0 && uc_elect_one()) {
+      if (!resident) alive = uc_wait(&wbar, (unsigned)done & 1u) && alive;
+      else if (done == 0) alive = uc_wait(&wbar, 0u) && alive;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned lbo_a = (unsigned)PW * 16u, lbo_b = (unsigned)kTnNP * 16u;
+      const unsigned long long da0 = uc_desc(uc_smem_u32(win), lbo_a, 128);
+      const unsigned long long db0 = uc_desc(uc_smem_u32(wts), lbo_b, 128) + (resident ? (unsigned)step * (wts_bytes >> 4) : 0u);
+      const unsigned a_lo_off = (unsigned)(NQ * PW), b_lo_off = (unsigned)(NQ * kTnNP);    // 16-byte units
+      for (int mt = 0; mt < a.MT; ++mt) {
+        const unsigned dcol = tmem + (unsigned)(mt * kTnNP);
+#pragma unroll
+        for (int ks = 0; ks < KC / 8; ++ks) {                            // one MMA covers 8 channels = 2 quads
+          const unsigned long long a_raw = da0 + (unsigned)(128 * mt + 2 * ks * PW), a_lo = a_raw + a_lo_off;
+          const unsigned long long b_raw = db0 + (unsigned)(2 * ks * kTnNP);
+          uc_mma_tf32(dcol, a_raw, b_raw, idesc, (done == 0 && ks == 0) ? 0u : 1u);
+          uc_mma_tf32(dcol, a_raw, b_raw + b_lo_off, idesc, 1u);
+          uc_mma_tf32(dcol, a_lo, b_raw, idesc, 1u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(uc_smem_u32(&bar)) : "memory");
+    }
+    __syncwarp();
+    step = next_step(step + 1);
+    ++done;
+    if (step < nsteps) load_chunk(step / NZ, d + (step % NZ) - zoff);
+  }
+  alive = uc_wait(&bar, (unsigned)(done - 1) & 1u) && alive;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!alive) {
+    if (tid == 0) atomicExch(error_flag, 1);
+    __trap();
+  }
+
+  // epilogue: shifted row sum over the nine taps, one tap (8 columns of every row) through shared memory at a time
+  float* stage = reinterpret_cast<float*>(uc_smem);                    // [PW][8] floats (the window is no longer needed)
+  float acc[NPOS][kTnCo];
+#pragma unroll
+  for (int j = 0; j < NPOS; ++j)
+#pragma unroll
+    for (int c = 0; c < kTnCo; ++c) acc[j][c] = 0.0f;
+  const int quarter = warp & 3;
+  for (int tap = 0; tap < 9; ++tap) {
+    for (int mt = warp >> 2; mt < a.MT; mt += kUcThreads / 128) {
+      unsigned r[8];
+      const unsigned taddr = tmem + ((unsigned)(32 * quarter) << 16) + (unsigned)(mt * kTnNP + tap * kTnCo);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float4* dst = reinterpret_cast<float4*>(stage + (size_t)(128 * mt + 32 * quarter + lane) * kTnCo);
+      dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+      dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+    }
+    __syncthreads();
+    const int shift = (tap / 3) * Wp + (tap % 3);                      // row of tap (dy, dx) for output o: o + (dy+1)*Wp + (dx+1)
+#pragma unroll
+    for (int j = 0; j < NPOS; ++j) {
+      const int o = tid + j * kUcThreads;
+      if (o < a.nout) {
+        const float4* srcp = reinterpret_cast<const float4*>(stage + (size_t)(o + shift) * kTnCo);
+        const float4 s0 = srcp[0], s1 = srcp[1];
+        acc[j][0] += s0.x; acc[j][1] += s0.y; acc[j][2] += s0.z; acc[j][3] += s0.w;
+        acc[j][4] += s1.x; acc[j][5] += s1.y; acc[j][6] += s1.z; acc[j][7] += s1.w;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < NPOS; ++j) {
+    const int o = tid + j * kUcThreads;
+    const int q = q0 + o;
+    const int ry = q / Wp, rx = q - ry * Wp;
+    const int y = ry - 1, x = x0 - 1 + rx;
+    if (o < a.nout && y < a.H && rx >= 1 && rx <= a.TW && x < a.W) {
+      float* op = a.out + (long long)d * HW + (long long)y * a.W + x;
+#pragma unroll
+      for (int c = 0; c < kTnCo; ++c) {
+        if (c < a.Cout) {
+          float val = acc[j][c] * a.acc_scale;
+          if (a.scale) val *= __ldg(a.scale + c);
+          if (a.shift) val += __ldg(a.shift + c);
+          if (a.relu) val = fmaxf(val, 0.0f);
+          op[(long long)c * a.D * HW] = val;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+}
+
+struct UmmaConvTnPlan { UmmaConvTn conv; UmmaPackTn pack; size_t smem, wpack_bytes; dim3 grid; };
+
+inline bool umma_conv_tn_plan(UmmaConvTnPlan& P, const float* in, long long in_cs, int Cin, int D, int H, int W, const float* w,
+                              long long w_co, long long w_ci, const float* scale, const float* shift, float* out, int Cout, int NZ,
+                              int relu, float acc_scale, void* wpack_buf, size_t wpack_cap) {
+  if (Cin % kUcKC || Cout < 1 || Cout > kTnCo || (NZ != 1 && NZ != 3)) return false;
+  P = UmmaConvTnPlan{};
+  // strips and tiles: rows issued per useful output = 128*MT / (128*MT - 2*Wp - 2), three tiles (240 TMEM columns, 2 CTAs per SM)
+  int TW = 0, MT = 0;
+  double best = 1e30;
+  for (int nstr = 1; nstr <= 64; ++nstr) {
+    const int tw = (W + nstr - 1) / nstr, wp = tw + 2;
+    if (tw < 16 && nstr > 1) break;
+    for (int mt = 1; mt <= 3; ++mt) {
+      const int nout = 128 * mt - 2 * wp - 2;
+      if (nout < 32) continue;
+      const double runs = (double)((H * wp + nout - 1) / nout);
+      double cost = 128.0 * mt * runs * nstr;
+      if (tw < 32) cost *= 1.15;
+      if (cost < best) { best = cost; TW = tw; MT = mt; }
+    }
+  }
+  if (TW == 0) return false;
+  static const bool k16 = getenv("SATMVS_UMMA_TN_K16") != nullptr;     // 16-channel steps: measured no faster (332 against 322 us)
+  const int KC = (k16 && Cin % 16 == 0) ? 16 : 8;
+  P.wpack_bytes = (size_t)Cin / 4 * NZ * 2 * kTnNP * 16;               // independent of KC
+  if (wpack_buf == nullptr || wpack_cap < P.wpack_bytes || (reinterpret_cast<uintptr_t>(wpack_buf) & 15)) return false;
+  P.pack = UmmaPackTn{w, w_co, w_ci, Cin, Cout, NZ, KC, static_cast<float4*>(wpack_buf)};
+  UmmaConvTn& c = P.conv;
+  c.in = in; c.in_cs = in_cs; c.wpack = static_cast<const float4*>(wpack_buf); c.scale = scale; c.shift = shift; c.out = out;
+  c.Cin = Cin; c.Cout = Cout; c.D = D; c.H = H; c.W = W; c.NZ = NZ;
+  c.TW = TW; c.strips = ceil_div(W, TW); c.MT = MT; c.nout = 128 * MT - 2 * (TW + 2) - 2;
+  c.acc_scale = acc_scale; c.relu = relu;
+  const size_t win_bytes = (size_t)2 * (KC / 4) * 128 * MT * 16, step_bytes = (size_t)2 * (KC / 4) * kTnNP * 16;
+  c.wts_resident = step_bytes * (Cin / KC) * NZ <= 64 * 1024;
+  P.smem = win_bytes + (c.wts_resident ? step_bytes * (Cin / KC) * NZ : step_bytes);
+  P.grid = dim3(c.strips * ceil_div((long long)H * (TW + 2), c.nout), D, 1);
+  return true;
+}
+
+inline int umma_conv_tn_launch(const UmmaConvTnPlan& P, int* error_flag, cudaStream_t st, const char* what) {
+  const int total = P.pack.Cin / 4 * P.pack.NZ * 2 * kTnNP;
+  umma_pack_weights_tn_kernel<<<ceil_div(total, 256), 256, 0, st>>>(P.pack);
+  static thread_local int ready_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (ready_dev != dev) {
+    cudaFuncSetAttribute(umma_conv_tn_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute(umma_conv_tn_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute(umma_conv_tn_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute(umma_conv_tn_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    ready_dev = dev;
+  }
+  const bool k16 = P.pack.KC == 16;
+  if (P.conv.NZ == 1) {
+    if (k16) umma_conv_tn_kernel<1, 16><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+    else umma_conv_tn_kernel<1, 8><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  } else {
+    if (k16) umma_conv_tn_kernel<3, 16><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+    else umma_conv_tn_kernel<3, 8><<<P.grid, kUcThreads, P.smem, st>>>(P.conv, error_flag);
+  }
+  return check_launch(what);
+}
+
 }  // namespace satmvs

@@ -40,7 +40,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
-_ENGINES = {"auto": 0, "tcgen05": 1, "ffma": 2}
+_ENGINES = {"auto": 0, "tcgen05": 1, "ffma": 2, "tcgen05_tn": 3}
 
 
 def conv_block(x, weight, scale=None, shift=None, *, stride=1, relu=False, acc_scale=1.0, engine="auto"):
