@@ -276,23 +276,25 @@ direct_deconv2x_kernel(const __grid_constant__ DirectDeconv a) {
       }
     }
     __syncthreads();
-    for (int c = 0; c < nci; ++c) {
+    // rows of input channel c (two rows x 5 values); the next channel's loads are issued before this channel's FMAs
+    auto load_rows = [&](int c, float (&r0)[kDdPx + 1], float (&r1)[kDdPx + 1]) {
       const float* rp = in0 + (long long)(c0 + c) * a.in_cs;
-      float r0[kDdPx + 1], r1[kDdPx + 1];
-      {
-        float4 m = make_float4(0.f, 0.f, 0.f, 0.f), n = m;
-        float e0 = 0.f, e1 = 0.f;
-        if (ok) {
-          m = __ldg(reinterpret_cast<const float4*>(rp));
-          if (rok) e0 = __ldg(rp + kDdPx);
-          if (row1) {
-            n = __ldg(reinterpret_cast<const float4*>(rp + a.Wi));
-            if (rok) e1 = __ldg(rp + a.Wi + kDdPx);
-          }
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f), n = m;
+      float e0 = 0.f, e1 = 0.f;
+      if (ok) {
+        m = __ldg(reinterpret_cast<const float4*>(rp));
+        if (rok) e0 = __ldg(rp + kDdPx);
+        if (row1) {
+          n = __ldg(reinterpret_cast<const float4*>(rp + a.Wi));
+          if (rok) e1 = __ldg(rp + a.Wi + kDdPx);
         }
-        r0[0] = m.x; r0[1] = m.y; r0[2] = m.z; r0[3] = m.w; r0[4] = e0;
-        r1[0] = n.x; r1[1] = n.y; r1[2] = n.z; r1[3] = n.w; r1[4] = e1;
       }
+      r0[0] = m.x; r0[1] = m.y; r0[2] = m.z; r0[3] = m.w; r0[4] = e0;
+      r1[0] = n.x; r1[1] = n.y; r1[2] = n.z; r1[3] = n.w; r1[4] = e1;
+    };
+    float ra0[kDdPx + 1], ra1[kDdPx + 1], rb0[kDdPx + 1], rb1[kDdPx + 1];
+    load_rows(0, ra0, ra1);
+    auto fma_rows = [&](int c, const float (&r0)[kDdPx + 1], const float (&r1)[kDdPx + 1]) {
       float wv[9][kDdCo];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
@@ -309,6 +311,13 @@ direct_deconv2x_kernel(const __grid_constant__ DirectDeconv a) {
           acc[i][1][2 * j + 1] = fmaf(r1[j + 1], wv[0][i], fmaf(r1[j], wv[2][i],
                                  fmaf(r0[j + 1], wv[6][i], fmaf(r0[j], wv[8][i], acc[i][1][2 * j + 1]))));
         }
+    };
+#pragma unroll 1
+    for (int c = 0; c < nci; c += 2) {
+      if (c + 1 < nci) load_rows(c + 1, rb0, rb1);
+      fma_rows(c, ra0, ra1);
+      if (c + 2 < nci) load_rows(c + 2, ra0, ra1);
+      if (c + 1 < nci) fma_rows(c + 1, rb0, rb1);
     }
   }
   if (!ok) return;
