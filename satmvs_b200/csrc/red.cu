@@ -24,6 +24,7 @@
 #include "umma_conv.cuh"
 #include "packed.cuh"
 #include "prof.cuh"
+#include "red_cluster.cuh"
 namespace cg = cooperative_groups;
 
 namespace satmvs {
@@ -950,6 +951,32 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
   // ---- B. recurrence over planes ----
   bool persistent = false;
   {
+    // Default: one launch, one 16-CTA cluster per UNet level (red_cluster.cuh).  Shapes it does not take (rows not a
+    // multiple of 4 pixels, strips beyond the shared-memory limit) and SATMVS_RED_NO_CLUSTER=1 run the per-plane chain.
+    const bool no_cluster = getenv("SATMVS_RED_NO_CLUSTER") != nullptr;   // read per call: tests toggle it
+    if (!no_cluster) {
+      ClArgs ca{};
+      ca.D = D;
+      for (int l = 0; l < 4; ++l) {
+        RedLevel& L = P.lv[l];
+        ClLevel& R = ca.l[l];
+        const long long px = (long long)L.h * L.w;
+        R.s = L.s; R.s_cs = (long long)(D + 1) * px;
+        R.gx = L.gx; R.g_cs = (long long)D * px;
+        R.ox = L.ox; R.o_cs = (long long)D * px;
+        R.rh = L.rh;
+        R.gate_w = wt->gate_w[l] + (size_t)L.cx * 9; R.out_w = wt->out_w[l] + (size_t)L.cx * 9;
+        R.w_co = (long long)(L.cx + L.ch) * 9;
+        R.rn_w = wt->rn_w[l]; R.rn_b = wt->rn_b[l]; R.un_w = wt->un_w[l]; R.un_b = wt->un_b[l];
+        R.on_w = wt->on_w[l]; R.on_b = wt->on_b[l];
+        R.inv_n = 1.0 / ((double)L.ch * (double)px);
+        R.ch = L.ch; R.h = L.h; R.w = L.w; R.px = (int)px;
+      }
+      ProfScope prof(kProfGruGate, st);     // one class: the cluster kernel has no per-phase boundary
+      RUN(red_cluster_launch(ca, st, &persistent));
+    }
+  }
+  if (!persistent) {
     RecArgs ra{};
     ra.stats = P.stats; ra.D = D;
     static const bool dbg_timers = getenv("SATMVS_RED_DEBUG_TIMERS") != nullptr;

@@ -61,6 +61,26 @@ def test_volume_vs_oracle(C, D, H, W):
     assert maxdiff(got, want) < 2e-4 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("C,D,H,W", [(32, 12, 32, 64), (32, 4, 96, 192), (8, 3, 8, 32), (16, 2, 40, 96)])
+def test_cluster_recurrence_equals_kernel_chain(C, D, H, W, monkeypatch):
+    """The one-launch cluster recurrence (red_cluster.cuh) and the per-plane kernel chain compute the same
+    arithmetic graph with different summation orders over the input-channel chunks."""
+    sd = synth.make_red_weights(C, seed=7)
+    m = satmvs_b200.RED_Regularization(C, 8)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    x = synth.make_features(1, 1, C * D, H, W, seed=11)[0].view(1, C, D, H, W).abs().to(DEV)
+    monkeypatch.delenv("SATMVS_RED_NO_CLUSTER", raising=False)
+    a = m(x).clone()
+    monkeypatch.setenv("SATMVS_RED_NO_CLUSTER", "1")
+    b = m(x).clone()
+    monkeypatch.delenv("SATMVS_RED_NO_CLUSTER", raising=False)
+    want = regnets.red_regularization(x.cpu(), sd)
+    scale = max(1.0, want.abs().max().item())
+    assert maxdiff(a, b) < 5e-5 * scale
+    assert maxdiff(a, want) < 2e-4 * scale
+
+
 def test_pred_stage_equals_train_stage():
     """Plane-streaming inference form == whole-volume form (the reference's two nets agree to
     1.7e-5 relative)."""
