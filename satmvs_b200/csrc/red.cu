@@ -56,6 +56,7 @@ struct RedLevel {
   float* gx;             // [2ch][D][h][w]   gates (x-half, then full gates in place)
   float* ox;             // [ch][D][h][w]    output conv (x-half, then full in place)
   float* rh;             // [ch][1][h][w]
+  float* ub;             // [ch][1][h][w]   update gate of the current plane (cluster recurrence)
   float* s;              // [ch][D+1][h][w]  state history; slot 0 = initial state
 };
 
@@ -68,6 +69,7 @@ struct RedPlan {
   char* wpack[4]; size_t wpack_bytes[4];
   int* umma_err;
   int* fuse_cnt;
+  int* cl_flags;         // [4][2][kClFlagStride] plane counters exchanged by the two clusters of a level
   size_t bytes;
 };
 
@@ -89,6 +91,7 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
     L.gx = take(2 * L.ch * D * px);
     L.ox = take(L.ch * D * px);
     L.rh = take(L.ch * px);
+    L.ub = take(L.ch * px);
     L.s = take(L.ch * (size_t)(D + 1) * px);
   }
   for (int i = 0; i < 3; ++i) {
@@ -106,6 +109,8 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   off += 256;
   p.fuse_cnt = reinterpret_cast<int*>(base + off);           // [D][4][2] level-barrier counters of the fused pointwise tails
   off += ((size_t)D * 4 * 2 * sizeof(int) + 255) / 256 * 256;
+  p.cl_flags = reinterpret_cast<int*>(base + off);
+  off += 4 * 2 * 32 * sizeof(int) + 6 * 16 * sizeof(unsigned long long);   // + debug counters
   p.bytes = off;
   return p;
 }
@@ -951,7 +956,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
   // ---- B. recurrence over planes ----
   bool persistent = false;
   {
-    // Default: one launch, one 16-CTA cluster per UNet level (red_cluster.cuh).  Shapes it does not take (rows not a
+    // Default: one launch, two 16-CTA clusters per UNet level (red_cluster.cuh).  Shapes it does not take (rows not a
     // multiple of 4 pixels, strips beyond the shared-memory limit) and SATMVS_RED_NO_CLUSTER=1 run the per-plane chain.
     const bool no_cluster = getenv("SATMVS_RED_NO_CLUSTER") != nullptr;   // read per call: tests toggle it
     if (!no_cluster) {
@@ -964,7 +969,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
         R.s = L.s; R.s_cs = (long long)(D + 1) * px;
         R.gx = L.gx; R.g_cs = (long long)D * px;
         R.ox = L.ox; R.o_cs = (long long)D * px;
-        R.rh = L.rh;
+        R.rh = L.rh; R.ub = L.ub;
         R.gate_w = wt->gate_w[l] + (size_t)L.cx * 9; R.out_w = wt->out_w[l] + (size_t)L.cx * 9;
         R.w_co = (long long)(L.cx + L.ch) * 9;
         R.rn_w = wt->rn_w[l]; R.rn_b = wt->rn_b[l]; R.un_w = wt->un_w[l]; R.un_b = wt->un_b[l];
@@ -973,7 +978,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
         R.ch = L.ch; R.h = L.h; R.w = L.w; R.px = (int)px;
       }
       ProfScope prof(kProfGruGate, st);     // one class: the cluster kernel has no per-phase boundary
-      RUN(red_cluster_launch(ca, st, &persistent));
+      RUN(red_cluster_launch(ca, P.cl_flags, st, &persistent));
     }
   }
   if (!persistent) {
