@@ -29,6 +29,14 @@
 
 namespace satmvs {
 
+#ifndef SATMVS_CL_UNROLL
+#define SATMVS_CL_UNROLL 4
+#endif
+
+#ifndef SATMVS_CL_UNROLL
+#define SATMVS_CL_UNROLL 4
+#endif
+constexpr int kClUnroll = SATMVS_CL_UNROLL;   // input channels per unrolled step of the conv loop (tuning knob)
 constexpr int kClSize = 16;              // CTAs per cluster (non-portable size, opt-in)
 constexpr int kClThreads = 576;          // 18 warps: 576 = ch/4 chunks x 288 / (ch/8) pixel quads at 96x192, every level
 constexpr int kClWarps = kClThreads / 32;
@@ -41,7 +49,7 @@ struct ClLevel {
   const float* ox; long long o_cs;       // output x-halves [ch][D][px]
   float* rh;                             // [ch][px]
   float* ub;                             // [ch][px]   update gate of the current plane (cluster B -> cluster A)
-  int* flags;                            // [0] = planes of h' published by A, [kClFlagStride] = planes of u published by B
+  int* flags;                            // [0] = planes of h' published by A, [kClFlagStride] = CTA-shares of u published by B (16 per plane)
   const float* gate_w; const float* out_w; long long w_co;   // hidden-state halves of the conv weights
   const float *rn_w, *rn_b, *un_w, *un_b, *on_w, *on_b;
   double inv_n;
@@ -80,7 +88,7 @@ __device__ __forceinline__ void cl_st_release(int* p, int v) { asm volatile("st.
 template <int CI>
 __device__ __forceinline__ void cl_conv_unit(const float* __restrict__ tile_px, int ci_stride, int pitch,
                                              const float* __restrict__ wsm, u64 (&acc2)[4][4]) {
-#pragma unroll 2
+#pragma unroll kClUnroll
   for (int c = 0; c < CI; ++c) {
     const float* tp = tile_px + c * ci_stride;
     u64 rr[3][6];
@@ -154,15 +162,17 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
     px_off0 = (long long)(y0 + ly0) * w + x0;
   };
 
-  // shared-memory layout.  A: [Wr][Wo][tile][part][own h]; B: [Wu(first level)][Wu(second level)][tile][part]
+  // shared-memory layout.  A: [Wr][Wo][tile][part][own h]; B: [Wu(first level)][Wu(second level)][tile 1][tile 2][part]
   const int lvA = roleB ? 2 * (cid - 4) : cid, lvB = roleB ? lvA + 1 : cid;
   const ClSmemPlan spA = cl_smem_plan(a.l[lvA].ch, a.l[lvA].w, a.l[lvA].R), spB = cl_smem_plan(a.l[lvB].ch, a.l[lvB].w, a.l[lvB].R);
   float* w0s = cl_smem;                     // [ci][tap][8]
   float* w1s = w0s + spA.wsm;               // [ci][tap][8]
-  float* tile = w1s + spB.wsm;              // [ci][R+2][pitch], pixel x at column 4 + x; borders are zero
-  float* part = tile + (spA.tile > spB.tile ? spA.tile : spB.tile);   // [chunk][8][NPX]
-  float* keepH = part + (spA.part > spB.part ? spA.part : spB.part);  // this CTA's own channels of h (A)
-  const int tile_floats = spA.tile > spB.tile ? spA.tile : spB.tile;
+  float* tile0 = w1s + spB.wsm;             // [ci][R+2][pitch], pixel x at column 4 + x; borders stay zero
+  float* tile1 = roleB ? tile0 + spA.tile : tile0;
+  float* tile = tile0;
+  float* part = tile1 + spB.tile;           // [chunk][8][NPX]
+  float* keepH = part + spA.part;           // this CTA's own channels of h (A)
+  const int tile_floats = roleB ? spA.tile + spB.tile : spA.tile;
 
   // ---- once: filters resident, tile zero ----
   for (int k = 0; k < 2; ++k) {
@@ -327,7 +337,7 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
     for (int d = 0; d < a.D; ++d) {
       for (int sub = 0; sub < 2; ++sub) {
         setup(sub ? lvB : lvA);
-        for (int i = tid; i < tile_floats; i += kClThreads) tile[i] = 0.0f;   // the two levels lay the tile out differently
+        tile = sub ? tile1 : tile0;
         const long long plane_g = (long long)d * Lp->px;
         wait_flag(Lp->flags, d);                             // h[d] published by cluster A (slot 0: before the launch)
         double ss = 0.0, sq = 0.0;
@@ -345,8 +355,8 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
                                        cl_sigmoid(fmaf(g.z, ca, cb)), cl_sigmoid(fmaf(g.w, ca, cb)));
           *reinterpret_cast<float4*>(Lp->ub + (long long)(c_own + co) * Lp->px + (long long)(y0 + ly) * w + x) = u;
         }
-        cluster.sync();                                      // u[d] of the whole level is in L2
-        if (rank == 0 && tid == 0) { __threadfence(); cl_st_release(Lp->flags + kClFlagStride, d + 1); }
+        __syncthreads();                                     // this CTA's share of u[d] is written: count it (16 per plane)
+        if (tid == 0) { __threadfence(); atomicAdd(Lp->flags + kClFlagStride, 1); }
       }
     }
   } else {
@@ -393,7 +403,7 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
       cluster.barrier_arrive();                              // #3: output-conv sums are published
       mark(7);
       // the update gate of this plane (cluster B, normally long finished): loads fly across the barrier
-      wait_flag(Lp->flags + kClFlagStride, d + 1);
+      wait_flag(Lp->flags + kClFlagStride, kClSize * (d + 1));
       float4 uv[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -460,7 +470,7 @@ inline size_t red_cluster_smem_bytes(const ClArgs& a, int smem_optin) {
   }
   for (int c = 0; c < 2; ++c) {                                                                // role B of levels 2c, 2c + 1
     const ClSmemPlan &p = sp[2 * c], &q = sp[2 * c + 1];
-    const size_t b = (size_t)(p.wsm + q.wsm + (p.tile > q.tile ? p.tile : q.tile) + (p.part > q.part ? p.part : q.part)) * sizeof(float);
+    const size_t b = (size_t)(p.wsm + q.wsm + p.tile + q.tile + (p.part > q.part ? p.part : q.part)) * sizeof(float);
     need = b > need ? b : need;
   }
   if (need + kClStaticSmemBytes > (size_t)smem_optin) return 0;
