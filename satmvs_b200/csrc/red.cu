@@ -56,7 +56,7 @@ struct RedLevel {
   float* gx;             // [2ch][D][h][w]   gates (x-half, then full gates in place)
   float* ox;             // [ch][D][h][w]    output conv (x-half, then full in place)
   float* rh;             // [ch][1][h][w]
-  float* ub;             // [ch][1][h][w]   update gate of the current plane (cluster recurrence)
+  float* ub;             // [2][ch][h][w]   update gate of the current / next plane (cluster recurrence)
   float* s;              // [ch][D+1][h][w]  state history; slot 0 = initial state
 };
 
@@ -91,7 +91,7 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
     L.gx = take(2 * L.ch * D * px);
     L.ox = take(L.ch * D * px);
     L.rh = take(L.ch * px);
-    L.ub = take(L.ch * px);
+    L.ub = take(2 * L.ch * px);
     L.s = take(L.ch * (size_t)(D + 1) * px);
   }
   for (int i = 0; i < 3; ++i) {
@@ -110,7 +110,7 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   p.fuse_cnt = reinterpret_cast<int*>(base + off);           // [D][4][2] level-barrier counters of the fused pointwise tails
   off += ((size_t)D * 4 * 2 * sizeof(int) + 255) / 256 * 256;
   p.cl_flags = reinterpret_cast<int*>(base + off);
-  off += 4 * 2 * 32 * sizeof(int) + 6 * 16 * sizeof(unsigned long long);   // + debug counters
+  off += 4 * 2 * 32 * sizeof(int) + 8 * 16 * sizeof(unsigned long long);   // + debug counters
   p.bytes = off;
   return p;
 }

@@ -48,7 +48,7 @@ struct ClLevel {
   const float* gx; long long g_cs;       // gate x-halves [2ch][D][px]
   const float* ox; long long o_cs;       // output x-halves [ch][D][px]
   float* rh;                             // [ch][px]
-  float* ub;                             // [ch][px]   update gate of the current plane (cluster B -> cluster A)
+  float* ub;                             // [2][ch][px] update gate of the current / next plane (clusters B -> cluster A)
   int* flags;                            // [0] = planes of h' published by A, [kClFlagStride] = CTA-shares of u published by B (16 per plane)
   const float* gate_w; const float* out_w; long long w_co;   // hidden-state halves of the conv weights
   const float *rn_w, *rn_b, *un_w, *un_b, *on_w, *on_b;
@@ -56,7 +56,7 @@ struct ClLevel {
   int ch, h, w, px;
   int CG, R;                             // channel groups (ch / 8), rows per strip (ceil(h / (16 / CG)))
 };
-struct ClArgs { ClLevel l[4]; int D; unsigned long long* dbg; };   // dbg: [6 clusters][16 slots] SM cycles per phase (SATMVS_RED_DEBUG)
+struct ClArgs { ClLevel l[4]; int D; int nb; unsigned long long* dbg; };   // nb: clusters in role B (2 or 3);   // dbg: [6 clusters][16 slots] SM cycles per phase (SATMVS_RED_DEBUG)
 
 struct ClSmemPlan { int wsm, tile, part, keep, total_floats; };
 __host__ __device__ inline ClSmemPlan cl_smem_plan(int ch, int w, int R) {
@@ -123,8 +123,9 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
   __shared__ double stat_out[2][2];         // this CTA's partial (sum, sum of squares): [0] first conv of a plane, [1] second
   __shared__ float coef[kClK][2];           // GroupNorm scale / shift of the current norm for this CTA's 8 channels
 
-  // clusters 0..3: role A of level cid; clusters 4, 5: role B of levels {0, 1} and {2, 3}, alternating (B carries a third
-  // of A's convolution work per level, so one B cluster keeps two levels ahead of their A clusters)
+  // clusters 0..3: role A of level cid; clusters 4..4+nb-1: role B, taking the (plane, level) tasks round-robin (a task
+  // depends only on that level's h[d], and B carries a third of A's convolution work per level, so two or three B
+  // clusters keep four A clusters supplied)
   const int cid = blockIdx.x / kClSize;
   const bool roleB = cid >= 4;
   const int rank = (int)cluster.block_rank();
@@ -162,29 +163,49 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
     px_off0 = (long long)(y0 + ly0) * w + x0;
   };
 
-  // shared-memory layout.  A: [Wr][Wo][tile][part][own h]; B: [Wu(first level)][Wu(second level)][tile 1][tile 2][part]
-  const int lvA = roleB ? 2 * (cid - 4) : cid, lvB = roleB ? lvA + 1 : cid;
-  const ClSmemPlan spA = cl_smem_plan(a.l[lvA].ch, a.l[lvA].w, a.l[lvA].R), spB = cl_smem_plan(a.l[lvB].ch, a.l[lvB].w, a.l[lvB].R);
-  float* w0s = cl_smem;                     // [ci][tap][8]
-  float* w1s = w0s + spA.wsm;               // [ci][tap][8]
-  float* tile0 = w1s + spB.wsm;             // [ci][R+2][pitch], pixel x at column 4 + x; borders stay zero
-  float* tile1 = roleB ? tile0 + spA.tile : tile0;
-  float* tile = tile0;
-  float* part = tile1 + spB.tile;           // [chunk][8][NPX]
-  float* keepH = part + spA.part;           // this CTA's own channels of h (A)
-  const int tile_floats = roleB ? spA.tile + spB.tile : spA.tile;
+  // shared-memory layout.  A: [Wr][Wo][tile][part][own h]; B: [Wu of levels 0..3][tile (largest level)][part (largest level)]
+  float *w0s, *w1s, *tile, *part, *keepH;
+  int tile_floats;
+  if (!roleB) {
+    const ClSmemPlan sp = cl_smem_plan(a.l[cid].ch, a.l[cid].w, a.l[cid].R);
+    w0s = cl_smem;                          // [ci][tap][8] reset-gate filters
+    w1s = w0s + sp.wsm;                     // [ci][tap][8] output-conv filters
+    tile = w1s + sp.wsm;                    // [ci][R+2][pitch], pixel x at column 4 + x; borders stay zero
+    part = tile + sp.tile;                  // [chunk][8][NPX]
+    keepH = part + sp.part;                 // this CTA's own channels of h
+    tile_floats = sp.tile;
+  } else {
+    int wtot = 0, tmax = 0;
+    for (int l = 0; l < 4; ++l) {
+      const ClSmemPlan sp = cl_smem_plan(a.l[l].ch, a.l[l].w, a.l[l].R);
+      wtot += sp.wsm; tmax = sp.tile > tmax ? sp.tile : tmax;
+    }
+    w0s = w1s = cl_smem;                    // level l's update-gate filters start at w0s + 72 * (sum of ch below l)
+    tile = cl_smem + wtot;
+    part = tile + tmax;
+    keepH = part;
+    tile_floats = tmax;
+  }
+  auto wu_of = [&](int lv) { int off = 0; for (int l = 0; l < lv; ++l) off += a.l[l].ch * 72; return w0s + off; };
 
   // ---- once: filters resident, tile zero ----
-  for (int k = 0; k < 2; ++k) {
-    setup(k ? lvB : lvA);
-    float* dst = k ? w1s : w0s;
-    const float* src = (roleB || k == 0) ? Lp->gate_w + (long long)(roleB ? ch : 0) * Lp->w_co : Lp->out_w;
+  if (!roleB) {
+    setup(cid);
     for (int i = tid; i < ch * 9 * 8; i += kClThreads) {
       const int co = i & 7, r = i >> 3;     // r = ci * 9 + tap
-      dst[i] = __ldg(src + (long long)(c_own + co) * Lp->w_co + r);
+      w0s[i] = __ldg(Lp->gate_w + (long long)(c_own + co) * Lp->w_co + r);
+      w1s[i] = __ldg(Lp->out_w + (long long)(c_own + co) * Lp->w_co + r);
+    }
+  } else {
+    for (int lv = 0; lv < 4; ++lv) {
+      setup(lv);
+      float* dst = wu_of(lv);
+      for (int i = tid; i < ch * 9 * 8; i += kClThreads) {
+        const int co = i & 7, r = i >> 3;
+        dst[i] = __ldg(Lp->gate_w + (long long)(ch + c_own + co) * Lp->w_co + r);
+      }
     }
   }
-  setup(lvA);
   for (int i = tid; i < tile_floats; i += kClThreads) tile[i] = 0.0f;
   __syncthreads();
 
@@ -327,37 +348,47 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
     __syncthreads();
   };
   auto wait_flag = [&](const int* flag, int target) {
-    if (tid == 0) while (cl_ld_acquire(flag) < target) { }
+    if (tid == 0) {
+      // bounded spin: the partner cluster is co-resident (checked by the host), so this normally takes a few polls; if it
+      // never arrives (~4 s) the kernel traps and the error surfaces at the caller's next synchronisation instead of a hang
+      const long long t0 = clock64();
+      while (cl_ld_acquire(flag) < target)
+        if (clock64() - t0 > (1LL << 33)) __trap();
+    }
     __syncthreads();
   };
 
 
   if (roleB) {
-    // ================= cluster B: u[d] = sigmoid(GN_u(GX_u[d] + conv(h[d]; Wu))) for two levels in turn =================
-    for (int d = 0; d < a.D; ++d) {
-      for (int sub = 0; sub < 2; ++sub) {
-        setup(sub ? lvB : lvA);
-        tile = sub ? tile1 : tile0;
-        const long long plane_g = (long long)d * Lp->px;
-        wait_flag(Lp->flags, d);                             // h[d] published by cluster A (slot 0: before the launch)
-        double ss = 0.0, sq = 0.0;
-        conv_phase(Lp->s + plane_g, Lp->s_cs, sub ? w1s : w0s, Lp->gx + (long long)(ch + c_own) * Lp->g_cs + plane_g, Lp->g_cs,
-                   d + 1 < a.D, ss, sq, [] {});
-        publish_stats(sub, ss, sq);
-        cluster.sync();
-        gather_coef(sub, Lp->un_w, Lp->un_b);
-        for (int o = tid; o < pw_items; o += kClThreads) {
-          const int co = cl_div(o, dv_npx4), p4 = o - co * npx4;
-          const int ly = cl_div(p4, dv_w4), x = (p4 - ly * w4) << 2;
-          const float4 g = *reinterpret_cast<const float4*>(part + (long long)co * NPX + 4 * p4);
-          const float ca = coef[co][0], cb = coef[co][1];
-          const float4 u = make_float4(cl_sigmoid(fmaf(g.x, ca, cb)), cl_sigmoid(fmaf(g.y, ca, cb)),
-                                       cl_sigmoid(fmaf(g.z, ca, cb)), cl_sigmoid(fmaf(g.w, ca, cb)));
-          *reinterpret_cast<float4*>(Lp->ub + (long long)(c_own + co) * Lp->px + (long long)(y0 + ly) * w + x) = u;
-        }
-        __syncthreads();                                     // this CTA's share of u[d] is written: count it (16 per plane)
-        if (tid == 0) { __threadfence(); atomicAdd(Lp->flags + kClFlagStride, 1); }
+    // ================= clusters B: u[d] = sigmoid(GN_u(GX_u[d] + conv(h[d]; Wu))), tasks (d, level) round-robin =================
+    int nt = 0;
+    for (int t = cid - 4; t < 4 * a.D; t += a.nb, ++nt) {
+      const int d = t >> 2, lv = t & 3;
+      setup(lv);
+      const float* wu = wu_of(lv);
+      {   // the levels lay the tile out differently: clear it (float4; tile sizes are multiples of 4 floats)
+        float4* t4 = reinterpret_cast<float4*>(tile);
+        for (int i = tid; i < (tile_floats >> 2); i += kClThreads) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      const long long plane_g = (long long)d * Lp->px;
+      wait_flag(Lp->flags, d);                               // h[d] published by cluster A (slot 0: before the launch)
+      double ss = 0.0, sq = 0.0;
+      conv_phase(Lp->s + plane_g, Lp->s_cs, wu, Lp->gx + (long long)(ch + c_own) * Lp->g_cs + plane_g, Lp->g_cs,
+                 d + 1 < a.D, ss, sq, [] {});
+      publish_stats(nt & 1, ss, sq);
+      cluster.sync();
+      gather_coef(nt & 1, Lp->un_w, Lp->un_b);
+      for (int o = tid; o < pw_items; o += kClThreads) {
+        const int co = cl_div(o, dv_npx4), p4 = o - co * npx4;
+        const int ly = cl_div(p4, dv_w4), x = (p4 - ly * w4) << 2;
+        const float4 g = *reinterpret_cast<const float4*>(part + (long long)co * NPX + 4 * p4);
+        const float ca = coef[co][0], cb = coef[co][1];
+        const float4 u = make_float4(cl_sigmoid(fmaf(g.x, ca, cb)), cl_sigmoid(fmaf(g.y, ca, cb)),
+                                     cl_sigmoid(fmaf(g.z, ca, cb)), cl_sigmoid(fmaf(g.w, ca, cb)));
+        *reinterpret_cast<float4*>(Lp->ub + ((long long)(d & 1) * ch + c_own + co) * Lp->px + (long long)(y0 + ly) * w + x) = u;
+      }
+      __syncthreads();                                       // this CTA's share of u[d] is written: count it (16 per plane)
+      if (tid == 0) { __threadfence(); atomicAdd(Lp->flags + kClFlagStride, 1); }
     }
   } else {
     // ================= cluster A =================
@@ -412,7 +443,7 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
         if (o < pw_items) {
           const int co = cl_div(o, dv_npx4), p4 = o - co * npx4;
           const int ly = cl_div(p4, dv_w4), x = (p4 - ly * w4) << 2;
-          uv[k] = __ldcg(reinterpret_cast<const float4*>(Lp->ub + (long long)(c_own + co) * Lp->px + (long long)(y0 + ly) * w + x));
+          uv[k] = __ldcg(reinterpret_cast<const float4*>(Lp->ub + ((long long)(d & 1) * ch + c_own + co) * Lp->px + (long long)(y0 + ly) * w + x));
         }
       }
       mark(8);
@@ -426,7 +457,7 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
         const int co = cl_div(o, dv_npx4), p4 = o - co * npx4;
         const int ly = cl_div(p4, dv_w4), x = (p4 - ly * w4) << 2;
         const long long goff = (long long)(y0 + ly) * w + x;
-        const float4 u = upre ? *upre : __ldcg(reinterpret_cast<const float4*>(Lp->ub + (long long)(c_own + co) * Lp->px + goff));
+        const float4 u = upre ? *upre : __ldcg(reinterpret_cast<const float4*>(Lp->ub + ((long long)(d & 1) * ch + c_own + co) * Lp->px + goff));
         const float4 y = *reinterpret_cast<const float4*>(part + (long long)co * NPX + 4 * p4);
         const float4 hv = *reinterpret_cast<const float4*>(keepH + (long long)co * NPX + 4 * p4);
         const float ca = coef[co][0], cb = coef[co][1];
@@ -468,9 +499,12 @@ inline size_t red_cluster_smem_bytes(const ClArgs& a, int smem_optin) {
     const size_t b = (size_t)sp[l].total_floats * sizeof(float);                             // role A of level l
     need = b > need ? b : need;
   }
-  for (int c = 0; c < 2; ++c) {                                                                // role B of levels 2c, 2c + 1
-    const ClSmemPlan &p = sp[2 * c], &q = sp[2 * c + 1];
-    const size_t b = (size_t)(p.wsm + q.wsm + p.tile + q.tile + (p.part > q.part ? p.part : q.part)) * sizeof(float);
+  {                                                                                            // role B: every level's filters
+    int wtot = 0, tmax = 0, pmax = 0;
+    for (int l = 0; l < 4; ++l) {
+      wtot += sp[l].wsm; tmax = sp[l].tile > tmax ? sp[l].tile : tmax; pmax = sp[l].part > pmax ? sp[l].part : pmax;
+    }
+    const size_t b = (size_t)(wtot + tmax + pmax) * sizeof(float);
     need = b > need ? b : need;
   }
   if (need + kClStaticSmemBytes > (size_t)smem_optin) return 0;
@@ -511,17 +545,23 @@ inline int red_cluster_launch(ClArgs& a, int* flags_base, cudaStream_t st, bool*
   attr[0].val.clusterDim.x = kClSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int nclusters = 0;
+  cfg.gridDim = dim3(7 * kClSize);
   if ((e = cudaOccupancyMaxActiveClusters(&nclusters, red_cluster_kernel, &cfg)) != cudaSuccess || nclusters < 6)
     { if (verbose) fprintf(stderr, "red_cluster_launch: max active clusters %d\n", nclusters); return declined("fewer than 6 co-resident clusters", e); }
+  // two role-B clusters keep the four A clusters supplied (measured: a third one changes nothing, 1.31 ms either way);
+  // SATMVS_RED_THREE_B=1 uses the seventh co-resident cluster anyway
+  static const bool three_b = getenv("SATMVS_RED_THREE_B") != nullptr;
+  a.nb = (nclusters >= 7 && three_b) ? 3 : 2;
+  cfg.gridDim = dim3((4 + a.nb) * kClSize);
   cudaMemsetAsync(flags_base, 0, 4 * 2 * kClFlagStride * sizeof(int), st);
   a.dbg = verbose ? reinterpret_cast<unsigned long long*>(flags_base + 4 * 2 * kClFlagStride) : nullptr;
   if ((e = cudaLaunchKernelEx(&cfg, red_cluster_kernel, a)) != cudaSuccess) return declined("launch", e);
 #ifdef SATMVS_CL_TIMERS
   if (verbose) {
-    unsigned long long h[6 * 16];
+    unsigned long long h[7 * 16] = {};
     cudaStreamSynchronize(st);
     cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    for (int c = 0; c < 6; ++c) {
+    for (int c = 0; c < 4 + a.nb; ++c) {
       fprintf(stderr, "red_cluster_launch: cluster %d kcycles per phase slot:", c);
       for (int i = 0; i < 16; ++i) fprintf(stderr, " %.0f", h[c * 16 + i] * 1e-3);
       fprintf(stderr, "\n");
