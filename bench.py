@@ -438,6 +438,9 @@ def run_ours(args, w):
                     k["kernel"] = "red_cluster_kernel (whole depth recurrence: 6 clusters x 16 CTAs = 96 of 148 SMs)"
                     k["us_per_plane"] = 1e3 * t_ms / prof_steps / w["D"]
                     k["fp32_ffma_frac"] = fl / (t_ms / prof_steps * 1e-3) / (148 * 128 * 2 * 1.965e9)
+                    k["bound_note"] = ("sequential-in-depth recurrence: latency-bound (L2 round trips + barriers between the two "
+                                       "convolutions of a plane); N = 8 output channels per CTA rules out tcgen05, so the useful "
+                                       "fraction is fp32_ffma_frac (FFMA peak of all 148 SMs), not the tensor figure")
                 ach = fl / (t_ms / prof_steps * 1e-3) / 1e12
                 note = ("tcgen05 kind::tf32, 3 MMAs per useful multiply-add (hi*hi + hi*lo + lo*hi) + FFMA2 direct kernels for the "
                         "rest; useful flops against the dense bf16 tensor peak" if name == "conv_batched"
@@ -449,8 +452,11 @@ def run_ours(args, w):
         line["kernels"] = kernels
         dom = next((k for k in kernels if "roofline" in k), None)
         if dom is not None:
-            line["roofline"] = dict(dom["roofline"], kernel=dom["class"], share_of_step=dom["share"],
+            line["roofline"] = dict(dom["roofline"], kernel=dom.get("kernel", dom["class"]), share_of_step=dom["share"],
                                     avg_launch_us=dom["avg_launch_us"], peak_source=peak_src)
+            for extra in ("fp32_ffma_frac", "us_per_plane", "bound_note"):
+                if extra in dom:
+                    line["roofline"][extra] = dom[extra]
         sw = next((k for k in kernels if k["class"] == "sweep"), None)
         if sw is not None and dom is not sw:
             line["roofline_sweep"] = dict(sw["roofline"], kernel="sweep", share_of_step=sw["share"],
