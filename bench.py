@@ -625,6 +625,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version there at
+    # communicator creation) are sent to stderr, and print() keeps the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         if w["stage"] == "cascade":   # the reference arm times one bounded stage-1 sample of the cascade's first stage
             w = dict(WORKLOADS["cfg2_stage1"], D=48, desc=w["desc"] + " [reference arm: stage 1 only]")
