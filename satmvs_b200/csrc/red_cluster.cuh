@@ -123,9 +123,10 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
   __shared__ double stat_out[2][2];         // this CTA's partial (sum, sum of squares): [0] first conv of a plane, [1] second
   __shared__ float coef[kClK][2];           // GroupNorm scale / shift of the current norm for this CTA's 8 channels
 
-  // clusters 0..3: role A of level cid; clusters 4..4+nb-1: role B, taking the (plane, level) tasks round-robin (a task
-  // depends only on that level's h[d], and B carries a third of A's convolution work per level, so two or three B
-  // clusters keep four A clusters supplied)
+  // clusters 0..3: role A of level cid; clusters 4, 5: role B of levels {0, 1} and {2, 3} (B carries a third of A's
+  // convolution work per level; a B200 keeps seven such clusters resident, so a B cluster serves two levels and the
+  // second level's tile is prefetched behind the first level's tail.  Measured with the clock64 marks below: a B cluster
+  // needs ~42 k cycles per plane for its two levels against ~37 k for an A cluster, so A waits ~10 % of a plane for u)
   const int cid = blockIdx.x / kClSize;
   const bool roleB = cid >= 4;
   const int rank = (int)cluster.block_rank();
@@ -175,18 +176,18 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
     keepH = part + sp.part;                 // this CTA's own channels of h
     tile_floats = sp.tile;
   } else {
-    int wtot = 0, tmax = 0;
-    for (int l = 0; l < 4; ++l) {
-      const ClSmemPlan sp = cl_smem_plan(a.l[l].ch, a.l[l].w, a.l[l].R);
-      wtot += sp.wsm; tmax = sp.tile > tmax ? sp.tile : tmax;
-    }
-    w0s = w1s = cl_smem;                    // level l's update-gate filters start at w0s + 72 * (sum of ch below l)
-    tile = cl_smem + wtot;
-    part = tile + tmax;
+    // levels la = 2 (cid - 4) and lb = la + 1: both filter banks and both tiles stay resident
+    const int la = 2 * (cid - 4);
+    const ClSmemPlan spa = cl_smem_plan(a.l[la].ch, a.l[la].w, a.l[la].R), spb = cl_smem_plan(a.l[la + 1].ch, a.l[la + 1].w, a.l[la + 1].R);
+    w0s = cl_smem;                          // Wu of level la
+    w1s = w0s + spa.wsm;                    // Wu of level lb
+    tile = w1s + spb.wsm;                   // tile of level la, then tile of level lb
+    part = tile + spa.tile + spb.tile;
     keepH = part;
-    tile_floats = tmax;
+    tile_floats = spa.tile + spb.tile;
   }
-  auto wu_of = [&](int lv) { int off = 0; for (int l = 0; l < lv; ++l) off += a.l[l].ch * 72; return w0s + off; };
+  float* const tile0 = tile;
+  float* const tile1 = roleB ? tile + cl_smem_plan(a.l[2 * (cid - 4)].ch, a.l[2 * (cid - 4)].w, a.l[2 * (cid - 4)].R).tile : tile;
 
   // ---- once: filters resident, tile zero ----
   if (!roleB) {
@@ -197,9 +198,9 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
       w1s[i] = __ldg(Lp->out_w + (long long)(c_own + co) * Lp->w_co + r);
     }
   } else {
-    for (int lv = 0; lv < 4; ++lv) {
-      setup(lv);
-      float* dst = wu_of(lv);
+    for (int k = 0; k < 2; ++k) {
+      setup(2 * (cid - 4) + k);
+      float* dst = k ? w1s : w0s;
       for (int i = tid; i < ch * 9 * 8; i += kClThreads) {
         const int co = i & 7, r = i >> 3;
         dst[i] = __ldg(Lp->gate_w + (long long)(ch + c_own + co) * Lp->w_co + r);
@@ -240,7 +241,7 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
   // `before_stage` runs after the x-half loads are issued and before the tile is staged (the wait half of a split
   // cluster barrier goes there, so the loads fly across it).
   auto conv_phase = [&](const float* src, long long src_cs, const float* wsm, const float* pre, long long pre_cs,
-                        bool prefetch_next, double& st_s, double& st_q, auto&& before_stage) {
+                        bool prefetch_next, double& st_s, double& st_q, auto&& before_stage, bool staged_already = false) {
     u64 acc2[4][4];
     float4 pv[8];
 #pragma unroll
@@ -255,7 +256,7 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
       }
     }
     before_stage();
-    stage_tile(src, src_cs);
+    if (!staged_already) stage_tile(src, src_cs);
     mark(13);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -360,24 +361,12 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
 
 
   if (roleB) {
-    // ================= clusters B: u[d] = sigmoid(GN_u(GX_u[d] + conv(h[d]; Wu))), tasks (d, level) round-robin =================
-    int nt = 0;
-    for (int t = cid - 4; t < 4 * a.D; t += a.nb, ++nt) {
-      const int d = t >> 2, lv = t & 3;
-      setup(lv);
-      const float* wu = wu_of(lv);
-      {   // the levels lay the tile out differently: clear it (float4; tile sizes are multiples of 4 floats)
-        float4* t4 = reinterpret_cast<float4*>(tile);
-        for (int i = tid; i < (tile_floats >> 2); i += kClThreads) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const long long plane_g = (long long)d * Lp->px;
-      wait_flag(Lp->flags, d);                               // h[d] published by cluster A (slot 0: before the launch)
-      double ss = 0.0, sq = 0.0;
-      conv_phase(Lp->s + plane_g, Lp->s_cs, wu, Lp->gx + (long long)(ch + c_own) * Lp->g_cs + plane_g, Lp->g_cs,
-                 d + 1 < a.D, ss, sq, [] {});
-      publish_stats(nt & 1, ss, sq);
+    // ================= clusters B: u[d] = sigmoid(GN_u(GX_u[d] + conv(h[d]; Wu))) for levels la, lb in turn =================
+    const int la = 2 * (cid - 4), lb = la + 1;
+    // the tail of a task: sums -> scale / shift -> u -> L2, then this CTA's share is counted (16 per plane and level)
+    auto finish_task = [&](int which, int d) {
       cluster.sync();
-      gather_coef(nt & 1, Lp->un_w, Lp->un_b);
+      gather_coef(which, Lp->un_w, Lp->un_b);
       for (int o = tid; o < pw_items; o += kClThreads) {
         const int co = cl_div(o, dv_npx4), p4 = o - co * npx4;
         const int ly = cl_div(p4, dv_w4), x = (p4 - ly * w4) << 2;
@@ -387,8 +376,37 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
                                      cl_sigmoid(fmaf(g.z, ca, cb)), cl_sigmoid(fmaf(g.w, ca, cb)));
         *reinterpret_cast<float4*>(Lp->ub + ((long long)(d & 1) * ch + c_own + co) * Lp->px + (long long)(y0 + ly) * w + x) = u;
       }
-      __syncthreads();                                       // this CTA's share of u[d] is written: count it (16 per plane)
+      __syncthreads();
       if (tid == 0) { __threadfence(); atomicAdd(Lp->flags + kClFlagStride, 1); }
+    };
+    for (int d = 0; d < a.D; ++d) {
+      double ss = 0.0, sq = 0.0;
+      // ---- level la ----
+      setup(la); tile = tile0;
+      mark(-1);
+      wait_flag(Lp->flags, d);                               // h[d] published by cluster A (slot 0: before the launch)
+      mark(0);
+      conv_phase(Lp->s + (long long)d * Lp->px, Lp->s_cs, w0s, Lp->gx + (long long)(ch + c_own) * Lp->g_cs + (long long)d * Lp->px,
+                 Lp->g_cs, d + 1 < a.D, ss, sq, [] {});
+      publish_stats(0, ss, sq);
+      // level lb's tile flies (cp.async into its own buffer) while la's sums cross the cluster
+      setup(lb); tile = tile1;
+      mark(1);
+      wait_flag(Lp->flags, d);
+      mark(2);
+      stage_tile(Lp->s + (long long)d * Lp->px, Lp->s_cs);
+      setup(la); tile = tile0;
+      finish_task(0, d);
+      mark(4);
+      // ---- level lb ----
+      setup(lb); tile = tile1;
+      ss = 0.0; sq = 0.0;
+      conv_phase(Lp->s + (long long)d * Lp->px, Lp->s_cs, w1s, Lp->gx + (long long)(ch + c_own) * Lp->g_cs + (long long)d * Lp->px,
+                 Lp->g_cs, d + 1 < a.D, ss, sq, [] {}, true);
+      publish_stats(1, ss, sq);
+      mark(5);
+      finish_task(1, d);
+      mark(6);
     }
   } else {
     // ================= cluster A =================
@@ -499,12 +517,9 @@ inline size_t red_cluster_smem_bytes(const ClArgs& a, int smem_optin) {
     const size_t b = (size_t)sp[l].total_floats * sizeof(float);                             // role A of level l
     need = b > need ? b : need;
   }
-  {                                                                                            // role B: every level's filters
-    int wtot = 0, tmax = 0, pmax = 0;
-    for (int l = 0; l < 4; ++l) {
-      wtot += sp[l].wsm; tmax = sp[l].tile > tmax ? sp[l].tile : tmax; pmax = sp[l].part > pmax ? sp[l].part : pmax;
-    }
-    const size_t b = (size_t)(wtot + tmax + pmax) * sizeof(float);
+  for (int c = 0; c < 2; ++c) {                                                                // role B of levels 2c, 2c + 1
+    const ClSmemPlan &p = sp[2 * c], &q = sp[2 * c + 1];
+    const size_t b = (size_t)(p.wsm + q.wsm + p.tile + q.tile + (p.part > q.part ? p.part : q.part)) * sizeof(float);
     need = b > need ? b : need;
   }
   if (need + kClStaticSmemBytes > (size_t)smem_optin) return 0;
@@ -545,14 +560,10 @@ inline int red_cluster_launch(ClArgs& a, int* flags_base, cudaStream_t st, bool*
   attr[0].val.clusterDim.x = kClSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int nclusters = 0;
-  cfg.gridDim = dim3(7 * kClSize);
   if ((e = cudaOccupancyMaxActiveClusters(&nclusters, red_cluster_kernel, &cfg)) != cudaSuccess || nclusters < 6)
     { if (verbose) fprintf(stderr, "red_cluster_launch: max active clusters %d\n", nclusters); return declined("fewer than 6 co-resident clusters", e); }
-  // two role-B clusters keep the four A clusters supplied (measured: a third one changes nothing, 1.31 ms either way);
-  // SATMVS_RED_THREE_B=1 uses the seventh co-resident cluster anyway
-  static const bool three_b = getenv("SATMVS_RED_THREE_B") != nullptr;
-  a.nb = (nclusters >= 7 && three_b) ? 3 : 2;
-  cfg.gridDim = dim3((4 + a.nb) * kClSize);
+  a.nb = 2;
+  cfg.gridDim = dim3(6 * kClSize);
   cudaMemsetAsync(flags_base, 0, 4 * 2 * kClFlagStride * sizeof(int), st);
   a.dbg = verbose ? reinterpret_cast<unsigned long long*>(flags_base + 4 * 2 * kClFlagStride) : nullptr;
   if ((e = cudaLaunchKernelEx(&cfg, red_cluster_kernel, a)) != cudaSuccess) return declined("launch", e);
