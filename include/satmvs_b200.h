@@ -129,6 +129,13 @@ int satmvs_rpc_localise(const double* rpc, const double* samp, const double* lin
 int satmvs_rpc_project(const double* rpc, const double* lat, const double* lon, const double* hei,
                        int64_t n, double* samp, double* line, void* stream);
 
+/* ---- bilinear gather of a height map at projected positions (geometric-consistency filter) ----
+ * tools/rpc_filter.py:29-30: cv2.remap(depth_src, x, y, INTER_LINEAR, BORDER_CONSTANT, borderValue) with float32 maps:
+ * coordinates rounded to 1/32 pixel, out-of-range taps replaced by `border` one by one.
+ * src device float[Hs*Ws]; mapx / mapy / out device float[n]. */
+int satmvs_remap_bilinear(const float* src, int Hs, int Ws, const float* mapx, const float* mapy, int64_t n,
+                          float border, float* out, void* stream);
+
 /* ---- soft-argmin heads ----
  * mode 0: RED train head (networks/casred.py:58-62): softmax over D, depth = sum p*d, conf = max p.
  * mode 1: CasMVS head (networks/casmvs.py:66-74): conf = sum of the 4 probabilities around the

@@ -11,3 +11,4 @@ from .module import RED_Regularization, slice_RED_Regularization, CostRegNet, de
 from .stages import stage_train_red, stage_pred_red, stage_casmvs, cascade
 from .depth_range import get_depth_range_samples, stage_depth_hypotheses  # noqa: F401
 from . import data_io  # noqa: F401  (PFM / RPC text formats)
+from . import rpc_filter  # noqa: F401  (geometric-consistency filter, tools/rpc_filter.py)

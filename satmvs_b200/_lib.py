@@ -32,6 +32,7 @@ _SIGNATURES = {
     "satmvs_cost_volume_homo_bwd": ([_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "satmvs_rpc_localise": ([_P, _P, _P, _P, _L, _P, _P, _P], _I),
     "satmvs_rpc_project": ([_P, _P, _P, _P, _L, _P, _P, _P], _I),
+    "satmvs_remap_bilinear": ([_P, _I, _I, _P, _P, _L, C.c_float, _P, _P], _I),
     "satmvs_softargmin_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "satmvs_softargmin_stream_update": ([_P, _P, _I, _I, _I, _P, _P], _I),
     "satmvs_softargmin_stream_finish": ([_P, _I, _I, _P, _P, _P], _I),
