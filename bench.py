@@ -446,7 +446,8 @@ def run_ours(args, w):
                         "rest; useful flops against the dense bf16 tensor peak" if name == "conv_batched"
                         else "fp32 FFMA2 kernels (latency-bound recurrence / decoder) measured against the dense bf16 tensor peak")
                 k["roofline"] = {"bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
-                                 "traffic": None, "algorithmic_flops_per_step": fl, "note": note}
+                                 "traffic": ncu_traffic("red_cluster", w) if cluster else None,
+                                 "algorithmic_flops_per_step": fl, "note": note}
             kernels.append(k)
         kernels.sort(key=lambda k: -k["share"])
         line["kernels"] = kernels
