@@ -139,7 +139,9 @@ int satmvs_remap_bilinear(const float* src, int Hs, int Ws, const float* mapx, c
 /* ---- soft-argmin heads ----
  * mode 0: RED train head (networks/casred.py:58-62): softmax over D, depth = sum p*d, conf = max p.
  * mode 1: CasMVS head (networks/casmvs.py:66-74): conf = sum of the 4 probabilities around the
- *         regressed plane index.  logits device [D,H,W]; depth as above; out_* device [H,W]. */
+ *         regressed plane index.  logits device [D,H,W]; depth as above; out_* device [H,W].
+ * mode 2: depth_regression (modules/module.py:433-439): `logits` holds probabilities, depth = sum p*d;
+ *         out_conf may be NULL. */
 int satmvs_softargmin_fwd(const float* logits, const float* depth, int depth_per_pixel, int mode,
                           int D, int H, int W, float* out_depth, float* out_conf, void* stream);
 
@@ -160,6 +162,10 @@ int satmvs_softargmin_stream_finish(const double* state, int H, int W,
  *   out device [D,h,w] hypotheses on the stage grid (h = Himg/scale, w = Wimg/scale). */
 int satmvs_depth_hypotheses(const float* prev_depth, int hp, int wp, const float* depth_range, int n_range,
                             int D, float interval, int Himg, int Wimg, int h, int w, float* out, void* stream);
+
+/* F.interpolate(x, [ho, wo], mode="bilinear", align_corners=False) over N planes: the resize of the
+ * hypotheses inside depth_regression (modules/module.py:437).  in device [N,hi,wi], out device [N,ho,wo]. */
+int satmvs_resize_bilinear(const float* in, int N, int hi, int wi, int ho, int wo, float* out, void* stream);
 
 /* ---- RED regulariser: 2-D conv-GRU UNet recurring over depth planes ----
  * RED_Regularization.forward (modules/module.py:614-649) with D planes, and, with D = 1 and explicit

@@ -15,8 +15,8 @@ the oracle is pinned against *outputs of the reference itself*: `oracle/make_gol
 imports the unmodified reference from `/root/reference` in the build container, runs it on
 seeded synthetic inputs and commits the input/output vectors under `tests/golden/`.
 `tests/test_oracle_golden.py` checks this restatement against those vectors (bit-exact for the
-fp64 geometry, <=1e-6 for the fp32 network outputs), and, when `/root/reference` is present,
-`tests/test_oracle_vs_reference.py` re-runs the live comparison.
+fp64 geometry, <=1e-6 for the fp32 network outputs); `python oracle/make_golden.py --out /tmp/x`
+re-generates the vectors from the live reference when `/root/reference` is present.
 
 Third-party arithmetic on the path (`F.grid_sample`, `F.interpolate`, conv/BN/GN) lives in
 PyTorch (reference pin: pytorch 1.4.0, `environment.yml:121`; here torch 2.11).  The bilinear

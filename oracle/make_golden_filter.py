@@ -39,6 +39,17 @@ def main():
     mask2, avg2 = ns["filter_depth"](depths, rp, 0.5, 1.0, 2)
     np.savez_compressed(os.path.join(OUT, "rpc_filter.npz"), rpcs=rp, depths=depths, prob=prob, sampled=sampled, x_reproj=xr,
                         y_reproj=yr, x_src=xs, y_src=ys, mask=mask, avg=avg, mask2=mask2, avg2=avg2)
+    # cv2.remap alone on random coordinates (inside, on the 1/32 rounding boundaries, across the border): pins the
+    # numpy restatement oracle/remap.py and the CUDA kernel satmvs_remap_bilinear bit for bit
+    import cv2
+    src = depths[2]
+    mx = rng.uniform(-3, W + 3, (64, 96)).astype(np.float32)
+    my = rng.uniform(-3, H + 3, (64, 96)).astype(np.float32)
+    mx[0, :32] = (np.arange(32) + 0.5) / 32 + 7            # exact ties of cvRound(x * 32): round-half-even
+    my[0, :32] = (np.arange(32) * 2 + 1) / 64 + 5
+    mx[1, :4] = [np.nan, np.inf, -np.inf, 1e30]
+    out = cv2.remap(src, mx, my, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=-999)
+    np.savez_compressed(os.path.join(OUT, "remap_cv2.npz"), src=src, mapx=mx, mapy=my, out=out)
     print("mask fraction", mask.mean(), mask2.mean(), "sampled range", sampled.min(), sampled.max())
 
 

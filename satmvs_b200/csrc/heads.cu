@@ -3,6 +3,7 @@
 //   mode 0  RED train head  (networks/casred.py:58-62):   p = softmax_d(logits); depth = sum p*d; conf = max p
 //   mode 1  CasMVS head     (networks/casmvs.py:66-74):   conf = sum of the 4 probabilities around
 //           the regressed plane index (pad 1 before / 2 after, index = trunc(sum p*k) clamped)
+//   mode 2  depth_regression (modules/module.py:433-439) on given probabilities: depth = sum p*d only
 //   streaming fp64 head of the inference net (networks/casred.py:182-184, :218-236)
 //
 // One thread per pixel, planes strided by H*W so every load is 128-byte coalesced across the warp.
@@ -17,6 +18,15 @@ __global__ void softargmin_kernel(const float* __restrict__ logits, const float*
                                   float* __restrict__ out_depth, float* __restrict__ out_conf) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= HW) return;
+  if (mode == 2) {   // depth_regression on given probabilities (modules/module.py:433-439): sum_d p*d, nothing else
+    float acc = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      const float dv = depth_per_pixel ? __ldg(depth + (size_t)d * HW + pix) : __ldg(depth + d);
+      acc += __fmul_rn(__ldg(logits + (size_t)d * HW + pix), dv);
+    }
+    out_depth[pix] = acc;
+    return;
+  }
   // pass 1: max over planes (F.softmax subtracts the max)
   float mx = -INFINITY;
   for (int d = 0; d < D; ++d) mx = fmaxf(mx, __ldg(logits + (size_t)d * HW + pix));
@@ -74,8 +84,8 @@ extern "C" {
 
 int satmvs_softargmin_fwd(const float* logits, const float* depth, int depth_per_pixel, int mode,
                           int D, int H, int W, float* out_depth, float* out_conf, void* stream) {
-  SATMVS_REQUIRE(logits && depth && out_depth && out_conf);
-  SATMVS_REQUIRE(D >= 1 && H >= 1 && W >= 1 && (mode == 0 || mode == 1));
+  SATMVS_REQUIRE(logits && depth && out_depth && (out_conf || mode == 2));
+  SATMVS_REQUIRE(D >= 1 && H >= 1 && W >= 1 && mode >= 0 && mode <= 2);
   const int HW = H * W;
   ProfScope prof(kProfHead, (cudaStream_t)stream);
   softargmin_kernel<<<ceil_div(HW, 128), 128, 0, (cudaStream_t)stream>>>(logits, depth, depth_per_pixel, mode, D, HW,

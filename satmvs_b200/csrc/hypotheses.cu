@@ -69,9 +69,27 @@ __global__ void depth_hypotheses_kernel(const float* __restrict__ prev, int hp, 
   }
 }
 
+// F.interpolate(x, [ho, wo], mode="bilinear", align_corners=False) over N planes (depth_regression resizes the
+// hypotheses to the probability volume with it, modules/module.py:437)
+__global__ void resize_bilinear_kernel(const float* __restrict__ in, int N, int hi, int wi, int ho, int wo, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * ho * wo) return;
+  const int ox = (int)(i % wo), oy = (int)((i / wo) % ho), n = (int)(i / ((long long)wo * ho));
+  const Lin1 cy = lin_coeff(oy, hi, ho), cx = lin_coeff(ox, wi, wo);
+  const float* p = in + (size_t)n * hi * wi;
+  out[i] = cy.w0 * (cx.w0 * __ldg(p + cy.i0 * wi + cx.i0) + cx.w1 * __ldg(p + cy.i0 * wi + cx.i1)) +
+           cy.w1 * (cx.w0 * __ldg(p + cy.i1 * wi + cx.i0) + cx.w1 * __ldg(p + cy.i1 * wi + cx.i1));
+}
+
 }  // namespace satmvs
 
 using namespace satmvs;
+
+extern "C" int satmvs_resize_bilinear(const float* in, int N, int hi, int wi, int ho, int wo, float* out, void* stream) {
+  SATMVS_REQUIRE(in && out && N >= 1 && hi >= 1 && wi >= 1 && ho >= 1 && wo >= 1);
+  resize_bilinear_kernel<<<ceil_div((int64_t)N * ho * wo, 256), 256, 0, (cudaStream_t)stream>>>(in, N, hi, wi, ho, wo, out);
+  return check_launch("resize_bilinear_kernel");
+}
 
 extern "C" int satmvs_depth_hypotheses(const float* prev_depth, int hp, int wp, const float* depth_range, int n_range,
                                        int D, float interval, int Himg, int Wimg, int h, int w, float* out, void* stream) {

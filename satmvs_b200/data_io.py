@@ -24,10 +24,10 @@ def load_pfm(fname):
             raise Exception("Malformed PFM header.")
         width, height = int(dims[0]), int(dims[1])
         scale = float(f.readline().decode("latin-1").strip())
-        raw = np.frombuffer(f.read(), dtype="<f4" if scale < 0 else ">f4")
+        raw = np.frombuffer(bytearray(f.read()), dtype="<f4" if scale < 0 else ">f4")   # writable, like np.fromfile
     nc = _PFM_CHANNELS[magic]
     shape = (height, width, 3) if nc == 3 else (height, width)
-    return raw.reshape(shape)[::-1]
+    return np.ascontiguousarray(raw.reshape(shape)[::-1])
 
 
 def save_pfm(file, image, scale=1):

@@ -151,6 +151,11 @@ class _RedBase(nn.Module):
 
     def _run(self, volume: torch.Tensor, states_in, want_states: bool):
         """volume [B,C,D,H,W] -> logits [B,D,H,W] (+ final states)."""
+        if torch.is_grad_enabled() and (volume.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # inference only: no backward is implemented for the recurrence.  Failing here beats returning logits without
+            # a grad_fn, which would let `loss.backward()` (train.py:284) skip the regulariser and FeatureNet silently.
+            raise RuntimeError("satmvs_b200 RED regulariser is inference-only: call it under torch.no_grad() "
+                               "(or with parameters and input that do not require grad)")
         vol = _lib.require_cuda(volume, "volume")
         B, Cc, D, H, W = vol.shape
         if Cc != self.in_channels:
@@ -282,12 +287,4 @@ class CostRegNet(nn.Module):
         return out
 
 
-def depth_regression(p, depth_values):
-    """`depth_regression` (`modules/module.py:433-439`), kept for API parity: sum_d p*d on given
-    probabilities.  The fused softmax+regression kernel is `satmvs_b200.softargmin`."""
-    if depth_values.dim() <= 2:
-        depth_values = depth_values.view(*depth_values.shape, 1, 1)
-    else:
-        depth_values = torch.nn.functional.interpolate(depth_values, [p.shape[2], p.shape[3]], mode="bilinear",
-                                                       align_corners=False)
-    return torch.sum(p * depth_values, 1)
+from .regress import depth_regression  # noqa: E402,F401  (`modules/module.py:433-439`, on the heads kernel)

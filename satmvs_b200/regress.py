@@ -11,6 +11,37 @@ import torch
 from . import _lib
 
 
+def resize_bilinear(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """`F.interpolate(x, [H, W], mode="bilinear", align_corners=False)` for x [B,N,h,w] on the library kernel."""
+    x = _lib.require_cuda(x, "x")
+    B, N, h, w = x.shape
+    out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().satmvs_resize_bilinear(x.data_ptr(), B * N, h, w, H, W, out.data_ptr(), _lib.stream_ptr(x.device)),
+                   "resize_bilinear")
+    return out
+
+
+def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
+    """`depth_regression` (`modules/module.py:433-439`): sum_d p*d on given probabilities p [B,D,H,W];
+    depth_values [B,D] or [B,D,h,w] (resized bilinearly to p's grid like the reference)."""
+    p = _lib.require_cuda(p, "p")
+    B, D, H, W = p.shape
+    dv = _lib.require_cuda(depth_values, "depth_values")
+    per_pixel = 0
+    if dv.dim() > 2:
+        per_pixel = 1
+        if tuple(dv.shape[2:]) != (H, W):
+            dv = resize_bilinear(dv, H, W)
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        st = _lib.stream_ptr(p.device)
+        for b in range(B):
+            _lib.check(_lib.lib().satmvs_softargmin_fwd(p[b].data_ptr(), dv[b].data_ptr(), per_pixel, 2, D, H, W,
+                                                       depth[b].data_ptr(), None, st), "depth_regression")
+    return depth
+
+
 def softargmin(logits: torch.Tensor, depth_values: torch.Tensor, head: str = "red"):
     """softmax over D + expectation + confidence in one kernel.
     logits [B,D,H,W]; depth_values [B,D] or [B,D,H,W]; head 'red' (conf = max p) or 'casmvs'
@@ -24,8 +55,7 @@ def softargmin(logits: torch.Tensor, depth_values: torch.Tensor, head: str = "re
     elif tuple(dv.shape) == (B, D, H, W):
         per_pixel = 1
     else:
-        # depth_regression resizes hypotheses given at another resolution (module.py:437)
-        dv = torch.nn.functional.interpolate(dv, [H, W], mode="bilinear", align_corners=False).contiguous()
+        dv = resize_bilinear(dv, H, W)      # depth_regression resizes hypotheses given at another resolution (module.py:437)
         per_pixel = 1
     depth = torch.empty((B, H, W), dtype=torch.float32, device=lg.device)
     conf = torch.empty_like(depth)

@@ -23,7 +23,6 @@ import torch
 
 from . import _lib
 
-_HOST_CAM_CACHE: dict = {}
 _SWEEP_WS: dict = {}
 
 
@@ -39,18 +38,13 @@ def sweep_workspace(nbytes: int, device) -> torch.Tensor:
 
 def host_f64(cam: torch.Tensor) -> np.ndarray:
     """Camera tensors travel to the kernels by value, so they are needed on the host.  CPU
-    tensors are used directly; a CUDA tensor costs one small synchronising copy, cached on
-    (storage pointer, version) so a cascade stage pays it once."""
+    tensors are used directly; a CUDA tensor costs one small synchronising copy (<= 170 doubles
+    per view) on EVERY call: nothing is cached, because the reference re-uploads `cam_para` each
+    sample (`tools/utils.py:85`) and the caching allocator hands the same address to different
+    cameras, so no key short of the content identifies them."""
     if not cam.is_cuda:
         return np.ascontiguousarray(cam.detach().numpy(), dtype=np.float64)
-    key = (cam.data_ptr(), cam._version, tuple(cam.shape), tuple(cam.stride()), cam.device.index)
-    hit = _HOST_CAM_CACHE.get(key)
-    if hit is None:
-        if len(_HOST_CAM_CACHE) > 64:
-            _HOST_CAM_CACHE.clear()
-        hit = np.ascontiguousarray(cam.detach().cpu().numpy(), dtype=np.float64)
-        _HOST_CAM_CACHE[key] = hit
-    return hit
+    return np.ascontiguousarray(cam.detach().cpu().numpy(), dtype=np.float64)
 
 
 def _depth_arg(depth_values: torch.Tensor, B: int, H: int, W: int):

@@ -13,6 +13,25 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode(request):
+    """The regulariser is inference-only and says so when gradients are on (test_requires_no_grad)."""
+    if "test_requires_no_grad" in request.node.name:
+        yield
+        return
+    with torch.no_grad():
+        yield
+
+
+def test_requires_no_grad():
+    m = satmvs_b200.RED_Regularization(8, 8).to(DEV)
+    x = torch.rand(1, 8, 2, 8, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(x)
+    with torch.no_grad():
+        assert m(x).shape == (1, 2, 8, 8)
+
+
 def maxdiff(a, b):
     return (a.detach().cpu().double() - b.detach().cpu().double()).abs().max().item()
 

@@ -126,3 +126,17 @@ def test_cascade(golden, tag, head, wfn):
         rel = maxdiff(out[f"stage{s}"]["depth"], want) / want.abs().max().item()
         assert rel < 1e-5, (s, rel)
         assert maxdiff(out[f"stage{s}"]["photometric_confidence"], g[f"conf{s}"]) < 1e-4
+
+
+def test_remap_restatement_equals_cv2_bit_for_bit():
+    """oracle.remap against outputs of cv2.remap itself (random coordinates, exact 1/32 ties, border, non-finite) and
+    against the gather inside the reference filter (tests/golden/rpc_filter.npz: its own coordinates)."""
+    import os
+    import numpy as np
+    from oracle import remap
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(G, "remap_cv2.npz"))
+    assert np.array_equal(remap.remap_bilinear(g["src"], g["mapx"], g["mapy"], -999.0), g["out"])
+    f = np.load(os.path.join(G, "rpc_filter.npz"))
+    got = remap.remap_bilinear(f["depths"][1], f["x_src"].astype(np.float32), f["y_src"].astype(np.float32), -999.0)
+    assert np.array_equal(got, f["sampled"])
