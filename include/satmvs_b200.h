@@ -199,6 +199,11 @@ int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, 
                        const float* const* state_in, float* const* state_out, float* logits,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Which implementation of the depth recurrence the last satmvs_red_forward of this thread used: 2 = tensor-core cluster
+ * kernel (csrc/red_tc.cuh), 1 = FFMA cluster kernel (csrc/red_cluster.cuh), 0 = per-plane kernel chain, -1 = none yet.
+ * Diagnostic for tests and the bench line; SATMVS_RED_NO_TC=1 / SATMVS_RED_NO_CLUSTER=1 force the later ones. */
+int satmvs_red_last_path(void);
+
 /* ---- one convolution block of the regularisers ----
  * ConvReLU (modules/module.py:178-186): 3x3 per depth plane (NZ = 1); Conv3d (modules/module.py:324-366): 3x3x3 (NZ = 3);
  * padding 1, out = relu?( conv(in, w) * acc_scale * scale[co] + shift[co] ), scale / shift may be NULL.

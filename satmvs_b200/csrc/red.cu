@@ -25,6 +25,7 @@
 #include "packed.cuh"
 #include "prof.cuh"
 #include "red_cluster.cuh"
+#include "red_tc.cuh"
 namespace cg = cooperative_groups;
 
 namespace satmvs {
@@ -70,6 +71,7 @@ struct RedPlan {
   int* umma_err;
   int* fuse_cnt;
   int* cl_flags;         // [4][2][kClFlagStride] plane counters exchanged by the two clusters of a level
+  char* tcpack[4];       // packed hidden-state filters of the tensor-core recurrence (red_tc.cuh)
   size_t bytes;
 };
 
@@ -111,6 +113,8 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   off += ((size_t)D * 4 * 2 * sizeof(int) + 255) / 256 * 256;
   p.cl_flags = reinterpret_cast<int*>(base + off);
   off += 4 * 2 * 32 * sizeof(int) + 8 * 16 * sizeof(unsigned long long);   // + debug counters
+  off = (off + 255) / 256 * 256;
+  for (int l = 0; l < 4; ++l) { p.tcpack[l] = base + off; off += (tc_pack_bytes(chs[l]) + 255) / 256 * 256; }
   p.bytes = off;
   return p;
 }
@@ -859,7 +863,11 @@ static int launch_plane_conv(const ConvProblem& p, int stride, cudaStream_t st, 
 
 using namespace satmvs;
 
+static thread_local int g_red_last_path = -1;
+
 extern "C" {
+
+int satmvs_red_last_path(void) { return g_red_last_path; }
 
 size_t satmvs_red_workspace_bytes(int C, int D, int H, int W) {
   if (C < 1 || D < 1 || H < 8 || W < 8 || (H % 8) || (W % 8)) return 0;
@@ -959,7 +967,43 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     // Default: one launch, two 16-CTA clusters per UNet level (red_cluster.cuh).  Shapes it does not take (rows not a
     // multiple of 4 pixels, strips beyond the shared-memory limit) and SATMVS_RED_NO_CLUSTER=1 run the per-plane chain.
     const bool no_cluster = getenv("SATMVS_RED_NO_CLUSTER") != nullptr;   // read per call: tests toggle it
-    if (!no_cluster) {
+    const bool no_tc = getenv("SATMVS_RED_NO_TC") != nullptr;
+    if (!no_cluster && !no_tc) {
+      // Default: the recurrence on the tensor cores, one 16-CTA cluster per level (red_tc.cuh)
+      TcArgs ta{};
+      ta.D = D;
+      const float* gwh[4]; const float* owh[4]; long long wco[4];
+      for (int l = 0; l < 4; ++l) {
+        RedLevel& L = P.lv[l];
+        TcLevel& R = ta.l[l];
+        const long long px = (long long)L.h * L.w;
+        R.s = L.s; R.s_cs = (long long)(D + 1) * px;
+        R.gx = L.gx; R.g_cs = (long long)D * px;
+        R.ox = L.ox; R.o_cs = (long long)D * px;
+        R.rn_w = wt->rn_w[l]; R.rn_b = wt->rn_b[l]; R.un_w = wt->un_w[l]; R.un_b = wt->un_b[l];
+        R.on_w = wt->on_w[l]; R.on_b = wt->on_b[l];
+        R.inv_n = 1.0 / ((double)L.ch * (double)px);
+        R.ch = L.ch; R.h = L.h; R.w = L.w; R.px = (int)px;
+        gwh[l] = wt->gate_w[l] + (size_t)L.cx * 9; owh[l] = wt->out_w[l] + (size_t)L.cx * 9;
+        wco[l] = (long long)(L.cx + L.ch) * 9;
+      }
+      static const bool tc_dbg = getenv("SATMVS_RED_DEBUG") != nullptr;
+      long long* dbg = tc_dbg ? reinterpret_cast<long long*>(P.cl_flags + 4 * 2 * 32) : nullptr;
+      ProfScope prof(kProfGruGate, st);
+      RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, st, &persistent));
+      if (persistent) g_red_last_path = 2;
+      if (persistent && tc_dbg) {
+        long long h[4 * 12] = {};
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int c = 0; c < 4; ++c) {
+          fprintf(stderr, "red_tc: level %d kcycles per phase slot:", c);
+          for (int i = 0; i < 12; ++i) fprintf(stderr, " %.0f", h[c * 12 + i] * 1e-3);
+          fprintf(stderr, "\n");
+        }
+      }
+    }
+    if (!persistent && !no_cluster) {
       ClArgs ca{};
       ca.D = D;
       for (int l = 0; l < 4; ++l) {
@@ -979,8 +1023,10 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       }
       ProfScope prof(kProfGruGate, st);     // one class: the cluster kernel has no per-phase boundary
       RUN(red_cluster_launch(ca, P.cl_flags, st, &persistent));
+      if (persistent) g_red_last_path = 1;
     }
   }
+  if (!persistent) g_red_last_path = 0;
   if (!persistent) {
     RecArgs ra{};
     ra.stats = P.stats; ra.D = D;

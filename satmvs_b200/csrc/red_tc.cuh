@@ -34,7 +34,7 @@ namespace satmvs {
 
 constexpr int kTcThreads = 512, kTcWarps = kTcThreads / 32, kTcCluster = 16;
 constexpr int kTcKG[4] = {1, 1, 2, 8};        // K-groups per level
-constexpr int kTcMaxP[4] = {3, 1, 1, 3};      // output positions per thread (register budget: CK * MAXP <= 24)
+constexpr int kTcMaxP[4] = {3, 1, 1, 1};      // output positions per thread (register budget: CK * MAXP <= 24)
 
 struct TcLevel {
   float* s; long long s_cs;                   // state history [ch][D+1][px]: channel stride; slot stride = px
@@ -175,7 +175,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
       const int x = i % w; int r = i / w;
       const int yy = ylo + r % (yhi - ylo + 1); const int qd = r / (yhi - ylo + 1);
       const float* sp = L.s + (long long)(kg * CK + 4 * qd) * L.s_cs + (long long)yy * w + x;
-      const float4 v = make_float4(__ldg(sp), __ldg(sp + L.s_cs), __ldg(sp + 2 * L.s_cs), __ldg(sp + 3 * L.s_cs));
+      const float4 v = make_float4(sp[0], sp[L.s_cs], sp[2 * L.s_cs], sp[3 * L.s_cs]);
       const int wi = (yy - y0 + 1) * Wp + x + 1;
       win[qd * PWa + wi] = v;
       win[(NQ + qd) * PWa + wi] = make_float4(tc_lo(v.x), tc_lo(v.y), tc_lo(v.z), tc_lo(v.w));
@@ -451,18 +451,11 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     alive = uc_wait(&sh.mbar_mma, ph_mma) && alive; ph_mma ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     mark(5);
-    float (&u_)[MAXP][2 * CK] = acc;                                       // u lives in acc[j][CK ..]; the output sums go to acc[j][0 .. CK)
-    {
-      float o[MAXP][2 * CK];
-      read_back(NO, NBO, 1, o);
-      if (KG > 1) { tc_cluster_sync(); }                                  // #D
-      alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
-      finish_sums(1, o);
-#pragma unroll
-      for (int j = 0; j < MAXP; ++j)
-#pragma unroll
-        for (int c = 0; c < CK; ++c) acc[j][c] = o[j][c];
-    }
+    // u lives in acc[j][CK ..]; the output sums replace the (consumed) reset-gate half acc[j][0 .. CK)
+    read_back(NO, NBO, 1, acc);
+    if (KG > 1) { tc_cluster_sync(); }                                    // #D
+    alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
+    finish_sums(1, acc);
     {
       double st[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -489,7 +482,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
       float* sp = L.s + (long long)(kg * CK) * L.s_cs + (long long)(d + 1) * L.px + gp_[j];
 #pragma unroll
       for (int c = 0; c < CK; ++c) {
-        const float uu = u_[j][CK + c];
+        const float uu = acc[j][CK + c];
         hn[c] = uu * hown[j][c] + (1.0f - uu) * tc_tanh(fmaf(acc[j][c], sh.coef[2][c][0], sh.coef[2][c][1]));
         sp[(long long)c * L.s_cs] = hn[c];
       }
@@ -537,7 +530,7 @@ inline int red_tc_launch(TcArgs& a, const float* const* gate_w_h, const float* c
     TcLevel& L = a.l[l];
     if (L.ch != (8 << l) || L.w % 4 || L.w < 4 || L.h < 1) return SATMVS_OK;
     const TcGeom g = tc_geom(L.ch, kTcKG[l], L.h, L.w);
-    if (g.MT > 4 * kTcMaxP[l] || (size_t)g.PWa * 16 >= (1u << 18)) {
+    if (g.MT > 4 * kTcMaxP[l] || g.MT * 4 * L.ch > 512 || (size_t)g.PWa * 16 >= (1u << 18)) {
       if (verbose) fprintf(stderr, "red_tc_launch: level %d needs %d tiles per CTA\n", l, g.MT);
       return SATMVS_OK;
     }

@@ -80,24 +80,54 @@ def test_volume_vs_oracle(C, D, H, W):
     assert maxdiff(got, want) < 2e-4 * max(1.0, want.abs().max().item())
 
 
-@pytest.mark.parametrize("C,D,H,W", [(32, 12, 32, 64), (32, 4, 96, 192), (8, 3, 8, 32), (16, 2, 40, 96)])
-def test_cluster_recurrence_equals_kernel_chain(C, D, H, W, monkeypatch):
-    """The one-launch cluster recurrence (red_cluster.cuh) and the per-plane kernel chain compute the same
-    arithmetic graph with different summation orders over the input-channel chunks."""
+@pytest.mark.parametrize("C,D,H,W", [(32, 12, 32, 64), (32, 4, 96, 192), (8, 3, 8, 32), (16, 2, 40, 96), (8, 5, 64, 96)])
+def test_recurrence_paths_agree(C, D, H, W, monkeypatch):
+    """Three implementations of the depth recurrence compute the same arithmetic graph: the tensor-core cluster kernel
+    (red_tc.cuh: 3xTF32 split, K-split partial sums), the FFMA cluster kernel (red_cluster.cuh) and the per-plane kernel
+    chain; they differ in summation order only."""
+    from satmvs_b200 import _lib
     sd = synth.make_red_weights(C, seed=7)
     m = satmvs_b200.RED_Regularization(C, 8)
     m.load_state_dict(sd)
     m = m.to(DEV)
     x = synth.make_features(1, 1, C * D, H, W, seed=11)[0].view(1, C, D, H, W).abs().to(DEV)
-    monkeypatch.delenv("SATMVS_RED_NO_CLUSTER", raising=False)
-    a = m(x).clone()
-    monkeypatch.setenv("SATMVS_RED_NO_CLUSTER", "1")
-    b = m(x).clone()
-    monkeypatch.delenv("SATMVS_RED_NO_CLUSTER", raising=False)
+    outs, paths = {}, {}
+    for name, env in (("tc", {}), ("cluster", {"SATMVS_RED_NO_TC": "1"}), ("chain", {"SATMVS_RED_NO_CLUSTER": "1"})):
+        for k in ("SATMVS_RED_NO_TC", "SATMVS_RED_NO_CLUSTER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        outs[name] = m(x).clone()
+        torch.cuda.synchronize()
+        paths[name] = _lib.lib().satmvs_red_last_path()
+    for k in ("SATMVS_RED_NO_TC", "SATMVS_RED_NO_CLUSTER"):
+        monkeypatch.delenv(k, raising=False)
+    assert paths["chain"] == 0
+    if W % 32 == 0:                       # every level keeps rows of a multiple of 4 pixels: the tensor-core kernel takes it
+        assert paths["tc"] == 2, paths
     want = regnets.red_regularization(x.cpu(), sd)
     scale = max(1.0, want.abs().max().item())
-    assert maxdiff(a, b) < 5e-5 * scale
-    assert maxdiff(a, want) < 2e-4 * scale
+    errs = {k: maxdiff(v, want) / scale for k, v in outs.items()}
+    assert maxdiff(outs["tc"], outs["chain"]) < 5e-5 * scale, errs
+    assert maxdiff(outs["cluster"], outs["chain"]) < 5e-5 * scale, errs
+    assert max(errs.values()) < 2e-4, errs
+
+
+def test_tensor_core_recurrence_carries_states():
+    """slice form (D = 1, explicit states in and out) through the tensor-core kernel == oracle."""
+    from satmvs_b200 import _lib
+    C, H, W = 16, 32, 64
+    sd = synth.make_red_weights(C, seed=3)
+    m = make_reg(satmvs_b200.slice_RED_Regularization, C, seed=3)
+    g = torch.Generator().manual_seed(5)
+    cost = torch.rand(1, C, H, W, generator=g)
+    states = [torch.randn(1, c, H >> l, W >> l, generator=g) * 0.5 for l, c in enumerate((8, 16, 32, 64))]
+    want = regnets.red_slice(cost, *states, sd)
+    got = m(cost.to(DEV), *[s.to(DEV) for s in states])
+    torch.cuda.synchronize()
+    assert _lib.lib().satmvs_red_last_path() == 2
+    for a, b in zip(got, want):
+        assert maxdiff(a, b) < 2e-4 * max(1.0, b.abs().max().item())
 
 
 def test_pred_stage_equals_train_stage():
