@@ -32,7 +32,8 @@
 
 namespace satmvs {
 
-constexpr int kTcThreads = 512, kTcWarps = kTcThreads / 32, kTcCluster = 16;
+constexpr int kTcEpiWarps = 16, kTcThreads = 32 * kTcEpiWarps, kTcWarps = kTcThreads / 32, kTcCluster = 16;
+constexpr int kTcIssuer = kTcEpiWarps - 1;   // warp that issues the MMAs and bulk copies: its tiles (3, 7, 11) are the fewest, and a 17th warp would cap registers at 96
 constexpr int kTcKG[4] = {1, 1, 2, 8};        // K-groups per level
 constexpr int kTcMaxP[4] = {3, 1, 1, 1};      // output positions per thread (register budget: CK * MAXP <= 24)
 
@@ -125,16 +126,17 @@ struct TcShared {
   double stat_out[2][4];                      // this CTA's (sum, sum^2) x {r, u} after the gate conv; {o} after the output conv
   double red[4][kTcWarps];
   float coef[3][16][2];                       // GroupNorm scale / shift of this CTA's channels: r, u, o
-  unsigned long long mbar_mma, mbar_pre;
+  unsigned long long mbar_tile[16], mbar_pre;      // MMAs of tile mt complete; x-halves landed
   unsigned tmem_base;
+  long long t_prev, t_acc[12];                // SATMVS_RED_DEBUG: cycles thread 0 spends per phase slot
 };
 
-template <int CH, int KG, int MAXP>
+template <int CH, int KG, int MAXP, int STASH>   // STASH: 0 none, 1 in the dead half of the gate accumulators (KG == 1), 2 own TMEM columns
 __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int* err, long long* dbg, unsigned char* smem, TcShared& sh) {
   constexpr int CK = CH / KG, NQ = CK / 4, KS = CK / 8;
   constexpr int NG = 2 * CH, NBG = 2 * NG, NO = CH, NBO = 2 * NO;
   constexpr int N2O = NO >= 16 ? NO : NBO;                 // an M = 128 MMA needs N >= 16: level 0 multiplies lo(x) by [W | lo(W)] (the extra lo*lo term is exact anyway)
-  static_assert(CK % 8 == 0 && CK <= 16 && CK * MAXP <= 24, "register budget");
+  static_assert(CK % 8 == 0 && CK <= 16 && CK * MAXP <= 24 && (STASH != 1 || KG == 1), "register budget");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned rank = tc_cluster_ctarank();
   const int strip = (int)rank / KG, kg = (int)rank % KG;
@@ -153,7 +155,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
   // ---- once: barriers, TMEM, zero window, filters, initial state ----
   constexpr int kTmemCols = MAXP * 4 * NBG <= 512 ? 512 : 512;
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_mma)));
+    for (int i = 0; i < 16; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_tile[i])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_pre)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,7 +185,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
   }
   // x-halves of this strip by bulk copies: conv 0 = gates (r and u rows of this CTA's channels), conv 1 = output
   auto issue_pre = [&](int conv, int d) {
-    if (tid != 0) return;
+    if (tid != 32 * kTcIssuer) return;                                    // lane 0 of the issuer warp
     const unsigned bar = uc_smem_u32(&sh.mbar_pre);
     const int nchan = conv == 0 ? 2 * CK : CK;
     const unsigned bytes = (unsigned)(nrows * w) * 4u;
@@ -205,120 +207,148 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
   const unsigned tmem = sh.tmem_base;
 
   // ---- this thread's output positions: TMEM lane = 32*(warp%4) + lane of tile mt = warp/4 + 4j ----
-  int q_[MAXP], wi_[MAXP], sp_[MAXP]; long long gp_[MAXP]; bool ok_[MAXP]; int halo_[MAXP];
+  // fl_: bit 0 = a pixel of the strip, bit 1 = also the bottom halo (row R+1) of the strip above, bit 2 = also the top halo
+  // (row 0) of the strip below
+  int q_[MAXP], sp_[MAXP], fl_[MAXP];
 #pragma unroll
   for (int j = 0; j < MAXP; ++j) {
     const int mt = (warp >> 2) + 4 * j;
     const int q = mt * 128 + (warp & 3) * 32 + lane;
     const int ly = q / Wp, x = q - ly * Wp;
-    ok_[j] = q < npos && x < w;
-    q_[j] = q; wi_[j] = q + Wp + 1; sp_[j] = ly * w + x; gp_[j] = (long long)(y0 + ly) * w + x;
-    // halo duty: first row -> bottom halo (row R+1) of the strip above; last row -> top halo (row 0) of the strip below
-    halo_[j] = 0;
-    if (ok_[j] && ly == 0 && y0 > 0) halo_[j] |= 1;
-    if (ok_[j] && ly == nrows - 1 && y0 + nrows < L.h) halo_[j] |= 2;
-    if (ok_[j] && nrows == 1 && y0 > 0 && y0 + nrows < L.h) halo_[j] = 3;
+    const bool ok = warp < kTcEpiWarps && q < npos && x < w;
+    q_[j] = q; sp_[j] = ly * w + x;
+    fl_[j] = ok ? 1 : 0;
+    if (ok && ly == 0 && y0 > 0) fl_[j] |= 2;
+    if (ok && ly == nrows - 1 && y0 + nrows < L.h) fl_[j] |= 4;
   }
   const unsigned win_s = uc_smem_u32(win), recv_s = uc_smem_u32(recv);
+  const int ocol0 = STASH ? L.MT * NBG : 0;                                // first TMEM column of the output-conv accumulators
+  const int scol0 = L.MT * (NBG + NBO);                                    // STASH == 2: first column of the parked u / h values
 
   auto idesc_of = [](int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(128 >> 4) << 24); };
-  // one convolution of a plane on the tensor core: issued by one elected lane of warp 0, completion on mbar_mma
-  auto issue_conv = [&](const float4* wts, int NB, int N2) {
-    if (warp == 0) {
-      if (uc_elect_one()) {
-        if (MTa == 0) {
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(uc_smem_u32(&sh.mbar_mma)) : "memory");
-        } else {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned id1 = idesc_of(NB), id2 = idesc_of(N2);
-          const unsigned long long da0 = uc_desc(win_s, (unsigned)PWa * 16u, 128), db0 = uc_desc(uc_smem_u32(wts), (unsigned)NB * 16u, 128);
-          const unsigned a_lo_off = (unsigned)(NQ * PWa);                  // 16-byte units
-          for (int mt = 0; mt < MTa; ++mt) {
-            const unsigned dcol = tmem + (unsigned)(mt * NB);
+  // MMAs of tiles [t_lo, t_hi) of one convolution, issued by one elected lane of the issuer warp; every tile commits to
+  // its own mbarrier so that its read-back overlaps the MMAs of the tiles behind it
+  auto issue_tiles = [&](const float4* wts, int NB, int N2, int col0, int t_lo, int t_hi) {
+    if (warp == kTcIssuer) {                                              // tcgen05.mma issue blocks while the queue is full: this warp's own read-back comes last
+      if (uc_elect_one() && t_lo < t_hi) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned id1 = idesc_of(NB), id2 = idesc_of(N2);
+        const unsigned long long da0 = uc_desc(win_s, (unsigned)PWa * 16u, 128), db0 = uc_desc(uc_smem_u32(wts), (unsigned)NB * 16u, 128);
+        const unsigned a_lo_off = (unsigned)(NQ * PWa);                  // 16-byte units
+        for (int mt = t_lo; mt < t_hi; ++mt) {
+          const unsigned dcol = tmem + (unsigned)(col0 + mt * NB);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-              for (int ks = 0; ks < KS; ++ks) {
-                const unsigned shift = (unsigned)(128 * mt + (tap / 3) * Wp + (tap % 3) + 2 * ks * PWa);
-                const unsigned long long b = db0 + (unsigned)((tap * KS + ks) * 2 * NB);
-                uc_mma_tf32(dcol, da0 + shift, b, id1, (tap == 0 && ks == 0) ? 0u : 1u);
-                uc_mma_tf32(dcol, da0 + shift + a_lo_off, b, id2, 1u);
-              }
+            for (int ks = 0; ks < KS; ++ks) {
+              const unsigned shift = (unsigned)(128 * mt + (tap / 3) * Wp + (tap % 3) + 2 * ks * PWa);
+              const unsigned long long bb = db0 + (unsigned)((tap * KS + ks) * 2 * NB);
+              uc_mma_tf32(dcol, da0 + shift, bb, id1, (tap == 0 && ks == 0) ? 0u : 1u);
+              uc_mma_tf32(dcol, da0 + shift + a_lo_off, bb, id2, 1u);
             }
           }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(uc_smem_u32(&sh.mbar_mma)) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(uc_smem_u32(&sh.mbar_tile[mt])) : "memory");
         }
       }
       __syncwarp();
     }
   };
+  // Tiles that read a halo row (outputs of the first / last row of the strip) wait for the neighbours; the tiles between
+  // them only need this CTA's own rows.  Called after the window stores: [every thread] fence + cluster arrive happened.
+  const int t_first = (Wp - 1) / 128 + 1, t_last = nrows >= 3 ? ((nrows - 1) * Wp) / 128 : 0;     // interior tiles [t_first, t_last)
+  auto issue_conv_split = [&](const float4* wts, int NB, int N2, int col0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                                      // this CTA's rows are in the window
+    if (t_first < t_last) issue_tiles(wts, NB, N2, col0, t_first, t_last);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); // the neighbours' halo rows too
+    if (t_first < t_last) { issue_tiles(wts, NB, N2, col0, 0, t_first); issue_tiles(wts, NB, N2, col0, t_last, MTa); }
+    else issue_tiles(wts, NB, N2, col0, 0, MTa);
+  };
 
-  // accumulator read-back of one conv: acc[j][c] = this CTA's own N columns (raw + lo halves added); on the K-split levels
-  // the columns owned by the other K-groups are pushed into their receive buffers
-  auto read_back = [&](int N, int NB, int nparts, float (&acc)[MAXP][2 * CK]) {
+  unsigned ph_mma = 0, ph_pre = 0;
+  bool alive = true;
+  auto lane_base = [&](int j, int NB, int col0) {                         // TMEM address of this thread's row of tile j's accumulators
+    return tmem + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(col0 + ((warp >> 2) + 4 * j) * NB);
+  };
+  // accumulator read-back of one position: v[part*CK + c] = this CTA's own columns (raw + lo halves added); on the K-split
+  // levels the columns owned by the other K-groups are pushed into their receive buffers.  Warp-uniform call.
+  auto read_pos = [&](int j, int N, int NB, int col0, int nparts, float (&v)[2 * CK]) {
+    alive = uc_wait(&sh.mbar_tile[(warp >> 2) + 4 * j], ph_mma) && alive;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = lane_base(j, NB, col0);
 #pragma unroll
-    for (int j = 0; j < MAXP; ++j) {
-      const int mt = (warp >> 2) + 4 * j;
-      if (mt >= MTa) continue;                                             // warp-uniform
-      const unsigned tbase = tmem + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(mt * NB);
-      for (int part = 0; part < nparts; ++part) {                          // gates: r columns, u columns
+    for (int part = 0; part < 2; ++part) {                                 // gates: r columns, u columns
+      if (part >= nparts) break;
 #pragma unroll
-        for (int owner = 0; owner < KG; ++owner) {
+      for (int owner = 0; owner < KG; ++owner) {
 #pragma unroll
-          for (int c8 = 0; c8 < CK / 8; ++c8) {
-            const int col = part * CH + owner * CK + c8 * 8;
-            float a[8], b[8];
-            tc_tmem_ld8(tbase + (unsigned)col, a);
-            tc_tmem_ld8(tbase + (unsigned)(N + col), b);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int c8 = 0; c8 < CK / 8; ++c8) {
+          const int col = part * CH + owner * CK + c8 * 8;
+          float a[8], b[8];
+          tc_tmem_ld8(tbase + (unsigned)col, a);
+          tc_tmem_ld8(tbase + (unsigned)(N + col), b);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] += b[i];
-            if (KG == 1 || owner == kg) {
-              if (part == 0) {
+          for (int i = 0; i < 8; ++i) a[i] += b[i];
+          if (KG == 1 || owner == kg) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[j][c8 * 8 + i] = a[i];
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[j][CK + c8 * 8 + i] = a[i];
-              }
-            } else if (ok_[j]) {
-              const int slot = kg < owner ? kg : kg - 1;
-              const int f4 = part * (CK / 4) + c8 * 2;
-              const unsigned la = recv_s + (unsigned)(((slot * (2 * CK / 4) + f4) * NPP + q_[j]) * 16);
-              const unsigned ra = tc_mapa(la, (unsigned)(strip * KG + owner));
-              tc_st_remote(ra, make_float4(a[0], a[1], a[2], a[3]));
-              tc_st_remote(ra + (unsigned)NPP * 16u, make_float4(a[4], a[5], a[6], a[7]));
-            }
+            for (int i = 0; i < 8; ++i) v[part * CK + c8 * 8 + i] = a[i];
+          } else if (fl_[j] & 1) {
+            const int slot = kg < owner ? kg : kg - 1;
+            const int f4 = part * (CK / 4) + c8 * 2;
+            const unsigned la = recv_s + (unsigned)(((slot * (2 * CK / 4) + f4) * NPP + q_[j]) * 16);
+            const unsigned ra = tc_mapa(la, (unsigned)(strip * KG + owner));
+            tc_st_remote(ra, make_float4(a[0], a[1], a[2], a[3]));
+            tc_st_remote(ra + (unsigned)NPP * 16u, make_float4(a[4], a[5], a[6], a[7]));
           }
         }
       }
     }
   };
   // own partial + the partials received from the other K-groups (fixed order) + the x-half
-  auto finish_sums = [&](int nparts, float (&acc)[MAXP][2 * CK]) {
+  auto add_recv_pre = [&](int j, int nparts, float (&v)[2 * CK]) {
 #pragma unroll
-    for (int j = 0; j < MAXP; ++j) {
-      if (!ok_[j]) continue;
-      for (int part = 0; part < nparts; ++part) {
+    for (int part = 0; part < 2; ++part) {
+      if (part >= nparts) break;
 #pragma unroll
-        for (int f = 0; f < CK / 4; ++f) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (KG > 1) {
-            for (int slot = 0; slot < KG - 1; ++slot) {
-              const float4 t = recv[(slot * (2 * CK / 4) + part * (CK / 4) + f) * NPP + q_[j]];
-              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-            }
-          }
-          const float* pp = pre + (size_t)(part * CK + 4 * f) * Rw + sp_[j];
-          if (part == 0) {
-            acc[j][4 * f + 0] += v.x + pp[0]; acc[j][4 * f + 1] += v.y + pp[Rw];
-            acc[j][4 * f + 2] += v.z + pp[2 * Rw]; acc[j][4 * f + 3] += v.w + pp[3 * Rw];
-          } else {
-            acc[j][CK + 4 * f + 0] += v.x + pp[0]; acc[j][CK + 4 * f + 1] += v.y + pp[Rw];
-            acc[j][CK + 4 * f + 2] += v.z + pp[2 * Rw]; acc[j][CK + 4 * f + 3] += v.w + pp[3 * Rw];
+      for (int f = 0; f < CK / 4; ++f) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (KG > 1) {
+          for (int slot = 0; slot < KG - 1; ++slot) {
+            const float4 r4 = recv[(slot * (2 * CK / 4) + part * (CK / 4) + f) * NPP + q_[j]];
+            t.x += r4.x; t.y += r4.y; t.z += r4.z; t.w += r4.w;
           }
         }
+        const float* pp = pre + (size_t)(part * CK + 4 * f) * Rw + sp_[j];
+        v[part * CK + 4 * f + 0] += t.x + pp[0]; v[part * CK + 4 * f + 1] += t.y + pp[Rw];
+        v[part * CK + 4 * f + 2] += t.z + pp[2 * Rw]; v[part * CK + 4 * f + 3] += t.w + pp[3 * Rw];
       }
+    }
+  };
+  // TMEM as a register-file extension (STASH levels): CK values of this thread's row at column `col` of tile j's gate region
+  auto stash_addr = [&](int j, int which) {                               // which: 0 = update-gate pre-activation, 1 = h
+    return STASH == 1 ? lane_base(j, NBG, 0) + (unsigned)((1 + which) * CK)
+                      : lane_base(j, 2 * CK, scol0) + (unsigned)(which * CK);
+  };
+  auto stash_st = [&](int j, int which, const float* v) {
+    const unsigned ta = stash_addr(j, which);
+#pragma unroll
+    for (int c8 = 0; c8 < CK / 8; ++c8)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   :: "r"(ta + (unsigned)(8 * c8)), "r"(__float_as_uint(v[8 * c8])), "r"(__float_as_uint(v[8 * c8 + 1])),
+                      "r"(__float_as_uint(v[8 * c8 + 2])), "r"(__float_as_uint(v[8 * c8 + 3])), "r"(__float_as_uint(v[8 * c8 + 4])),
+                      "r"(__float_as_uint(v[8 * c8 + 5])), "r"(__float_as_uint(v[8 * c8 + 6])), "r"(__float_as_uint(v[8 * c8 + 7])) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  };
+  auto stash_ld = [&](int j, int which, float* v) {
+    const unsigned ta = stash_addr(j, which);
+#pragma unroll
+    for (int c8 = 0; c8 < CK / 8; ++c8) {
+      float t[8];
+      tc_tmem_ld8(ta + (unsigned)(8 * c8), t);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * c8 + i] = t[i];
     }
   };
   // block-wide sums of up to four quantities -> sh.stat_out[which]
@@ -333,7 +363,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     __syncthreads();
     if (tid < 4) {
       double t = 0.0;
-      if (tid < n) for (int i = 0; i < kTcWarps; ++i) t += sh.red[tid][i];
+      if (tid < n) for (int i = 0; i < kTcEpiWarps; ++i) t += sh.red[tid][i];
       sh.stat_out[which][tid] = t;
     }
   };
@@ -362,19 +392,20 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
   };
   // write CK channels of one position into the window (raw + lo) and into the neighbours' halo rows
   auto store_window = [&](int j, const float (&v)[CK]) {
+    const int wi = q_[j] + Wp + 1;
 #pragma unroll
     for (int f = 0; f < NQ; ++f) {
       const float4 raw = make_float4(v[4 * f], v[4 * f + 1], v[4 * f + 2], v[4 * f + 3]);
       const float4 lo = make_float4(tc_lo(raw.x), tc_lo(raw.y), tc_lo(raw.z), tc_lo(raw.w));
-      win[f * PWa + wi_[j]] = raw;
-      win[(NQ + f) * PWa + wi_[j]] = lo;
-      if (halo_[j]) {
-        const int x1 = wi_[j] % Wp;                                        // x + 1
-        if (halo_[j] & 1) {                                                // row R+1 of the strip above (it has R rows)
+      win[f * PWa + wi] = raw;
+      win[(NQ + f) * PWa + wi] = lo;
+      if (fl_[j] & 6) {
+        const int x1 = wi % Wp;                                            // x + 1
+        if (fl_[j] & 2) {                                                  // row R+1 of the strip above (it has R rows)
           const unsigned ra = tc_mapa(win_s + (unsigned)((f * PWa + (R + 1) * Wp + x1) * 16), rank - KG);
           tc_st_remote(ra, raw); tc_st_remote(ra + (unsigned)(NQ * PWa) * 16u, lo);
         }
-        if (halo_[j] & 2) {                                                // row 0 of the strip below
+        if (fl_[j] & 4) {                                                  // row 0 of the strip below
           const unsigned ra = tc_mapa(win_s + (unsigned)((f * PWa + x1) * 16), rank + KG);
           tc_st_remote(ra, raw); tc_st_remote(ra + (unsigned)(NQ * PWa) * 16u, lo);
         }
@@ -382,121 +413,164 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     }
   };
 
-  long long t_prev = 0, t_acc[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) t_acc[i] = 0;
+  if (tid == 0) for (int i = 0; i < 12; ++i) sh.t_acc[i] = 0;
   auto mark = [&](int slot) {
-    if (dbg != nullptr && tid == 0) { const long long t = clock64(); if (slot >= 0) t_acc[slot] += t - t_prev; t_prev = t; }
+    if (dbg != nullptr && tid == 0) { const long long t = clock64(); if (slot >= 0) sh.t_acc[slot] += t - sh.t_prev; sh.t_prev = t; }
   };
 
-  unsigned ph_mma = 0, ph_pre = 0;
-  bool alive = true;
-  float hown[MAXP][CK];
-  float acc[MAXP][2 * CK];
+  // Per-position state that lives across the cluster barriers: keep = reset-gate pre-activation, later the output-conv
+  // pre-activation, later h'.  The update-gate pre-activation and h of the own channels are parked in TMEM on the STASH
+  // levels (columns [CK, 2CK) and [2CK, 3CK) of the position's gate accumulators, dead after the read-back).
+  float keep[MAXP][CK];
+  float ukeep[MAXP][STASH ? 1 : CK], hkeep[MAXP][STASH ? 1 : CK];
+  issue_tiles(wg, NBG, NG, 0, 0, MTa);                                     // gates of plane 0
   for (int d = 0; d < D; ++d) {
     mark(-1);
-    // ================= gates: G = GX[d] + conv(h; Wg) =================
-    issue_conv(wg, NBG, NG);
-    alive = uc_wait(&sh.mbar_mma, ph_mma) && alive; ph_mma ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    mark(0);
-    read_back(NG, NBG, 2, acc);
-    if (KG > 1) { tc_cluster_sync(); }                                    // #A: every K-group's partial sums have landed
-    alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
-    finish_sums(2, acc);
+    // ================= gates: G = GX[d] + conv(h; Wg)  (MMAs already in flight) =================
+    double st[4] = {0.0, 0.0, 0.0, 0.0};
     {
-      double st[4] = {0.0, 0.0, 0.0, 0.0};
+      float v[MAXP][2 * CK];
+      if (KG > 1) {
+#pragma unroll
+        for (int j = 0; j < MAXP; ++j)
+          if ((warp >> 2) + 4 * j < MTa && warp < kTcEpiWarps) read_pos(j, NG, NBG, 0, 2, v[j]);
+        tc_cluster_sync();                                                 // #A: every K-group's partial sums have landed
+      }
+      alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
 #pragma unroll
       for (int j = 0; j < MAXP; ++j) {
-        if (!ok_[j]) continue;
-        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        if ((warp >> 2) + 4 * j >= MTa || warp >= kTcEpiWarps) continue;  // warp-uniform
+        if (KG == 1) read_pos(j, NG, NBG, 0, 2, v[j]);
+        if (fl_[j] & 1) {
+          add_recv_pre(j, 2, v[j]);
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < CK; ++c) {
-          s0 += acc[j][c]; q0 = fmaf(acc[j][c], acc[j][c], q0);
-          s1 += acc[j][CK + c]; q1 = fmaf(acc[j][CK + c], acc[j][CK + c], q1);
+          for (int c = 0; c < CK; ++c) {
+            s0 += v[j][c]; q0 = fmaf(v[j][c], v[j][c], q0);
+            s1 += v[j][CK + c]; q1 = fmaf(v[j][CK + c], v[j][CK + c], q1);
+          }
+          st[0] += (double)s0; st[1] += (double)q0; st[2] += (double)s1; st[3] += (double)q1;
         }
-        st[0] += (double)s0; st[1] += (double)q0; st[2] += (double)s1; st[3] += (double)q1;
+#pragma unroll
+        for (int c = 0; c < CK; ++c) keep[j][c] = v[j][c];
+        if (STASH) stash_st(j, 0, &v[j][CK]);
+        else {
+#pragma unroll
+          for (int c = 0; c < CK; ++c) ukeep[j][STASH ? 0 : c] = v[j][CK + c];
+        }
       }
-      publish_stats(0, 4, st);
     }
+    ph_mma ^= 1u;
+    mark(0);
+    publish_stats(0, 4, st);
     mark(1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tc_cluster_sync();                                                     // #B: sums of every CTA are published; all gate MMAs are complete
     mark(2);
-    gather_coef(0, 2, 0, L.rn_w, L.rn_b, L.un_w, L.un_b);
     issue_pre(1, d);                                                       // every thread is past its reads of the gate x-halves
-    // r*h -> window (own rows + halos); u replaces the update-gate pre-activation; h of the own channels is kept
+    gather_coef(0, 2, 0, L.rn_w, L.rn_b, L.un_w, L.un_b);
+    mark(10);
+    // r*h -> window (own rows + halos); h of the own channels is kept for the state update
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {
-      if (!ok_[j]) continue;
-      float rh[CK];
+      if ((warp >> 2) + 4 * j >= MTa || warp >= kTcEpiWarps) continue;    // warp-uniform
+      float hv[CK], rh[CK];
+      const int wi = q_[j] + Wp + 1;
 #pragma unroll
       for (int f = 0; f < NQ; ++f) {
-        const float4 hv = win[f * PWa + wi_[j]];
-        hown[j][4 * f] = hv.x; hown[j][4 * f + 1] = hv.y; hown[j][4 * f + 2] = hv.z; hown[j][4 * f + 3] = hv.w;
+        const float4 h4 = win[f * PWa + wi];
+        hv[4 * f] = h4.x; hv[4 * f + 1] = h4.y; hv[4 * f + 2] = h4.z; hv[4 * f + 3] = h4.w;
       }
 #pragma unroll
       for (int c = 0; c < CK; ++c) {
-        rh[c] = tc_sigmoid(fmaf(acc[j][c], sh.coef[0][c][0], sh.coef[0][c][1])) * hown[j][c];
-        acc[j][CK + c] = tc_sigmoid(fmaf(acc[j][CK + c], sh.coef[1][c][0], sh.coef[1][c][1]));
+        const float2 cf = *reinterpret_cast<const float2*>(&sh.coef[0][c][0]);
+        rh[c] = tc_sigmoid(fmaf(keep[j][c], cf.x, cf.y)) * hv[c];
       }
-      store_window(j, rh);
+      if (fl_[j] & 1) store_window(j, rh);
+      if (STASH) stash_st(j, 1, hv);
+      else {
+#pragma unroll
+        for (int c = 0; c < CK; ++c) hkeep[j][STASH ? 0 : c] = hv[c];
+      }
     }
+    mark(11);
     asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); // #C: r*h of the strip and its halos (wait inside issue_conv_split)
     mark(3);
-    tc_cluster_sync();                                                     // #C: r*h of the strip and its halos is in place everywhere
-    mark(4);
     // ================= output: O = OX[d] + conv(r*h; Wo) =================
-    issue_conv(wo, NBO, N2O);
-    alive = uc_wait(&sh.mbar_mma, ph_mma) && alive; ph_mma ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    mark(5);
-    // u lives in acc[j][CK ..]; the output sums replace the (consumed) reset-gate half acc[j][0 .. CK)
-    read_back(NO, NBO, 1, acc);
-    if (KG > 1) { tc_cluster_sync(); }                                    // #D
-    alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
-    finish_sums(1, acc);
+    issue_conv_split(wo, NBO, N2O, ocol0);
+    mark(4);
+    st[0] = st[1] = st[2] = st[3] = 0.0;
     {
-      double st[4] = {0.0, 0.0, 0.0, 0.0};
+      float v[MAXP][2 * CK];
+      if (KG > 1) {
+#pragma unroll
+        for (int j = 0; j < MAXP; ++j)
+          if ((warp >> 2) + 4 * j < MTa && warp < kTcEpiWarps) read_pos(j, NO, NBO, ocol0, 1, v[j]);
+        tc_cluster_sync();                                                 // #D
+      }
+      alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
 #pragma unroll
       for (int j = 0; j < MAXP; ++j) {
-        if (!ok_[j]) continue;
-        float s0 = 0.f, q0 = 0.f;
+        if ((warp >> 2) + 4 * j >= MTa || warp >= kTcEpiWarps) continue;
+        if (KG == 1) read_pos(j, NO, NBO, ocol0, 1, v[j]);
+        if (fl_[j] & 1) {
+          add_recv_pre(j, 1, v[j]);
+          float s0 = 0.f, q0 = 0.f;
 #pragma unroll
-        for (int c = 0; c < CK; ++c) { s0 += acc[j][c]; q0 = fmaf(acc[j][c], acc[j][c], q0); }
-        st[0] += (double)s0; st[1] += (double)q0;
+          for (int c = 0; c < CK; ++c) { s0 += v[j][c]; q0 = fmaf(v[j][c], v[j][c], q0); }
+          st[0] += (double)s0; st[1] += (double)q0;
+        }
+#pragma unroll
+        for (int c = 0; c < CK; ++c) keep[j][c] = v[j][c];
       }
-      publish_stats(1, 2, st);
     }
+    ph_mma ^= 1u;
+    mark(5);
+    publish_stats(1, 2, st);
     mark(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tc_cluster_sync();                                                     // #E
     mark(7);
-    gather_coef(1, 1, 2, L.on_w, L.on_b, L.on_w, L.on_b);
     if (d + 1 < D) issue_pre(0, d + 1);
-    // h' = u*h + (1-u)*tanh(GN_o(O)) -> window, halos, state history (module.py:57)
+    gather_coef(1, 1, 2, L.on_w, L.on_b, L.on_w, L.on_b);
+    // h' = u*h + (1-u)*tanh(GN_o(O)) -> window and halos now, the state history after the barrier arrive (module.py:57)
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {
-      if (!ok_[j]) continue;
-      float hn[CK];
-      float* sp = L.s + (long long)(kg * CK) * L.s_cs + (long long)(d + 1) * L.px + gp_[j];
+      if ((warp >> 2) + 4 * j >= MTa || warp >= kTcEpiWarps) continue;
+      float uv[CK], hv[CK];
+      if (STASH) { stash_ld(j, 0, uv); stash_ld(j, 1, hv); }
+      else {
+#pragma unroll
+        for (int c = 0; c < CK; ++c) { uv[c] = ukeep[j][STASH ? 0 : c]; hv[c] = hkeep[j][STASH ? 0 : c]; }
+      }
 #pragma unroll
       for (int c = 0; c < CK; ++c) {
-        const float uu = acc[j][CK + c];
-        hn[c] = uu * hown[j][c] + (1.0f - uu) * tc_tanh(fmaf(acc[j][c], sh.coef[2][c][0], sh.coef[2][c][1]));
-        sp[(long long)c * L.s_cs] = hn[c];
+        const float2 cu = *reinterpret_cast<const float2*>(&sh.coef[1][c][0]);
+        const float2 co = *reinterpret_cast<const float2*>(&sh.coef[2][c][0]);
+        const float uu = tc_sigmoid(fmaf(uv[c], cu.x, cu.y));
+        keep[j][c] = uu * hv[c] + (1.0f - uu) * tc_tanh(fmaf(keep[j][c], co.x, co.y));
       }
-      store_window(j, hn);
+      if (fl_[j] & 1) store_window(j, keep[j]);
     }
     asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); // #F: h[d+1] (wait inside issue_conv_split)
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {                                       // global stores drain behind the barrier and the next MMAs
+      if (!(fl_[j] & 1)) continue;
+      float* sp = L.s + (long long)(kg * CK) * L.s_cs + (long long)(d + 1) * L.px + (long long)y0 * w + sp_[j];
+#pragma unroll
+      for (int c = 0; c < CK; ++c) sp[(long long)c * L.s_cs] = keep[j][c];
+    }
     mark(8);
-    tc_cluster_sync();                                                     // #F: h[d+1] is in place everywhere
+    if (d + 1 < D) issue_conv_split(wg, NBG, NG, 0);
+    else asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     mark(9);
   }
   if (!alive && tid == 0) atomicExch(err, 1);
   if (dbg != nullptr && tid == 0 && (rank == 0))
 #pragma unroll
-    for (int i = 0; i < 12; ++i) dbg[(blockIdx.x / kTcCluster) * 12 + i] = t_acc[i];
+    for (int i = 0; i < 12; ++i) dbg[(blockIdx.x / kTcCluster) * 12 + i] = sh.t_acc[i];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   tc_cluster_sync();                                                       // no CTA leaves while a peer may still write into its shared memory
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
@@ -507,10 +581,13 @@ red_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   __shared__ TcShared sh;
   const int lv = blockIdx.x / kTcCluster;
-  if (lv == 0) tc_level_run<8, kTcKG[0], kTcMaxP[0]>(a.l[0], a.D, a.err, a.dbg, tc_smem, sh);
-  else if (lv == 1) tc_level_run<16, kTcKG[1], kTcMaxP[1]>(a.l[1], a.D, a.err, a.dbg, tc_smem, sh);
-  else if (lv == 2) tc_level_run<32, kTcKG[2], kTcMaxP[2]>(a.l[2], a.D, a.err, a.dbg, tc_smem, sh);
-  else tc_level_run<64, kTcKG[3], kTcMaxP[3]>(a.l[3], a.D, a.err, a.dbg, tc_smem, sh);
+#ifndef TC_ONLY
+#define TC_ONLY -1
+#endif
+  if (lv == 0 && (TC_ONLY < 0 || TC_ONLY == 0)) tc_level_run<8, kTcKG[0], kTcMaxP[0], 1>(a.l[0], a.D, a.err, a.dbg, tc_smem, sh);
+  else if (lv == 1 && (TC_ONLY < 0 || TC_ONLY == 1)) tc_level_run<16, kTcKG[1], kTcMaxP[1], 2>(a.l[1], a.D, a.err, a.dbg, tc_smem, sh);
+  else if (lv == 2 && (TC_ONLY < 0 || TC_ONLY == 2)) tc_level_run<32, kTcKG[2], kTcMaxP[2], 2>(a.l[2], a.D, a.err, a.dbg, tc_smem, sh);
+  else if (TC_ONLY < 0 || TC_ONLY == 3) tc_level_run<64, kTcKG[3], kTcMaxP[3], 0>(a.l[3], a.D, a.err, a.dbg, tc_smem, sh);
 }
 
 inline size_t tc_pack_bytes(int ch) { return (size_t)216 * ch * ch; }     // KG * 9 * (CK/8) * 2 * 6ch * 16
@@ -530,7 +607,11 @@ inline int red_tc_launch(TcArgs& a, const float* const* gate_w_h, const float* c
     TcLevel& L = a.l[l];
     if (L.ch != (8 << l) || L.w % 4 || L.w < 4 || L.h < 1) return SATMVS_OK;
     const TcGeom g = tc_geom(L.ch, kTcKG[l], L.h, L.w);
-    if (g.MT > 4 * kTcMaxP[l] || g.MT * 4 * L.ch > 512 || (size_t)g.PWa * 16 >= (1u << 18)) {
+    // TMEM columns: MT tiles x 4ch gate columns; level 0 keeps its 2ch output-conv columns next to them (the gate region
+    // parks u and h meanwhile)
+    // (level 0: 6ch; levels 1, 2: 6ch + 2*CK parked columns; level 3: 4ch, output accumulators reuse them)
+    const int tmem_cols = g.MT * (l == 0 ? 6 * L.ch : l == 3 ? 4 * L.ch : 6 * L.ch + 2 * L.ch / kTcKG[l]);
+    if (g.MT > 4 * kTcMaxP[l] || tmem_cols > 512 || (size_t)g.PWa * 16 >= (1u << 18)) {
       if (verbose) fprintf(stderr, "red_tc_launch: level %d needs %d tiles per CTA\n", l, g.MT);
       return SATMVS_OK;
     }

@@ -3,6 +3,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, satmvs_b200
+torch.set_grad_enabled(False)
 from satmvs_b200 import synth
 C, D, H, W = (int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (32, 64, 96, 192)))
 m = satmvs_b200.RED_Regularization(C, 8)
