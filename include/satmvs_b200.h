@@ -199,8 +199,9 @@ int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, 
                        const float* const* state_in, float* const* state_out, float* logits,
                        void* workspace, size_t workspace_bytes, void* stream);
 
-/* Which implementation of the depth recurrence the last satmvs_red_forward of this thread used: 2 = tensor-core cluster
- * kernel (csrc/red_tc.cuh), 1 = FFMA cluster kernel (csrc/red_cluster.cuh), 0 = per-plane kernel chain, -1 = none yet.
+/* Which implementation of the depth recurrence the last satmvs_red_forward of this thread used: 3 = tensor-core cluster
+ * kernel (csrc/red_tc.cuh) running concurrently with the batched convolutions that feed it (side stream, per-plane ready
+ * counters; SATMVS_RED_NO_OVERLAP=1 disables), 2 = the same kernel after them, 1 = FFMA cluster kernel (csrc/red_cluster.cuh), 0 = per-plane kernel chain, -1 = none yet.
  * Diagnostic for tests and the bench line; SATMVS_RED_NO_TC=1 / SATMVS_RED_NO_CLUSTER=1 force the later ones. */
 int satmvs_red_last_path(void);
 

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "prof.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace satmvs {
 static thread_local char g_error[512] = "";
@@ -30,6 +31,23 @@ int satmvs_profile_end(float* ms_by_class, int* launches_by_class) {
   satmvs::ProfState& s = satmvs::prof_state();
   s.on = false;
   cudaDeviceSynchronize();
+  if (getenv("SATMVS_PROF_DUMP")) {   // timeline of every instrumented launch, relative to the first recorded event
+    cudaEvent_t ref = nullptr;
+    float best = 0.0f;
+    for (int p = 0; p < satmvs::kProfCount; ++p)
+      for (cudaEvent_t e : s.ev[p]) {
+        if (!ref) { ref = e; continue; }
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ref, e) == cudaSuccess && ms < best) { best = ms; }
+      }
+    for (int p = 0; p < satmvs::kProfCount && ref; ++p)
+      for (size_t i = 0; i + 1 < s.ev[p].size(); i += 2) {
+        float a = 0.0f, b = 0.0f;
+        cudaEventElapsedTime(&a, ref, s.ev[p][i]);
+        cudaEventElapsedTime(&b, ref, s.ev[p][i + 1]);
+        fprintf(stderr, "prof class %d launch %zu: %.1f .. %.1f us\n", p, i / 2, (a - best) * 1e3f, (b - best) * 1e3f);
+      }
+  }
   for (int p = 0; p < satmvs::kProfCount; ++p) {
     float tot = 0.0f;
     for (size_t i = 0; i + 1 < s.ev[p].size(); i += 2) {

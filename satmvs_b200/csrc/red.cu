@@ -72,6 +72,7 @@ struct RedPlan {
   int* fuse_cnt;
   int* cl_flags;         // [4][2][kClFlagStride] plane counters exchanged by the two clusters of a level
   char* tcpack[4];       // packed hidden-state filters of the tensor-core recurrence (red_tc.cuh)
+  int* ready;            // [4][D] per-(level, plane) completion counters of the batched x-half convs (overlapped flow)
   size_t bytes;
 };
 
@@ -115,6 +116,8 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   off += 4 * 2 * 32 * sizeof(int) + 8 * 16 * sizeof(unsigned long long);   // + debug counters
   off = (off + 255) / 256 * 256;
   for (int l = 0; l < 4; ++l) { p.tcpack[l] = base + off; off += (tc_pack_bytes(chs[l]) + 255) / 256 * 256; }
+  p.ready = reinterpret_cast<int*>(base + off);
+  off += ((size_t)4 * D * sizeof(int) + 255) / 256 * 256;
   p.bytes = off;
   return p;
 }
@@ -859,6 +862,36 @@ static int launch_plane_conv(const ConvProblem& p, int stride, cudaStream_t st, 
   return launch_by_cout(p, st, what);
 }
 
+// Side streams of the overlapped flow (per host thread and device; created once, live as long as the library): `rec` runs the
+// recurrence (highest priority: its 64 CTAs must become resident before the producers fill the machine), `lv[1..3]` run the
+// batched convs of levels 1..3 (level 0 stays on the caller's stream) so that chunk c of level l overlaps chunk c+1 of level l-1.
+constexpr int kRedMaxChunks = 32;
+struct RedSideStream {
+  cudaStream_t rec = nullptr, lv[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t chunk[3][kRedMaxChunks];
+  int dev = -1; bool ok = false;
+};
+static RedSideStream& red_side_stream() {
+  static thread_local RedSideStream s[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  RedSideStream& r = s[dev & 15];
+  if (r.dev != dev) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    bool ok = cudaStreamCreateWithPriority(&r.rec, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&r.join[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 1; i < 4 && ok; ++i) ok = cudaStreamCreateWithPriority(&r.lv[i], cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i)
+      for (int c = 0; c < kRedMaxChunks && ok; ++c) ok = cudaEventCreateWithFlags(&r.chunk[i][c], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    r.ok = ok; r.dev = dev;
+  }
+  return r;
+}
+
 }  // namespace satmvs
 
 using namespace satmvs;
@@ -911,97 +944,183 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     return launch_plane_conv(p, 2, st, "red encoder");
   };
   static const bool no_umma = getenv("SATMVS_NO_UMMA") != nullptr;
-  for (int l = 0; l < 4; ++l) {   // x-halves of the GRU convolutions, bias folded in (module.py:29-30, :44-45)
+  // x-halves of the GRU convolutions, bias folded in (module.py:29-30, :44-45).  Gate and output x-halves share their input
+  // (and so does the stride-2 encoder that feeds the next level): one tensor-core launch with two or three heads
+  // (umma_conv.cuh); level 4's fused N does not fit (192 columns of packed weights) and takes one launch per head.
+  struct XPlan { UmmaConvPlan u[3]; int n; bool sig[3]; bool enc_done; const char* what[3]; } xp[4];
+  bool all_umma = !no_umma;
+  for (int l = 0; l < 4; ++l) {
     RedLevel& L = P.lv[l];
+    XPlan& X = xp[l];
+    X.n = 0; X.enc_done = false;
+    if (no_umma) continue;
     const long long kin = (long long)(L.cx + L.ch) * 9;
-    if (!no_umma) {
-      // gate and output x-halves share their input (and so does the stride-2 encoder that feeds the next level):
-      // one tensor-core launch with two or three heads (umma_conv.cuh)
-      const float sgn = (l == 0) ? -1.0f : 1.0f;
-      UmmaPackHead wh[3] = {{wt->gate_w[l], kin, 9, 2 * L.ch, 0}, {wt->out_w[l], kin, 9, L.ch, 0}, {nullptr, 0, 0, 0, 0}};
-      UmmaHead oh[3] = {{nullptr, wt->gate_b[l], L.gx, 2 * L.ch, 0, sgn, 0, 1}, {nullptr, wt->out_b[l], L.ox, L.ch, 0, sgn, 0, 1}, {}};
-      UmmaConvPlan up;
-      if (l < 3) {
-        wh[2] = UmmaPackHead{wt->conv_w[l], (long long)ech[l] * 9, 9, ech[l + 1], 0};
-        oh[2] = UmmaHead{nullptr, nullptr, P.e[l], ech[l + 1], 0, sgn, 1, 2};
-        if (umma_conv_plan(up, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 3, wh, oh, P.wpack[l], P.wpack_bytes[l])) {
-          ProfScope prof(kProfConvBatched, st);
-          RUN(umma_conv_launch(up, P.umma_err, st, "red gate/output x-halves + encoder (tcgen05)"));
-          continue;
-        }
-        RUN(run_encoder(l));
-      }
-      if (umma_conv_plan(up, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 2, wh, oh, P.wpack[l], P.wpack_bytes[l])) {
-        ProfScope prof(kProfConvBatched, st);
-        RUN(umma_conv_launch(up, P.umma_err, st, "red gate/output x-halves (tcgen05)"));
-        continue;
-      }
-      // the fused N does not fit (level 4: 192 columns of packed weights): one launch per head
-      UmmaConvPlan ug, uo;
-      const size_t half = (P.wpack_bytes[l] * 2 / 3 + 255) / 256 * 256;
-      if (umma_conv_plan(ug, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 1, wh, oh, P.wpack[l], half) &&
-          umma_conv_plan(uo, xin[l], (long long)D * L.h * L.w, L.cx, D, L.h, L.w, 1, wh + 1, oh + 1, P.wpack[l] + half,
-                         P.wpack_bytes[l] - half)) {
-        ProfScope prof(kProfConvBatched, st);
-        RUN(umma_conv_launch(ug, P.umma_err, st, "red gate x-half (tcgen05)"));
-        RUN(umma_conv_launch(uo, P.umma_err, st, "red output x-half (tcgen05)"));
-        continue;
-      }
+    const float sgn = (l == 0) ? -1.0f : 1.0f;
+    const long long pl = (long long)D * L.h * L.w;
+    // heads: 0 = gates, 1 = output, 2 = the stride-2 encoder of the next level (levels 0..2)
+    UmmaPackHead wh[3] = {{wt->gate_w[l], kin, 9, 2 * L.ch, 0}, {wt->out_w[l], kin, 9, L.ch, 0}, {nullptr, 0, 0, 0, 0}};
+    UmmaHead oh[3] = {{nullptr, wt->gate_b[l], L.gx, 2 * L.ch, 0, sgn, 0, 1}, {nullptr, wt->out_b[l], L.ox, L.ch, 0, sgn, 0, 1}, {}};
+    const int nh = l < 3 ? 3 : 2;
+    if (l < 3) {
+      wh[2] = UmmaPackHead{wt->conv_w[l], (long long)ech[l] * 9, 9, ech[l + 1], 0};
+      oh[2] = UmmaHead{nullptr, nullptr, P.e[l], ech[l + 1], 0, sgn, 1, 2};
     }
-    if (no_umma && l < 3) RUN(run_encoder(l));
+    // group the heads into as few launches as fit: [G O E], else [G O] [E], else [G] [O] [E]; packed weights back to back
+    const int splits[3][3] = {{nh, 0, 0}, {2, nh - 2, 0}, {1, 1, nh - 2}};
+    const char* names[3][3] = {{"red gate/output x-halves + encoder (tcgen05)", "", ""},
+                               {"red gate/output x-halves (tcgen05)", "red encoder (tcgen05)", ""},
+                               {"red gate x-half (tcgen05)", "red output x-half (tcgen05)", "red encoder (tcgen05)"}};
+    for (int t = 0; t < 3 && X.n == 0; ++t) {
+      size_t off = 0;
+      int h0 = 0, n = 0;
+      bool ok = true;
+      for (int g = 0; g < 3 && ok; ++g) {
+        const int cnt = splits[t][g];
+        if (cnt == 0) continue;
+        ok = off < P.wpack_bytes[l] &&
+             umma_conv_plan(X.u[n], xin[l], pl, L.cx, D, L.h, L.w, cnt, wh + h0, oh + h0, P.wpack[l] + off, P.wpack_bytes[l] - off,
+                            1, /*perf_rules=*/h0 < 2);
+        if (ok) {
+          X.sig[n] = h0 < 2;                                 // launches that write gate / output x-halves count towards ready[]
+          X.what[n] = names[t][g];
+          off += (X.u[n].wpack_bytes + 255) / 256 * 256;
+          h0 += cnt; ++n;
+        }
+      }
+      if (ok) { X.n = n; X.enc_done = l < 3; }
+    }
+    if (X.n == 0) all_umma = false;
+  }
+  // launches the batched convs of level l for planes [d0, d0 + np) (np = 0: all planes, weights packed on the way)
+  auto run_xhalf = [&](int l, int d0, int np, bool pack, int* ready, cudaStream_t xs) -> int {
+    RedLevel& L = P.lv[l];
+    XPlan& X = xp[l];
+    if (l < 3 && !X.enc_done) { int r0 = run_encoder(l); if (r0) return r0; }
+    if (X.n > 0) {
+      ProfScope prof(kProfConvBatched, xs);
+      for (int i = 0; i < X.n; ++i) {
+        int r0 = umma_conv_launch(X.u[i], P.umma_err, xs, X.what[i], pack, d0, np, X.sig[i] ? ready : nullptr);
+        if (r0) return r0;
+      }
+      return SATMVS_OK;
+    }
+    const long long kin = (long long)(L.cx + L.ch) * 9;
     ConvProblem g = plane_conv(xin[l], L.cx, D, L.h, L.w, wt->gate_w[l], kin, 9, L.gx, 2 * L.ch, D, L.h, L.w, 1);
     g.Qd = D; g.Qh = L.h; g.Qw = L.w;
     g.shift = wt->gate_b[l];
     g.acc_scale = (l == 0) ? -1.0f : 1.0f;
-    { ProfScope prof(kProfConvBatched, st); RUN(launch_plane_conv(g, 1, st, "red gate x-half")); }
+    { ProfScope prof(kProfConvBatched, st); int r0 = launch_plane_conv(g, 1, st, "red gate x-half"); if (r0) return r0; }
     ConvProblem o = plane_conv(xin[l], L.cx, D, L.h, L.w, wt->out_w[l], kin, 9, L.ox, L.ch, D, L.h, L.w, 1);
     o.Qd = D; o.Qh = L.h; o.Qw = L.w;
     o.shift = wt->out_b[l];
     o.acc_scale = (l == 0) ? -1.0f : 1.0f;
-    { ProfScope prof(kProfConvBatched, st); RUN(launch_plane_conv(o, 1, st, "red output x-half")); }
-  }
+    { ProfScope prof(kProfConvBatched, st); int r0 = launch_plane_conv(o, 1, st, "red output x-half"); if (r0) return r0; }
+    return SATMVS_OK;
+  };
 
-  // ---- B. recurrence over planes ----
+  // ---- A + B overlapped (default): the tensor-core recurrence (64 SMs) is launched FIRST on a side stream and trails the
+  // batched convs, which run chunk by chunk on the remaining SMs and count finished planes in P.ready ----
   bool persistent = false;
-  {
-    // Default: one launch, two 16-CTA clusters per UNet level (red_cluster.cuh).  Shapes it does not take (rows not a
-    // multiple of 4 pixels, strips beyond the shared-memory limit) and SATMVS_RED_NO_CLUSTER=1 run the per-plane chain.
-    const bool no_cluster = getenv("SATMVS_RED_NO_CLUSTER") != nullptr;   // read per call: tests toggle it
-    const bool no_tc = getenv("SATMVS_RED_NO_TC") != nullptr;
-    if (!no_cluster && !no_tc) {
-      // Default: the recurrence on the tensor cores, one 16-CTA cluster per level (red_tc.cuh)
-      TcArgs ta{};
-      ta.D = D;
-      const float* gwh[4]; const float* owh[4]; long long wco[4];
-      for (int l = 0; l < 4; ++l) {
-        RedLevel& L = P.lv[l];
-        TcLevel& R = ta.l[l];
-        const long long px = (long long)L.h * L.w;
-        R.s = L.s; R.s_cs = (long long)(D + 1) * px;
-        R.gx = L.gx; R.g_cs = (long long)D * px;
-        R.ox = L.ox; R.o_cs = (long long)D * px;
-        R.rn_w = wt->rn_w[l]; R.rn_b = wt->rn_b[l]; R.un_w = wt->un_w[l]; R.un_b = wt->un_b[l];
-        R.on_w = wt->on_w[l]; R.on_b = wt->on_b[l];
-        R.inv_n = 1.0 / ((double)L.ch * (double)px);
-        R.ch = L.ch; R.h = L.h; R.w = L.w; R.px = (int)px;
-        gwh[l] = wt->gate_w[l] + (size_t)L.cx * 9; owh[l] = wt->out_w[l] + (size_t)L.cx * 9;
-        wco[l] = (long long)(L.cx + L.ch) * 9;
+  const bool no_cluster = getenv("SATMVS_RED_NO_CLUSTER") != nullptr;   // read per call: tests toggle it
+  const bool no_tc = getenv("SATMVS_RED_NO_TC") != nullptr;
+  const bool no_overlap = getenv("SATMVS_RED_NO_OVERLAP") != nullptr;
+  static const bool tc_dbg = getenv("SATMVS_RED_DEBUG") != nullptr;
+  long long* dbg = tc_dbg ? reinterpret_cast<long long*>(P.cl_flags + 4 * 2 * 32) : nullptr;
+  auto tc_args = [&](bool with_ready) {
+    TcArgs ta{};
+    ta.d_begin = 0; ta.d_end = D;
+    for (int l = 0; l < 4; ++l) {
+      RedLevel& L = P.lv[l];
+      TcLevel& R = ta.l[l];
+      const long long px = (long long)L.h * L.w;
+      R.s = L.s; R.s_cs = (long long)(D + 1) * px;
+      R.gx = L.gx; R.g_cs = (long long)D * px;
+      R.ox = L.ox; R.o_cs = (long long)D * px;
+      R.rn_w = wt->rn_w[l]; R.rn_b = wt->rn_b[l]; R.un_w = wt->un_w[l]; R.un_b = wt->un_b[l];
+      R.on_w = wt->on_w[l]; R.on_b = wt->on_b[l];
+      R.inv_n = 1.0 / ((double)L.ch * (double)px);
+      R.ch = L.ch; R.h = L.h; R.w = L.w; R.px = (int)px;
+      if (with_ready) {
+        R.ready = P.ready + (size_t)l * D;
+        R.expected = 0;
+        for (int i = 0; i < xp[l].n; ++i) if (xp[l].sig[i]) R.expected += (int)xp[l].u[i].grid.x;
       }
-      static const bool tc_dbg = getenv("SATMVS_RED_DEBUG") != nullptr;
-      long long* dbg = tc_dbg ? reinterpret_cast<long long*>(P.cl_flags + 4 * 2 * 32) : nullptr;
-      ProfScope prof(kProfGruGate, st);
-      RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, st, &persistent));
-      if (persistent) g_red_last_path = 2;
-      if (persistent && tc_dbg) {
-        long long h[4 * 12] = {};
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        for (int c = 0; c < 4; ++c) {
-          fprintf(stderr, "red_tc: level %d kcycles per phase slot:", c);
-          for (int i = 0; i < 12; ++i) fprintf(stderr, " %.0f", h[c * 12 + i] * 1e-3);
-          fprintf(stderr, "\n");
+    }
+    return ta;
+  };
+  const float* gwh[4]; const float* owh[4]; long long wco[4];
+  for (int l = 0; l < 4; ++l) {
+    gwh[l] = wt->gate_w[l] + (size_t)P.lv[l].cx * 9; owh[l] = wt->out_w[l] + (size_t)P.lv[l].cx * 9;
+    wco[l] = (long long)(P.lv[l].cx + P.lv[l].ch) * 9;
+  }
+  auto tc_report = [&]() {
+    if (!tc_dbg) return;
+    long long h[4 * 16] = {};
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int c = 0; c < 4; ++c) {
+      fprintf(stderr, "red_tc: level %d kcycles per phase slot:", c);
+      for (int i = 0; i < 16; ++i) fprintf(stderr, " %.0f", h[c * 16 + i] * 1e-3);
+      fprintf(stderr, "\n");
+    }
+  };
+  bool xhalf_done = false, xpacked = false;
+  if (all_umma && !no_cluster && !no_tc && !no_overlap) {
+    RedSideStream& side = red_side_stream();
+    // Event-ordered pipeline (no kernel ever spins on another one): the caller's stream produces the x-halves chunk by chunk,
+    // the side stream runs the recurrence over chunk c as soon as the producers of chunk c are done (state carried through
+    // the history slots), i.e. concurrently with the producers of chunk c + 1 on the 84 SMs the recurrence leaves free.
+    // Chunk schedule: the producers of a chunk cost ~125 us of launch latencies + ~7.5 us per plane, the recurrence ~21 us per
+    // plane + ~30 us per launch, so two chunks of 16 planes get the consumer going and one big chunk finishes the volume
+    // (measured at cfg-2, profiles/r02_red_overlap_notes.md: [8]x8 1.99 ms, [16]x4 1.95 ms per forward against 2.03 sequential)
+    static const int kChunk = getenv("SATMVS_RED_CHUNK") ? atoi(getenv("SATMVS_RED_CHUNK")) : 16;
+    int cstart[kRedMaxChunks + 1], nchunks = 0;
+    cstart[0] = 0;
+    if (kChunk > 0 && D >= 2 * kChunk) {
+      while (cstart[nchunks] < D && nchunks < kRedMaxChunks) {
+        const int left = D - cstart[nchunks];
+        const int take = (nchunks >= 2 || left < 2 * kChunk) ? left : kChunk;
+        cstart[nchunks + 1] = cstart[nchunks] + take;
+        ++nchunks;
+      }
+    }
+    if (side.ok && nchunks > 1 && cstart[nchunks] == D) {
+      for (int l = 0; l < 4; ++l)
+        for (int i = 0; i < xp[l].n; ++i) umma_conv_pack(xp[l].u[i], st);
+      xpacked = true;
+      cudaEventRecord(side.fork, st);
+      cudaStreamWaitEvent(side.rec, side.fork, 0);
+      TcArgs ta = tc_args(false);
+      for (int c = 0; c < nchunks; ++c) {
+        const int d0 = cstart[c], np = cstart[c + 1] - cstart[c];
+        if (c == 0 || persistent) {
+          for (int l = 0; l < 4; ++l) RUN(run_xhalf(l, d0, np, false, nullptr, st));
+          cudaEventRecord(side.chunk[0][c], st);
+          cudaStreamWaitEvent(side.rec, side.chunk[0][c], 0);
+          ta.d_begin = d0; ta.d_end = d0 + np;
+          bool ran = false;
+          ProfScope prof(kProfGruGate, side.rec);
+          RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, side.rec, &ran, c == 0));
+          if (c == 0) persistent = ran;
+          if (!ran) break;                                                 // shape not taken: the sequential flow below finishes the job
         }
       }
+      cudaEventRecord(side.join[0], side.rec);
+      cudaStreamWaitEvent(st, side.join[0], 0);
+      if (persistent) { g_red_last_path = 3; xhalf_done = true; tc_report(); }
+    }
+  }
+  if (!xhalf_done)
+    for (int l = 0; l < 4; ++l) RUN(run_xhalf(l, 0, 0, !xpacked, nullptr, st));
+
+  // ---- B. recurrence over planes (when it did not run overlapped above) ----
+  {
+    if (!persistent && !no_cluster && !no_tc) {
+      // the recurrence on the tensor cores, one 16-CTA cluster per level (red_tc.cuh), after the batched convs
+      TcArgs ta = tc_args(false);
+      ProfScope prof(kProfGruGate, st);
+      RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, st, &persistent));
+      if (persistent) { g_red_last_path = 2; tc_report(); }
     }
     if (!persistent && !no_cluster) {
       ClArgs ca{};

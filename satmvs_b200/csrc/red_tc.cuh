@@ -46,8 +46,9 @@ struct TcLevel {
   double inv_n;                               // 1 / (ch * px)
   int ch, h, w, px;
   int R, MT, PWa, NPP;                        // rows per strip, 128-position tiles, window positions, positions padded to 32
-};
-struct TcArgs { TcLevel l[4]; int D; int* err; long long* dbg; };
+  const int* ready; int expected;             // optional: ready[d] reaches `expected` when the x-halves of plane d are in memory
+};                                            // (their producers run concurrently on the SMs this kernel leaves free)
+struct TcArgs { TcLevel l[4]; int d_begin, d_end; int* err; long long* dbg; };   // planes [d_begin, d_end): state read from history slot d_begin
 
 struct TcGeom { int R, MT, PWa, NPP; size_t smem; };
 // geometry + dynamic shared memory of one level (host and device agree on the carve-up through this function)
@@ -123,16 +124,16 @@ __device__ __forceinline__ float tc_sigmoid(float x) { return __fdividef(1.0f, 1
 __device__ __forceinline__ float tc_tanh(float x) { return fmaf(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f); }
 
 struct TcShared {
-  double stat_out[2][4];                      // this CTA's (sum, sum^2) x {r, u} after the gate conv; {o} after the output conv
+  double stat_in[2][kTcCluster][4];           // (sum, sum^2) x {r, u} after the gate conv / {o} after the output conv, pushed by every rank of the cluster
   double red[4][kTcWarps];
   float coef[3][16][2];                       // GroupNorm scale / shift of this CTA's channels: r, u, o
   unsigned long long mbar_tile[16], mbar_pre;      // MMAs of tile mt complete; x-halves landed
   unsigned tmem_base;
-  long long t_prev, t_acc[12];                // SATMVS_RED_DEBUG: cycles thread 0 spends per phase slot
+  long long t_prev, t_acc[16];                // SATMVS_RED_DEBUG: cycles thread 0 spends per phase slot
 };
 
 template <int CH, int KG, int MAXP, int STASH>   // STASH: 0 none, 1 in the dead half of the gate accumulators (KG == 1), 2 own TMEM columns
-__device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int* err, long long* dbg, unsigned char* smem, TcShared& sh) {
+__device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin, const int D, int* err, long long* dbg, unsigned char* smem, TcShared& sh) {
   constexpr int CK = CH / KG, NQ = CK / 4, KS = CK / 8;
   constexpr int NG = 2 * CH, NBG = 2 * NG, NO = CH, NBO = 2 * NO;
   constexpr int N2O = NO >= 16 ? NO : NBO;                 // an M = 128 MMA needs N >= 16: level 0 multiplies lo(x) by [W | lo(W)] (the extra lo*lo term is exact anyway)
@@ -176,7 +177,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     for (int i = tid; i < items; i += kTcThreads) {
       const int x = i % w; int r = i / w;
       const int yy = ylo + r % (yhi - ylo + 1); const int qd = r / (yhi - ylo + 1);
-      const float* sp = L.s + (long long)(kg * CK + 4 * qd) * L.s_cs + (long long)yy * w + x;
+      const float* sp = L.s + (long long)(kg * CK + 4 * qd) * L.s_cs + (long long)d_begin * L.px + (long long)yy * w + x;
       const float4 v = make_float4(sp[0], sp[L.s_cs], sp[2 * L.s_cs], sp[3 * L.s_cs]);
       const int wi = (yy - y0 + 1) * Wp + x + 1;
       win[qd * PWa + wi] = v;
@@ -185,21 +186,35 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
   }
   // x-halves of this strip by bulk copies: conv 0 = gates (r and u rows of this CTA's channels), conv 1 = output
   auto issue_pre = [&](int conv, int d) {
-    if (tid != 32 * kTcIssuer) return;                                    // lane 0 of the issuer warp
+    if (warp != kTcIssuer) return;                                        // one channel per lane of the issuer warp
     const unsigned bar = uc_smem_u32(&sh.mbar_pre);
     const int nchan = conv == 0 ? 2 * CK : CK;
     const unsigned bytes = (unsigned)(nrows * w) * 4u;
-    if (nrows == 0) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); return; }
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)nchan) : "memory");
-    for (int i = 0; i < nchan; ++i) {
+    if (lane == 0) {
+      if (L.ready != nullptr && nrows > 0) {     // the producers of this plane's x-halves may still be running
+        const long long t0 = clock64();
+        int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(L.ready + d) : "memory");
+          if (v < L.expected && clock64() - t0 > (1LL << 32)) { atomicExch(err, 2); break; }      // ~2 s: give up loudly, never hang
+        } while (v < L.expected);
+        asm volatile("fence.proxy.async;" ::: "memory");                 // acquired by the generic proxy, read by the TMA engine
+      }
+      if (nrows == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+      else asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)nchan) : "memory");
+    }
+    __syncwarp();
+    if (nrows > 0 && lane < nchan) {
+      const int i = lane;
       const float* src = conv == 0
           ? L.gx + (long long)((i < CK ? 0 : CH) + kg * CK + (i < CK ? i : i - CK)) * L.g_cs + (long long)d * L.px + (long long)y0 * w
           : L.ox + (long long)(kg * CK + i) * L.o_cs + (long long)d * L.px + (long long)y0 * w;
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(uc_smem_u32(pre + (size_t)i * Rw)), "l"(src), "r"(bytes), "r"(bar) : "memory");
     }
+    __syncwarp();
   };
-  issue_pre(0, 0);
+  issue_pre(0, d_begin);
   asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy stores (window, filters) -> tensor-core reads
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   tc_cluster_sync();
@@ -351,8 +366,9 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
       for (int i = 0; i < 8; ++i) v[8 * c8 + i] = t[i];
     }
   };
-  // block-wide sums of up to four quantities -> sh.stat_out[which]
-  auto publish_stats = [&](int which, int n, double (&v)[4]) {
+  // block-wide sums of four quantities, pushed into stat_in[which][my rank] of every CTA of the cluster (the cluster barrier
+  // that follows publishes them): no remote load sits behind the barrier
+  auto publish_stats = [&](int which, double (&v)[4]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -361,26 +377,36 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
 #pragma unroll
       for (int k = 0; k < 4; ++k) sh.red[k][warp] = v[k];
     __syncthreads();
-    if (tid < 4) {
-      double t = 0.0;
-      if (tid < n) for (int i = 0; i < kTcEpiWarps; ++i) t += sh.red[tid][i];
-      sh.stat_out[which][tid] = t;
+    if (warp == 0) {
+      double t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] = lane < kTcEpiWarps ? sh.red[k][lane] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], off);
+      if (lane < kTcCluster) {                                             // lane l -> rank l
+        const unsigned ra = tc_mapa(uc_smem_u32(&sh.stat_in[which][rank][0]), (unsigned)lane);
+        asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" :: "r"(ra), "d"(t[0]), "d"(t[1]) : "memory");
+        asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" :: "r"(ra + 16u), "d"(t[2]), "d"(t[3]) : "memory");
+      }
     }
   };
-  // after the cluster barrier: warp 0 gathers the level's sums from the 16 ranks (butterfly in rank order: every CTA gets
-  // the same bits) and lanes < CK turn them into scale / shift; norm k uses sums (2k, 2k+1) and coef slot cslot + k
+  // after the cluster barrier: warp 0 adds the 16 ranks' sums (butterfly in rank order: every CTA gets the same bits) and
+  // lanes < CK turn them into scale / shift; norm k uses sums (2k, 2k+1) and coef slot cslot + k
   auto gather_coef = [&](int which, int nnorm, int cslot, const float* w0, const float* b0, const float* w1, const float* b1) {
     if (warp == 0) {
-      const int rk = lane & 15, half = lane >> 4;
-      double v0 = tc_ld_remote_f64(tc_mapa(uc_smem_u32(&sh.stat_out[which][2 * half]), (unsigned)rk));
-      double v1 = tc_ld_remote_f64(tc_mapa(uc_smem_u32(&sh.stat_out[which][2 * half + 1]), (unsigned)rk));
+      double t[4];
 #pragma unroll
-      for (int off = 8; off > 0; off >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, off); v1 += __shfl_xor_sync(0xffffffffu, v1, off); }
+      for (int k = 0; k < 4; ++k) t[k] = sh.stat_in[which][lane & 15][k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], off);
       for (int k = 0; k < nnorm; ++k) {
-        const double S = __shfl_sync(0xffffffffu, v0, 16 * k), Q = __shfl_sync(0xffffffffu, v1, 16 * k);
         if (lane < CK) {
-          const double mean = S * L.inv_n;
-          const float var = (float)fmax(Q * L.inv_n - mean * mean, 0.0);
+          const double mean = t[2 * k] * L.inv_n;
+          const float var = (float)fmax(t[2 * k + 1] * L.inv_n - mean * mean, 0.0);
           const float rstd = rsqrtf(var + 1e-5f);
           const float* gw = k == 0 ? w0 : w1; const float* gb = k == 0 ? b0 : b1;
           const float ca = __ldg(gw + kg * CK + lane) * rstd;
@@ -413,7 +439,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     }
   };
 
-  if (tid == 0) for (int i = 0; i < 12; ++i) sh.t_acc[i] = 0;
+  if (tid == 0) for (int i = 0; i < 16; ++i) sh.t_acc[i] = 0;
   auto mark = [&](int slot) {
     if (dbg != nullptr && tid == 0) { const long long t = clock64(); if (slot >= 0) sh.t_acc[slot] += t - sh.t_prev; sh.t_prev = t; }
   };
@@ -424,7 +450,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
   float keep[MAXP][CK];
   float ukeep[MAXP][STASH ? 1 : CK], hkeep[MAXP][STASH ? 1 : CK];
   issue_tiles(wg, NBG, NG, 0, 0, MTa);                                     // gates of plane 0
-  for (int d = 0; d < D; ++d) {
+  for (int d = d_begin; d < D; ++d) {
     mark(-1);
     // ================= gates: G = GX[d] + conv(h; Wg)  (MMAs already in flight) =================
     double st[4] = {0.0, 0.0, 0.0, 0.0};
@@ -434,7 +460,9 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
 #pragma unroll
         for (int j = 0; j < MAXP; ++j)
           if ((warp >> 2) + 4 * j < MTa && warp < kTcEpiWarps) read_pos(j, NG, NBG, 0, 2, v[j]);
+        mark(12);
         tc_cluster_sync();                                                 // #A: every K-group's partial sums have landed
+        mark(13);
       }
       alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
 #pragma unroll
@@ -462,7 +490,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     }
     ph_mma ^= 1u;
     mark(0);
-    publish_stats(0, 4, st);
+    publish_stats(0, st);
     mark(1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tc_cluster_sync();                                                     // #B: sums of every CTA are published; all gate MMAs are complete
@@ -500,6 +528,20 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     // ================= output: O = OX[d] + conv(r*h; Wo) =================
     issue_conv_split(wo, NBO, N2O, ocol0);
     mark(4);
+    // u = sigmoid(GN_u(G_u)) while the tensor core works on the output conv
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      if ((warp >> 2) + 4 * j >= MTa || warp >= kTcEpiWarps) continue;
+      float uv[CK];
+      if (STASH) stash_ld(j, 0, uv);
+#pragma unroll
+      for (int c = 0; c < CK; ++c) {
+        const float2 cu = *reinterpret_cast<const float2*>(&sh.coef[1][c][0]);
+        if (STASH) uv[c] = tc_sigmoid(fmaf(uv[c], cu.x, cu.y));
+        else ukeep[j][STASH ? 0 : c] = tc_sigmoid(fmaf(ukeep[j][STASH ? 0 : c], cu.x, cu.y));
+      }
+      if (STASH) stash_st(j, 0, uv);
+    }
     st[0] = st[1] = st[2] = st[3] = 0.0;
     {
       float v[MAXP][2 * CK];
@@ -507,7 +549,9 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
 #pragma unroll
         for (int j = 0; j < MAXP; ++j)
           if ((warp >> 2) + 4 * j < MTa && warp < kTcEpiWarps) read_pos(j, NO, NBO, ocol0, 1, v[j]);
+        mark(14);
         tc_cluster_sync();                                                 // #D
+        mark(15);
       }
       alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
 #pragma unroll
@@ -527,7 +571,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
     }
     ph_mma ^= 1u;
     mark(5);
-    publish_stats(1, 2, st);
+    publish_stats(1, st);
     mark(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tc_cluster_sync();                                                     // #E
@@ -546,9 +590,8 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
       }
 #pragma unroll
       for (int c = 0; c < CK; ++c) {
-        const float2 cu = *reinterpret_cast<const float2*>(&sh.coef[1][c][0]);
         const float2 co = *reinterpret_cast<const float2*>(&sh.coef[2][c][0]);
-        const float uu = tc_sigmoid(fmaf(uv[c], cu.x, cu.y));
+        const float uu = uv[c];
         keep[j][c] = uu * hv[c] + (1.0f - uu) * tc_tanh(fmaf(keep[j][c], co.x, co.y));
       }
       if (fl_[j] & 1) store_window(j, keep[j]);
@@ -570,7 +613,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int D, int*
   if (!alive && tid == 0) atomicExch(err, 1);
   if (dbg != nullptr && tid == 0 && (rank == 0))
 #pragma unroll
-    for (int i = 0; i < 12; ++i) dbg[(blockIdx.x / kTcCluster) * 12 + i] = sh.t_acc[i];
+    for (int i = 0; i < 16; ++i) dbg[(blockIdx.x / kTcCluster) * 16 + i] = sh.t_acc[i];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   tc_cluster_sync();                                                       // no CTA leaves while a peer may still write into its shared memory
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
@@ -584,10 +627,10 @@ red_tc_kernel(const __grid_constant__ TcArgs a) {
 #ifndef TC_ONLY
 #define TC_ONLY -1
 #endif
-  if (lv == 0 && (TC_ONLY < 0 || TC_ONLY == 0)) tc_level_run<8, kTcKG[0], kTcMaxP[0], 1>(a.l[0], a.D, a.err, a.dbg, tc_smem, sh);
-  else if (lv == 1 && (TC_ONLY < 0 || TC_ONLY == 1)) tc_level_run<16, kTcKG[1], kTcMaxP[1], 2>(a.l[1], a.D, a.err, a.dbg, tc_smem, sh);
-  else if (lv == 2 && (TC_ONLY < 0 || TC_ONLY == 2)) tc_level_run<32, kTcKG[2], kTcMaxP[2], 2>(a.l[2], a.D, a.err, a.dbg, tc_smem, sh);
-  else if (TC_ONLY < 0 || TC_ONLY == 3) tc_level_run<64, kTcKG[3], kTcMaxP[3], 0>(a.l[3], a.D, a.err, a.dbg, tc_smem, sh);
+  if (lv == 0 && (TC_ONLY < 0 || TC_ONLY == 0)) tc_level_run<8, kTcKG[0], kTcMaxP[0], 1>(a.l[0], a.d_begin, a.d_end, a.err, a.dbg, tc_smem, sh);
+  else if (lv == 1 && (TC_ONLY < 0 || TC_ONLY == 1)) tc_level_run<16, kTcKG[1], kTcMaxP[1], 2>(a.l[1], a.d_begin, a.d_end, a.err, a.dbg, tc_smem, sh);
+  else if (lv == 2 && (TC_ONLY < 0 || TC_ONLY == 2)) tc_level_run<32, kTcKG[2], kTcMaxP[2], 2>(a.l[2], a.d_begin, a.d_end, a.err, a.dbg, tc_smem, sh);
+  else if (TC_ONLY < 0 || TC_ONLY == 3) tc_level_run<64, kTcKG[3], kTcMaxP[3], 0>(a.l[3], a.d_begin, a.d_end, a.err, a.dbg, tc_smem, sh);
 }
 
 inline size_t tc_pack_bytes(int ch) { return (size_t)216 * ch * ch; }     // KG * 9 * (CK/8) * 2 * 6ch * 16
@@ -596,7 +639,7 @@ inline size_t tc_pack_bytes(int ch) { return (size_t)216 * ch * ch; }     // KG 
 // of 4 pixels, more tiles per CTA than a thread can hold, shared memory), and the caller then uses the FFMA cluster kernel
 // or the per-plane chain.  `wpack[l]` = tc_pack_bytes(ch_l) bytes of scratch per level.
 inline int red_tc_launch(TcArgs& a, const float* const* gate_w_h, const float* const* out_w_h, const long long* w_co,
-                         char* const* wpack, int* err_flag, long long* dbg, cudaStream_t st, bool* launched) {
+                         char* const* wpack, int* err_flag, long long* dbg, cudaStream_t st, bool* launched, bool pack = true) {
   *launched = false;
   static const bool verbose = getenv("SATMVS_RED_DEBUG") != nullptr;
   int dev = 0, optin = 0;
@@ -642,9 +685,11 @@ inline int red_tc_launch(TcArgs& a, const float* const* gate_w_h, const float* c
   if ((e = cudaOccupancyMaxActiveClusters(&nclusters, red_tc_kernel, &cfg)) != cudaSuccess || nclusters < 4)
     return declined("fewer than 4 co-resident clusters", e);
   for (int l = 0; l < 4; ++l) {
-    TcPack p{gate_w_h[l], out_w_h[l], w_co[l], a.l[l].ch, kTcKG[l], reinterpret_cast<float4*>(wpack[l])};
-    const int total = (int)(tc_pack_bytes(a.l[l].ch) / 16);
-    tc_pack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(p);
+    if (pack) {
+      TcPack p{gate_w_h[l], out_w_h[l], w_co[l], a.l[l].ch, kTcKG[l], reinterpret_cast<float4*>(wpack[l])};
+      const int total = (int)(tc_pack_bytes(a.l[l].ch) / 16);
+      tc_pack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(p);
+    }
     a.l[l].wpack = reinterpret_cast<const float4*>(wpack[l]);
   }
   a.err = err_flag; a.dbg = dbg;

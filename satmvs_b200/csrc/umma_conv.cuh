@@ -57,6 +57,8 @@ struct UmmaConv2d {
   int PW;                  // window positions = 128*MT + 2*Wp + 2
   int nheads;
   UmmaHead head[kUcMaxHeads];
+  int d0;                  // first plane of this launch (blockIdx.y counts from it): a conv over D planes can be launched in chunks
+  int* ready;              // optional per-plane counters [D]: every CTA adds 1 to ready[d] once its outputs are visible device-wide
 };
 
 struct UmmaPackHead { const float* w; long long w_co, w_ci; int Cout, n0; };
@@ -141,7 +143,7 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Wp = a.TW + 2, HW = a.H * a.W;
-  const int d = blockIdx.y;
+  const int d = blockIdx.y + a.d0;
   const int run = blockIdx.x / a.strips, sx = blockIdx.x - run * a.strips;
   const int x0 = sx * a.TW;                                            // first useful column of the strip
   const int q0 = Wp + run * (128 * a.MT);                              // first output position of this CTA (row y = 0 starts at Wp)
@@ -307,8 +309,10 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (a.ready != nullptr) __threadfence();                             // consumers on other SMs poll ready[d] (red_tc.cuh)
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+  if (a.ready != nullptr && tid == 32) { __threadfence(); atomicAdd(a.ready + d, 1); }
 }
 
 // Plan + launch.  Returns -1 when the layer does not fit this kernel (the caller then uses the direct FFMA kernel).
@@ -369,9 +373,19 @@ inline bool umma_conv_plan(UmmaConvPlan& P, const float* in, long long in_cs, in
   return true;
 }
 
-inline int umma_conv_launch(const UmmaConvPlan& P, int* error_flag, cudaStream_t st, const char* what) {
+inline void umma_conv_pack(const UmmaConvPlan& P, cudaStream_t st) {
   const int total = (P.pack.Cin / kUcKC) * P.pack.NZ * 2 * 9 * 2 * P.pack.NP;
   umma_pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(P.pack);
+}
+
+// pack = false: the packed weights are already in place (umma_conv_pack); planes [d0, d0 + nplanes) only when nplanes > 0;
+// ready: optional per-plane completion counters (UmmaConv2d::ready)
+inline int umma_conv_launch(const UmmaConvPlan& P0, int* error_flag, cudaStream_t st, const char* what, bool pack = true,
+                            int d0 = 0, int nplanes = 0, int* ready = nullptr) {
+  UmmaConvPlan P = P0;
+  if (pack) umma_conv_pack(P, st);
+  P.conv.d0 = d0; P.conv.ready = ready;
+  if (nplanes > 0) P.grid.y = nplanes;
   static thread_local int ready_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);

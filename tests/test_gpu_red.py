@@ -92,19 +92,21 @@ def test_recurrence_paths_agree(C, D, H, W, monkeypatch):
     m = m.to(DEV)
     x = synth.make_features(1, 1, C * D, H, W, seed=11)[0].view(1, C, D, H, W).abs().to(DEV)
     outs, paths = {}, {}
-    for name, env in (("tc", {}), ("cluster", {"SATMVS_RED_NO_TC": "1"}), ("chain", {"SATMVS_RED_NO_CLUSTER": "1"})):
-        for k in ("SATMVS_RED_NO_TC", "SATMVS_RED_NO_CLUSTER"):
+    for name, env in (("tc", {}), ("tc_seq", {"SATMVS_RED_NO_OVERLAP": "1"}), ("cluster", {"SATMVS_RED_NO_TC": "1"}),
+                      ("chain", {"SATMVS_RED_NO_CLUSTER": "1"})):
+        for k in ("SATMVS_RED_NO_TC", "SATMVS_RED_NO_CLUSTER", "SATMVS_RED_NO_OVERLAP"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         outs[name] = m(x).clone()
         torch.cuda.synchronize()
         paths[name] = _lib.lib().satmvs_red_last_path()
-    for k in ("SATMVS_RED_NO_TC", "SATMVS_RED_NO_CLUSTER"):
+    for k in ("SATMVS_RED_NO_TC", "SATMVS_RED_NO_CLUSTER", "SATMVS_RED_NO_OVERLAP"):
         monkeypatch.delenv(k, raising=False)
     assert paths["chain"] == 0
+    assert torch.equal(outs["tc"], outs["tc_seq"])          # same kernels, same bits: only the launch order differs
     if W % 32 == 0:                       # every level keeps rows of a multiple of 4 pixels: the tensor-core kernel takes it
-        assert paths["tc"] == 2, paths
+        assert paths["tc"] in (2, 3), paths   # 3 = overlapped with the batched convs on a side stream
     want = regnets.red_regularization(x.cpu(), sd)
     scale = max(1.0, want.abs().max().item())
     errs = {k: maxdiff(v, want) / scale for k, v in outs.items()}
@@ -125,7 +127,7 @@ def test_tensor_core_recurrence_carries_states():
     want = regnets.red_slice(cost, *states, sd)
     got = m(cost.to(DEV), *[s.to(DEV) for s in states])
     torch.cuda.synchronize()
-    assert _lib.lib().satmvs_red_last_path() == 2
+    assert _lib.lib().satmvs_red_last_path() in (2, 3)
     for a, b in zip(got, want):
         assert maxdiff(a, b) < 2e-4 * max(1.0, b.abs().max().item())
 
