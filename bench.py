@@ -53,6 +53,21 @@ WORKLOADS = {
 }
 
 
+L2_NOTE = "GPU arm: L2 flushed (256 MiB write) between timed iterations, outside the timed events"
+
+
+def config_of(w, args, **extra):
+    """The workload description: the SAME dict in our arm and in the reference arm."""
+    c = {"workload": w["desc"], "name": args.workload, "B": w["B"], "V": w["V"], "C": w["C"], "D": w["D"], "H": w["H"],
+         "W": w["W"], "geo_model": w["geo"], "hypotheses": "per-pixel [B,D,H,W]", "l2": L2_NOTE}
+    c.update(extra)
+    return c
+
+
+def warmup_of(args):
+    return max(args.warmup, 3)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -240,7 +255,7 @@ def run_cascade(args, w):
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs)
 
-    warm = max(args.warmup, 3)
+    warm = warmup_of(args)
     for _ in range(warm):
         step(feats, dr)
     barrier()
@@ -347,7 +362,7 @@ def run_ours(args, w):
         torch.cuda.synchronize()
         return [s.elapsed_time(e) for s, e in evs]
 
-    warm = max(args.warmup, 3)
+    warm = warmup_of(args)
     for _ in range(warm):
         flush.zero_()
         step(fe, cams, dv)
@@ -367,6 +382,8 @@ def run_ours(args, w):
         f_d = [f.to(dev, non_blocking=True) for f in fe_p]
         d_d = dv_p.to(dev, non_blocking=True)
         res = step(f_d, cams, d_d)
+        if w["stage"] in ("build", "sharded"):
+            res = (res[0][:, :, 0],)           # the volume stays on the device for the regulariser: read back ONE plane [B,C,H,W]
         if not outs_host:
             outs_host.extend(torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res)
         for h, r in zip(outs_host, res):
@@ -402,13 +419,16 @@ def run_ours(args, w):
             "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong" if sharded_run else "weak", "vs_baseline": None, "dtype": "f32 (camera geometry f64)",
             "data": "synthetic",
-            "config": {"workload": w["desc"], "name": args.workload, "B": w["B"], "V": w["V"], "C": w["C"], "D": w["D"],
-                       "H": w["H"], "W": w["W"], "geo_model": w["geo"], "hypotheses": "per-pixel [B,D,H,W]",
-                       "l2": "flushed (256 MiB write) between timed iterations",
-                       "sharding": (f"depth planes split over ranks, gather={args.gather}" if sharded_run else "one stack per rank")},
+            "config": config_of(w, args),
+            "sharding": (f"depth planes split over ranks, gather={args.gather}" if sharded_run else "one stack per rank, no data-path collective"),
             "clocks": clk.summary(),
             "e2e": {"value": voxels * units / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "ms_median": sorted(e2e_times)[len(e2e_times) // 2],
+                    "what": ("pinned host features + hypotheses -> H2D -> operator API -> D2H of "
+                             + ("one plane of the variance volume (the volume itself feeds the regulariser on the device)"
+                                if w["stage"] in ("build", "sharded") else "depth + confidence maps"))},
+            "ms_median": sorted(times)[len(times) // 2],
             "gpu_launches": int(sum(prof.launches.values()) / prof_steps * args.steps),
         }
         # per kernel class: share of the step, achieved rate against the bound that applies
@@ -462,12 +482,89 @@ def run_ours(args, w):
         if sw is not None and dom is not sw:
             line["roofline_sweep"] = dict(sw["roofline"], kernel="sweep", share_of_step=sw["share"],
                                           avg_launch_us=sw["avg_launch_us"], peak_source=peak_src)
+        if w["stage"] == "red_train":
+            line["red_path"] = {3: "tcgen05 cluster recurrence (red_tc_kernel), overlapped with the batched convs",
+                                2: "tcgen05 cluster recurrence (red_tc_kernel)", 1: "FFMA cluster recurrence (red_cluster_kernel)",
+                                0: "per-plane kernel chain"}.get(_lib.lib().satmvs_red_last_path(), "?")
+        if not args.no_cpu_baseline:
+            line["parity"] = parity_block(w, dev, step, fe_h, cams, dv_h)
         if world == 1 and not args.no_cpu_baseline:
             line["gpu_eager_baseline"] = gpu_eager_baseline(w, dev, fe, cams, dv)
             line["cpu_baseline"] = cpu_baseline(w, budget_s=20.0)
+    sh = None
+    if not sharded_run and not args.no_sharded:
+        del fe, dv
+        torch.cuda.empty_cache()
+        sh = sharded_block(args, dev, rank, world, barrier, flush)
+    if rank == 0:
+        if sh is not None:
+            line["sharded"] = sh
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_block(args, dev, rank, world, barrier, flush):
+    """The path north_star names for the multi-GPU box (BASELINE configs[3]): the 5-view 192-plane sweep (192x384 grid,
+    C 32, 1.81 GB volume) with its depth planes split over the ranks of THIS launch, timed in the same run as the replica
+    number: build only (no exchange), build + one NCCL all-gather, and the sweep that stores straight into every peer's
+    volume (plain peer stores / one multimem.st per value through the NVLink-switch multicast mapping).  Device time,
+    max over ranks, L2 flushed between iterations.  NVLink figure: bytes every rank must RECEIVE (the other ranks' slabs)
+    / time, against the measured 770 GB/s per direction (B200_PROFILING.md)."""
+    import satmvs_b200
+    from satmvs_b200 import sharded
+    import torch.distributed as dist
+    w = WORKLOADS["cfg4_sharded192"]
+    fe_h, cams, dv_h = make_inputs(w, seed=0)
+    fe = [f.to(dev) for f in fe_h]
+    dv = dv_h.to(dev)
+    V = w["V"]
+    vol_bytes = w["B"] * w["C"] * w["D"] * w["H"] * w["W"] * 4
+    voxels = w["B"] * w["V"] * w["D"] * w["H"] * w["W"]
+    iters = 10
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        t = torch.tensor([sum(ts) / len(ts), min(ts)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    out = {"workload": w["desc"], "config": {k: w[k] for k in ("B", "V", "C", "D", "H", "W")}, "n_gpus": world,
+           "volume_bytes": vol_bytes, "timing": f"mean and best of {iters} iterations, max over ranks, CUDA events, L2 flushed",
+           "modes": {}}
+    single = timed(lambda: satmvs_b200.build_cost_volume(fe[0], fe[1:], cams[:, 0], [cams[:, v] for v in range(1, V)], dv, w["geo"]))
+    out["single_gpu"] = {"ms": single[0], "ms_best": single[1], "voxels_per_s": voxels / (single[0] * 1e-3),
+                         "note": "all 192 planes on one GPU (every rank times it; max over ranks)"}
+    if world > 1:
+        ingress = vol_bytes * (world - 1) / world
+        for mode in ("none", "nccl", "fused", "multimem"):
+            try:
+                t = timed(lambda: sharded.build_cost_volume_sharded(fe[0], fe[1:], cams[:, 0], [cams[:, v] for v in range(1, V)],
+                                                                    dv, w["geo"], mode=mode))
+                m = {"ms": t[0], "ms_best": t[1], "voxels_per_s": voxels / (t[0] * 1e-3), "speedup_vs_single_gpu": single[0] / t[0]}
+                if mode != "none":
+                    m["nvlink_ingress_gb_per_s_per_gpu"] = ingress / (t[0] * 1e-3) / 1e9
+                    m["nvlink_frac_of_770"] = m["nvlink_ingress_gb_per_s_per_gpu"] / 770.0
+                    m["egress_bytes_per_gpu"] = vol_bytes / world * (1 if mode == "multimem" else world - 1)
+                out["modes"][mode] = m
+            except Exception as ex:
+                out["modes"][mode] = {"unavailable": repr(ex)[:200]}
+            barrier()
+        out["ingress_bound_ms"] = ingress / 770e9 * 1e3
+        out["note"] = ("every rank must receive (G-1)/G of the 1.81 GB fp32 volume: at 770 GB/s per direction that alone is "
+                       f"{out['ingress_bound_ms']:.2f} ms, against {single[0]:.2f} ms to build the whole volume on one GPU -- gathering "
+                       "the raw volume cannot scale; the build itself (mode none) does")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -570,9 +667,21 @@ def use_all_host_threads():
     torch.set_num_threads(max(1, n))
 
 
+def cpu_planes(w):
+    """Planes of the stack the CPU arms time per step: ALL of them when a step stays around a second (the BASELINE configs that
+    fit one GPU), else a bounded sample of 16 (every plane costs the same: the per-plane work does not depend on D)."""
+    return w["D"] if w["D"] * w["H"] * w["W"] * w["V"] <= 4_000_000 else min(w["D"], 16)
+
+
+def cpu_sample_note(w, planes):
+    if planes == w["D"]:
+        return f"the whole stack: all {planes} planes per step"
+    return f"bounded sample: the first {planes} of {w['D']} planes per step (value = voxels of the sample / its time)"
+
+
 def cpu_baseline(w, budget_s=20.0):
     use_all_host_threads()
-    planes = min(w["D"], 16)
+    planes = cpu_planes(w)
     run, vox = oracle_step(w, planes)
     run()
     ts = []
@@ -583,10 +692,38 @@ def cpu_baseline(w, budget_s=20.0):
         ts.append(time.perf_counter() - t0)
     best = min(ts)
     return {"value": vox / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle (restatement of networks/casred.py:10-64 + modules/warping.py, module.py) on the first {planes} of "
-                      f"{w['D']} planes of the same stack, best of {len(ts)}, torch-CPU {torch.get_num_threads()} threads of "
-                      f"{os.cpu_count()} logical cores",
+            "sample": f"oracle (restatement of networks/casred.py:10-64 + modules/warping.py, module.py), {cpu_sample_note(w, planes)}, "
+                      f"best of {len(ts)}, torch-CPU {torch.get_num_threads()} threads of {os.cpu_count()} logical cores",
             "seconds_per_sample": best}
+
+
+def parity_block(w, dev, step, fe_h, cams, dv_h):
+    """'MAE vs reference' (BASELINE.json:metric): our result on the bench's own inputs against the oracle on the same inputs,
+    outside every timed region.  north_star bound: relative L-inf <= 1e-3 on depth."""
+    from oracle import stages, volume
+    from satmvs_b200 import synth
+    try:
+        with torch.no_grad():
+            got = step([f.to(dev) for f in fe_h], cams, dv_h.to(dev))
+            if w["stage"] == "red_train":
+                want = stages.stage_train_red(fe_h, cams, dv_h, synth.make_red_weights(w["C"]), w["geo"])["depth"]
+            elif w["stage"] == "casmvs":
+                want = stages.stage_casmvs(fe_h, cams, dv_h, synth.make_costregnet_weights(w["C"]), w["geo"])["depth"]
+            elif w["stage"] == "build":
+                want = volume.variance_cost_volume(fe_h, cams, dv_h, w["geo"])
+            else:
+                return None
+        g = got[0].detach().cpu().double()
+        d = (g - want.double()).abs()
+        out = {"vs": "oracle (CPU restatement of the reference, pinned on the reference's own outputs: tests/golden)",
+               "quantity": "variance volume" if w["stage"] == "build" else "depth map",
+               "mae": d.mean().item(), "max_abs": d.max().item(), "rel_linf": d.max().item() / want.abs().max().item(),
+               "bound_rel_linf": 1e-3}
+        if w["stage"] == "build":
+            out["bit_identical_fraction"] = (got[0].detach().cpu() == want).float().mean().item()
+        return out
+    except Exception as ex:
+        return {"unavailable": repr(ex)[:200]}
 
 
 def run_reference(args, w):
@@ -594,9 +731,10 @@ def run_reference(args, w):
     if rank != 0:
         return
     use_all_host_threads()
-    planes = min(w["D"], 16)
+    planes = cpu_planes(w)
     run, vox = oracle_step(w, planes)
-    for _ in range(min(args.warmup, 2)):
+    warm = warmup_of(args)
+    for _ in range(warm):
         run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -604,13 +742,12 @@ def run_reference(args, w):
     dt = (time.perf_counter() - t0) / args.steps
     val = vox / dt
     cb = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-          "sample": f"oracle port of the reference torch-CPU path, first {planes} of {w['D']} planes per step"}
+          "sample": f"oracle port of the reference torch-CPU path, {cpu_sample_note(w, planes)}"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (camera geometry f64)", "data": "synthetic",
-        "config": {"workload": w["desc"], "name": args.workload, "B": w["B"], "V": w["V"], "C": w["C"], "D": w["D"],
-                   "H": w["H"], "W": w["W"], "geo_model": w["geo"]},
+        "config": config_of(w, args),
         "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -622,8 +759,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_stage1", choices=sorted(WORKLOADS))
-    ap.add_argument("--gather", default="nccl", choices=["none", "nccl", "fused"])
+    ap.add_argument("--gather", default="nccl", choices=["none", "nccl", "fused", "multimem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the depth-sharded 192-plane block of the default line")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version there at

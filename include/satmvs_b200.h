@@ -73,6 +73,8 @@ int satmvs_cost_volume_homo_fwd(const float* ref_fea, const float* const* src_fe
  * pointers of every rank's volume (CUDA IPC / symmetric memory), the store loop IS the all-gather:
  * each value is written once per peer over NVLink while the sweep is still computing, and the slab
  * never makes a second trip through HBM.  The caller provides the cross-rank barrier afterwards.
+ * n_outs == -1: outs[0] is an NVLink-switch MULTICAST address of the symmetric volume (NVLS): every value leaves the SM
+ * once as a multimem.st and the switch replicates it to all GPUs (egress 1x instead of (G-1)x).
  * workspace: optional caller-owned scratch of n_src*C*H*W*4 bytes (16-byte aligned).  When given and C is
  * a multiple of 4, the source features are re-packed to 4-channel words and the vectorised kernel runs
  * (same results); with NULL the scalar kernel runs.  satmvs_cost_volume_*_fwd == this with d0 = 0,

@@ -40,6 +40,11 @@ namespace satmvs {
 
 constexpr int kSweepThreads = 128;
 
+// store through an NVLink-switch multicast mapping (symmetric memory): the switch replicates the write to every GPU
+__device__ __forceinline__ void mc_store(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
 template <class Geo>
 struct SweepArgs {
   const float* ref_fea;                       // [C,H,W] (variance mode) or nullptr
@@ -48,6 +53,7 @@ struct SweepArgs {
   const float* depth;                         // [D] or [D,H,W]
   float* out[SATMVS_MAX_PEERS];               // each [C,out_D,H,W]; every buffer receives the same planes
   int n_out;                                  // 1, or the number of peer GPUs written over NVLink (fused all-gather)
+  int multicast;                              // out[0] is an NVLS multicast address: ONE multimem.st per value reaches every GPU
   int out_D, out_d0;                          // planes of the output tensor, first plane written by this launch
   int C, D, H, W;                             // D = planes swept by this launch
   int depth_per_pixel;
@@ -116,7 +122,8 @@ sweep_fwd_kernel(const __grid_constant__ SweepArgs<Geo> a) {
         }
         if (active) {
           // one store per destination: the local volume, or every peer's volume (NVLink posted writes)
-          for (int o = 0; o < a.n_out; ++o) __stcs(a.out[o] + oidx + (size_t)k * plane_stride, res);
+          if (a.multicast) mc_store(a.out[0] + oidx + (size_t)k * plane_stride, res);
+          else for (int o = 0; o < a.n_out; ++o) __stcs(a.out[o] + oidx + (size_t)k * plane_stride, res);
         }
       }
     }
@@ -224,7 +231,10 @@ sweep_fwd_vec4_kernel(const __grid_constant__ SweepArgs<Geo> a) {
           for (int o = 0; o < a.n_out; ++o) {
             float* op = a.out[o] + oidx + (size_t)k * plane_stride;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) __stcs(op + (size_t)j * a.out_D * plane_stride, res[j]);
+            for (int j = 0; j < 4; ++j) {
+              if (a.multicast) mc_store(op + (size_t)j * a.out_D * plane_stride, res[j]);
+              else __stcs(op + (size_t)j * a.out_D * plane_stride, res[j]);
+            }
           }
         }
       }
@@ -379,10 +389,16 @@ sweep_fwd_v3_kernel(const __grid_constant__ SweepArgs<Geo> a) {
         upk(res, lo, hi);
         if (active) {
           if (kMultiOut) {
-            for (int o = 0; o < a.n_out; ++o) {
-              char* ob = reinterpret_cast<char*>(a.out[o]) + obase + (size_t)(2 * j) * ostride;
-              __stcs(reinterpret_cast<float*>(ob + upix), lo);
-              __stcs(reinterpret_cast<float*>(ob + ostride + upix), hi);
+            if (a.multicast) {
+              char* ob = reinterpret_cast<char*>(a.out[0]) + obase + (size_t)(2 * j) * ostride;
+              mc_store(reinterpret_cast<float*>(ob + upix), lo);
+              mc_store(reinterpret_cast<float*>(ob + ostride + upix), hi);
+            } else {
+              for (int o = 0; o < a.n_out; ++o) {
+                char* ob = reinterpret_cast<char*>(a.out[o]) + obase + (size_t)(2 * j) * ostride;
+                __stcs(reinterpret_cast<float*>(ob + upix), lo);
+                __stcs(reinterpret_cast<float*>(ob + ostride + upix), hi);
+              }
             }
           } else {
             char* ob = reinterpret_cast<char*>(a.out[0]) + obase + (size_t)(2 * j) * ostride;
@@ -818,10 +834,16 @@ sweep_fwd_v5_kernel(const __grid_constant__ SweepArgs<Geo> a, int tiles_x) {
         upk(res, lo, hi);
         if (store) {
           if (kMultiOut) {
-            for (int o = 0; o < a.n_out; ++o) {
-              char* ob = reinterpret_cast<char*>(a.out[o]) + obase + (size_t)(2 * j) * ostride;
-              __stcs(reinterpret_cast<float*>(ob), lo);
-              __stcs(reinterpret_cast<float*>(ob + ostride), hi);
+            if (a.multicast) {
+              char* ob = reinterpret_cast<char*>(a.out[0]) + obase + (size_t)(2 * j) * ostride;
+              mc_store(reinterpret_cast<float*>(ob), lo);
+              mc_store(reinterpret_cast<float*>(ob + ostride), hi);
+            } else {
+              for (int o = 0; o < a.n_out; ++o) {
+                char* ob = reinterpret_cast<char*>(a.out[o]) + obase + (size_t)(2 * j) * ostride;
+                __stcs(reinterpret_cast<float*>(ob), lo);
+                __stcs(reinterpret_cast<float*>(ob + ostride), hi);
+              }
             }
           } else {
             __stcs(reinterpret_cast<float*>(op), lo);
@@ -880,7 +902,7 @@ static int launch_v5(const SweepArgs<Geo>& a, cudaStream_t st, bool after_pack) 
     cudaLaunchKernelEx(&cfg, kern, a, tiles_x);
   };
   // (both instantiations have the same function type, so the opt-in is keyed on the kernel itself)
-  if (a.n_out > 1) {
+  if (a.n_out > 1 || a.multicast) {
     allow_dynamic_smem<sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, true>>(smem);
     run(sweep_fwd_v5_kernel<Geo, TH, DK, CH, WINPX, MINB, kVariance, true>);
   } else {
@@ -1055,7 +1077,7 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
     // Opt-in (SATMVS_SWEEP_TMA=1): the TMA-staged variant is bit-identical but measured 161 us against 110 us for
     // v3 at cfg-2 (single-buffered staging, 2 CTAs x 3 warps per SM): profiles/r01_sweep_v3_notes.md.
     static const bool use_tma = getenv("SATMVS_SWEEP_TMA") != nullptr;
-    if (use_tma && a.n_out == 1 && a.C % SATMVS_CH == 0 && a.W < 32768 && a.H < 32768) {
+    if (use_tma && a.n_out == 1 && !a.multicast && a.C % SATMVS_CH == 0 && a.W < 32768 && a.H < 32768) {
       constexpr int NS = Geo::kNumSrc;
       constexpr size_t smem = v4_smem_bytes<DK, NS, SATMVS_CH>();
       if (smem <= 200 * 1024) {
@@ -1076,8 +1098,8 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
       const int rc = dispatch_v5<Geo, kVariance>(a, st, a.packed_now != 0 && !prof_state().on);
       if (rc >= 0) return rc;
     }
-    if (a.n_out > 1 && a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
-    else if (a.n_out > 1) sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
+    if ((a.n_out > 1 || a.multicast) && a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
+    else if (a.n_out > 1 || a.multicast) sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, true><<<grid, kSweepThreads, 0, st>>>(a);
     else if (a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
     else sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
     return check_launch("sweep_fwd_v3_kernel");
@@ -1185,6 +1207,8 @@ int satmvs_cost_volume_rpc_fwd_sharded(const float* ref_fea, const float* const*
                                        float* const* outs, int n_outs, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_dims(n_src, C, D, H, W)) return e;
   SATMVS_REQUIRE(ref_fea && src_feas && ref_rpc && src_rpcs && depth && outs);
+  const int multicast = n_outs == -1;          // outs[0] is a multicast address
+  if (multicast) n_outs = 1;
   SATMVS_REQUIRE(n_outs >= 1 && n_outs <= SATMVS_MAX_PEERS && d0 >= 0 && d0 + D <= D_total);
   for (int o = 0; o < n_outs; ++o) SATMVS_REQUIRE(outs[o] != nullptr);
   SATMVS_DISPATCH_NSRC(n_src, {
@@ -1192,7 +1216,7 @@ int satmvs_cost_volume_rpc_fwd_sharded(const float* ref_fea, const float* const*
     fill_common(a, depth, depth_per_pixel, n_src, C, D, H, W);
     a.ref_fea = ref_fea;
     for (int o = 0; o < n_outs; ++o) a.out[o] = outs[o];
-    a.n_out = n_outs; a.out_D = D_total; a.out_d0 = d0;
+    a.n_out = n_outs; a.multicast = multicast; a.out_D = D_total; a.out_d0 = d0;
     for (int v = 0; v < NSRC; ++v) a.src_fea[v] = src_feas[v < n_src ? v : 0];
     if (int e = pack_sources(a, src_feas, n_src, NSRC, workspace, workspace_bytes, (cudaStream_t)stream)) return e;
     fill_rpc_geo(a.geo, n_src, ref_rpc, src_rpcs, H, W);
@@ -1217,6 +1241,8 @@ int satmvs_cost_volume_homo_fwd_sharded(const float* ref_fea, const float* const
                                         float* const* outs, int n_outs, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_dims(n_src, C, D, H, W)) return e;
   SATMVS_REQUIRE(ref_fea && src_feas && ref_proj && src_projs && depth && outs);
+  const int multicast = n_outs == -1;          // outs[0] is a multicast address
+  if (multicast) n_outs = 1;
   SATMVS_REQUIRE(n_outs >= 1 && n_outs <= SATMVS_MAX_PEERS && d0 >= 0 && d0 + D <= D_total);
   for (int o = 0; o < n_outs; ++o) SATMVS_REQUIRE(outs[o] != nullptr);
   SATMVS_DISPATCH_NSRC(n_src, {
@@ -1224,7 +1250,7 @@ int satmvs_cost_volume_homo_fwd_sharded(const float* ref_fea, const float* const
     fill_common(a, depth, depth_per_pixel, n_src, C, D, H, W);
     a.ref_fea = ref_fea;
     for (int o = 0; o < n_outs; ++o) a.out[o] = outs[o];
-    a.n_out = n_outs; a.out_D = D_total; a.out_d0 = d0;
+    a.n_out = n_outs; a.multicast = multicast; a.out_D = D_total; a.out_d0 = d0;
     for (int v = 0; v < NSRC; ++v) a.src_fea[v] = src_feas[v < n_src ? v : 0];
     if (int e = pack_sources(a, src_feas, n_src, NSRC, workspace, workspace_bytes, (cudaStream_t)stream)) return e;
     if (int e = fill_homo_geo(a.geo, n_src, ref_proj, src_projs, H, W)) return e;

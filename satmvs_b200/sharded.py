@@ -8,7 +8,12 @@ var[B, C, D, H, W]; features and cameras are replicated.  Reassembly:
   mode "fused"  the sweep kernel itself stores every value into each peer's full volume through
                 peer-mapped pointers (torch symmetric memory = CUDA IPC over NVLink), so the gather
                 overlaps the sweep and needs no second pass; one barrier at the end;
+  mode "multimem"  like "fused", but through the NVLink-switch multicast mapping of the symmetric volume (NVLS): every
+                value leaves the SM once as a `multimem.st` and the switch replicates it, so egress is 1x instead of (G-1)x;
   mode "none"   no exchange: returns the local slab (build-only scaling).
+
+The "fused" / "multimem" modes return the cached symmetric-memory volume itself: a BORROWED buffer, valid until the next
+call with the same shape on the same group (clone it to keep it).
 
 The plumbing is torch.distributed (NCCL on GPUs, gloo in the CPU tests); the data path is the C ABI's
 `satmvs_cost_volume_*_fwd_sharded`.
@@ -48,11 +53,12 @@ _SYMM_CACHE: dict = {}
 def _symmetric_volume(shape, device, group):
     """A [B, C, D, H, W] volume every rank can write into: returns (local tensor, peer pointers, handle)."""
     import torch.distributed._symmetric_memory as symm_mem
-    key = (tuple(shape), device.index, id(group))
+    grp = group if group is not None else dist.group.WORLD
+    key = (tuple(shape), device.index, grp.group_name)       # the group's name, not id(): ids are recycled after destroy
     hit = _SYMM_CACHE.get(key)
     if hit is None:
         t = symm_mem.empty(shape, dtype=torch.float32, device=device)
-        hdl = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+        hdl = symm_mem.rendezvous(t, group=grp)
         hit = (t, [int(p) for p in hdl.buffer_ptrs], hdl)
         _SYMM_CACHE[key] = hit
     return hit
@@ -68,7 +74,7 @@ def build_cost_volume_sharded(ref_fea, src_feas, ref_cam, src_cams, depth_values
     D = depth_values.shape[1]
     d0, d1 = plane_range(D, rank, world)
     shard = depth_values[:, d0:d1].contiguous()
-    if mode != "fused":
+    if mode not in ("fused", "multimem"):
         fn = builder or build_cost_volume
         slab = fn(ref_fea, src_feas, ref_cam, src_cams, shard, geo_model)
         if mode == "none" or world == 1:
@@ -87,6 +93,12 @@ def build_cost_volume_sharded(ref_fea, src_feas, ref_cam, src_cams, depth_values
     s = np.stack([_check_cam(host_f64(c), B, geo_model, "src camera") for c in src_cams])
     depth, per_pixel = _depth_arg(shard, B, H, W)
     vol, peers, hdl = _symmetric_volume((B, C, D, H, W), ref.device, group)
+    mc = 0
+    if mode == "multimem":
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("mode='multimem' needs an NVLS multicast mapping of the symmetric volume "
+                               "(NVSwitch + multicast support); use mode='fused'")
     fn = _lib.lib().satmvs_cost_volume_rpc_fwd_sharded if geo_model == "rpc" else _lib.lib().satmvs_cost_volume_homo_fwd_sharded
     per_b = C * D * H * W * 4
     ws = sweep_workspace(len(srcs) * C * H * W * 4, ref.device)
@@ -94,10 +106,10 @@ def build_cost_volume_sharded(ref_fea, src_feas, ref_cam, src_cams, depth_values
     with torch.cuda.device(ref.device):
         st = _lib.stream_ptr(ref.device)
         for b in range(B):
-            outs = _lib.ptr_array([p + b * per_b for p in peers])
+            outs = _lib.ptr_array([mc + b * per_b] if mc else [p + b * per_b for p in peers])
             cams = np.ascontiguousarray(s[:, b])
             _lib.check(fn(ref[b].data_ptr(), _lib.ptr_array([x[b].data_ptr() for x in srcs]), len(srcs), _dptr(r[b]),
-                          _dptr(cams), depth[b].data_ptr(), per_pixel, C, d1 - d0, H, W, d0, D, outs, len(peers),
+                          _dptr(cams), depth[b].data_ptr(), per_pixel, C, d1 - d0, H, W, d0, D, outs, -1 if mc else len(peers),
                           ws.data_ptr(), ws.numel(), st),
                        "cost_volume_fwd_sharded")
     hdl.barrier()                      # every rank's planes have landed everywhere
