@@ -45,9 +45,14 @@ WORKLOADS = {
                         desc="3-view 768x384, 64 planes, stage 1 with the CostRegNet (3-D UNet) regulariser"),
     "cfg5_build": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="pinhole", stage="build",
                        desc="pin-hole homography sweep 3-view 768x384, 64 planes, cost-volume build"),
-    "cfg3_cascade": dict(B=1, V=3, C=32, D=48, H=96, W=192, geo="rpc", stage="cascade",
+    "cfg3_cascade": dict(B=1, V=3, C=32, D=48, H=96, W=192, geo="rpc", stage="cascade", img_hw=(384, 768), ndepths=(48, 32, 8),
+                         head="red_train", reg="RED_Regularization",
                          desc="3-view 768x384, cascade 48/32/8 planes, full casred (three stages: hypotheses, fused RPC cost "
                               "volume, RED regulariser, soft-argmin), 1xB200"),
+    "cfg1_pred": dict(B=1, V=3, C=32, D=32, H=32, W=64, geo="rpc", stage="cascade", img_hw=(128, 256), ndepths=(32, 16, 8),
+                      head="red_pred", reg="slice_RED_Regularization",
+                      desc="3-view 256x128, cascade 32/16/8 planes, geo_model=rpc, model=red PREDICT path (plane streaming: one "
+                           "hypothesis swept, one recurrent regulariser step, fp64 online soft-argmin per plane)"),
     "cfg4_sharded192": dict(B=1, V=5, C=32, D=192, H=192, W=384, geo="rpc", stage="sharded",
                             desc="5-view 1536x768, 192 planes single-stage, cost-volume build depth-sharded across ranks"),
 }
@@ -223,7 +228,7 @@ def run_cascade(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    img_hw, ndepths, chans, scales = (384, 768), (48, 32, 8), (32, 16, 8), (4, 2, 1)
+    img_hw, ndepths, chans, scales = tuple(w["img_hw"]), tuple(w["ndepths"]), (32, 16, 8), (4, 2, 1)
     V = w["V"]
     feats_h = [synth.make_features(1, V, c, img_hw[0] // sc, img_hw[1] // sc, seed=rank * 10 + i)
                for i, (c, sc) in enumerate(zip(chans, scales))]
@@ -231,7 +236,7 @@ def run_cascade(args, w):
     drange = torch.tensor([[0.0, 1000.0]])
     regs = []
     for i, c in enumerate(chans):
-        m = satmvs_b200.RED_Regularization(c, 8)
+        m = getattr(satmvs_b200, w["reg"])(c, 8)
         m.load_state_dict(synth.make_red_weights(c, seed=100 + i))
         regs.append(m.to(dev).eval())
     feats = [[f.to(dev) for f in fs] for fs in feats_h]
@@ -239,7 +244,7 @@ def run_cascade(args, w):
 
     def step(fs, dr_):
         with torch.no_grad():
-            out = satmvs_b200.cascade(fs, cams, dr_, regs, img_hw=img_hw, ndepths=ndepths, head="red_train")
+            out = satmvs_b200.cascade(fs, cams, dr_, regs, img_hw=img_hw, ndepths=ndepths, head=w["head"])
         return out["depth"], out["photometric_confidence"]
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -305,9 +310,8 @@ def run_cascade(args, w):
         line = {"metric": METRIC, "value": voxels * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (camera geometry f64)", "data": "synthetic",
-                "config": {"workload": w["desc"], "name": args.workload, "B": 1, "V": V, "C": list(chans), "D": list(ndepths),
-                           "image_hw": list(img_hw), "scales": list(scales), "geo_model": "rpc",
-                           "l2": "flushed (256 MiB write) between timed iterations", "sharding": "one stack per rank"},
+                "config": cascade_config(w, args), "sharding": "one stack per rank, no data-path collective",
+                "planes_per_s": sum(ndepths) * world / (ms * 1e-3), "us_per_plane": ms * 1e3 / sum(ndepths),
                 "clocks": clk.summary(),
                 "e2e": {"value": voxels * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
@@ -315,9 +319,73 @@ def run_cascade(args, w):
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                              "kernel": "sweep (three stages)", "algorithmic_bytes_per_step": sweep_bytes,
                              "share_of_step": sw["share"], "peak_source": peak_src}}
+        if not args.no_cpu_baseline:
+            from oracle import stages
+            use_all_host_threads()
+            sds = [synth.make_red_weights(c, seed=100 + i) for i, c in enumerate(chans)]
+            try:
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    want = stages.cascade(feats_h, cams, drange, sds, img_hw=img_hw, ndepths=ndepths, head=w["head"])
+                    cpu_s = time.perf_counter() - t0
+                    got = step(feats, dr)[0].cpu().double()
+                dd = (got - want["depth"].double()).abs()
+                line["parity"] = {"vs": "oracle cascade (CPU restatement of the reference network from the feature maps on)",
+                                  "quantity": "final depth map", "mae": dd.mean().item(), "max_abs": dd.max().item(),
+                                  "rel_linf": dd.max().item() / want["depth"].abs().max().item(), "bound_rel_linf": 1e-3}
+                if world == 1:
+                    line["cpu_baseline"] = {"value": voxels / cpu_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                            "sample": "the whole cascade once on the same inputs (oracle port of "
+                                                      "networks/casred.py from the feature maps on), torch-CPU",
+                                            "seconds_per_sample": cpu_s}
+            except Exception as ex:
+                line["parity"] = {"unavailable": repr(ex)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cascade_config(w, args):
+    return {"workload": w["desc"], "name": args.workload, "B": 1, "V": w["V"], "C": [32, 16, 8], "D": list(w["ndepths"]),
+            "image_hw": list(w["img_hw"]), "scales": [4, 2, 1], "geo_model": "rpc", "l2": L2_NOTE}
+
+
+def run_reference_cascade(args, w):
+    """Reference arm of the cascade workloads: the oracle cascade on the host cores (whole cascade per step)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import stages
+    from satmvs_b200 import synth
+    use_all_host_threads()
+    img_hw, ndepths, chans, scales = tuple(w["img_hw"]), tuple(w["ndepths"]), (32, 16, 8), (4, 2, 1)
+    V = w["V"]
+    feats = [synth.make_features(1, V, c, img_hw[0] // sc, img_hw[1] // sc, seed=i) for i, (c, sc) in enumerate(zip(chans, scales))]
+    cams = [synth.make_rpc_stack(1, V, img_hw[0] // sc, img_hw[1] // sc) for sc in scales]
+    sds = [synth.make_red_weights(c, seed=100 + i) for i, c in enumerate(chans)]
+    drange = torch.tensor([[0.0, 1000.0]])
+    voxels = sum(V * d * (img_hw[0] // sc) * (img_hw[1] // sc) for d, sc in zip(ndepths, scales))
+    big = voxels > 20_000_000                    # cfg-3 takes ~9 s per cascade on the host: bound the run
+    steps = min(args.steps, 3) if big else args.steps
+    warm = 1 if big else warmup_of(args)
+
+    def run():
+        with torch.no_grad():
+            return stages.cascade(feats, cams, drange, sds, img_hw=img_hw, ndepths=ndepths, head=w["head"])
+    for _ in range(warm):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    val = voxels / dt
+    cb = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+          "sample": f"oracle port of the reference cascade on the host cores, whole cascade per step, {steps} timed steps"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (camera geometry f64)", "data": "synthetic", "config": cascade_config(w, args),
+        "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
 
 
 def run_ours(args, w):
@@ -639,19 +707,32 @@ def gpu_eager_baseline(w, dev, fe, cams, dv):
                                     "peak_alloc_bytes": torch.cuda.max_memory_allocated(dev)}
         if w["stage"] in ("red_train", "casmvs"):
             run, vox = oracle_step(w, w["D"], device=dev)
-            for _ in range(2):
-                run()
-            torch.cuda.synchronize()
-            best = float("inf")
-            for _ in range(3):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                run()
-                e.record()
+
+            def best_of(n):
+                for _ in range(2):
+                    run()
                 torch.cuda.synchronize()
-                best = min(best, s.elapsed_time(e))
+                best = float("inf")
+                for _ in range(n):
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    run()
+                    e.record()
+                    torch.cuda.synchronize()
+                    best = min(best, s.elapsed_time(e))
+                return best
+            best = best_of(3)
             out["stage"] = {"value": vox / (best * 1e-3), "unit": UNIT, "ms": best,
-                            "kind": "port of the whole stage on CUDA tensors (ATen/cuDNN eager, best of 3)"}
+                            "kind": "port of the whole stage on CUDA tensors (ATen/cuDNN eager, fp32, best of 3)"}
+            if w["stage"] == "casmvs":        # cuDNN with TF32 tensor cores allowed: the fastest the reference's 3-D UNet can run here
+                old = torch.backends.cudnn.allow_tf32
+                torch.backends.cudnn.allow_tf32 = True
+                try:
+                    b2 = best_of(3)
+                finally:
+                    torch.backends.cudnn.allow_tf32 = old
+                out["stage_cudnn_tf32"] = {"value": vox / (b2 * 1e-3), "unit": UNIT, "ms": b2,
+                                           "kind": "same with torch.backends.cudnn.allow_tf32 = True (not the reference's numerics)"}
     except Exception as ex:  # an OOM in the baseline must not lose the bench line
         out["unavailable"] = repr(ex)[:200]
     return out
@@ -771,9 +852,10 @@ def main():
     os.dup2(2, 1)
     sys.stdout = real_stdout
     if args.impl == "reference":
-        if w["stage"] == "cascade":   # the reference arm times one bounded stage-1 sample of the cascade's first stage
-            w = dict(WORKLOADS["cfg2_stage1"], D=48, desc=w["desc"] + " [reference arm: stage 1 only]")
-        run_reference(args, w)
+        if w["stage"] == "cascade":
+            run_reference_cascade(args, w)
+        else:
+            run_reference(args, w)
     elif w["stage"] == "cascade":
         run_cascade(args, w)
     else:
