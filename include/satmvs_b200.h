@@ -153,6 +153,10 @@ int satmvs_softargmin_fwd(const float* logits, const float* depth, int depth_per
  * finish: depth = depth_acc/(exp_sum+1e-10), conf = max_e/(exp_sum+1e-10) -> fp32 [H,W]. */
 int satmvs_softargmin_stream_update(const float* reg, const float* depth_plane, int depth_per_pixel,
                                     int H, int W, double* state, void* stream);
+/* The same update for K consecutive planes in one launch (reg device [K,H,W], depth device [K,H,W] or [K]): planes are
+ * accumulated in order with the per-plane arithmetic of satmvs_softargmin_stream_update. */
+int satmvs_softargmin_stream_update_planes(const float* reg, const float* depth, int depth_per_pixel, int K,
+                                           int H, int W, double* state, void* stream);
 int satmvs_softargmin_stream_finish(const double* state, int H, int W,
                                     float* out_depth, float* out_conf, void* stream);
 
@@ -206,6 +210,22 @@ int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, 
  * counters; SATMVS_RED_NO_OVERLAP=1 disables), 2 = the same kernel after them, 1 = FFMA cluster kernel (csrc/red_cluster.cuh), 0 = per-plane kernel chain, -1 = none yet.
  * Diagnostic for tests and the bench line; SATMVS_RED_NO_TC=1 / SATMVS_RED_NO_CLUSTER=1 force the later ones. */
 int satmvs_red_last_path(void);
+
+/* ---- FeatureNet: the 2-D UNet in front of the plane sweep (modules/module.py:442-543, arch_mode "unet", num_stage 3) ----
+ * Replaces `self.feature(img)` of networks/casred.py:116-119 / :288-290 for ALL views of a stack in one call.
+ *   block[i]: conv weight + inference-mode BatchNorm folded to scale / shift, in the reference's order
+ *     0 conv0.0 [b,3,3,3]   1 conv0.1 [b,b,3,3]      2 conv1.0 [2b,b,5,5] (stride 2)   3 conv1.1   4 conv1.2 [2b,2b,3,3]
+ *     5 conv2.0 [4b,2b,5,5] (stride 2)   6 conv2.1   7 conv2.2 [4b,4b,3,3]
+ *     8 deconv1.deconv [4b,2b,3,3] (ConvTranspose2d, stride 2)   9 deconv1.conv [2b,4b,3,3]
+ *    10 deconv2.deconv [2b,b,3,3]                               11 deconv2.conv [b,2b,3,3]
+ *   out_w[k]: the bare 1x1 heads out1 [4b,4b], out2 [2b,2b], out3 [b,b] (no bias).
+ *   images [3,V,H,W] (channel-major, the V views as planes); out1 [4b,V,H/4,W/4], out2 [2b,V,H/2,W/2], out3 [b,V,H,W]
+ *   = outputs["stage1".."stage3"] of every view.  H and W multiples of 4. */
+typedef struct satmvs_conv_bn { const float* w; const float* scale; const float* shift; } satmvs_conv_bn;
+typedef struct satmvs_featurenet_weights { satmvs_conv_bn block[12]; const float* out_w[3]; } satmvs_featurenet_weights;
+size_t satmvs_featurenet_workspace_bytes(int base_channels, int V, int H, int W);
+int satmvs_featurenet_forward(const satmvs_featurenet_weights* w, const float* images, int base_channels, int V, int H, int W,
+                              float* out1, float* out2, float* out3, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- one convolution block of the regularisers ----
  * ConvReLU (modules/module.py:178-186): 3x3 per depth plane (NZ = 1); Conv3d (modules/module.py:324-366): 3x3x3 (NZ = 3);

@@ -142,6 +142,26 @@ def golden_regularisers(ref):
     save("red_slice", cost=x[:, :, 0], s1=st[0], s2=st[1], s3=st[2], s4=st[3], reg=reg, n1=n1, n2=n2, n3=n3, n4=n4)
 
 
+def golden_featurenet(ref):
+    """`FeatureNet(8, num_stage=3, arch_mode="unet")` in eval mode on three small views (`modules/module.py:442-543`)."""
+    import contextlib
+    sd = synth.make_featurenet_weights(8)
+    with open(os.devnull, "w") as devnull, contextlib.redirect_stdout(devnull):
+        m = ref.module.FeatureNet(base_channels=8, stride=4, num_stage=3, arch_mode="unet")
+    m.load_state_dict(sd)
+    m.eval()
+    g = torch.Generator().manual_seed(23)
+    imgs = [torch.rand(1, 3, 40, 56, generator=g) for _ in range(3)]
+    arrays = {}
+    with torch.no_grad():
+        for v, im in enumerate(imgs):
+            out = m(im)
+            arrays[f"img{v}"] = im
+            for k in ("stage1", "stage2", "stage3"):
+                arrays[f"{k}_v{v}"] = out[k]
+    save("featurenet", **arrays)
+
+
 def golden_heads(ref):
     rng = np.random.default_rng(41)
     B, D, H, W = 2, 8, 12, 20
@@ -208,6 +228,10 @@ def golden_cascade(ref):
         save(f"cascade_{tag}", **arrays)
 
 
+def main_featurenet_only():
+    golden_featurenet(reference_loader.load())
+
+
 def main():
     torch.set_num_threads(8)
     ref = reference_loader.load()
@@ -219,7 +243,11 @@ def main():
     golden_heads(ref)
     golden_hypotheses(ref)
     golden_cascade(ref)
+    golden_featurenet(ref)
 
 
 if __name__ == "__main__":
-    main()
+    if "--featurenet" in sys.argv:
+        main_featurenet_only()
+    else:
+        main()

@@ -104,3 +104,32 @@ def red_regularization(volume: torch.Tensor, sd: dict) -> torch.Tensor:
         reg, *states = red_slice(volume[:, :, d], *states, sd)
         out.append(reg)
     return torch.stack(out, dim=1).squeeze(2)
+
+
+def featurenet(x: torch.Tensor, sd: dict) -> dict:
+    """`FeatureNet.forward` (`modules/module.py:506-543`), arch_mode "unet", three stages, eval-mode BatchNorm
+    (`Conv2d` / `Deconv2d` blocks `:78-159`, `DeConv2dFuse` `:303-321`).  x [B,3,H,W] -> {"stage1", "stage2", "stage3"}."""
+    import torch.nn.functional as F
+
+    def bn(y, name):
+        return F.batch_norm(y, sd[name + ".bn.running_mean"], sd[name + ".bn.running_var"], sd[name + ".bn.weight"],
+                            sd[name + ".bn.bias"], False, 0.1, 1e-5)
+
+    def conv(y, name, stride=1, pad=1):
+        return F.relu(bn(F.conv2d(y, sd[name + ".conv.weight"], None, stride, pad), name))
+
+    def fuse(x_pre, y, name):
+        h, w = y.shape[2:]
+        d = F.conv_transpose2d(y, sd[name + ".deconv.conv.weight"], None, 2, 1, 1)[:, :, :2 * h, :2 * w]
+        d = F.relu(bn(d, name + ".deconv"))
+        return conv(torch.cat((d, x_pre), 1), name + ".conv")
+
+    conv0 = conv(conv(x, "conv0.0"), "conv0.1")
+    conv1 = conv(conv(conv(conv0, "conv1.0", 2, 2), "conv1.1"), "conv1.2")
+    conv2 = conv(conv(conv(conv1, "conv2.0", 2, 2), "conv2.1"), "conv2.2")
+    out = {"stage1": F.conv2d(conv2, sd["out1.weight"])}
+    f1 = fuse(conv1, conv2, "deconv1")
+    out["stage2"] = F.conv2d(f1, sd["out2.weight"])
+    f2 = fuse(conv0, f1, "deconv2")
+    out["stage3"] = F.conv2d(f2, sd["out3.weight"])
+    return out

@@ -7,7 +7,7 @@ Host code mirrors the reference's operator interface (`modules/warping.py`, `mod
 from .warping import rpc_warping, rpc_warping_enisum, homo_warping, build_cost_volume  # noqa: F401
 from .regress import softargmin, StreamingSoftArgmin  # noqa: F401
 from .rpc_tensor import RPCModelParameter  # noqa: F401
-from .module import RED_Regularization, slice_RED_Regularization, CostRegNet, depth_regression, conv_block  # noqa: F401
+from .module import RED_Regularization, slice_RED_Regularization, CostRegNet, FeatureNet, depth_regression, conv_block  # noqa: F401
 from .stages import stage_train_red, stage_pred_red, stage_casmvs, cascade
 from .depth_range import get_depth_range_samples, stage_depth_hypotheses  # noqa: F401
 from . import data_io  # noqa: F401  (PFM / RPC text formats)

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "satmvs_remap_bilinear": ([_P, _I, _I, _P, _P, _L, C.c_float, _P, _P], _I),
     "satmvs_softargmin_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "satmvs_softargmin_stream_update": ([_P, _P, _I, _I, _I, _P, _P], _I),
+    "satmvs_softargmin_stream_update_planes": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_softargmin_stream_finish": ([_P, _I, _I, _P, _P, _P], _I),
     "satmvs_resize_bilinear": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_depth_hypotheses": ([_P, _I, _I, _P, _I, _I, C.c_float, _I, _I, _I, _I, _P, _P], _I),
@@ -43,6 +44,8 @@ _SIGNATURES = {
     "satmvs_red_forward": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, C.c_size_t, _P], _I),
     "satmvs_conv_workspace_bytes": ([_I, _I, _I], C.c_size_t),
     "satmvs_conv_forward": ([_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P, _I, _P, C.c_size_t, _P], _I),
+    "satmvs_featurenet_workspace_bytes": ([_I, _I, _I, _I], C.c_size_t),
+    "satmvs_featurenet_forward": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, C.c_size_t, _P], _I),
     "satmvs_costreg_workspace_bytes": ([_I, _I, _I, _I], C.c_size_t),
     "satmvs_costreg_forward": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, C.c_size_t, _P], _I),
 }
@@ -70,7 +73,7 @@ def lib():
 
 
 PROFILE_CLASSES = ("sweep", "conv_batched", "gru_gate_conv", "gru_output_conv", "gru_pointwise", "red_decoder",
-                   "costreg", "heads")
+                   "costreg", "heads", "featurenet")
 
 
 class profile:

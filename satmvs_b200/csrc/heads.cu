@@ -67,6 +67,23 @@ __global__ void softargmin_stream_update_kernel(const float* __restrict__ reg, c
   if (me[pix] < e) me[pix] = e;
 }
 
+// K planes in their order, same arithmetic per plane as the single-plane update: the chunked plane-streaming stage
+// (satmvs_b200/stages.py) feeds the regularised planes of a whole chunk at once
+__global__ void softargmin_stream_update_planes_kernel(const float* __restrict__ reg, const float* __restrict__ depth,
+                                                       int depth_per_pixel, int K, int HW, double* __restrict__ state) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  double es = state[pix], da = state[HW + pix], me = state[2 * (size_t)HW + pix];
+  for (int k = 0; k < K; ++k) {
+    const double e = exp((double)__ldg(reg + (size_t)k * HW + pix));
+    const double dv = (double)(depth_per_pixel ? __ldg(depth + (size_t)k * HW + pix) : __ldg(depth + k));
+    es = es + e;
+    da = dv * e + da;
+    if (me < e) me = e;
+  }
+  state[pix] = es; state[HW + pix] = da; state[2 * (size_t)HW + pix] = me;
+}
+
 __global__ void softargmin_stream_finish_kernel(const double* __restrict__ state, int HW,
                                                 float* __restrict__ out_depth, float* __restrict__ out_conf) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,6 +117,14 @@ int satmvs_softargmin_stream_update(const float* reg, const float* depth_plane, 
   softargmin_stream_update_kernel<<<ceil_div(HW, 128), 128, 0, (cudaStream_t)stream>>>(reg, depth_plane, depth_per_pixel,
                                                                                        HW, state);
   return check_launch("softargmin_stream_update_kernel");
+}
+
+int satmvs_softargmin_stream_update_planes(const float* reg, const float* depth, int depth_per_pixel, int K,
+                                           int H, int W, double* state, void* stream) {
+  SATMVS_REQUIRE(reg && depth && state && K >= 1 && H >= 1 && W >= 1);
+  const int HW = H * W;
+  softargmin_stream_update_planes_kernel<<<ceil_div(HW, 128), 128, 0, (cudaStream_t)stream>>>(reg, depth, depth_per_pixel, K, HW, state);
+  return check_launch("softargmin_stream_update_planes_kernel");
 }
 
 int satmvs_softargmin_stream_finish(const double* state, int H, int W,

@@ -8,7 +8,7 @@
 namespace satmvs {
 
 enum ProfPhase { kProfSweep = 0, kProfConvBatched, kProfGruGate, kProfGruOutput, kProfGruPointwise, kProfDecoder,
-                 kProfCostReg, kProfHead, kProfCount };
+                 kProfCostReg, kProfHead, kProfFeature, kProfCount };
 
 struct ProfState {
   bool on = false;

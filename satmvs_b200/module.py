@@ -197,6 +197,12 @@ class slice_RED_Regularization(_RedBase):
         logits, st = self._run(cost.unsqueeze(2), [state1, state2, state3, state4], True)
         return (logits, *st)
 
+    def forward_planes(self, volume, state1, state2, state3, state4):
+        """K consecutive slices in one call: volume [B,C,K,H,W] -> (reg [B,K,H,W], state1..state4 after the last slice).
+        Equal to K calls of `forward` with the states carried (the recurrence runs inside the library)."""
+        logits, st = self._run(volume, [state1, state2, state3, state4], True)
+        return (logits, *st)
+
 
 class _CostRegWeights(C.Structure):
     _fields_ = [("conv_w", _F * 10), ("bn_scale", _F * 10), ("bn_shift", _F * 10), ("prob_w", _F)]
@@ -285,6 +291,123 @@ class CostRegNet(nn.Module):
                 _lib.check(_lib.lib().satmvs_costreg_forward(C.byref(w), x[b].data_ptr(), Cc, self.base_channels, D, H, W,
                                                             out[b].data_ptr(), ws.data_ptr(), ws.numel(), st), "costreg_forward")
         return out
+
+
+class _FeatWeights(C.Structure):
+    _fields_ = [("block", _F * 36), ("out_w", _F * 3)]        # 12 x (w, scale, shift)
+
+
+class Conv2d(nn.Module):
+    """Parameter container for the reference's `Conv2d` block (`modules/module.py:78-118`): conv (bias iff no bn) + bn + relu."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        assert bn and relu
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, bias=False, **kwargs)
+        self.kernel_size, self.stride, self.relu = kernel_size, stride, relu
+        self.bn = nn.BatchNorm2d(out_channels, momentum=bn_momentum)
+
+
+class Deconv2d(nn.Module):
+    """Parameter container for the reference's `Deconv2d` block (`modules/module.py:121-159`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        assert bn and relu and stride == 2
+        self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=stride, bias=False, **kwargs)
+        self.stride, self.relu = stride, relu
+        self.bn = nn.BatchNorm2d(out_channels, momentum=bn_momentum)
+
+
+class DeConv2dFuse(nn.Module):
+    """`DeConv2dFuse` (`modules/module.py:303-321`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, relu=True, bn=True, bn_momentum=0.1):
+        super().__init__()
+        self.deconv = Deconv2d(in_channels, out_channels, kernel_size, stride=2, padding=1, output_padding=1, bn=True, relu=relu,
+                               bn_momentum=bn_momentum)
+        self.conv = Conv2d(2 * out_channels, out_channels, kernel_size, stride=1, padding=1, bn=bn, relu=relu, bn_momentum=bn_momentum)
+
+
+class FeatureNet(nn.Module):
+    """`FeatureNet` (`modules/module.py:442-543`), arch_mode "unet", three stages: the reference's constructor, sub-module names
+    and parameter shapes (reference checkpoints load unchanged), forward on the library's kernels (inference-mode BatchNorm).
+
+    forward(x [B,3,H,W]) -> {"stage1": [B,4b,H/4,W/4], "stage2": [B,2b,H/2,W/2], "stage3": [B,b,H,W]} like the reference;
+    forward_views([img_0 .. img_{V-1}]) runs every view of a stack through each layer in one launch and returns the V dicts
+    (`networks/casred.py:116-119` calls the net once per view)."""
+
+    def __init__(self, base_channels, num_stage=3, stride=4, arch_mode="unet"):
+        super().__init__()
+        if arch_mode != "unet" or num_stage != 3:
+            raise NotImplementedError("satmvs_b200.FeatureNet implements the configuration the cascades use: unet, 3 stages")
+        b = base_channels
+        self.arch_mode, self.stride, self.base_channels, self.num_stage = arch_mode, stride, b, num_stage
+        self.conv0 = nn.Sequential(Conv2d(3, b, 3, 1, padding=1), Conv2d(b, b, 3, 1, padding=1))
+        self.conv1 = nn.Sequential(Conv2d(b, b * 2, 5, stride=2, padding=2), Conv2d(b * 2, b * 2, 3, 1, padding=1),
+                                   Conv2d(b * 2, b * 2, 3, 1, padding=1))
+        self.conv2 = nn.Sequential(Conv2d(b * 2, b * 4, 5, stride=2, padding=2), Conv2d(b * 4, b * 4, 3, 1, padding=1),
+                                   Conv2d(b * 4, b * 4, 3, 1, padding=1))
+        self.out1 = nn.Conv2d(b * 4, b * 4, 1, bias=False)
+        self.deconv1 = DeConv2dFuse(b * 4, b * 2, 3)
+        self.deconv2 = DeConv2dFuse(b * 2, b, 3)
+        self.out2 = nn.Conv2d(b * 2, b * 2, 1, bias=False)
+        self.out3 = nn.Conv2d(b, b, 1, bias=False)
+        self.out_channels = [4 * b, 2 * b, b]
+
+    def _weights(self) -> _FeatWeights:
+        w = _FeatWeights()
+        keep = []
+
+        def ptr(t):
+            t = _lib.require_cuda(t.detach(), "parameter")
+            keep.append(t)
+            return t.data_ptr()
+
+        blocks = [self.conv0[0], self.conv0[1], self.conv1[0], self.conv1[1], self.conv1[2], self.conv2[0], self.conv2[1],
+                  self.conv2[2], self.deconv1.deconv, self.deconv1.conv, self.deconv2.deconv, self.deconv2.conv]
+        for i, blk in enumerate(blocks):
+            scale = blk.bn.weight.detach() * torch.rsqrt(blk.bn.running_var + blk.bn.eps)
+            shift = blk.bn.bias.detach() - blk.bn.running_mean * scale
+            w.block[3 * i], w.block[3 * i + 1], w.block[3 * i + 2] = ptr(blk.conv.weight), ptr(scale), ptr(shift)
+        for i, m in enumerate((self.out1, self.out2, self.out3)):
+            w.out_w[i] = ptr(m.weight)
+        w._keep = keep
+        return w
+
+    def forward_views(self, images):
+        if self.training:
+            raise RuntimeError("satmvs_b200.FeatureNet implements inference-mode BatchNorm only; call .eval()")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("satmvs_b200.FeatureNet is inference-only: call it under torch.no_grad()")
+        imgs = [_lib.require_cuda(i, "image") for i in images]
+        B, c3, H, W = imgs[0].shape
+        if c3 != 3 or any(i.shape != imgs[0].shape for i in imgs):
+            raise ValueError("images must be V tensors [B, 3, H, W] of one shape")
+        V, b = len(imgs), self.base_channels
+        nbytes = _lib.lib().satmvs_featurenet_workspace_bytes(b, V, H, W)
+        if nbytes == 0:
+            raise ValueError("FeatureNet needs H and W to be multiples of 4")
+        ws = _workspace(nbytes, imgs[0].device)
+        x = torch.stack(imgs, dim=2).contiguous()                        # [B, 3, V, H, W]: the views ride the plane axis
+        dev = x.device
+        o1 = torch.empty((B, 4 * b, V, H // 4, W // 4), dtype=torch.float32, device=dev)
+        o2 = torch.empty((B, 2 * b, V, H // 2, W // 2), dtype=torch.float32, device=dev)
+        o3 = torch.empty((B, b, V, H, W), dtype=torch.float32, device=dev)
+        w = self._weights()
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            for bi in range(B):
+                _lib.check(_lib.lib().satmvs_featurenet_forward(C.byref(w), x[bi].data_ptr(), b, V, H, W, o1[bi].data_ptr(),
+                                                               o2[bi].data_ptr(), o3[bi].data_ptr(), ws.data_ptr(), ws.numel(), st),
+                           "featurenet_forward")
+        return [{"stage1": o1[:, :, v].contiguous(), "stage2": o2[:, :, v].contiguous(), "stage3": o3[:, :, v].contiguous()}
+                for v in range(V)]
+
+    def forward(self, x):
+        return self.forward_views([x])[0]
 
 
 from .regress import depth_regression  # noqa: E402,F401  (`modules/module.py:433-439`, on the heads kernel)

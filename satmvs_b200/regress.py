@@ -87,6 +87,19 @@ class StreamingSoftArgmin:
                     reg[b].data_ptr(), dp[b].data_ptr(), per_pixel, self.H, self.W, self.state[b].data_ptr(), st),
                     "softargmin_stream_update")
 
+    def update_planes(self, reg: torch.Tensor, depth_planes: torch.Tensor) -> None:
+        """K planes at once: reg [B,K,H,W]; depth_planes [B,K,H,W] or [B,K].  Same arithmetic, plane by plane in order."""
+        reg = _lib.require_cuda(reg, "reg")
+        K = reg.shape[1]
+        dp = _lib.require_cuda(depth_planes, "depth_planes")
+        per_pixel = 1 if dp.dim() == 4 else 0
+        with torch.cuda.device(reg.device):
+            st = _lib.stream_ptr(reg.device)
+            for b in range(self.B):
+                _lib.check(_lib.lib().satmvs_softargmin_stream_update_planes(
+                    reg[b].data_ptr(), dp[b].data_ptr(), per_pixel, K, self.H, self.W, self.state[b].data_ptr(), st),
+                    "softargmin_stream_update_planes")
+
     def finish(self):
         depth = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.state.device)
         conf = torch.empty_like(depth)

@@ -39,20 +39,28 @@ def stage_casmvs(features, cams, depth_values, regulariser, geo_model="rpc"):
     return {"depth": depth, "photometric_confidence": conf}
 
 
-def stage_pred_red(features, cams, depth_values, regulariser, geo_model="rpc"):
-    """Plane-streaming stage of the inference net: per plane, sweep one hypothesis, one recurrent
-    regulariser step (states carried), streaming fp64 soft-argmin.  O(H*W) memory.
-    regulariser: `satmvs_b200.module.slice_RED_Regularization`."""
+def stage_pred_red(features, cams, depth_values, regulariser, geo_model="rpc", chunk=16):
+    """Plane-streaming stage of the inference net (`compute_depth_when_pred`, `networks/casred.py:161-238`): sweep, one
+    recurrent regulariser step per plane (states carried), streaming fp64 soft-argmin -- in chunks of `chunk` planes: ONE
+    fused sweep builds the chunk's variance planes, ONE library call runs the recurrence over them (tensor-core cluster
+    kernel, states in / out), ONE launch folds them into the fp64 running sums.  Memory stays O(chunk * C * H * W) whatever D
+    is; chunk = 1 is the reference's literal per-plane loop.  regulariser: `satmvs_b200.module.slice_RED_Regularization`."""
     ref, srcs, ref_cam, src_cams = _split(features, cams)
     B, _, H, W = ref.shape
     dev = ref.device
     states = [torch.zeros((B, c, H >> l, W >> l), dtype=torch.float32, device=dev) for l, c in enumerate((8, 16, 32, 64))]
     head = StreamingSoftArgmin(B, H, W, dev)
-    for d in range(depth_values.shape[1]):
-        plane = depth_values[:, d:d + 1].contiguous()
-        var = build_cost_volume(ref, srcs, ref_cam, src_cams, plane, geo_model)
-        reg, *states = regulariser(var.squeeze(2), *states)
-        head.update(reg, plane)
+    D = depth_values.shape[1]
+    chunk = max(1, int(chunk))
+    for d0 in range(0, D, chunk):
+        planes = depth_values[:, d0:d0 + chunk].contiguous()
+        var = build_cost_volume(ref, srcs, ref_cam, src_cams, planes, geo_model)
+        if planes.shape[1] == 1:
+            reg, *states = regulariser(var.squeeze(2), *states)
+            head.update(reg, planes)
+        else:
+            reg, *states = regulariser.forward_planes(var, *states)
+            head.update_planes(reg, planes)
     depth, conf = head.finish()
     return {"depth": depth, "photometric_confidence": conf}
 

@@ -146,6 +146,33 @@ def make_costregnet_weights(in_channels: int, base: int = 8, seed: int = 11) -> 
     return sd
 
 
+def make_featurenet_weights(base: int = 8, seed: int = 17) -> dict[str, torch.Tensor]:
+    """State-dict for `FeatureNet(base, num_stage=3, arch_mode="unet")` (`modules/module.py:442-480`) with the reference's
+    parameter names; BN running statistics are non-trivial so that the eval-mode folding is exercised."""
+    rng = np.random.default_rng(seed)
+    sd: dict[str, torch.Tensor] = {}
+
+    def block(name, cin, cout, k, transposed=False):
+        shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+        sd[f"{name}.conv.weight"] = _uniform(rng, shape, (1.0 / (cin * k * k)) ** 0.5 * 1.7)
+        sd[f"{name}.bn.weight"] = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+        sd[f"{name}.bn.bias"] = torch.from_numpy(rng.normal(0, 0.1, cout).astype(np.float32))
+        sd[f"{name}.bn.running_mean"] = torch.from_numpy(rng.normal(0, 0.1, cout).astype(np.float32))
+        sd[f"{name}.bn.running_var"] = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+        sd[f"{name}.bn.num_batches_tracked"] = torch.tensor(1, dtype=torch.long)
+
+    b = base
+    block("conv0.0", 3, b, 3); block("conv0.1", b, b, 3)
+    block("conv1.0", b, 2 * b, 5); block("conv1.1", 2 * b, 2 * b, 3); block("conv1.2", 2 * b, 2 * b, 3)
+    block("conv2.0", 2 * b, 4 * b, 5); block("conv2.1", 4 * b, 4 * b, 3); block("conv2.2", 4 * b, 4 * b, 3)
+    sd["out1.weight"] = _uniform(rng, (4 * b, 4 * b, 1, 1), (1.0 / (4 * b)) ** 0.5 * 1.7)
+    block("deconv1.deconv", 4 * b, 2 * b, 3, transposed=True); block("deconv1.conv", 4 * b, 2 * b, 3)
+    block("deconv2.deconv", 2 * b, b, 3, transposed=True); block("deconv2.conv", 2 * b, b, 3)
+    sd["out2.weight"] = _uniform(rng, (2 * b, 2 * b, 1, 1), (1.0 / (2 * b)) ** 0.5 * 1.7)
+    sd["out3.weight"] = _uniform(rng, (b, b, 1, 1), (1.0 / b) ** 0.5 * 1.7)
+    return sd
+
+
 def make_red_weights(in_channels: int, base: int = 8, seed: int = 13) -> dict[str, torch.Tensor]:
     """State-dict for `RED_Regularization` / `slice_RED_Regularization(in_channels, base)`
     (`modules/module.py:595-610`, `:653-668`; identical keys)."""

@@ -151,6 +151,23 @@ def test_pred_stage_equals_train_stage():
     assert maxdiff(tb["photometric_confidence"], want["photometric_confidence"]) < 1e-4
 
 
+@pytest.mark.parametrize("chunk", [1, 4, 16])
+def test_pred_stage_chunked_equals_per_plane_loop(chunk):
+    """The chunked plane-streaming stage (one sweep + one recurrence call + one head update per chunk) == the reference's
+    literal per-plane loop (chunk = 1) == the oracle."""
+    B, V, C, D, H, W = 1, 3, 16, 10, 32, 64
+    fe = [f.to(DEV) for f in synth.make_features(B, V, C, H, W, seed=4)]
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv = synth.make_depth_planes(B, D, H, W).to(DEV)
+    sd = synth.make_red_weights(C)
+    m = make_reg(satmvs_b200.slice_RED_Regularization, C)
+    got = satmvs_b200.stage_pred_red(fe, rp, dv, m, "rpc", chunk=chunk)
+    want = stages.stage_pred_red([f.cpu() for f in fe], rp, dv.cpu(), sd, "rpc")
+    scale = want["depth"].abs().max().item()
+    assert maxdiff(got["depth"], want["depth"]) < 1e-4 * scale
+    assert maxdiff(got["photometric_confidence"], want["photometric_confidence"]) < 1e-4
+
+
 def test_reference_checkpoint_keys():
     """state_dict keys/shapes are the reference's (`train.py:216-219` checkpoints must load)."""
     m = satmvs_b200.RED_Regularization(32, 8)

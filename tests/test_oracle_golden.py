@@ -140,3 +140,14 @@ def test_remap_restatement_equals_cv2_bit_for_bit():
     f = np.load(os.path.join(G, "rpc_filter.npz"))
     got = remap.remap_bilinear(f["depths"][1], f["x_src"].astype(np.float32), f["y_src"].astype(np.float32), -999.0)
     assert np.array_equal(got, f["sampled"])
+
+
+def test_featurenet_restatement_equals_reference(golden):
+    """oracle.regnets.featurenet against outputs of the unmodified reference FeatureNet (eval mode, three views)."""
+    g = golden("featurenet")
+    sd = synth.make_featurenet_weights(8)
+    with torch.no_grad():
+        for v in range(3):
+            out = regnets.featurenet(g[f"img{v}"], sd)
+            for k in ("stage1", "stage2", "stage3"):
+                assert maxdiff(out[k], g[f"{k}_v{v}"]) == 0.0
