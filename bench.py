@@ -559,6 +559,9 @@ def run_ours(args, w):
         if world == 1 and not args.no_cpu_baseline:
             line["gpu_eager_baseline"] = gpu_eager_baseline(w, dev, fe, cams, dv)
             line["cpu_baseline"] = cpu_baseline(w, budget_s=20.0)
+    fnb = None
+    if rank == 0 and not sharded_run and not args.no_sharded:
+        fnb = featurenet_block(dev, flush)
     sh = None
     if not sharded_run and not args.no_sharded:
         del fe, dv
@@ -567,9 +570,44 @@ def run_ours(args, w):
     if rank == 0:
         if sh is not None:
             line["sharded"] = sh
+        if fnb is not None:
+            line["featurenet"] = fnb
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def featurenet_block(dev, flush, V=3, H=384, W=768):
+    """FeatureNet (the 2-D UNet in front of the sweep, modules/module.py:442-543) on the V views of one 768x384 stack:
+    device time of the library call (all views per launch), outside the headline step (the step starts from feature maps, as
+    BASELINE.json's configs do)."""
+    import satmvs_b200
+    from satmvs_b200 import synth
+    m = satmvs_b200.FeatureNet(8)
+    m.load_state_dict(synth.make_featurenet_weights(8))
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    imgs = [torch.rand(1, 3, H, W, generator=g).to(dev) for _ in range(V)]
+    with torch.no_grad():
+        for _ in range(3):
+            m.forward_views(imgs)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); m.forward_views(imgs); e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+    px = H * W
+    # (Cin, Cout, taps, pixels the MACs are counted on); transposed convs counted on their input pixels
+    layers = [(3, 8, 9, px), (8, 8, 9, px), (8, 16, 25, px // 4), (16, 16, 9, px // 4), (16, 16, 9, px // 4),
+              (16, 32, 25, px // 16), (32, 32, 9, px // 16), (32, 32, 9, px // 16), (32, 32, 1, px // 16),
+              (32, 16, 9, px // 16), (32, 16, 9, px // 4), (16, 16, 1, px // 4), (16, 8, 9, px // 4), (16, 8, 9, px), (8, 8, 1, px)]
+    flop = 2 * V * sum(ci * co * t * n for ci, co, t, n in layers)
+    ms = sorted(ts)[len(ts) // 2]
+    return {"views": V, "image_hw": [H, W], "ms": ms, "ms_best": min(ts), "megapixels_per_s": V * px / (ms * 1e-3) / 1e6,
+            "approx_tflops_fp32": flop / (ms * 1e-3) / 1e12,
+            "note": "fp32 FFMA implicit-GEMM engine; includes the [B,3,V,H,W] stacking copy and the per-view output copies"}
 
 
 def sharded_block(args, dev, rank, world, barrier, flush):

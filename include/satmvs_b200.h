@@ -34,6 +34,10 @@ extern "C" {
 
 enum { SATMVS_OK = 0, SATMVS_EINVAL = 1, SATMVS_ECUDA = 2 };
 
+/* Device-side failures detected inside a kernel (tensor-core completion timeout = 1, producer timeout = 2, cluster flag
+ * timeout = 3) are parked in pinned host memory instead of trapping the CUDA context: the next library call of the same host
+ * thread fails with SATMVS_ECUDA, and this function returns and clears the code (call it after synchronising). */
+int satmvs_async_error(void);
 int satmvs_abi_version(void);
 const char* satmvs_last_error(void);
 

@@ -18,6 +18,7 @@ _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 _SIGNATURES = {
     "satmvs_abi_version": ([], _I),
     "satmvs_last_error": ([], C.c_char_p),
+    "satmvs_async_error": ([], _I),
     "satmvs_profile_begin": ([], _I),
     "satmvs_profile_end": ([_P, _P], _I),
     "satmvs_cost_volume_rpc_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),

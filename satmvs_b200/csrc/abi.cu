@@ -13,6 +13,30 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
+struct AsyncErr { int* host = nullptr; int* dev = nullptr; int devid = -1; };
+static AsyncErr& async_err() {
+  static thread_local AsyncErr slot[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  AsyncErr& a = slot[dev & 15];
+  if (a.devid != dev) {
+    a.devid = dev;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&a.host), sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+      *a.host = 0;
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&a.dev), a.host, 0) != cudaSuccess) a.dev = nullptr;
+    }
+    if (a.dev == nullptr) cudaGetLastError();
+  }
+  return a;
+}
+int* async_error_devptr() { return async_err().dev; }
+int async_error_poll() {
+  AsyncErr& a = async_err();
+  if (a.host == nullptr) return 0;
+  const int v = *reinterpret_cast<volatile int*>(a.host);
+  if (v) *reinterpret_cast<volatile int*>(a.host) = 0;
+  return v;
+}
 ProfState& prof_state() {
   static thread_local ProfState s;
   return s;
@@ -63,6 +87,7 @@ int satmvs_profile_end(float* ms_by_class, int* launches_by_class) {
   return SATMVS_OK;
 }
 
+int satmvs_async_error(void) { return satmvs::async_error_poll(); }
 int satmvs_abi_version(void) { return SATMVS_ABI_VERSION; }
 const char* satmvs_last_error(void) { return satmvs::g_error; }
 }

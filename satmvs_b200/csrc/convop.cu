@@ -19,6 +19,7 @@ size_t satmvs_conv_workspace_bytes(int Cin, int Cout, int NZ) {
 int satmvs_conv_forward(const float* in, int Cin, int D, int H, int W, const float* w, const float* scale, const float* shift,
                         int Cout, int NZ, int stride, int relu, float acc_scale, float* out, int engine,
                         void* workspace, size_t workspace_bytes, void* stream) {
+  SATMVS_CHECK_ASYNC();
   SATMVS_REQUIRE(in && w && out);
   SATMVS_REQUIRE(Cin >= 1 && Cout >= 1 && D >= 1 && H >= 1 && W >= 1 && (NZ == 1 || NZ == 3) && (stride == 1 || stride == 2));
   SATMVS_REQUIRE(engine >= 0 && engine <= 3);

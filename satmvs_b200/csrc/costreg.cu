@@ -126,6 +126,7 @@ size_t satmvs_costreg_workspace_bytes(int base, int D, int H, int W) {
 
 int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int Cin, int base, int D, int H, int W,
                            float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  SATMVS_CHECK_ASYNC();
   SATMVS_REQUIRE(wt && x && out && workspace);
   SATMVS_REQUIRE(Cin >= 1 && base >= 1 && D >= 8 && H >= 8 && W >= 8 && D % 8 == 0 && H % 8 == 0 && W % 8 == 0);
   cudaStream_t st = (cudaStream_t)stream;

@@ -69,7 +69,6 @@ struct RedPlan {
   double* stats;         // [D][4][3][2]
   char* wpack[4]; size_t wpack_bytes[4];
   int* umma_err;
-  int* fuse_cnt;
   int* cl_flags;         // [4][2][kClFlagStride] plane counters exchanged by the two clusters of a level
   char* tcpack[4];       // packed hidden-state filters of the tensor-core recurrence (red_tc.cuh)
   int* ready;            // [4][D] per-(level, plane) completion counters of the batched x-half convs (overlapped flow)
@@ -110,8 +109,6 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   }
   p.umma_err = reinterpret_cast<int*>(base + off);
   off += 256;
-  p.fuse_cnt = reinterpret_cast<int*>(base + off);           // [D][4][2] level-barrier counters of the fused pointwise tails
-  off += ((size_t)D * 4 * 2 * sizeof(int) + 255) / 256 * 256;
   p.cl_flags = reinterpret_cast<int*>(base + off);
   off += 4 * 2 * 32 * sizeof(int) + 8 * 16 * sizeof(unsigned long long);   // + debug counters
   off = (off + 255) / 256 * 256;
@@ -168,55 +165,6 @@ __global__ void gru_reset_kernel(const __grid_constant__ GruArgs a) {
   L.rh[e] = r * __ldg(L.hprev + c * L.scs + p);
 }
 
-// Vectorised forms: one thread = 4 consecutive pixels of one channel (every level's plane size is a multiple of 4),
-// 128-bit loads and stores, a quarter of the CTAs.  `begin` / `total` are then counted in groups of 4.
-__global__ void gru_reset4_kernel(const __grid_constant__ GruArgs a) {
-  pdl_release();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  pdl_wait();
-  if (i >= a.total) return;
-  int li = 0;
-#pragma unroll
-  for (int k = 1; k < 4; ++k) if (i >= a.l[k].begin) li = k;
-  const GruLevelArgs& L = a.l[li];
-  const int px4 = L.px >> 2;
-  const int e = i - L.begin, c = e / px4, p = (e - c * px4) << 2;
-  float ga, gb;
-  gn_coeff(L.stats, L.inv_n, __ldg(L.rn_w + c), __ldg(L.rn_b + c), ga, gb);
-  const float4 g = __ldg(reinterpret_cast<const float4*>(L.g + c * L.gcs + p));
-  const float4 h = __ldg(reinterpret_cast<const float4*>(L.hprev + c * L.scs + p));
-  float4 o;
-  o.x = sigmoidf_(fmaf(g.x, ga, gb)) * h.x; o.y = sigmoidf_(fmaf(g.y, ga, gb)) * h.y;
-  o.z = sigmoidf_(fmaf(g.z, ga, gb)) * h.z; o.w = sigmoidf_(fmaf(g.w, ga, gb)) * h.w;
-  *reinterpret_cast<float4*>(L.rh + (long long)c * L.px + p) = o;
-}
-
-__global__ void gru_update4_kernel(const __grid_constant__ GruArgs a) {
-  pdl_release();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  pdl_wait();
-  if (i >= a.total) return;
-  int li = 0;
-#pragma unroll
-  for (int k = 1; k < 4; ++k) if (i >= a.l[k].begin) li = k;
-  const GruLevelArgs& L = a.l[li];
-  const int px4 = L.px >> 2;
-  const int e = i - L.begin, c = e / px4, p = (e - c * px4) << 2;
-  float ua, ub, oa, ob;
-  gn_coeff(L.stats + 2, L.inv_n, __ldg(L.un_w + c), __ldg(L.un_b + c), ua, ub);
-  gn_coeff(L.stats + 4, L.inv_n, __ldg(L.on_w + c), __ldg(L.on_b + c), oa, ob);
-  const float4 g = __ldg(reinterpret_cast<const float4*>(L.g + (c + L.ch) * L.gcs + p));
-  const float4 y = __ldg(reinterpret_cast<const float4*>(L.o + c * L.ocs + p));
-  const float4 h = __ldg(reinterpret_cast<const float4*>(L.hprev + c * L.scs + p));
-  auto upd = [&](float gv, float yv, float hv) {
-    const float u = sigmoidf_(fmaf(gv, ua, ub));
-    return u * hv + (1.0f - u) * tanhf(fmaf(yv, oa, ob));       // module.py:57
-  };
-  float4 o;
-  o.x = upd(g.x, y.x, h.x); o.y = upd(g.y, y.y, h.y); o.z = upd(g.z, y.z, h.z); o.w = upd(g.w, y.w, h.w);
-  *reinterpret_cast<float4*>(L.hnext + c * L.scs + p) = o;
-}
-
 __global__ void gru_update_kernel(const __grid_constant__ GruArgs a) {
   pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,21 +204,8 @@ struct GruConvLevel {
   int ci_per_warp;                          // cin / ksplit (4 or 8)
   int px_groups;                            // CTAs per output-channel chunk
   int cta_begin;
-  // Fused pointwise tail (0 = none).  The GroupNorm that follows the conv needs the sums of the WHOLE level, so the
-  // CTAs of a level meet at a spin barrier in global memory (all CTAs of the launch are co-resident: checked by the
-  // host) and then apply the pointwise step to the outputs they still hold in registers:
-  //   1 (gate conv, r half only)  rh = sigmoid(GN_r(G_r)) * h                      (module.py:33-43)
-  //   2 (output conv)             h' = u*h + (1-u)*tanh(GN_o(O)), u = sigmoid(GN_u(G_u))   (module.py:46-57)
-  int fuse;
-  int* fuse_counter; int fuse_expected;
-  double fuse_inv_n;
-  const float *fuse_nw, *fuse_nb;           // GroupNorm affine of r (1) / o (2)
-  const float *fuse_uw, *fuse_ub;           // GroupNorm affine of u (2)
-  const float* fuse_h; long long fuse_h_cs; // current state
-  const float* fuse_gu; long long fuse_g_cs;// u-gate pre-activations of this plane (2)
-  float* fuse_dst; long long fuse_dst_cs;   // rh (1) / next state (2)
 };
-struct GruConvArgs { GruConvLevel l[4]; int early_wait; };
+struct GruConvArgs { GruConvLevel l[4]; };
 
 constexpr int kGcWarps = 8, kGcCo = 8, kGcPx = 4, kGcTilePx = 32 * kGcPx, kGcCi = 4;
 constexpr int kGcThreads = kGcWarps * 32;
@@ -284,17 +219,7 @@ template <bool kCoherent> __device__ __forceinline__ float4 ldf4(const float4* p
 
 template <bool kAligned, bool kCoherent>
 __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, float* wsm,
-                                              float (*part)[kGcCo][kGcTilePx], double (*red)[kGcWarps], bool stage_weights,
-                                              unsigned long long* dbg = nullptr) {
-  unsigned long long t_prev = 0;
-  auto tick = [&](int slot) {
-    if (dbg && threadIdx.x == 0) {
-      unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      if (slot >= 0) dbg[slot] += t - t_prev;
-      t_prev = t;
-    }
-  };
-  tick(-1);
+                                              float (*part)[kGcCo][kGcTilePx], double (*red)[kGcWarps], bool stage_weights) {
   const int co0 = (cta / L.px_groups) * kGcCo;
   const int tiles_per_cta = kGcWarps / L.ksplit;
   const int tile0 = (cta % L.px_groups) * tiles_per_cta;
@@ -349,7 +274,6 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
     for (int j = 0; j < kGcPx; ++j) acc[i][j] = 0.0f;
   pdl_wait();                 // inputs, addends and GroupNorm sums of the predecessor kernel are visible from here on
   __syncthreads();
-  tick(0);
 
   // input taps of one input channel for this lane's 4 pixels (predicated: zero padding)
   auto load_taps = [&](int ci, float (&v)[kGcPx][9]) {
@@ -449,7 +373,6 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
   }
   }
 
-  tick(1);
   // This thread's share of the CTA's outputs: output o = tid + NT*r is (tile-in-CTA q/8, channel q%8,
   // pixel tid%128) with q = r*NT/128 + tid/128, so the index math is compile time up to tid.
   // The addends are fetched now, so the loads fly during the partial-sum exchange.
@@ -469,10 +392,8 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
     *reinterpret_cast<float4*>(&part[warp][i][lane * kGcPx]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   __syncthreads();
 
-  tick(2);
   // fixed-order reduction over the k-parts, epilogue, GroupNorm sums
   float ssum = 0.0f, ssq = 0.0f;
-  float vals[kMaxOut / 2];
   auto epilogue = [&](auto ks_tag) {
     constexpr int KS = decltype(ks_tag)::value;
 #pragma unroll
@@ -487,14 +408,12 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
         const float val = sum + pre[r];
         L.out[(long long)(co0 + i) * L.out_cs + p] = val;
         ssum += val; ssq += val * val;
-        vals[r] = val;
       }
     }
   };
   if (L.ksplit == 2) epilogue(std::integral_constant<int, 2>{});
   else if (L.ksplit == 4) epilogue(std::integral_constant<int, 4>{});
   else epilogue(std::integral_constant<int, 8>{});
-  tick(3);
   double ds = ssum, dq = ssq;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, off); dq += __shfl_xor_sync(0xffffffffu, dq, off); }
@@ -507,61 +426,7 @@ __device__ __forceinline__ void gru_conv_unit(const GruConvLevel& L, int cta, fl
     atomicAdd(L.stats + 2 * grp, s);
     atomicAdd(L.stats + 2 * grp + 1, q);
   }
-  tick(4);
 
-  // ---- fused pointwise tail ----
-  if (L.fuse == 0 || (L.fuse == 1 && co0 >= L.stats_group)) return;      // the u half of the gates has no tail
-  // operands that do not depend on the level's sums: fetched before the barrier
-  const int KS = L.ksplit, nout = kMaxOut / KS;
-  float hv[kMaxOut / 2], gv[kMaxOut / 2];
-#pragma unroll
-  for (int r = 0; r < kMaxOut / 2; ++r) {
-    hv[r] = 0.0f; gv[r] = 0.0f;
-    if (r < nout) {
-      const int q = r * kRows + row_l;
-      const int p = (tile0 + (q >> 3)) * kGcTilePx + px_l;
-      if (p < npx) {
-        const int c = co0 + (q & 7);
-        hv[r] = __ldcg(L.fuse_h + (long long)c * L.fuse_h_cs + p);
-        if (L.fuse == 2) gv[r] = __ldcg(L.fuse_gu + (long long)c * L.fuse_g_cs + p);
-      }
-    }
-  }
-  if (tid == 0) {   // level barrier: this CTA's sums are published (fence) before it announces itself
-    __threadfence();
-    atomicAdd(L.fuse_counter, 1);
-    while (*reinterpret_cast<volatile int*>(L.fuse_counter) < L.fuse_expected) { }
-    __threadfence();
-  }
-  __syncthreads();
-  const double* st = L.stats;                                   // gate conv: r sums at +0; output conv: o sums (u sums at -2)
-  const double m0 = __ldcg(st) * L.fuse_inv_n;
-  const float rstd0 = rsqrtf((float)fmax(__ldcg(st + 1) * L.fuse_inv_n - m0 * m0, 0.0) + kGnEps);
-  double m1 = 0.0; float rstd1 = 0.0f;
-  if (L.fuse == 2) {
-    m1 = __ldcg(st - 2) * L.fuse_inv_n;
-    rstd1 = rsqrtf((float)fmax(__ldcg(st - 1) * L.fuse_inv_n - m1 * m1, 0.0) + kGnEps);
-  }
-#pragma unroll
-  for (int r = 0; r < kMaxOut / 2; ++r) {
-    if (r < nout) {
-      const int q = r * kRows + row_l;
-      const int p = (tile0 + (q >> 3)) * kGcTilePx + px_l;
-      if (p < npx) {
-        const int c = co0 + (q & 7);
-        const float a0 = __ldg(L.fuse_nw + c) * rstd0, b0 = __ldg(L.fuse_nb + c) - (float)m0 * a0;
-        float res;
-        if (L.fuse == 1) {
-          res = sigmoidf_(fmaf(vals[r], a0, b0)) * hv[r];
-        } else {
-          const float a1 = __ldg(L.fuse_uw + c) * rstd1, b1 = __ldg(L.fuse_ub + c) - (float)m1 * a1;
-          const float u = sigmoidf_(fmaf(gv[r], a1, b1));
-          res = u * hv[r] + (1.0f - u) * tanhf(fmaf(vals[r], a0, b0));       // module.py:57
-        }
-        L.fuse_dst[(long long)c * L.fuse_dst_cs + p] = res;
-      }
-    }
-  }
 }
 
 template <bool kAligned>
@@ -572,7 +437,6 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
   float (*part)[kGcCo][kGcTilePx] = reinterpret_cast<float (*)[kGcCo][kGcTilePx]>(gc_smem + 64 * 9 * kGcCo);   // 32 KB
   __shared__ double red[2][kGcWarps];
   pdl_release();
-  if (a.early_wait) pdl_wait();          // experiment knob (SATMVS_RED_EARLY_WAIT): no weight staging under the predecessor
   int li = 0;
 #pragma unroll
   for (int k = 1; k < 4; ++k) if ((int)blockIdx.x >= a.l[k].cta_begin) li = k;
@@ -583,212 +447,6 @@ gru_conv_kernel(const __grid_constant__ GruConvArgs a) {
   gru_conv_unit<kAligned, true>(a.l[li], blockIdx.x - a.l[li].cta_begin, wsm, part, red, true);
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Persistent recurrence: ONE cooperative launch runs phase B for all D planes.  Every CTA owns at most
-// one gate-conv unit and one output-conv unit for the whole sweep over depth, so their weights are
-// staged into shared memory once and stay resident; the four phases of a plane
-//     P1 gate conv (+GN sums) | E1 r*h | P2 output conv (+GN sums) | E2 state update
-// are separated by grid-wide barriers instead of kernel boundaries (no launch gaps, no cold restarts).
-// Tensors written inside the kernel are read back with ld.global.cg (coherent at L2).
-// ---------------------------------------------------------------------------------------------
-// out-of-line copy for the persistent kernel: its two call sites share one body and one register budget
-template <bool kAligned>
-__device__ __noinline__ void gru_conv_unit_coherent(const GruConvLevel& L, int cta, float* wsm,
-                                                    float (*part)[kGcCo][kGcTilePx], double (*red)[kGcWarps],
-                                                    bool stage_weights, unsigned long long* dbg) {
-  gru_conv_unit<kAligned, true>(L, cta, wsm, part, red, stage_weights, dbg);
-}
-
-struct RecLevel {
-  const float* s;  long long s_cs, s_ps;       // state history [ch][D+1][px]: channel stride, slot stride
-  float* gx;       long long g_cs;             // gates [2ch][D][px] (plane stride = px)
-  float* ox;       long long o_cs;             // output conv [ch][D][px]
-  float* rh;                                    // [ch][px]
-  const float* gate_w; const float* out_w; long long w_co;   // hidden-state halves of the conv weights
-  const float *rn_w, *rn_b, *un_w, *un_b, *on_w, *on_b;
-  double inv_n;
-  int ch, h, w, px;
-  int ksplit, ci_per_warp, px_groups1, px_groups2;
-  int p1_begin, p2_begin, e_begin;
-};
-struct RecArgs { RecLevel l[4]; double* stats; unsigned long long* dbg; int D; int p1_units, p2_units, e_total; };
-
-constexpr size_t kRecSmemBytes = (2 * 64 * 9 * kGcCo + kGcWarps * kGcCo * kGcTilePx) * sizeof(float);
-
-template <bool kAligned>
-__global__ void __launch_bounds__(kGcWarps * 32, 2)
-red_recurrence_kernel(const __grid_constant__ RecArgs a) {
-  extern __shared__ __align__(16) float rec_smem[];
-  float* wsm1 = rec_smem;
-  float* wsm2 = rec_smem + 64 * 9 * kGcCo;
-  float (*part)[kGcCo][kGcTilePx] = reinterpret_cast<float (*)[kGcCo][kGcTilePx]>(rec_smem + 2 * 64 * 9 * kGcCo);
-  __shared__ double red[2][kGcWarps];
-  cg::grid_group grid = cg::this_grid();
-  const int G = gridDim.x, bid = blockIdx.x;
-  const bool resident = (a.p1_units <= G);           // one unit per CTA per phase: weights staged once
-
-  auto level_of = [&](int unit, bool p2) {
-    int li = 0;
-#pragma unroll
-    for (int k = 1; k < 4; ++k) if (unit >= (p2 ? a.l[k].p2_begin : a.l[k].p1_begin)) li = k;
-    return li;
-  };
-  auto conv_level = [&](int li, int d, bool p2) {
-    const RecLevel& R = a.l[li];
-    GruConvLevel L{};
-    L.cin = R.ch; L.h = R.h; L.w_ = R.w; L.stats_group = R.ch;
-    L.ksplit = R.ksplit; L.ci_per_warp = R.ci_per_warp; L.w_co = R.w_co; L.cta_begin = 0;
-    double* st = a.stats + ((size_t)d * 4 + li) * 6;
-    if (!p2) {
-      L.in = R.s + (size_t)d * R.s_ps; L.in_cs = R.s_cs; L.w = R.gate_w;
-      L.pre = L.out = R.gx + (size_t)d * R.px; L.out_cs = R.g_cs; L.cout = 2 * R.ch;
-      L.stats = st; L.px_groups = R.px_groups1;
-    } else {
-      L.in = R.rh; L.in_cs = R.px; L.w = R.out_w;
-      L.pre = L.out = R.ox + (size_t)d * R.px; L.out_cs = R.o_cs; L.cout = R.ch;
-      L.stats = st + 4; L.px_groups = R.px_groups2;
-    }
-    return L;
-  };
-
-  unsigned long long tmark = 0, tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  auto mark = [&](int slot) {
-    if (a.dbg && bid == 0 && threadIdx.x == 0) {
-      unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      if (slot >= 0) tacc[slot] += t - tmark;
-      tmark = t;
-    }
-  };
-  mark(-1);
-  for (int d = 0; d < a.D; ++d) {
-    // ---- P1: gates[d] += conv(h[d]) ----
-    for (int u = bid; u < a.p1_units; u += G) {
-      const int li = level_of(u, false);
-      const GruConvLevel L = conv_level(li, d, false);
-      gru_conv_unit_coherent<kAligned>(L, u - a.l[li].p1_begin, wsm1, part, red, !resident || d == 0,
-                                       (a.dbg && bid == (int)(a.dbg[63] % gridDim.x)) ? a.dbg + 8 : nullptr);
-      if (!resident) __syncthreads();
-    }
-    mark(0);
-    grid.sync();
-    mark(1);
-    // ---- E1: rh = sigmoid(GN_r(G_r)) * h ----   (4 independent elements per iteration: loads first)
-    {
-      const int T = G * (kGcWarps * 32);
-      for (int i0 = bid * (kGcWarps * 32) + threadIdx.x; i0 < a.e_total; i0 += 4 * T) {
-        float gv[4], hv[4], ga[4], gb[4]; float* dst[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * T;
-          dst[u] = nullptr;
-          if (i < a.e_total) {
-            int li = 0;
-#pragma unroll
-            for (int k = 1; k < 4; ++k) if (i >= a.l[k].e_begin) li = k;
-            const RecLevel& R = a.l[li];
-            const int e = i - R.e_begin, c = e / R.px, p = e - c * R.px;
-            const double* st = a.stats + ((size_t)d * 4 + li) * 6;
-            const double mean = __ldcg(st) * R.inv_n;
-            const float rstd = rsqrtf((float)fmax(__ldcg(st + 1) * R.inv_n - mean * mean, 0.0) + kGnEps);
-            ga[u] = __ldg(R.rn_w + c) * rstd; gb[u] = __ldg(R.rn_b + c) - (float)mean * ga[u];
-            gv[u] = __ldcg(R.gx + (size_t)d * R.px + c * R.g_cs + p);
-            hv[u] = __ldcg(R.s + (size_t)d * R.s_ps + c * R.s_cs + p);
-            dst[u] = R.rh + e;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (dst[u]) *dst[u] = sigmoidf_(fmaf(gv[u], ga[u], gb[u])) * hv[u];
-      }
-    }
-    mark(2);
-    grid.sync();
-    mark(3);
-    // ---- P2: out[d] += conv(rh) ----
-    for (int u = bid; u < a.p2_units; u += G) {
-      const int li = level_of(u, true);
-      const GruConvLevel L = conv_level(li, d, true);
-      gru_conv_unit_coherent<kAligned>(L, u - a.l[li].p2_begin, wsm2, part, red, !resident || d == 0, nullptr);
-      if (!resident) __syncthreads();
-    }
-    mark(4);
-    grid.sync();
-    mark(5);
-    // ---- E2: h[d+1] = u*h + (1-u)*tanh(GN_o(O)) ----
-    {
-      const int T = G * (kGcWarps * 32);
-      for (int i0 = bid * (kGcWarps * 32) + threadIdx.x; i0 < a.e_total; i0 += 4 * T) {
-        float gv[4], ov[4], hv[4], ua[4], ub[4], oa[4], ob[4]; float* dst[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * T;
-          dst[u] = nullptr;
-          if (i < a.e_total) {
-            int li = 0;
-#pragma unroll
-            for (int k = 1; k < 4; ++k) if (i >= a.l[k].e_begin) li = k;
-            const RecLevel& R = a.l[li];
-            const int e = i - R.e_begin, c = e / R.px, p = e - c * R.px;
-            const double* st = a.stats + ((size_t)d * 4 + li) * 6;
-            const double um = __ldcg(st + 2) * R.inv_n, om = __ldcg(st + 4) * R.inv_n;
-            const float ur = rsqrtf((float)fmax(__ldcg(st + 3) * R.inv_n - um * um, 0.0) + kGnEps);
-            const float orr = rsqrtf((float)fmax(__ldcg(st + 5) * R.inv_n - om * om, 0.0) + kGnEps);
-            ua[u] = __ldg(R.un_w + c) * ur; ub[u] = __ldg(R.un_b + c) - (float)um * ua[u];
-            oa[u] = __ldg(R.on_w + c) * orr; ob[u] = __ldg(R.on_b + c) - (float)om * oa[u];
-            gv[u] = __ldcg(R.gx + (size_t)d * R.px + (c + R.ch) * R.g_cs + p);
-            ov[u] = __ldcg(R.ox + (size_t)d * R.px + c * R.o_cs + p);
-            hv[u] = __ldcg(R.s + (size_t)d * R.s_ps + c * R.s_cs + p);
-            dst[u] = const_cast<float*>(R.s) + (size_t)(d + 1) * R.s_ps + c * R.s_cs + p;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (dst[u]) {
-            const float uu = sigmoidf_(fmaf(gv[u], ua[u], ub[u]));
-            *dst[u] = uu * hv[u] + (1.0f - uu) * tanhf(fmaf(ov[u], oa[u], ob[u]));     // module.py:57
-          }
-      }
-    }
-    mark(6);
-    grid.sync();
-    mark(7);
-  }
-  if (a.dbg && bid == 0 && threadIdx.x == 0)
-    for (int i = 0; i < 8; ++i) a.dbg[i] = tacc[i];
-}
-
-// Launch the persistent recurrence if the device can keep enough CTAs co-resident; returns
-// SATMVS_OK + *launched = true on success, leaves *launched = false when the caller must fall back.
-static int red_recurrence_launch(RecArgs& ra, cudaStream_t st, bool* launched) {
-  *launched = false;
-  bool aligned = true;
-  for (int l = 0; l < 4; ++l) aligned = aligned && (ra.l[l].w % kGcPx == 0);
-  const void* fn = aligned ? (const void*)red_recurrence_kernel<true> : (const void*)red_recurrence_kernel<false>;
-  int dev = 0, coop = 0, sms = 0, per_sm = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (!coop) return SATMVS_OK;
-  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmemBytes) != cudaSuccess) {
-    cudaGetLastError();
-    return SATMVS_OK;
-  }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGcWarps * 32, kRecSmemBytes) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    return SATMVS_OK;
-  }
-  int grid = per_sm * sms;
-  if (grid > ra.p1_units) grid = ra.p1_units;
-  void* params[] = {&ra};
-  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kGcWarps * 32), params, kRecSmemBytes, st);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return SATMVS_OK;     // fall back to per-plane launches
-  }
-  *launched = true;
-  return SATMVS_OK;
-}
 
 static int gru_conv_launch(const GruConvArgs& c, int ctas, cudaStream_t st, const char* what, bool pdl) {
   bool aligned = true;
@@ -912,14 +570,15 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
                        void* workspace, size_t workspace_bytes, void* stream) {
   SATMVS_REQUIRE(wt && volume && logits && workspace);
   SATMVS_REQUIRE(C >= 1 && D >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
+  SATMVS_CHECK_ASYNC();
   cudaStream_t st = (cudaStream_t)stream;
   RedPlan P = red_plan(C, D, H, W, reinterpret_cast<char*>(workspace));
+  if (int* ae = async_error_devptr()) P.umma_err = ae;
   SATMVS_REQUIRE(workspace_bytes >= P.bytes);
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 
   cudaMemsetAsync(P.stats, 0, (size_t)D * 4 * 3 * 2 * sizeof(double), st);
-  cudaMemsetAsync(P.fuse_cnt, 0, (size_t)D * 4 * 2 * sizeof(int), st);
   for (int l = 0; l < 4; ++l) {   // slot 0 of the state history = the initial hidden state (zeros, module.py:617-620)
     RedLevel& L = P.lv[l];
     const size_t px = (size_t)L.h * L.w;
@@ -1146,73 +805,9 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     }
   }
   if (!persistent) g_red_last_path = 0;
-  if (!persistent) {
-    RecArgs ra{};
-    ra.stats = P.stats; ra.D = D;
-    static const bool dbg_timers = getenv("SATMVS_RED_DEBUG_TIMERS") != nullptr;
-    ra.dbg = dbg_timers ? reinterpret_cast<unsigned long long*>(P.stats + (size_t)D * 4 * 3 * 2) : nullptr;
-    if (ra.dbg) {
-      static unsigned long long dbg_block;
-      dbg_block = getenv("SATMVS_RED_DEBUG_BLOCK") ? strtoull(getenv("SATMVS_RED_DEBUG_BLOCK"), nullptr, 10) : 0ULL;
-      cudaMemsetAsync(ra.dbg, 0, 64 * sizeof(double), st);
-      cudaMemcpyAsync(ra.dbg + 63, &dbg_block, sizeof(dbg_block), cudaMemcpyHostToDevice, st);
-    }
-    int u1 = 0, u2 = 0, et = 0;
-    for (int l = 0; l < 4; ++l) {
-      RedLevel& L = P.lv[l];
-      RecLevel& R = ra.l[l];
-      const long long px = (long long)L.h * L.w;
-      R.s = L.s; R.s_cs = (long long)(D + 1) * px; R.s_ps = px;
-      R.gx = L.gx; R.g_cs = (long long)D * px;
-      R.ox = L.ox; R.o_cs = (long long)D * px;
-      R.rh = L.rh;
-      R.gate_w = wt->gate_w[l] + (size_t)L.cx * 9; R.out_w = wt->out_w[l] + (size_t)L.cx * 9;
-      R.w_co = (long long)(L.cx + L.ch) * 9;
-      R.rn_w = wt->rn_w[l]; R.rn_b = wt->rn_b[l]; R.un_w = wt->un_w[l]; R.un_b = wt->un_b[l];
-      R.on_w = wt->on_w[l]; R.on_b = wt->on_b[l];
-      R.inv_n = 1.0 / ((double)L.ch * (double)px);
-      R.ch = L.ch; R.h = L.h; R.w = L.w; R.px = (int)px;
-      GruConvLevel t{};
-      t.cin = L.ch; t.h = L.h; t.w_ = L.w;
-      t.cout = 2 * L.ch; R.p1_begin = u1; u1 = gru_conv_fill(t, u1); R.px_groups1 = t.px_groups;
-      t.cout = L.ch;     R.p2_begin = u2; u2 = gru_conv_fill(t, u2); R.px_groups2 = t.px_groups;
-      R.ksplit = t.ksplit; R.ci_per_warp = t.ci_per_warp;
-      R.e_begin = et; et += L.ch * (int)px;
-    }
-    ra.p1_units = u1; ra.p2_units = u2; ra.e_total = et;
-    // Opt-in (SATMVS_RED_PERSISTENT=1): measured 50.8 us/plane against 48 us/plane for the four per-plane
-    // launches at 96x192 (profiles/r01_red_recurrence_notes.md): the L2-only coherent loads and the waits at
-    // the grid barriers (level-4 units carry twice the work) cost more than the launch gaps they remove.
-    static const bool use_persist = getenv("SATMVS_RED_PERSISTENT") != nullptr;
-    if (use_persist) {
-      ProfScope prof(kProfGruGate, st);     // profiled as one class: the persistent kernel has no per-phase boundary
-      RUN(red_recurrence_launch(ra, st, &persistent));
-    }
-  }
   static const bool pdl = getenv("SATMVS_RED_NO_PDL") == nullptr;
-  // Fused pointwise tails (opt-in, SATMVS_RED_FUSE=1) need every CTA of a launch co-resident: their level barrier spins in
-  // global memory.  Measured at cfg-2: 3.29 ms/step fused against 2.90 ms with the four-kernel PDL chain -- the conv CTAs
-  // (128 registers, 2 per SM) now live through the barrier and the tail, so the next conv's CTAs cannot become resident
-  // early and its weight staging is no longer hidden (profiles/r01_red_recurrence_notes.md).
-  static const bool want_fuse = getenv("SATMVS_RED_FUSE") != nullptr;
-  int resident_ctas = 0;
-  if (want_fuse) {
-    bool aligned = true;
-    for (int l = 0; l < 4; ++l) aligned = aligned && (P.lv[l].w % kGcPx == 0);
-    constexpr size_t smem = (64 * 9 * kGcCo + kGcWarps * kGcCo * kGcTilePx) * sizeof(float);
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(gru_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const void* fn = aligned ? (const void*)gru_conv_kernel<true> : (const void*)gru_conv_kernel<false>;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGcThreads, smem) == cudaSuccess) resident_ctas = per_sm * sms;
-    else cudaGetLastError();
-  }
   for (int d = 0; d < D && !persistent; ++d) {
     GruConvArgs c1{}, c2{};
-    static const int early_wait = getenv("SATMVS_RED_EARLY_WAIT") ? atoi(getenv("SATMVS_RED_EARLY_WAIT")) : 0;
-    c1.early_wait = early_wait & 1; c2.early_wait = (early_wait >> 1) & 1;
     GruArgs ga{};
     int total = 0, ctas1 = 0, ctas2 = 0;
     for (int l = 0; l < 4; ++l) {
@@ -1247,57 +842,14 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       total += L.ch * (int)px;
     }
     ga.total = total;
-    // vectorised pointwise kernels: 4 pixels per thread when every plane size is a multiple of 4 and the bases are 16-byte aligned
-    GruArgs ga4 = ga;
-    // opt-in (SATMVS_RED_VEC4=1): 0.87 against 1.06 ms per step when timed launch by launch, but the PDL chain as a whole is
-    // slower with them (2.86 against 2.79 ms/step, same box): profiles/r01_red_recurrence_notes.md
-    static const bool want_vec4 = getenv("SATMVS_RED_VEC4") != nullptr;
-    bool vec4 = want_vec4;
-    {
-      int t4 = 0;
-      for (int l = 0; l < 4; ++l) {
-        GruLevelArgs& e = ga4.l[l];
-        vec4 = vec4 && (e.px % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.g) | reinterpret_cast<uintptr_t>(e.o) |
-                                            reinterpret_cast<uintptr_t>(e.hprev) | reinterpret_cast<uintptr_t>(e.hnext) |
-                                            reinterpret_cast<uintptr_t>(e.rh)) % 16 == 0);
-        e.begin = t4;
-        t4 += e.ch * (e.px / 4);
-      }
-      ga4.total = t4;
-    }
-    const bool fuse = want_fuse && ctas1 <= resident_ctas && ctas2 <= resident_ctas;
-    if (fuse) {
-      for (int l = 0; l < 4; ++l) {
-        RedLevel& L = P.lv[l];
-        const size_t px = (size_t)L.h * L.w;
-        GruConvLevel &a = c1.l[l], &b = c2.l[l];
-        a.fuse = 1; b.fuse = 2;
-        a.fuse_counter = P.fuse_cnt + ((size_t)d * 4 + l) * 2; b.fuse_counter = a.fuse_counter + 1;
-        a.fuse_expected = a.px_groups * (L.ch / kGcCo);      // the CTAs of the r half
-        b.fuse_expected = b.px_groups * (L.ch / kGcCo);
-        a.fuse_inv_n = b.fuse_inv_n = 1.0 / ((double)L.ch * (double)px);
-        a.fuse_nw = wt->rn_w[l]; a.fuse_nb = wt->rn_b[l];
-        b.fuse_nw = wt->on_w[l]; b.fuse_nb = wt->on_b[l]; b.fuse_uw = wt->un_w[l]; b.fuse_ub = wt->un_b[l];
-        a.fuse_h = b.fuse_h = L.s + (size_t)d * px; a.fuse_h_cs = b.fuse_h_cs = (long long)(D + 1) * px;
-        b.fuse_gu = L.gx + (size_t)d * px + (size_t)L.ch * D * px; b.fuse_g_cs = (long long)D * px;
-        a.fuse_dst = L.rh; a.fuse_dst_cs = (long long)px;
-        b.fuse_dst = L.s + (size_t)(d + 1) * px; b.fuse_dst_cs = (long long)(D + 1) * px;
-      }
-      // two launches per plane: gate conv + r*h, output conv + state update
-      { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates + reset)", pdl && d > 0)); }
-      { ProfScope prof(kProfGruOutput, st); RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output + update)", pdl)); }
-      continue;
-    }
     // the first gate conv follows the batched launches (plain stream order); everything after it is chained
     { ProfScope prof(kProfGruGate, st); RUN(gru_conv_launch(c1, ctas1, st, "gru_conv_kernel (gates)", pdl && d > 0)); }
     { ProfScope prof(kProfGruPointwise, st);
-      if (vec4) launch_chain(gru_reset4_kernel, ceil_div(ga4.total, 256), 256, 0, st, pdl, ga4);
-      else launch_chain(gru_reset_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
+      launch_chain(gru_reset_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
       RUN(check_launch("gru_reset_kernel")); }
     { ProfScope prof(kProfGruOutput, st); RUN(gru_conv_launch(c2, ctas2, st, "gru_conv_kernel (output)", pdl)); }
     { ProfScope prof(kProfGruPointwise, st);
-      if (vec4) launch_chain(gru_update4_kernel, ceil_div(ga4.total, 256), 256, 0, st, pdl, ga4);
-      else launch_chain(gru_update_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
+      launch_chain(gru_update_kernel, ceil_div(total, 256), 256, 0, st, pdl, ga);
       RUN(check_launch("gru_update_kernel")); }
   }
 

@@ -56,7 +56,7 @@ struct ClLevel {
   int ch, h, w, px;
   int CG, R;                             // channel groups (ch / 8), rows per strip (ceil(h / (16 / CG)))
 };
-struct ClArgs { ClLevel l[4]; int D; int nb; unsigned long long* dbg; };   // nb: clusters in role B (2 or 3);   // dbg: [6 clusters][16 slots] SM cycles per phase (SATMVS_RED_DEBUG)
+struct ClArgs { ClLevel l[4]; int D; int nb; unsigned long long* dbg; int* err; };   // nb: clusters in role B (2 or 3);   // dbg: [6 clusters][16 slots] SM cycles per phase (SATMVS_RED_DEBUG)
 
 struct ClSmemPlan { int wsm, tile, part, keep, total_floats; };
 __host__ __device__ inline ClSmemPlan cl_smem_plan(int ch, int w, int R) {
@@ -354,7 +354,7 @@ red_cluster_kernel(const __grid_constant__ ClArgs a) {
       // never arrives (~4 s) the kernel traps and the error surfaces at the caller's next synchronisation instead of a hang
       const long long t0 = clock64();
       while (cl_ld_acquire(flag) < target)
-        if (clock64() - t0 > (1LL << 33)) __trap();
+        if (clock64() - t0 > (1LL << 32)) { if (a.err) *reinterpret_cast<volatile int*>(a.err) = 3; break; }   // report (common.cuh), do not trap the context
     }
     __syncthreads();
   };
@@ -530,6 +530,7 @@ inline size_t red_cluster_smem_bytes(const ClArgs& a, int smem_optin) {
 // *launched stays false when the shape or the device does not take it (the caller then runs the per-plane chain).
 inline int red_cluster_launch(ClArgs& a, int* flags_base, cudaStream_t st, bool* launched) {
   *launched = false;
+  a.err = async_error_devptr();
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -196,7 +196,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
         int v;
         do {
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(L.ready + d) : "memory");
-          if (v < L.expected && clock64() - t0 > (1LL << 32)) { atomicExch(err, 2); break; }      // ~2 s: give up loudly, never hang
+          if (v < L.expected && clock64() - t0 > (1LL << 32)) { *reinterpret_cast<volatile int*>(err) = 2; break; }      // ~2 s: give up loudly, never hang
         } while (v < L.expected);
         asm volatile("fence.proxy.async;" ::: "memory");                 // acquired by the generic proxy, read by the TMA engine
       }
@@ -610,7 +610,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
     else asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     mark(9);
   }
-  if (!alive && tid == 0) atomicExch(err, 1);
+  if (!alive && tid == 0) *reinterpret_cast<volatile int*>(err) = 1;
   if (dbg != nullptr && tid == 0 && (rank == 0))
 #pragma unroll
     for (int i = 0; i < 16; ++i) dbg[(blockIdx.x / kTcCluster) * 16 + i] = sh.t_acc[i];

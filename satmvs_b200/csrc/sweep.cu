@@ -26,9 +26,6 @@
 #ifndef SATMVS_MIN_BLOCKS
 #define SATMVS_MIN_BLOCKS 1
 #endif
-#ifndef SATMVS_SWEEP_V
-#define SATMVS_SWEEP_V 3  // 2 = scalar vec4 kernel, 3 = smem records + packed f32x2 (v4 = 3 + TMA staging is a run-time opt-in)
-#endif
 #ifndef SATMVS_NP
 #define SATMVS_NP 4       // hypothesis planes evaluated in lock step in the v3 geometry phase
 #endif
@@ -159,87 +156,6 @@ __device__ __forceinline__ float4 tap_fetch4(const float4* __restrict__ f0, cons
   r.z = __fmaf_rn(d.z, t.w11, __fmaf_rn(c.z, t.w10, __fmaf_rn(b.z, t.w01, __fmul_rn(a.z, t.w00))));
   r.w = __fmaf_rn(d.w, t.w11, __fmaf_rn(c.w, t.w10, __fmaf_rn(b.w, t.w01, __fmul_rn(a.w, t.w00))));
   return r;
-}
-
-template <class Geo, int DK, bool kVariance>
-__global__ void __launch_bounds__(kSweepThreads, SATMVS_MIN_BLOCKS)
-sweep_fwd_vec4_kernel(const __grid_constant__ SweepArgs<Geo> a) {
-  constexpr int NSRC = Geo::kNumSrc;
-  const int HW = a.H * a.W;
-  const int pix = blockIdx.x * kSweepThreads + threadIdx.x;
-  const bool active = pix < HW;
-  const int pixc = active ? pix : HW - 1;
-  const int y = pixc / a.W, x = pixc - y * a.W;
-  const int d0 = blockIdx.y * DK;
-
-  Tap taps[DK][NSRC];
-  {
-    const typename Geo::Pixel px = a.geo.pixel(x, y);
-#pragma unroll
-    for (int k = 0; k < DK; ++k) {
-      const int d = min(d0 + k, a.D - 1);
-      const float h = a.depth_per_pixel ? __ldg(a.depth + (size_t)d * HW + pixc) : __ldg(a.depth + d);
-      const typename Geo::Plane pl = a.geo.plane(px, h);
-#pragma unroll
-      for (int v = 0; v < NSRC; ++v) {
-        float gx, gy;
-        a.geo.project(v, px, pl, gx, gy);
-        taps[k][v] = make_tap(gx, gy, a.H, a.W, a.half_w, a.half_h);
-        if (v >= a.n_src) { taps[k][v].w00 = taps[k][v].w01 = taps[k][v].w10 = taps[k][v].w11 = 0.0f; taps[k][v].off = 0; }
-      }
-    }
-  }
-
-  const size_t plane_stride = (size_t)HW;
-  const int C4 = a.C >> 2;
-  for (int q = 0; q < C4; ++q) {
-    float r[4] = {0.f, 0.f, 0.f, 0.f}, r2[4];
-    if (kVariance) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = __ldg(a.ref_fea + (size_t)(4 * q + j) * HW + pixc);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) r2[j] = __fmul_rn(r[j], r[j]);
-    const size_t oidx = ((size_t)(4 * q) * a.out_D + a.out_d0 + d0) * plane_stride + pix;
-#pragma unroll
-    for (int k = 0; k < DK; ++k) {
-      if (d0 + k < a.D) {
-        float s[4] = {r[0], r[1], r[2], r[3]}, qq[4] = {r2[0], r2[1], r2[2], r2[3]};
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int v = 0; v < NSRC; ++v) {
-          const float4* f0 = a.src_v4[v] + (size_t)q * HW;
-          val = tap_fetch4(f0, f0 + a.W, taps[k][v]);
-          if (kVariance) {
-            const float vv[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              s[j] = __fadd_rn(s[j], vv[j]);
-              qq[j] = __fadd_rn(qq[j], __fmul_rn(vv[j], vv[j]));
-            }
-          }
-        }
-        float res[4] = {val.x, val.y, val.z, val.w};
-        if (kVariance) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float m = div_const(s[j], a.num_views, a.inv_num_views);
-            res[j] = __fsub_rn(div_const(qq[j], a.num_views, a.inv_num_views), __fmul_rn(m, m));
-          }
-        }
-        if (active) {
-          for (int o = 0; o < a.n_out; ++o) {
-            float* op = a.out[o] + oidx + (size_t)k * plane_stride;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (a.multicast) mc_store(op + (size_t)j * a.out_D * plane_stride, res[j]);
-              else __stcs(op + (size_t)j * a.out_D * plane_stride, res[j]);
-            }
-          }
-        }
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -412,18 +328,22 @@ sweep_fwd_v3_kernel(const __grid_constant__ SweepArgs<Geo> a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// v4 of the forward sweep: v3 + the source window of the CTA staged in shared memory by the TMA engine.
-// A CTA owns a segment of one reference row x DK planes.  After the geometry phase the CTA knows, per
-// source view, the bounding box of all its taps; for every pass over CH channels it copies that box
-// (rows of the [C/4][H][W] float4 re-pack are contiguous, so one cp.async.bulk per (view, quad, row),
-// completion counted on an mbarrier) and every tap of the pass becomes a shared-memory read with fixed
-// latency.  v3 re-read the same lines from L2 for every plane (L1 hit rate 54 %, long-scoreboard stalls
-// 46-60 %); here each source pixel crosses L2->SM once per CTA and pass.  If a view's box does not fit the
-// staging buffer (steep geometry) the CTA reads that pass straight from global memory through the same
-// generic-pointer code path.
+// v5 of the forward sweep (default): 2-D reference tiles + TMA-staged, double-buffered source windows.
+//   CTA      = 32 x TH reference pixels (one warp per tile row) x DK planes; 3-4 CTAs per SM.
+//   phase A  fp64 geometry (lock-step planes) -> tap records in shared memory + per-view bounding box
+//            of the clamped tap origins (packed u16x2 min/max, warp redux, shared atomics).
+//   fix-up   each thread rewrites its own records into window-relative offsets (or global offsets
+//            when a view's box does not fit the staging buffer: steep geometry falls back to L1/L2).
+//   phase B  passes of CH (8) channels.  Warp 0 issues one cp.async.bulk per (view, quad, row) of the
+//            [C/4][H][W] float4 re-pack into stage (p+1)&1 BEFORE the CTA gathers pass p from stage p&1
+//            (completion on one mbarrier per stage), so the copy latency hides under the gather.  The
+//            pitch is padded to 8 pixels so that row breaks inside a quarter-warp stay conflict-free;
+//            every tap is an LDS.128 at base + immediate (no per-load address arithmetic).
+// The kernel is launched as a programmatic dependent of pack_vec4_kernel: its geometry phase overlaps
+// the re-pack, griddepcontrol.wait sits in front of the first read of the packed features.
+// Arithmetic and op order are those of v1/v3: results are bit-identical.
 // ------------------------------------------------------------------------------------------
-constexpr int kWinPx = 384;                    // staging capacity per (view, quad) in pixels (6 KB)
-
+// mbarrier / TMA bulk-copy helpers of the staged kernel
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -447,190 +367,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <class Geo, int DK, int CH, bool kVariance>
-__global__ void __launch_bounds__(kSweepThreads, SATMVS_MIN_BLOCKS)
-sweep_fwd_v4_kernel(const __grid_constant__ SweepArgs<Geo> a, int seg_w, int segs_per_row) {
-  constexpr int NSRC = Geo::kNumSrc;
-  constexpr int NP = DK < SATMVS_NP ? DK : SATMVS_NP;
-  constexpr int NQ = CH / 4;
-  extern __shared__ __align__(128) unsigned char v4_smem[];
-  float4* win = reinterpret_cast<float4*>(v4_smem);                                        // [NSRC][NQ][kWinPx]
-  int (*rec_xy)[kSweepThreads] = reinterpret_cast<int (*)[kSweepThreads]>(win + NSRC * NQ * kWinPx);
-  TapW (*rec_w)[kSweepThreads] = reinterpret_cast<TapW (*)[kSweepThreads]>(rec_xy + DK * NSRC);
-  __shared__ int bbox[NSRC][4];                 // xmin, xmax, ymin, ymax of the clamped tap origins
-  __shared__ __align__(8) unsigned long long mbar;
 
-  const int HW = a.H * a.W;
-  const int tid = threadIdx.x;
-  const int y = blockIdx.x / segs_per_row, x = (blockIdx.x % segs_per_row) * seg_w + tid;
-  const bool active = tid < seg_w && x < a.W;
-  const int xcl = min(x, a.W - 1);
-  const int pix = y * a.W + xcl;
-  const int d0 = blockIdx.y * DK;
-
-  if (tid < NSRC) { bbox[tid][0] = 1 << 30; bbox[tid][1] = -1; bbox[tid][2] = 1 << 30; bbox[tid][3] = -1; }
-  if (tid == 0) mbar_init(&mbar, 1);
-  __syncthreads();
-
-  {  // ---- phase A: geometry, records, bounding boxes ----
-    int bx0[NSRC], bx1[NSRC], by0[NSRC], by1[NSRC];
-#pragma unroll
-    for (int v = 0; v < NSRC; ++v) { bx0[v] = 1 << 30; bx1[v] = -1; by0[v] = 1 << 30; by1[v] = -1; }
-    const typename Geo::Pixel px = a.geo.pixel(xcl, y);
-#pragma unroll 1
-    for (int g = 0; g < DK; g += NP) {
-      float h[NP];
-#pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        const int d = min(d0 + g + k, a.D - 1);
-        h[k] = a.depth_per_pixel ? __ldg(a.depth + (size_t)d * HW + pix) : __ldg(a.depth + d);
-      }
-      a.geo.template grid_coords<NP>(px, h, [&](int k, int v, float gx, float gy) {
-        TapXY t = make_tap_xy(gx, gy, a.H, a.W, a.half_w, a.half_h);
-        if (v >= a.n_src || !active) { t.w00 = t.w01 = t.w10 = t.w11 = 0.0f; t.live = false; }
-        if (t.live) {
-#pragma unroll
-          for (int vv = 0; vv < NSRC; ++vv)
-            if (vv == v) { bx0[vv] = min(bx0[vv], t.xc); bx1[vv] = max(bx1[vv], t.xc); by0[vv] = min(by0[vv], t.yc); by1[vv] = max(by1[vv], t.yc); }
-        } else {
-          t.xc = -1; t.yc = -1;            // resolved to the window origin below (weights are zero)
-        }
-        rec_xy[(g + k) * NSRC + v][tid] = (t.yc << 16) | (t.xc & 0xffff);
-        rec_w[(g + k) * NSRC + v][tid] = TapW{t.w00, t.w01, t.w10, t.w11};
-      });
-    }
-#pragma unroll
-    for (int v = 0; v < NSRC; ++v) {
-      const int m0 = __reduce_min_sync(0xffffffffu, bx0[v]), m1 = __reduce_max_sync(0xffffffffu, bx1[v]);
-      const int m2 = __reduce_min_sync(0xffffffffu, by0[v]), m3 = __reduce_max_sync(0xffffffffu, by1[v]);
-      if ((tid & 31) == 0) { atomicMin(&bbox[v][0], m0); atomicMax(&bbox[v][1], m1); atomicMin(&bbox[v][2], m2); atomicMax(&bbox[v][3], m3); }
-    }
-  }
-  __syncthreads();
-
-  // window geometry per view (uniform): origin, pitch, rows; staged = fits the buffer
-  int xs[NSRC], ys[NSRC], wc[NSRC], rows[NSRC];
-  bool staged = true;
-#pragma unroll
-  for (int v = 0; v < NSRC; ++v) {
-    if (bbox[v][1] < 0) { xs[v] = 0; ys[v] = 0; wc[v] = 2; rows[v] = 2; }            // no live tap at all
-    else { xs[v] = bbox[v][0]; ys[v] = bbox[v][2]; wc[v] = bbox[v][1] - bbox[v][0] + 2; rows[v] = bbox[v][3] - bbox[v][2] + 2; }
-    staged = staged && (wc[v] * rows[v] <= kWinPx);
-  }
-
-  const unsigned upix = (unsigned)pix * 4u;
-  const size_t plane_bytes = (size_t)HW * sizeof(float);
-  const u64 vinv = pk(a.inv_num_views, a.inv_num_views), vneg = pk(-a.num_views, -a.num_views);
-  unsigned parity = 0;
-  for (int c0 = 0; c0 < a.C; c0 += CH) {
-    const int q0 = c0 >> 2;
-    if (staged) {
-      __syncthreads();                            // every thread is done reading the previous pass's window
-      if (tid == 0) {
-        unsigned total = 0;
-#pragma unroll
-        for (int v = 0; v < NSRC; ++v) total += (unsigned)(NQ * rows[v] * wc[v]) * 16u;
-        mbar_expect_tx(&mbar, total);             // armed before any copy is issued
-      }
-      __syncthreads();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads above -> async-proxy writes below
-      // one bulk copy per (view, quad, row), spread over the threads
-#pragma unroll
-      for (int v = 0; v < NSRC; ++v) {
-        const int n = NQ * rows[v];
-        for (int i = tid; i < n; i += (int)blockDim.x) {
-          const int qd = i / rows[v], r = i - qd * rows[v];
-          const float4* src = a.src_v4[v] + ((size_t)(q0 + qd) * a.H + ys[v] + r) * a.W + xs[v];
-          bulk_g2s(win + ((size_t)v * NQ + qd) * kWinPx + r * wc[v], src, (unsigned)wc[v] * 16u, &mbar);
-        }
-      }
-      mbar_wait(&mbar, parity);
-      parity ^= 1u;
-    }
-
-    u64 r[CH / 2];
-#pragma unroll
-    for (int j = 0; j < CH / 2; ++j) {
-      float lo = 0.f, hi = 0.f;
-      if (kVariance) {
-        const char* rb = reinterpret_cast<const char*>(a.ref_fea) + (size_t)(c0 + 2 * j) * plane_bytes;
-        lo = __ldg(reinterpret_cast<const float*>(rb + upix));
-        hi = __ldg(reinterpret_cast<const float*>(rb + plane_bytes + upix));
-      }
-      r[j] = pk(lo, hi);
-    }
-#pragma unroll 1
-    for (int k = 0; k < DK; ++k) {
-      if (d0 + k >= a.D) break;
-      u64 s[CH / 2], q[CH / 2];
-#pragma unroll
-      for (int j = 0; j < CH / 2; ++j) { s[j] = r[j]; q[j] = mul2_rounded(r[j], r[j]); }
-#pragma unroll
-      for (int v = 0; v < NSRC; ++v) {
-        const int xy = rec_xy[k * NSRC + v][tid];
-        const TapW w = rec_w[k * NSRC + v][tid];
-        int xc = (int)(short)(xy & 0xffff), yc = xy >> 16;
-        if (xc < 0) { xc = xs[v]; yc = ys[v]; }
-        const u64 w00 = pk(w.w00, w.w00), w01 = pk(w.w01, w.w01), w10 = pk(w.w10, w.w10), w11 = pk(w.w11, w.w11);
-        // generic pointers: the staged window or the global re-pack, same code
-        const float4* base; int pitch; size_t qstride;
-        if (staged) { base = win + (size_t)v * NQ * kWinPx + (yc - ys[v]) * wc[v] + (xc - xs[v]); pitch = wc[v]; qstride = kWinPx; }
-        else { base = a.src_v4[v] + (size_t)q0 * HW + (size_t)yc * a.W + xc; pitch = a.W; qstride = (size_t)HW; }
-#pragma unroll
-        for (int qd = 0; qd < NQ; ++qd) {
-          const float4* b0 = base + qd * qstride;
-          const float4 A = b0[0], B = b0[1], Cc = b0[pitch], Dd = b0[pitch + 1];
-          u64 lo = fma2(pk(Dd.x, Dd.y), w11, fma2(pk(Cc.x, Cc.y), w10, fma2(pk(B.x, B.y), w01, mul2(pk(A.x, A.y), w00))));
-          u64 hi = fma2(pk(Dd.z, Dd.w), w11, fma2(pk(Cc.z, Cc.w), w10, fma2(pk(B.z, B.w), w01, mul2(pk(A.z, A.w), w00))));
-          if (kVariance) {
-            s[2 * qd] = add2(s[2 * qd], lo);         q[2 * qd] = add2(q[2 * qd], mul2_rounded(lo, lo));
-            s[2 * qd + 1] = add2(s[2 * qd + 1], hi); q[2 * qd + 1] = add2(q[2 * qd + 1], mul2_rounded(hi, hi));
-          } else {
-            s[2 * qd] = lo; s[2 * qd + 1] = hi;
-          }
-        }
-      }
-      const size_t obase = ((size_t)c0 * a.out_D + a.out_d0 + d0 + k) * plane_bytes;
-      const size_t ostride = (size_t)a.out_D * plane_bytes;
-#pragma unroll
-      for (int j = 0; j < CH / 2; ++j) {
-        u64 res = s[j];
-        if (kVariance) {
-          u64 m = mul2(s[j], vinv);  m = fma2(fma2(vneg, m, s[j]), vinv, m);
-          u64 e = mul2(q[j], vinv);  e = fma2(fma2(vneg, e, q[j]), vinv, e);
-          res = sub2(e, mul2_rounded(m, m));
-        }
-        float lo, hi;
-        upk(res, lo, hi);
-        if (active) {
-          char* ob = reinterpret_cast<char*>(a.out[0]) + obase + (size_t)(2 * j) * ostride;
-          __stcs(reinterpret_cast<float*>(ob + upix), lo);
-          __stcs(reinterpret_cast<float*>(ob + ostride + upix), hi);
-        }
-      }
-    }
-  }
-}
-
-template <int DK, int NSRC, int CH>
-constexpr size_t v4_smem_bytes() { return (size_t)NSRC * (CH / 4) * kWinPx * 16 + (size_t)DK * NSRC * kSweepThreads * (4 + 16); }
-
-// ------------------------------------------------------------------------------------------
-// v5 of the forward sweep (default): 2-D reference tiles + TMA-staged, double-buffered source windows.
-//   CTA      = 32 x TH reference pixels (one warp per tile row) x DK planes; 3-4 CTAs per SM.
-//   phase A  fp64 geometry (lock-step planes) -> tap records in shared memory + per-view bounding box
-//            of the clamped tap origins (packed u16x2 min/max, warp redux, shared atomics).
-//   fix-up   each thread rewrites its own records into window-relative offsets (or global offsets
-//            when a view's box does not fit the staging buffer: steep geometry falls back to L1/L2).
-//   phase B  passes of CH (8) channels.  Warp 0 issues one cp.async.bulk per (view, quad, row) of the
-//            [C/4][H][W] float4 re-pack into stage (p+1)&1 BEFORE the CTA gathers pass p from stage p&1
-//            (completion on one mbarrier per stage), so the copy latency hides under the gather.  The
-//            pitch is padded to 8 pixels so that row breaks inside a quarter-warp stay conflict-free;
-//            every tap is an LDS.128 at base + immediate (no per-load address arithmetic).
-// The kernel is launched as a programmatic dependent of pack_vec4_kernel: its geometry phase overlaps
-// the re-pack, griddepcontrol.wait sits in front of the first read of the packed features.
-// Arithmetic and op order are those of v1/v3: results are bit-identical.
-// ------------------------------------------------------------------------------------------
 #ifndef SATMVS_V5_KUNROLL
 #define SATMVS_V5_KUNROLL 2
 #endif
@@ -1070,29 +807,6 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
   ProfScope prof(kProfSweep, st);
   a.neg_zero = -0.0f;
   if (a.src_v4[0] != nullptr) {
-#if SATMVS_SWEEP_V == 2
-    sweep_fwd_vec4_kernel<Geo, DK, kVariance><<<grid, kSweepThreads, 0, st>>>(a);
-    return check_launch("sweep_fwd_vec4_kernel");
-#else
-    // Opt-in (SATMVS_SWEEP_TMA=1): the TMA-staged variant is bit-identical but measured 161 us against 110 us for
-    // v3 at cfg-2 (single-buffered staging, 2 CTAs x 3 warps per SM): profiles/r01_sweep_v3_notes.md.
-    static const bool use_tma = getenv("SATMVS_SWEEP_TMA") != nullptr;
-    if (use_tma && a.n_out == 1 && !a.multicast && a.C % SATMVS_CH == 0 && a.W < 32768 && a.H < 32768) {
-      constexpr int NS = Geo::kNumSrc;
-      constexpr size_t smem = v4_smem_bytes<DK, NS, SATMVS_CH>();
-      if (smem <= 200 * 1024) {
-        auto kern = sweep_fwd_v4_kernel<Geo, DK, SATMVS_CH, kVariance>;
-        static thread_local int ready_dev = -1;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (ready_dev != dev) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ready_dev = dev; }
-        const int segs = ceil_div(a.W, kSweepThreads);
-        const int seg_w = ((ceil_div(a.W, segs) + 31) / 32) * 32;
-        dim3 g4(a.H * segs, ceil_div(a.D, DK));
-        kern<<<g4, seg_w, smem, st>>>(a, seg_w, segs);
-        return check_launch("sweep_fwd_v4_kernel");
-      }
-    }
     static const bool no_v5 = getenv("SATMVS_SWEEP_V3") != nullptr;
     if (!no_v5) {
       const int rc = dispatch_v5<Geo, kVariance>(a, st, a.packed_now != 0 && !prof_state().on);
@@ -1103,7 +817,6 @@ static int launch_fwd(SweepArgs<Geo>& a, cudaStream_t st) {
     else if (a.C % SATMVS_CH == 0) sweep_fwd_v3_kernel<Geo, DK, SATMVS_CH, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
     else sweep_fwd_v3_kernel<Geo, DK, 4, kVariance, false><<<grid, kSweepThreads, 0, st>>>(a);
     return check_launch("sweep_fwd_v3_kernel");
-#endif
   }
   sweep_fwd_kernel<Geo, DK, kVariance><<<grid, kSweepThreads, 0, st>>>(a);
   return check_launch("sweep_fwd_kernel");

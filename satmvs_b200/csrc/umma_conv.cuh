@@ -256,7 +256,7 @@ umma_conv2d_kernel(const __grid_constant__ UmmaConv2d a, int* error_flag) {
   alive = uc_wait(&bar, (unsigned)(done - 1) & 1u) && alive;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!alive) {            // a tensor-core completion never arrived: fail loudly (sticky CUDA error) instead of storing garbage
-    if (tid == 0) atomicExch(error_flag, 1);
+    if (tid == 0) *reinterpret_cast<volatile int*>(error_flag) = 1;
     __trap();
   }
 
@@ -586,7 +586,7 @@ umma_conv_tn_kernel(const __grid_constant__ UmmaConvTn a, int* error_flag) {
   alive = uc_wait(&bar, (unsigned)(done - 1) & 1u) && alive;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!alive) {
-    if (tid == 0) atomicExch(error_flag, 1);
+    if (tid == 0) *reinterpret_cast<volatile int*>(error_flag) = 1;
     __trap();
   }
 
