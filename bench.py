@@ -521,20 +521,27 @@ def run_ours(args, w):
             elif name in flops:
                 fl = flops[name]
                 cluster = name == "gru_gate_conv" and prof.launches["gru_output_conv"] == 0
-                if cluster:     # red_cluster_kernel: ONE launch runs gate convs, output convs and the pointwise steps of all planes
+                red_path = _lib.lib().satmvs_red_last_path()
+                if cluster:     # ONE kernel (possibly launched in plane chunks) runs gate convs, output convs and the pointwise steps of all planes
                     fl += flops["gru_output_conv"]
-                    k["kernel"] = "red_cluster_kernel (whole depth recurrence: 6 clusters x 16 CTAs = 96 of 148 SMs)"
+                    if red_path >= 2:
+                        k["kernel"] = ("red_tc_kernel (whole depth recurrence on tcgen05: 4 clusters x 16 CTAs = 64 of 148 SMs"
+                                       + (", launched per chunk of planes, overlapped with the batched convs)" if red_path == 3 else ")"))
+                        k["bound_note"] = ("sequential-in-depth recurrence: per plane two dependent convolutions (A-operand shared-memory "
+                                           "reads bound the small-N MMAs of levels 0/1), two cluster-wide GroupNorm reductions and two halo "
+                                           "exchanges; useful flops (1 MAC = 2 flop; the 3xTF32 split issues 3x as many) against the dense bf16 "
+                                           "tensor peak; ncu: sm__pipe_tensor_cycles_active in profiles/r02_red_tc.txt")
+                    else:
+                        k["kernel"] = "red_cluster_kernel (whole depth recurrence, FFMA2: 6 clusters x 16 CTAs = 96 of 148 SMs)"
+                        k["bound_note"] = "sequential-in-depth recurrence on fp32 FFMA2: latency-bound (L2 round trips + barriers)"
                     k["us_per_plane"] = 1e3 * t_ms / prof_steps / w["D"]
                     k["fp32_ffma_frac"] = fl / (t_ms / prof_steps * 1e-3) / (148 * 128 * 2 * 1.965e9)
-                    k["bound_note"] = ("sequential-in-depth recurrence: latency-bound (L2 round trips + barriers between the two "
-                                       "convolutions of a plane); N = 8 output channels per CTA rules out tcgen05, so the useful "
-                                       "fraction is fp32_ffma_frac (FFMA peak of all 148 SMs), not the tensor figure")
                 ach = fl / (t_ms / prof_steps * 1e-3) / 1e12
                 note = ("tcgen05 kind::tf32, 3 MMAs per useful multiply-add (hi*hi + hi*lo + lo*hi) + FFMA2 direct kernels for the "
                         "rest; useful flops against the dense bf16 tensor peak" if name == "conv_batched"
                         else "fp32 FFMA2 kernels (latency-bound recurrence / decoder) measured against the dense bf16 tensor peak")
                 k["roofline"] = {"bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
-                                 "traffic": ncu_traffic("red_cluster", w) if cluster else None,
+                                 "traffic": ncu_traffic("red_tc" if red_path >= 2 else "red_cluster", w) if cluster else None,
                                  "algorithmic_flops_per_step": fl, "note": note}
             kernels.append(k)
         kernels.sort(key=lambda k: -k["share"])
@@ -607,7 +614,7 @@ def featurenet_block(dev, flush, V=3, H=384, W=768):
     ms = sorted(ts)[len(ts) // 2]
     return {"views": V, "image_hw": [H, W], "ms": ms, "ms_best": min(ts), "megapixels_per_s": V * px / (ms * 1e-3) / 1e6,
             "approx_tflops_fp32": flop / (ms * 1e-3) / 1e12,
-            "note": "fp32 FFMA implicit-GEMM engine; includes the [B,3,V,H,W] stacking copy and the per-view output copies"}
+            "note": "3x3 stride-1 layers on tcgen05 (3xTF32), the rest on the fp32 FFMA implicit-GEMM engine; includes the [B,3,V,H,W] stacking copy and the per-view output copies"}
 
 
 def sharded_block(args, dev, rank, world, barrier, flush):

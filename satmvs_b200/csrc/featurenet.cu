@@ -7,9 +7,13 @@
 // plane (the conv engine's "depth" axis carries the views).  Inference-mode BatchNorm arrives folded to per-channel
 // scale / shift.  The two concatenations never happen: the skip tensors (conv0, conv1 outputs) are produced directly in the
 // upper channel halves of the concatenation buffers and the transposed convs write the lower halves.
-// Kernels: the fp32 implicit-GEMM engine (conv_engine.cuh) with 3x3 / 5x5-stride-2 / 1x1 / transposed-parity tap lists.
+// Kernels: the 3x3 stride-1 layers with >= 8 input channels (7 of the 15 layers, 60 % of the FLOPs) run on the tensor cores
+// (umma_conv.cuh: tcgen05 kind::tf32, 3-way split, fp32-faithful); the 3-channel first layer, the 5x5 stride-2 convs, the
+// transposed convs and the 1x1 heads on the fp32 implicit-GEMM engine (conv_engine.cuh).
 #include "conv_engine.cuh"
+#include "umma_conv.cuh"
 #include "prof.cuh"
+#include <cstdlib>
 
 namespace satmvs {
 
@@ -88,16 +92,22 @@ using namespace satmvs;
 
 extern "C" {
 
+static size_t fn_pack_bytes(int base) {   // packed tcgen05 weights of the seven tensor-core layers (Cin, Cout <= 4b), 256-byte slots
+  const size_t one = (size_t)(4 * base / 8 + 1) * 2 * 9 * 2 * ((4 * base + 15) / 16 * 16) * 16 + 256;
+  return 7 * one;
+}
+
 size_t satmvs_featurenet_workspace_bytes(int base, int V, int H, int W) {
   if (base < 1 || V < 1 || H < 4 || W < 4 || (H % 4) || (W % 4)) return 0;
   const size_t px = (size_t)V * H * W;
   // t0a b, cat2 2b, f2 b at full resolution; t1a 2b, t1b 2b, cat1 4b, f1 2b at 1/2; t2a, t2b, t2c 4b each at 1/4
   const size_t floats = (size_t)base * (4 * px + 10 * (px / 4) + 12 * (px / 16));
-  return floats * sizeof(float) + 16 * 256;
+  return floats * sizeof(float) + 16 * 256 + fn_pack_bytes(base) + 512;
 }
 
 int satmvs_featurenet_forward(const satmvs_featurenet_weights* wt, const float* images, int base, int V, int H, int W,
                               float* out1, float* out2, float* out3, void* workspace, size_t workspace_bytes, void* stream) {
+  SATMVS_CHECK_ASYNC();
   SATMVS_REQUIRE(wt && images && out1 && out2 && out3 && workspace);
   SATMVS_REQUIRE(base >= 1 && V >= 1 && H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0);
   SATMVS_REQUIRE(workspace_bytes >= satmvs_featurenet_workspace_bytes(base, V, H, W));
@@ -114,11 +124,28 @@ int satmvs_featurenet_forward(const satmvs_featurenet_weights* wt, const float* 
   FnTensor t1a = take(2 * b, H2, W2), t1b = take(2 * b, H2, W2), cat1 = take(4 * b, H2, W2), f1 = take(2 * b, H2, W2);
   FnTensor t2a = take(4 * b, H4, W4), t2b = take(4 * b, H4, W4), t2c = take(4 * b, H4, W4);
   const FnTensor o1{out1, 4 * b, H4, W4}, o2{out2, 2 * b, H2, W2}, o3{out3, b, H, W};
+  cur = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(cur) + 255) / 256 * 256);
+  int* tc_err = async_error_devptr() ? async_error_devptr() : reinterpret_cast<int*>(cur);
+  cur += 256;
+  const size_t pack_slot = fn_pack_bytes(b) / 7;
+  static const bool no_umma = getenv("SATMVS_NO_UMMA") != nullptr;
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
   ProfScope prof(kProfFeature, st);
   const satmvs_conv_bn* L = wt->block;
+  int tc_slot = 0;
   auto conv = [&](int i, const FnTensor& in, int in_off, int Cin, const FnTensor& out, int out_off, int Cout, int k, int s, const char* what) {
+    if (k == 3 && s == 1 && Cin % 8 == 0 && !no_umma && tc_slot < 7) {      // tensor cores: one head = this layer (folded BN + ReLU in the epilogue)
+      const long long cs = (long long)V * in.h * in.w;
+      UmmaPackHead wh{L[i].w, (long long)Cin * 9, 9, Cout, 0};
+      UmmaHead oh{L[i].scale, L[i].shift, out.p + (size_t)out_off * cs, Cout, 0, 1.0f, 1, 1};
+      UmmaConvPlan up;
+      char* pk = cur + (size_t)tc_slot * pack_slot;
+      if (umma_conv_plan(up, in.p + (size_t)in_off * cs, cs, Cin, V, in.h, in.w, 1, &wh, &oh, pk, pack_slot, 1, /*perf_rules=*/false)) {
+        ++tc_slot;
+        return umma_conv_launch(up, tc_err, st, what);
+      }
+    }
     ConvProblem p = fn_conv(in, in_off, Cin, L[i].w, L[i].scale, L[i].shift, 1, out, out_off, Cout, k, s, V);
     return fn_launch(p, st, what);
   };
