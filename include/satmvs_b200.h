@@ -209,6 +209,15 @@ int satmvs_red_forward(const satmvs_red_weights* w, const float* volume, int C, 
                        const float* const* state_in, float* const* state_out, float* logits,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with a caller-owned region for the packed tensor-core weights (satmvs_red_pack_bytes(C) bytes, 256-byte aligned):
+ * the packs are written on the first call and reused while *pack_tag (host memory) still holds the signature the library
+ * stored there; zero the tag whenever the weights change.  Saves ~11 small launches per forward. */
+size_t satmvs_red_pack_bytes(int C);
+int satmvs_red_forward_packed(const satmvs_red_weights* w, const float* volume, int C, int D, int H, int W,
+                              const float* const* state_in, float* const* state_out, float* logits,
+                              void* workspace, size_t workspace_bytes, void* pack, size_t pack_bytes,
+                              unsigned long long* pack_tag, void* stream);
+
 /* Which implementation of the depth recurrence the last satmvs_red_forward of this thread used: 3 = tensor-core cluster
  * kernel (csrc/red_tc.cuh) running concurrently with the batched convolutions that feed it (side stream, per-plane ready
  * counters; SATMVS_RED_NO_OVERLAP=1 disables), 2 = the same kernel after them, 1 = FFMA cluster kernel (csrc/red_cluster.cuh), 0 = per-plane kernel chain, -1 = none yet.

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "satmvs_red_workspace_bytes": ([_I, _I, _I, _I], C.c_size_t),
     "satmvs_red_last_path": ([], _I),
     "satmvs_red_forward": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, C.c_size_t, _P], _I),
+    "satmvs_red_pack_bytes": ([_I], C.c_size_t),
+    "satmvs_red_forward_packed": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _P], _I),
     "satmvs_conv_workspace_bytes": ([_I, _I, _I], C.c_size_t),
     "satmvs_conv_forward": ([_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, C.c_float, _P, _I, _P, C.c_size_t, _P], _I),
     "satmvs_featurenet_workspace_bytes": ([_I, _I, _I, _I], C.c_size_t),

@@ -73,12 +73,13 @@ struct RedPlan {
   char* tcpack[4];       // packed hidden-state filters of the tensor-core recurrence (red_tc.cuh)
   int* ready;            // [4][D] per-(level, plane) completion counters of the batched x-half convs (overlapped flow)
   size_t bytes;
+  size_t pack_bytes;     // bytes used in the external pack region (red_plan with pack_base)
 };
 
-static RedPlan red_plan(int C, int D, int H, int W, char* base) {
+static RedPlan red_plan(int C, int D, int H, int W, char* base, char* pack_base = nullptr) {
   RedPlan p{};
   p.C = C; p.D = D; p.H = H; p.W = W;
-  size_t off = 0;
+  size_t off = 0, poff = 0;
   auto take = [&](size_t nfloats) {
     float* r = reinterpret_cast<float*>(base + off);
     off += ((nfloats * sizeof(float) + 255) / 256) * 256;
@@ -103,16 +104,20 @@ static RedPlan red_plan(int C, int D, int H, int W, char* base) {
   p.stats = reinterpret_cast<double*>(base + off);
   off += ((size_t)D * 4 * 3 * 2 * sizeof(double) + 64 * sizeof(double) + 255) / 256 * 256;   // + 64 debug counters
   for (int l = 0; l < 4; ++l) {   // packed (raw, lo) x-half weights of the tensor-core convs, per level
-    p.wpack[l] = base + off;
     p.wpack_bytes[l] = (size_t)(p.lv[l].cx / 8 + 1) * 2 * 9 * 2 * ((5 * p.lv[l].ch + 15) / 16 * 16) * 16;   // gates 2ch + output ch + encoder 2ch
-    off += (p.wpack_bytes[l] + 255) / 256 * 256;
+    if (pack_base) { p.wpack[l] = pack_base + poff; poff += (p.wpack_bytes[l] + 255) / 256 * 256; }
+    else { p.wpack[l] = base + off; off += (p.wpack_bytes[l] + 255) / 256 * 256; }
   }
   p.umma_err = reinterpret_cast<int*>(base + off);
   off += 256;
   p.cl_flags = reinterpret_cast<int*>(base + off);
   off += 4 * 2 * 32 * sizeof(int) + 8 * 16 * sizeof(unsigned long long);   // + debug counters
   off = (off + 255) / 256 * 256;
-  for (int l = 0; l < 4; ++l) { p.tcpack[l] = base + off; off += (tc_pack_bytes(chs[l]) + 255) / 256 * 256; }
+  for (int l = 0; l < 4; ++l) {
+    if (pack_base) { p.tcpack[l] = pack_base + poff; poff += (tc_pack_bytes(chs[l]) + 255) / 256 * 256; }
+    else { p.tcpack[l] = base + off; off += (tc_pack_bytes(chs[l]) + 255) / 256 * 256; }
+  }
+  p.pack_bytes = poff;
   p.ready = reinterpret_cast<int*>(base + off);
   off += ((size_t)4 * D * sizeof(int) + 255) / 256 * 256;
   p.bytes = off;
@@ -565,16 +570,32 @@ size_t satmvs_red_workspace_bytes(int C, int D, int H, int W) {
   return red_plan(C, D, H, W, nullptr).bytes;
 }
 
+size_t satmvs_red_pack_bytes(int C) {
+  if (C < 1) return 0;
+  static char dummy[1];
+  return red_plan(C, 1, 8, 8, nullptr, dummy).pack_bytes;
+}
+
 int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C, int D, int H, int W,
                        const float* const* state_in, float* const* state_out, float* logits,
                        void* workspace, size_t workspace_bytes, void* stream) {
+  return satmvs_red_forward_packed(wt, volume, C, D, H, W, state_in, state_out, logits, workspace, workspace_bytes,
+                                   nullptr, 0, nullptr, stream);
+}
+
+int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume, int C, int D, int H, int W,
+                              const float* const* state_in, float* const* state_out, float* logits,
+                              void* workspace, size_t workspace_bytes, void* pack, size_t pack_bytes,
+                              unsigned long long* pack_tag, void* stream) {
   SATMVS_REQUIRE(wt && volume && logits && workspace);
   SATMVS_REQUIRE(C >= 1 && D >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
+  SATMVS_REQUIRE((pack == nullptr) == (pack_tag == nullptr));
   SATMVS_CHECK_ASYNC();
   cudaStream_t st = (cudaStream_t)stream;
-  RedPlan P = red_plan(C, D, H, W, reinterpret_cast<char*>(workspace));
+  RedPlan P = red_plan(C, D, H, W, reinterpret_cast<char*>(workspace), reinterpret_cast<char*>(pack));
   if (int* ae = async_error_devptr()) P.umma_err = ae;
   SATMVS_REQUIRE(workspace_bytes >= P.bytes);
+  SATMVS_REQUIRE(pack == nullptr || (pack_bytes >= P.pack_bytes && (reinterpret_cast<uintptr_t>(pack) & 255) == 0));
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 
@@ -650,6 +671,21 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     }
     if (X.n == 0) all_umma = false;
   }
+  // Packed tensor-core weights (umma x-half packs + recurrence packs) are a pure function of the weights and of the plan: with a
+  // caller-owned pack region they are written once and reused while *pack_tag matches the plan's signature (the caller zeroes
+  // the tag when the weights change)
+  unsigned long long sig = 1469598103934665603ULL;
+  {
+    auto mix = [&](unsigned long long v) { sig ^= v; sig *= 1099511628211ULL; };
+    mix((unsigned)C); mix((unsigned)D); mix((unsigned)H); mix((unsigned)W);
+    for (int l = 0; l < 4; ++l) {
+      mix((unsigned)xp[l].n);
+      for (int i = 0; i < xp[l].n; ++i) { mix((unsigned)xp[l].u[i].conv.NP); mix((unsigned)xp[l].u[i].conv.nheads); }
+    }
+    mix(getenv("SATMVS_RED_NO_TC") ? 2u : 3u);
+    if (sig == 0) sig = 1;
+  }
+  const bool do_pack = !(pack_tag != nullptr && *pack_tag == sig);
   // launches the batched convs of level l for planes [d0, d0 + np) (np = 0: all planes, weights packed on the way)
   auto run_xhalf = [&](int l, int d0, int np, bool pack, int* ready, cudaStream_t xs) -> int {
     RedLevel& L = P.lv[l];
@@ -744,8 +780,9 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       }
     }
     if (side.ok && nchunks > 1 && cstart[nchunks] == D) {
-      for (int l = 0; l < 4; ++l)
-        for (int i = 0; i < xp[l].n; ++i) umma_conv_pack(xp[l].u[i], st);
+      if (do_pack)
+        for (int l = 0; l < 4; ++l)
+          for (int i = 0; i < xp[l].n; ++i) umma_conv_pack(xp[l].u[i], st);
       xpacked = true;
       cudaEventRecord(side.fork, st);
       cudaStreamWaitEvent(side.rec, side.fork, 0);
@@ -759,7 +796,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
           ta.d_begin = d0; ta.d_end = d0 + np;
           bool ran = false;
           ProfScope prof(kProfGruGate, side.rec);
-          RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, side.rec, &ran, c == 0));
+          RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, side.rec, &ran, c == 0 && do_pack));
           if (c == 0) persistent = ran;
           if (!ran) break;                                                 // shape not taken: the sequential flow below finishes the job
         }
@@ -770,7 +807,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
     }
   }
   if (!xhalf_done)
-    for (int l = 0; l < 4; ++l) RUN(run_xhalf(l, 0, 0, !xpacked, nullptr, st));
+    for (int l = 0; l < 4; ++l) RUN(run_xhalf(l, 0, 0, !xpacked && do_pack, nullptr, st));
 
   // ---- B. recurrence over planes (when it did not run overlapped above) ----
   {
@@ -778,7 +815,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
       // the recurrence on the tensor cores, one 16-CTA cluster per level (red_tc.cuh), after the batched convs
       TcArgs ta = tc_args(false);
       ProfScope prof(kProfGruGate, st);
-      RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, st, &persistent));
+      RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, st, &persistent, do_pack));
       if (persistent) { g_red_last_path = 2; tc_report(); }
     }
     if (!persistent && !no_cluster) {
@@ -934,6 +971,7 @@ int satmvs_red_forward(const satmvs_red_weights* wt, const float* volume, int C,
                           cudaMemcpyDeviceToDevice, st);
       }
 #undef RUN
+  if (pack_tag != nullptr) *pack_tag = sig;
   return check_launch("satmvs_red_forward");
 }
 

@@ -40,6 +40,19 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+def _param_key(module: nn.Module):
+    """Identity of a module's parameters and buffers: (storage pointer, in-place version) of each.  Derived tensors (folded
+    BatchNorm, packed tensor-core weights) are cached on this key and recomputed when a checkpoint is loaded, the module
+    is moved, or an optimiser step modifies a parameter in place."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def _fold_bn(blk):
+    scale = blk.bn.weight.detach() * torch.rsqrt(blk.bn.running_var + blk.bn.eps)
+    shift = blk.bn.bias.detach() - blk.bn.running_mean * scale
+    return scale.contiguous(), shift.contiguous()
+
+
 _ENGINES = {"auto": 0, "tcgen05": 1, "ffma": 2, "tcgen05_tn": 3}
 
 
@@ -165,6 +178,15 @@ class _RedBase(nn.Module):
             raise ValueError("RED regulariser needs H and W to be multiples of 8")
         ws = _workspace(nbytes, vol.device)
         w = self._weights()
+        # packed tensor-core weights live in a buffer of the module and are reused while the parameters are unchanged
+        key = (_param_key(self), vol.device)
+        pk = getattr(self, "_pack", None)
+        if pk is None or pk[0] != key:
+            buf = torch.empty(int(_lib.lib().satmvs_red_pack_bytes(Cc)) + 256, dtype=torch.uint8, device=vol.device)
+            pk = (key, buf, C.c_ulonglong(0))
+            object.__setattr__(self, "_pack", pk)
+        pbuf, ptag = pk[1], pk[2]
+        pptr = (pbuf.data_ptr() + 255) // 256 * 256
         logits = torch.empty((B, D, H, W), dtype=torch.float32, device=vol.device)
         out_states = None
         if want_states:
@@ -177,8 +199,10 @@ class _RedBase(nn.Module):
             for b in range(B):
                 sin = _lib.ptr_array([s[b].data_ptr() for s in states_in]) if states_in is not None else None
                 sout = _lib.ptr_array([s[b].data_ptr() for s in out_states]) if out_states is not None else None
-                _lib.check(_lib.lib().satmvs_red_forward(C.byref(w), vol[b].data_ptr(), Cc, D, H, W, sin, sout,
-                                                        logits[b].data_ptr(), ws.data_ptr(), ws.numel(), st), "red_forward")
+                _lib.check(_lib.lib().satmvs_red_forward_packed(C.byref(w), vol[b].data_ptr(), Cc, D, H, W, sin, sout,
+                                                               logits[b].data_ptr(), ws.data_ptr(), ws.numel(), pptr,
+                                                               pbuf.numel() - (pptr - pbuf.data_ptr()), C.byref(ptag), st),
+                           "red_forward")
         return logits, out_states
 
 
@@ -255,6 +279,10 @@ class CostRegNet(nn.Module):
         self.prob = nn.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
 
     def _weights(self) -> _CostRegWeights:
+        key = _param_key(self)
+        hit = getattr(self, "_wcache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         w = _CostRegWeights()
         keep = []
 
@@ -265,11 +293,11 @@ class CostRegNet(nn.Module):
 
         for i, name in enumerate(self._BLOCKS):
             blk = getattr(self, name)
-            scale = blk.bn.weight.detach() * torch.rsqrt(blk.bn.running_var + blk.bn.eps)
-            shift = blk.bn.bias.detach() - blk.bn.running_mean * scale
+            scale, shift = _fold_bn(blk)
             w.conv_w[i], w.bn_scale[i], w.bn_shift[i] = ptr(blk.conv.weight), ptr(scale), ptr(shift)
         w.prob_w = ptr(self.prob.weight)
         w._keep = keep
+        object.__setattr__(self, "_wcache", (key, w))
         return w
 
     def forward(self, x):
@@ -358,6 +386,10 @@ class FeatureNet(nn.Module):
         self.out_channels = [4 * b, 2 * b, b]
 
     def _weights(self) -> _FeatWeights:
+        key = _param_key(self)
+        hit = getattr(self, "_wcache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         w = _FeatWeights()
         keep = []
 
@@ -369,12 +401,12 @@ class FeatureNet(nn.Module):
         blocks = [self.conv0[0], self.conv0[1], self.conv1[0], self.conv1[1], self.conv1[2], self.conv2[0], self.conv2[1],
                   self.conv2[2], self.deconv1.deconv, self.deconv1.conv, self.deconv2.deconv, self.deconv2.conv]
         for i, blk in enumerate(blocks):
-            scale = blk.bn.weight.detach() * torch.rsqrt(blk.bn.running_var + blk.bn.eps)
-            shift = blk.bn.bias.detach() - blk.bn.running_mean * scale
+            scale, shift = _fold_bn(blk)
             w.block[3 * i], w.block[3 * i + 1], w.block[3 * i + 2] = ptr(blk.conv.weight), ptr(scale), ptr(shift)
         for i, m in enumerate((self.out1, self.out2, self.out3)):
             w.out_w[i] = ptr(m.weight)
         w._keep = keep
+        object.__setattr__(self, "_wcache", (key, w))
         return w
 
     def forward_views(self, images):

@@ -168,6 +168,25 @@ def test_pred_stage_chunked_equals_per_plane_loop(chunk):
     assert maxdiff(got["photometric_confidence"], want["photometric_confidence"]) < 1e-4
 
 
+def test_packed_weight_cache_follows_the_parameters():
+    """The packed tensor-core weights are cached in the module; an in-place parameter update (optimiser step, checkpoint
+    load) must invalidate them."""
+    C, D, H, W = 16, 3, 32, 64
+    sd = synth.make_red_weights(C, seed=9)
+    m = make_reg(satmvs_b200.RED_Regularization, C, seed=9)
+    x = synth.make_features(1, 1, C * D, H, W, seed=2)[0].view(1, C, D, H, W).abs()
+    a = m(x.to(DEV)).clone()
+    assert torch.equal(a, m(x.to(DEV)))                       # second call: cached packs, same bits
+    with torch.no_grad():
+        for name in ("conv_gru1.gate_conv.weight", "conv_gru3.output_conv.weight", "conv2.conv.weight"):
+            dict(m.named_parameters())[name].mul_(0.5)
+            sd[name] = sd[name] * 0.5
+    b = m(x.to(DEV))
+    want = regnets.red_regularization(x, sd)
+    assert maxdiff(b, want) < 2e-4 * max(1.0, want.abs().max().item())
+    assert maxdiff(a, b) > 1e-3
+
+
 def test_reference_checkpoint_keys():
     """state_dict keys/shapes are the reference's (`train.py:216-219` checkpoints must load)."""
     m = satmvs_b200.RED_Regularization(32, 8)
