@@ -29,7 +29,7 @@ def softargmin_casmvs(logits: torch.Tensor, depth_values: torch.Tensor):
     p = F.softmax(logits, dim=1)
     depth = depth_regression(p, depth_values)
     sum4 = 4 * F.avg_pool3d(F.pad(p.unsqueeze(1), pad=(0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
-    idx = depth_regression(p, torch.arange(D, dtype=torch.float)).long()
+    idx = depth_regression(p, torch.arange(D, dtype=torch.float, device=p.device)).long()   # casmvs.py:70 (device= p.device there)
     idx = idx.clamp(min=0, max=D - 1)
     return depth, torch.gather(sum4, 1, idx.unsqueeze(1)).squeeze(1)
 

@@ -366,16 +366,20 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
       for (int i = 0; i < 8; ++i) v[8 * c8 + i] = t[i];
     }
   };
+  // (A K-group-only mbarrier handshake instead of the cluster barriers #A / #D was measured and is no faster: the wait is
+  // the drain of the st.shared::cluster stores, ~4 k cycles for 19 KB at level 2, not the barrier: profiles/r02_red_overlap_notes.md)
   // block-wide sums of four quantities, pushed into stat_in[which][my rank] of every CTA of the cluster (the cluster barrier
   // that follows publishes them): no remote load sits behind the barrier
-  auto publish_stats = [&](int which, double (&v)[4]) {
+  auto publish_stats = [&](int which, float (&v)[4]) {
+    // a warp holds <= 96 positions x CK channels: fp32 is exact enough for their sum (the reference accumulates GroupNorm
+    // statistics in fp32 throughout); across warps and CTAs the sums continue in fp64
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
     if (lane == 0)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) sh.red[k][warp] = v[k];
+      for (int k = 0; k < 4; ++k) sh.red[k][warp] = (double)v[k];
     __syncthreads();
     if (warp == 0) {
       double t[4];
@@ -453,7 +457,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
   for (int d = d_begin; d < D; ++d) {
     mark(-1);
     // ================= gates: G = GX[d] + conv(h; Wg)  (MMAs already in flight) =================
-    double st[4] = {0.0, 0.0, 0.0, 0.0};
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
     {
       float v[MAXP][2 * CK];
       if (KG > 1) {
@@ -477,7 +481,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
             s0 += v[j][c]; q0 = fmaf(v[j][c], v[j][c], q0);
             s1 += v[j][CK + c]; q1 = fmaf(v[j][CK + c], v[j][CK + c], q1);
           }
-          st[0] += (double)s0; st[1] += (double)q0; st[2] += (double)s1; st[3] += (double)q1;
+          st[0] += s0; st[1] += q0; st[2] += s1; st[3] += q1;
         }
 #pragma unroll
         for (int c = 0; c < CK; ++c) keep[j][c] = v[j][c];
@@ -506,7 +510,8 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
       const int wi = q_[j] + Wp + 1;
 #pragma unroll
       for (int f = 0; f < NQ; ++f) {
-        const float4 h4 = win[f * PWa + wi];
+        // lanes past the strip's positions would read the halo row the strip below is writing right now: they read nothing
+        const float4 h4 = (fl_[j] & 1) ? win[f * PWa + wi] : make_float4(0.f, 0.f, 0.f, 0.f);
         hv[4 * f] = h4.x; hv[4 * f + 1] = h4.y; hv[4 * f + 2] = h4.z; hv[4 * f + 3] = h4.w;
       }
 #pragma unroll
@@ -542,7 +547,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
       }
       if (STASH) stash_st(j, 0, uv);
     }
-    st[0] = st[1] = st[2] = st[3] = 0.0;
+    st[0] = st[1] = st[2] = st[3] = 0.f;
     {
       float v[MAXP][2 * CK];
       if (KG > 1) {
@@ -563,7 +568,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
           float s0 = 0.f, q0 = 0.f;
 #pragma unroll
           for (int c = 0; c < CK; ++c) { s0 += v[j][c]; q0 = fmaf(v[j][c], v[j][c], q0); }
-          st[0] += (double)s0; st[1] += (double)q0;
+          st[0] += s0; st[1] += q0;
         }
 #pragma unroll
         for (int c = 0; c < CK; ++c) keep[j][c] = v[j][c];
