@@ -750,12 +750,12 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
   }
   auto tc_report = [&]() {
     if (!tc_dbg) return;
-    long long h[4 * 16] = {};
+    long long h[4 * 20] = {};
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     for (int c = 0; c < 4; ++c) {
       fprintf(stderr, "red_tc: level %d kcycles per phase slot:", c);
-      for (int i = 0; i < 16; ++i) fprintf(stderr, " %.0f", h[c * 16 + i] * 1e-3);
+      for (int i = 0; i < 20; ++i) fprintf(stderr, " %.0f", h[c * 20 + i] * 1e-3);
       fprintf(stderr, "\n");
     }
   };

@@ -63,7 +63,8 @@ __host__ __device__ inline TcGeom tc_geom(int ch, int KG, int h, int w) {
   const size_t wts = (size_t)9 * (CK / 8) * 2 * (6 * ch) * 16;           // gates [raw | lo] 4ch rows + output 2ch rows
   const size_t pre = (size_t)2 * CK * g.R * w * 4;
   const size_t recv = (size_t)(KG - 1) * (2 * CK / 4) * g.NPP * 16;
-  g.smem = win + wts + pre + recv;
+  const size_t send = KG == 2 ? recv : 0;                                // K-pair levels stage their outgoing partial sums for one bulk copy
+  g.smem = win + wts + pre + recv + send;
   return g;
 }
 
@@ -128,8 +129,10 @@ struct TcShared {
   double red[4][kTcWarps];
   float coef[3][16][2];                       // GroupNorm scale / shift of this CTA's channels: r, u, o
   unsigned long long mbar_tile[16], mbar_pre;      // MMAs of tile mt complete; x-halves landed
+  unsigned long long mbar_halo;                    // the neighbouring strips' halo rows have landed in the window (complete_tx)
+  unsigned long long mbar_x;                       // K-pair levels: the partner's partial sums have landed in recv (complete_tx)
   unsigned tmem_base;
-  long long t_prev, t_acc[16];                // SATMVS_RED_DEBUG: cycles thread 0 spends per phase slot
+  long long t_prev, t_acc[20];                // SATMVS_RED_DEBUG: cycles thread 0 spends per phase slot
 };
 
 template <int CH, int KG, int MAXP, int STASH>   // STASH: 0 none, 1 in the dead half of the gate accumulators (KG == 1), 2 own TMEM columns
@@ -152,12 +155,16 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
   float4* wo = wg + 9 * KS * 2 * NBG;                      // [tap 9][ks][kq 2][NBO]
   float* pre = reinterpret_cast<float*>(wo + 9 * KS * 2 * NBO);   // [2*CK][R*w]: x-halves of the conv whose epilogue comes next
   float4* recv = reinterpret_cast<float4*>(pre + 2 * CK * Rw);    // [src KG-1][f4 2*CK/4][NPP]: partial sums pushed by the other K-groups
+  constexpr bool BULK = (KG == 2);                                // one partner: its columns are staged locally and travel as ONE
+  float4* send = recv + (KG - 1) * (2 * CK / 4) * NPP;            // cp.async.bulk into its recv (DSMEM through the TMA engine)
 
   // ---- once: barriers, TMEM, zero window, filters, initial state ----
   constexpr int kTmemCols = MAXP * 4 * NBG <= 512 ? 512 : 512;
   if (tid == 0) {
     for (int i = 0; i < 16; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_tile[i])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_pre)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_x)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_smem_u32(&sh.mbar_halo)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -268,20 +275,44 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
       __syncwarp();
     }
   };
-  // Tiles that read a halo row (outputs of the first / last row of the strip) wait for the neighbours; the tiles between
-  // them only need this CTA's own rows.  Called after the window stores: [every thread] fence + cluster arrive happened.
+  bool alive = true;
+  // Halo rows travel as bulk copies (TMA engine, shared::cta -> shared::cluster): after a conv input (r*h or h') is in this
+  // CTA's window, the issuer warp sends the first / last own row of every (part, channel quad) -- Wp contiguous float4 each --
+  // into the halo row of the strip above / below, completing on THAT CTA's mbarrier; no thread issues remote stores and no
+  // cluster barrier is needed for the halos.  Tiles that read a halo row (outputs of the first / last row of the strip) wait
+  // for the incoming bytes; the tiles between them only need this CTA's own rows and are issued first.
+  // Hazards: a neighbour overwrites my halo rows only after the stats barrier that follows my MMAs over them (#B / #E); my
+  // own rows are overwritten only after the next stats barrier, which the neighbours reach after consuming my copy.
+  const bool nb_up = nrows > 0 && y0 > 0, nb_dn = nrows > 0 && y0 + nrows < L.h;
+  const unsigned halo_row_bytes = (unsigned)Wp * 16u;
+  const unsigned halo_in_bytes = (unsigned)((nb_up ? 1 : 0) + (nb_dn ? 1 : 0)) * 2u * NQ * halo_row_bytes;
+  unsigned ph_halo = 0;
   const int t_first = (Wp - 1) / 128 + 1, t_last = nrows >= 3 ? ((nrows - 1) * Wp) / 128 : 0;     // interior tiles [t_first, t_last)
   auto issue_conv_split = [&](const float4* wts, int NB, int N2, int col0) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                                                      // this CTA's rows are in the window
+    __syncthreads();                                                      // this CTA's rows are in the window (every writer fenced the async proxy)
+    if (warp == kTcIssuer && halo_in_bytes > 0) {
+      const unsigned bar = uc_smem_u32(&sh.mbar_halo);
+      if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(halo_in_bytes) : "memory");
+      // lane = dir * 2*NQ + part * NQ + quad
+      const int dir = lane / (2 * NQ), pq = lane - dir * (2 * NQ);
+      if (dir < 2 && ((dir == 0 && nb_up) || (dir == 1 && nb_dn))) {
+        const int src_row = dir == 0 ? 1 : nrows, dst_row = dir == 0 ? R + 1 : 0;
+        const unsigned nb = dir == 0 ? rank - KG : rank + KG;
+        const unsigned src = win_s + (unsigned)((pq * PWa + src_row * Wp) * 16);
+        const unsigned dst = tc_mapa(win_s + (unsigned)((pq * PWa + dst_row * Wp) * 16), nb);
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "r"(src), "r"(halo_row_bytes), "r"(tc_mapa(bar, nb)) : "memory");
+      }
+      __syncwarp();
+    }
     if (t_first < t_last) issue_tiles(wts, NB, N2, col0, t_first, t_last);
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); // the neighbours' halo rows too
+    if (warp == kTcIssuer && halo_in_bytes > 0) { alive = uc_wait(&sh.mbar_halo, ph_halo) && alive; ph_halo ^= 1u; }
     if (t_first < t_last) { issue_tiles(wts, NB, N2, col0, 0, t_first); issue_tiles(wts, NB, N2, col0, t_last, MTa); }
     else issue_tiles(wts, NB, N2, col0, 0, MTa);
   };
 
   unsigned ph_mma = 0, ph_pre = 0;
-  bool alive = true;
   auto lane_base = [&](int j, int NB, int col0) {                         // TMEM address of this thread's row of tile j's accumulators
     return tmem + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(col0 + ((warp >> 2) + 4 * j) * NB);
   };
@@ -308,6 +339,12 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
           if (KG == 1 || owner == kg) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[part * CK + c8 * 8 + i] = a[i];
+          } else if (BULK) {
+            const int f4 = part * (CK / 4) + c8 * 2;                       // staged locally (the whole [f4][NPP] block travels)
+            if (q_[j] < NPP) {
+              send[f4 * NPP + q_[j]] = make_float4(a[0], a[1], a[2], a[3]);
+              send[(f4 + 1) * NPP + q_[j]] = make_float4(a[4], a[5], a[6], a[7]);
+            }
           } else if (fl_[j] & 1) {
             const int slot = kg < owner ? kg : kg - 1;
             const int f4 = part * (CK / 4) + c8 * 2;
@@ -366,8 +403,25 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
       for (int i = 0; i < 8; ++i) v[8 * c8 + i] = t[i];
     }
   };
-  // (A K-group-only mbarrier handshake instead of the cluster barriers #A / #D was measured and is no faster: the wait is
-  // the drain of the st.shared::cluster stores, ~4 k cycles for 19 KB at level 2, not the barrier: profiles/r02_red_overlap_notes.md)
+  // K-split exchange.  The wait behind per-thread st.shared::cluster pushes is the drain of those stores (~4 k cycles for 19 KB at
+  // level 2, whatever the barrier: a K-group-only mbarrier handshake was measured no faster, profiles/r02_red_overlap_notes.md).
+  // K-pair levels therefore stage their partner's columns locally and send them as ONE cp.async.bulk shared::cta ->
+  // shared::cluster (TMA engine) that completes on the partner's mbarrier; the staging buffer is free again once the partner has
+  // passed the next cluster barrier (it waited for these bytes before arriving there).
+  unsigned ph_x = 0;
+  auto exchange = [&](int nparts) {
+    if (!BULK) { tc_cluster_sync(); return; }
+    const unsigned bytes = (unsigned)(nparts * (CK / 4) * NPP) * 16u;
+    asm volatile("fence.proxy.async;" ::: "memory");                     // staged by the generic proxy, read by the TMA engine
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned bar = uc_smem_u32(&sh.mbar_x), peer = (unsigned)(strip * KG + (kg ^ 1));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");   // what I will receive
+      asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(tc_mapa(recv_s, peer)), "r"(uc_smem_u32(send)), "r"(bytes), "r"(tc_mapa(bar, peer)) : "memory");
+    }
+    alive = uc_wait(&sh.mbar_x, ph_x) && alive; ph_x ^= 1u;
+  };
   // block-wide sums of four quantities, pushed into stat_in[which][my rank] of every CTA of the cluster (the cluster barrier
   // that follows publishes them): no remote load sits behind the barrier
   auto publish_stats = [&](int which, float (&v)[4]) {
@@ -420,7 +474,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
     }
     __syncthreads();
   };
-  // write CK channels of one position into the window (raw + lo) and into the neighbours' halo rows
+  // write CK channels of one position into the window (raw + lo); the halo rows leave as bulk copies (issue_conv_split)
   auto store_window = [&](int j, const float (&v)[CK]) {
     const int wi = q_[j] + Wp + 1;
 #pragma unroll
@@ -429,21 +483,10 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
       const float4 lo = make_float4(tc_lo(raw.x), tc_lo(raw.y), tc_lo(raw.z), tc_lo(raw.w));
       win[f * PWa + wi] = raw;
       win[(NQ + f) * PWa + wi] = lo;
-      if (fl_[j] & 6) {
-        const int x1 = wi % Wp;                                            // x + 1
-        if (fl_[j] & 2) {                                                  // row R+1 of the strip above (it has R rows)
-          const unsigned ra = tc_mapa(win_s + (unsigned)((f * PWa + (R + 1) * Wp + x1) * 16), rank - KG);
-          tc_st_remote(ra, raw); tc_st_remote(ra + (unsigned)(NQ * PWa) * 16u, lo);
-        }
-        if (fl_[j] & 4) {                                                  // row 0 of the strip below
-          const unsigned ra = tc_mapa(win_s + (unsigned)((f * PWa + x1) * 16), rank + KG);
-          tc_st_remote(ra, raw); tc_st_remote(ra + (unsigned)(NQ * PWa) * 16u, lo);
-        }
-      }
     }
   };
 
-  if (tid == 0) for (int i = 0; i < 16; ++i) sh.t_acc[i] = 0;
+  if (tid == 0) for (int i = 0; i < 20; ++i) sh.t_acc[i] = 0;
   auto mark = [&](int slot) {
     if (dbg != nullptr && tid == 0) { const long long t = clock64(); if (slot >= 0) sh.t_acc[slot] += t - sh.t_prev; sh.t_prev = t; }
   };
@@ -465,7 +508,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
         for (int j = 0; j < MAXP; ++j)
           if ((warp >> 2) + 4 * j < MTa && warp < kTcEpiWarps) read_pos(j, NG, NBG, 0, 2, v[j]);
         mark(12);
-        tc_cluster_sync();                                                 // #A: every K-group's partial sums have landed
+        exchange(2);                                                       // #A: every K-group's partial sums have landed
         mark(13);
       }
       alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
@@ -528,7 +571,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
     }
     mark(11);
     asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); // #C: r*h of the strip and its halos (wait inside issue_conv_split)
+    // (#C: the halos of r*h leave and arrive as bulk copies inside issue_conv_split: no cluster barrier)
     mark(3);
     // ================= output: O = OX[d] + conv(r*h; Wo) =================
     issue_conv_split(wo, NBO, N2O, ocol0);
@@ -555,7 +598,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
         for (int j = 0; j < MAXP; ++j)
           if ((warp >> 2) + 4 * j < MTa && warp < kTcEpiWarps) read_pos(j, NO, NBO, ocol0, 1, v[j]);
         mark(14);
-        tc_cluster_sync();                                                 // #D
+        exchange(1);                                                       // #D
         mark(15);
       }
       alive = uc_wait(&sh.mbar_pre, ph_pre) && alive; ph_pre ^= 1u;
@@ -583,6 +626,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
     mark(7);
     if (d + 1 < D) issue_pre(0, d + 1);
     gather_coef(1, 1, 2, L.on_w, L.on_b, L.on_w, L.on_b);
+    mark(16);
     // h' = u*h + (1-u)*tanh(GN_o(O)) -> window and halos now, the state history after the barrier arrive (module.py:57)
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {
@@ -601,8 +645,11 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
       }
       if (fl_[j] & 1) store_window(j, keep[j]);
     }
+    mark(17);
     asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); // #F: h[d+1] (wait inside issue_conv_split)
+    mark(18);
+    // (#F: likewise for h[d+1])
+    mark(19);
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {                                       // global stores drain behind the barrier and the next MMAs
       if (!(fl_[j] & 1)) continue;
@@ -612,13 +659,12 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
     }
     mark(8);
     if (d + 1 < D) issue_conv_split(wg, NBG, NG, 0);
-    else asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     mark(9);
   }
   if (!alive && tid == 0) *reinterpret_cast<volatile int*>(err) = 1;
   if (dbg != nullptr && tid == 0 && (rank == 0))
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dbg[(blockIdx.x / kTcCluster) * 16 + i] = sh.t_acc[i];
+    for (int i = 0; i < 20; ++i) dbg[(blockIdx.x / kTcCluster) * 20 + i] = sh.t_acc[i];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   tc_cluster_sync();                                                       // no CTA leaves while a peer may still write into its shared memory
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
