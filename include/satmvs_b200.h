@@ -270,6 +270,34 @@ size_t satmvs_costreg_workspace_bytes(int base_channels, int D, int H, int W);
 int satmvs_costreg_forward(const satmvs_costreg_weights* w, const float* x, int Cin, int base_channels,
                            int D, int H, int W, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training form of the Conv3d / Deconv3d blocks (modules/module.py:324-410; train.py:267-287 runs model.train() and
+ * loss.backward()) ----
+ * satmvs_conv3d_raw: out = conv(in) without BatchNorm / activation, weight read as w[co * w_co + ci * w_ci + tap];
+ *   NZ 3: 3x3x3 on [C,D,H,W];  NZ 1: 3x3 per plane.  mode 0: stride 1, padding 1;  1: stride 2, padding 1 (even sizes);
+ *   2: stride 1 with mirrored taps (with w_co / w_ci swapped this is the data gradient of mode 0);
+ *   3: transposed, stride 2, padding 1, output_padding 1 (nn.ConvTranspose3d; reading a Conv3d weight [Cout,Cin,..] with
+ *      w_ci = Cin*taps, w_co = taps it is the data gradient of mode 1, and mode 1 reading a ConvTranspose3d weight is the data
+ *      gradient of mode 3).
+ * satmvs_conv3d_wgrad: dw[co * dw_co + ci * dw_ci + tap] (+)= sum_o dy[co, o] x[ci, stride * o + k - 1]  (padding 1);
+ *   for a transposed block call it with x = the output gradient (large tensor) and dy = the block input (small tensor), stride 2.
+ * satmvs_bn_train_fwd / _bwd: BatchNorm3d on batch statistics (+ ReLU, + skip tensor added after the ReLU, module.py:573-575)
+ *   on [B,C,n] tensors (n % 4 == 0); mean / var (biased) are outputs of _fwd and inputs of _bwd; acc = 2 C doubles of scratch;
+ *   dz2 (may be null) is a second gradient added to dz (a block output that also feeds a skip connection).
+ * satmvs_softargmin_bwd: gradient of depth = sum_d softmax(logits)_d * depth_d to the logits [D,H,W] (casmvs.py:66-68). */
+int satmvs_conv3d_raw(const float* in, int Cin, int Di, int Hi, int Wi, const float* w, long long w_co, long long w_ci,
+                      int NZ, int mode, float* out, int Cout, void* stream);
+size_t satmvs_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int Di, int Hi, int Wi, int NZ, int stride);
+int satmvs_conv3d_wgrad(const float* x, int Cin, int Di, int Hi, int Wi, const float* dy, int Cout, int NZ, int stride,
+                        float* dw, long long dw_co, long long dw_ci, int accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int satmvs_bn_train_fwd(const float* y, int B, int C, long long n, const float* gamma, const float* beta, float eps, int relu,
+                        const float* post_add, float* z, float* mean, float* var, double* acc, void* stream);
+int satmvs_bn_train_bwd(const float* dz, const float* dz2, const float* y, int B, int C, long long n, const float* gamma, const float* beta,
+                        const float* mean, const float* var, float eps, int relu, float* dy, float* dgamma, float* dbeta,
+                        double* acc, void* stream);
+int satmvs_softargmin_bwd(const float* logits, const float* depth_values, int per_pixel, int D, int H, int W,
+                          const float* grad_depth, float* grad_logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

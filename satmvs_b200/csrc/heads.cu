@@ -93,6 +93,27 @@ __global__ void softargmin_stream_finish_kernel(const double* __restrict__ state
   out_conf[pix] = (float)(state[2 * (size_t)HW + pix] / tot);
 }
 
+// gradient of depth = sum_d p_d * dv_d (p = softmax over planes) to the logits: dL/dlogit_d = g * p_d * (dv_d - depth)
+__global__ void softargmin_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ depth, int depth_per_pixel,
+                                      int D, int HW, const float* __restrict__ grad_depth, float* __restrict__ grad_logits) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  float mx = -INFINITY;
+  for (int d = 0; d < D; ++d) mx = fmaxf(mx, __ldg(logits + (size_t)d * HW + pix));
+  float se = 0.0f, acc = 0.0f;
+  for (int d = 0; d < D; ++d) {
+    const float e = expf(__ldg(logits + (size_t)d * HW + pix) - mx);
+    const float dv = depth_per_pixel ? __ldg(depth + (size_t)d * HW + pix) : __ldg(depth + d);
+    se += e; acc += e * dv;
+  }
+  const float inv = 1.0f / se, mean = acc * inv, g = __ldg(grad_depth + pix);
+  for (int d = 0; d < D; ++d) {
+    const float p = expf(__ldg(logits + (size_t)d * HW + pix) - mx) * inv;
+    const float dv = depth_per_pixel ? __ldg(depth + (size_t)d * HW + pix) : __ldg(depth + d);
+    grad_logits[(size_t)d * HW + pix] = g * p * (dv - mean);
+  }
+}
+
 }  // namespace satmvs
 
 using namespace satmvs;
@@ -133,6 +154,15 @@ int satmvs_softargmin_stream_finish(const double* state, int H, int W,
   const int HW = H * W;
   softargmin_stream_finish_kernel<<<ceil_div(HW, 128), 128, 0, (cudaStream_t)stream>>>(state, HW, out_depth, out_conf);
   return check_launch("softargmin_stream_finish_kernel");
+}
+
+int satmvs_softargmin_bwd(const float* logits, const float* depth, int depth_per_pixel, int D, int H, int W,
+                          const float* grad_depth, float* grad_logits, void* stream) {
+  SATMVS_REQUIRE(logits && depth && grad_depth && grad_logits && D >= 1 && H >= 1 && W >= 1);
+  const int HW = H * W;
+  softargmin_bwd_kernel<<<ceil_div(HW, 128), 128, 0, (cudaStream_t)stream>>>(logits, depth, depth_per_pixel, D, HW, grad_depth,
+                                                                             grad_logits);
+  return check_launch("softargmin_bwd_kernel");
 }
 
 }  // extern "C"

@@ -759,6 +759,82 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
       fprintf(stderr, "\n");
     }
   };
+  // ---- C. decoder over planes [d0, d0 + np): U_l = relu(convT_s2(U_{l+1})) + S_l  (module.py:633-642) ----
+  auto run_decoder = [&](int d0, int np, cudaStream_t st) -> int {
+  const float* up_in = P.lv[3].s;
+  for (int l = 2; l >= 0; --l) {
+    RedLevel& L = P.lv[l];          // output level
+    RedLevel& Lin = P.lv[l + 1];
+    ConvGroup g{};
+    int n = 0;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        ConvProblem p;
+        conv_problem_defaults(p);
+        p.in = up_in; p.w = wt->upconv_w[l]; p.out = P.u[l];
+        p.Cin = Lin.ch; p.Cout = L.ch;
+        p.Di = D + 1; p.Hi = Lin.h; p.Wi = Lin.w; p.Do = D + 1; p.Ho = L.h; p.Wo = L.w;
+        p.w_ci_stride = (long long)L.ch * 9; p.w_co_stride = 9;       // ConvTranspose2d weight [Cin][Cout][3][3]
+        p.Qd = np; p.Qh = Lin.h; p.Qw = Lin.w;
+        p.q2i_add[0] = 1 + d0; p.q2o_add[0] = 1 + d0;                  // slots d0+1..d0+np
+        p.q2o_mul[1] = 2; p.q2o_mul[2] = 2; p.q2o_add[1] = py; p.q2o_add[2] = px;
+        conv_taps_deconv_class(p, false, 0, py, px);
+        p.relu = 1;
+        p.post_add = L.s;
+        conv_finalize(p);
+        g.p[n++] = p;
+      }
+    g.n = n;
+    {
+      ProfScope prof(kProfDecoder, st);
+      // slots d0+1..d0+np of the [C][D+1][h][w] tensors are np contiguous planes starting 1+d0 planes into each channel
+      DirectDeconv dd{};
+      const long long pin = (long long)Lin.h * Lin.w, pout = (long long)L.h * L.w;
+      dd.in = up_in + (1 + d0) * pin; dd.in_cs = (long long)(D + 1) * pin;
+      dd.w = wt->upconv_w[l]; dd.post_add = L.s + (1 + d0) * pout; dd.out = P.u[l] + (1 + d0) * pout; dd.out_cs = (long long)(D + 1) * pout;
+      dd.Cin = Lin.ch; dd.Cout = L.ch; dd.Dn = np; dd.Hi = Lin.h; dd.Wi = Lin.w; dd.relu = 1;
+      static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+      if (!no_direct && direct_deconv_supported(dd)) {
+        RUN(direct_deconv_launch(dd, st, "red upconv (direct)"));
+      } else {
+        if (L.ch >= 32) RUN(conv_launch<Tile32>(g, st, "red upconv")); else if (L.ch >= 16) RUN(conv_launch<Tile16>(g, st, "red upconv"));
+        else RUN(conv_launch<Tile8>(g, st, "red upconv"));
+      }
+    }
+    up_in = P.u[l];
+  }
+  {  // upconv2d: ConvTranspose2d(8, 1, k3, stride 1, pad 1) with bias (module.py:610, :643): out[o] = sum_k in[o+1-k] w[k]
+    ConvProblem p;
+    conv_problem_defaults(p);
+    p.in = P.u[0]; p.w = wt->upconv2d_w; p.out = logits + (size_t)d0 * H * W;
+    p.Cin = 8; p.Cout = 1;
+    p.Di = D + 1; p.Hi = H; p.Wi = W; p.Do = np; p.Ho = H; p.Wo = W;
+    p.w_ci_stride = 9; p.w_co_stride = 9;
+    p.Qd = np; p.Qh = H; p.Qw = W;
+    p.q2i_add[0] = 1 + d0;
+    int n = 0;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) { p.tap_dz[n] = 0; p.tap_dy[n] = 1 - ky; p.tap_dx[n] = 1 - kx; p.tap_w[n] = ky * 3 + kx; ++n; }
+    p.ntaps = n;
+    p.shift = wt->upconv2d_b;
+    // out[o] = sum_k in[o+1-k] w[k] = sum_k' in[o-1+k'] w[8-k']: a 3x3 correlation with mirrored taps
+    DirectConv dc{};
+    dc.in = P.u[0] + (size_t)(1 + d0) * H * W;        // slot 1 + d0 of the [8][D+1][H][W] decoder tensor
+    dc.w = wt->upconv2d_w; dc.shift = wt->upconv2d_b; dc.out = logits + (size_t)d0 * H * W;
+    dc.Cin = 8; dc.Cout = 1; dc.Di = np; dc.Hi = H; dc.Wi = W; dc.Do = np; dc.Ho = H; dc.Wo = W;
+    dc.w_co = 9; dc.w_ci = 9; dc.acc_scale = 1.0f; dc.relu = 0; dc.flip = 1;
+    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+    ProfScope prof(kProfDecoder, st);
+    if (!no_direct && direct_conv_supported(dc, 1, 1)) {
+      // the input tensor has D+1 planes per channel: express it as Di = D with the channel stride of D+1 planes
+      RUN(direct_conv_launch_cs(dc, (long long)(D + 1) * H * W, st, "red upconv2d (direct)"));
+    } else {
+      RUN(launch_one<Tile8>(p, st, "red upconv2d"));
+    }
+  }
+  return SATMVS_OK;
+  };
+  bool decoded = false;
   bool xhalf_done = false, xpacked = false;
   if (all_umma && !no_cluster && !no_tc && !no_overlap) {
     RedSideStream& side = red_side_stream();
@@ -769,9 +845,20 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
     // plane + ~30 us per launch, so two chunks of 16 planes get the consumer going and one big chunk finishes the volume
     // (measured at cfg-2, profiles/r02_red_overlap_notes.md: [8]x8 1.99 ms, [16]x4 1.95 ms per forward against 2.03 sequential)
     static const int kChunk = getenv("SATMVS_RED_CHUNK") ? atoi(getenv("SATMVS_RED_CHUNK")) : 16;
+    static const bool chunked_decoder = getenv("SATMVS_RED_NO_CHUNKED_DECODER") == nullptr;
     int cstart[kRedMaxChunks + 1], nchunks = 0;
     cstart[0] = 0;
-    if (kChunk > 0 && D >= 2 * kChunk) {
+    if (const char* sched = getenv("SATMVS_RED_SCHED")) {          // tuning: "8,16,16" = chunk sizes, the rest in a last chunk
+      for (const char* q = sched; *q && nchunks < kRedMaxChunks - 1 && cstart[nchunks] < D;) {
+        const int take = atoi(q);
+        if (take <= 0) break;
+        cstart[nchunks + 1] = cstart[nchunks] + (take < D - cstart[nchunks] ? take : D - cstart[nchunks]);
+        ++nchunks;
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+      if (cstart[nchunks] < D) { cstart[nchunks + 1] = D; ++nchunks; }
+    } else if (kChunk > 0 && D >= 2 * kChunk) {
       while (cstart[nchunks] < D && nchunks < kRedMaxChunks) {
         const int left = D - cstart[nchunks];
         const int take = (nchunks >= 2 || left < 2 * kChunk) ? left : kChunk;
@@ -799,7 +886,17 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
           RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, side.rec, &ran, c == 0 && do_pack));
           if (c == 0) persistent = ran;
           if (!ran) break;                                                 // shape not taken: the sequential flow below finishes the job
+          cudaEventRecord(side.chunk[1][c], side.rec);
         }
+      }
+      if (persistent && chunked_decoder) {
+        // the decoder of chunk c follows the producers of all chunks on the caller's stream and starts when the recurrence has
+        // left chunk c behind: only the last chunk's decoder stays on the critical path
+        for (int c = 0; c < nchunks; ++c) {
+          cudaStreamWaitEvent(st, side.chunk[1][c], 0);
+          RUN(run_decoder(cstart[c], cstart[c + 1] - cstart[c], st));
+        }
+        decoded = true;
       }
       cudaEventRecord(side.join[0], side.rec);
       cudaStreamWaitEvent(st, side.join[0], 0);
@@ -890,78 +987,7 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
       RUN(check_launch("gru_update_kernel")); }
   }
 
-  // ---- C. decoder over all planes: U_l = relu(convT_s2(U_{l+1})) + S_l  (module.py:633-642) ----
-  const float* up_in = P.lv[3].s;
-  for (int l = 2; l >= 0; --l) {
-    RedLevel& L = P.lv[l];          // output level
-    RedLevel& Lin = P.lv[l + 1];
-    ConvGroup g{};
-    int n = 0;
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px) {
-        ConvProblem p;
-        conv_problem_defaults(p);
-        p.in = up_in; p.w = wt->upconv_w[l]; p.out = P.u[l];
-        p.Cin = Lin.ch; p.Cout = L.ch;
-        p.Di = D + 1; p.Hi = Lin.h; p.Wi = Lin.w; p.Do = D + 1; p.Ho = L.h; p.Wo = L.w;
-        p.w_ci_stride = (long long)L.ch * 9; p.w_co_stride = 9;       // ConvTranspose2d weight [Cin][Cout][3][3]
-        p.Qd = D; p.Qh = Lin.h; p.Qw = Lin.w;
-        p.q2i_add[0] = 1; p.q2o_add[0] = 1;                            // slots 1..D
-        p.q2o_mul[1] = 2; p.q2o_mul[2] = 2; p.q2o_add[1] = py; p.q2o_add[2] = px;
-        conv_taps_deconv_class(p, false, 0, py, px);
-        p.relu = 1;
-        p.post_add = L.s;
-        conv_finalize(p);
-        g.p[n++] = p;
-      }
-    g.n = n;
-    {
-      ProfScope prof(kProfDecoder, st);
-      // slots 1..D of the [C][D+1][h][w] tensors are D contiguous planes starting one plane into each channel
-      DirectDeconv dd{};
-      const long long pin = (long long)Lin.h * Lin.w, pout = (long long)L.h * L.w;
-      dd.in = up_in + pin; dd.in_cs = (long long)(D + 1) * pin;
-      dd.w = wt->upconv_w[l]; dd.post_add = L.s + pout; dd.out = P.u[l] + pout; dd.out_cs = (long long)(D + 1) * pout;
-      dd.Cin = Lin.ch; dd.Cout = L.ch; dd.Dn = D; dd.Hi = Lin.h; dd.Wi = Lin.w; dd.relu = 1;
-      static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
-      if (!no_direct && direct_deconv_supported(dd)) {
-        RUN(direct_deconv_launch(dd, st, "red upconv (direct)"));
-      } else {
-        if (L.ch >= 32) RUN(conv_launch<Tile32>(g, st, "red upconv")); else if (L.ch >= 16) RUN(conv_launch<Tile16>(g, st, "red upconv"));
-        else RUN(conv_launch<Tile8>(g, st, "red upconv"));
-      }
-    }
-    up_in = P.u[l];
-  }
-  {  // upconv2d: ConvTranspose2d(8, 1, k3, stride 1, pad 1) with bias (module.py:610, :643): out[o] = sum_k in[o+1-k] w[k]
-    ConvProblem p;
-    conv_problem_defaults(p);
-    p.in = P.u[0]; p.w = wt->upconv2d_w; p.out = logits;
-    p.Cin = 8; p.Cout = 1;
-    p.Di = D + 1; p.Hi = H; p.Wi = W; p.Do = D; p.Ho = H; p.Wo = W;
-    p.w_ci_stride = 9; p.w_co_stride = 9;
-    p.Qd = D; p.Qh = H; p.Qw = W;
-    p.q2i_add[0] = 1;
-    int n = 0;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) { p.tap_dz[n] = 0; p.tap_dy[n] = 1 - ky; p.tap_dx[n] = 1 - kx; p.tap_w[n] = ky * 3 + kx; ++n; }
-    p.ntaps = n;
-    p.shift = wt->upconv2d_b;
-    // out[o] = sum_k in[o+1-k] w[k] = sum_k' in[o-1+k'] w[8-k']: a 3x3 correlation with mirrored taps
-    DirectConv dc{};
-    dc.in = P.u[0] + (size_t)H * W;                 // slot 1 of the [8][D+1][H][W] decoder tensor
-    dc.w = wt->upconv2d_w; dc.shift = wt->upconv2d_b; dc.out = logits;
-    dc.Cin = 8; dc.Cout = 1; dc.Di = D; dc.Hi = H; dc.Wi = W; dc.Do = D; dc.Ho = H; dc.Wo = W;
-    dc.w_co = 9; dc.w_ci = 9; dc.acc_scale = 1.0f; dc.relu = 0; dc.flip = 1;
-    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
-    ProfScope prof(kProfDecoder, st);
-    if (!no_direct && direct_conv_supported(dc, 1, 1)) {
-      // the input tensor has D+1 planes per channel: express it as Di = D with the channel stride of D+1 planes
-      RUN(direct_conv_launch_cs(dc, (long long)(D + 1) * H * W, st, "red upconv2d (direct)"));
-    } else {
-      RUN(launch_one<Tile8>(p, st, "red upconv2d"));
-    }
-  }
+  if (!decoded) RUN(run_decoder(0, D, st));
   if (state_out)
     for (int l = 0; l < 4; ++l)
       if (state_out[l]) {

@@ -1,0 +1,442 @@
+// train.cu — the training form of the Conv3d / Deconv3d blocks of CostRegNet (modules/module.py:324-410, :546-577) as C-ABI
+// primitives: train.py:267-287 runs the network in train() mode (BatchNorm3d on batch statistics) and calls loss.backward().
+//
+//   forward of a block    y = conv(x, W)                       satmvs_conv3d_raw     (modes 0 / 1: conv stride 1 / 2, 3: transposed)
+//                         z = relu(BN_batch(y)) [+ skip]       satmvs_bn_train_fwd
+//   backward of a block   dy = BN'(relu'(dz))                  satmvs_bn_train_bwd   (also d gamma, d beta)
+//                         dx = conv^T(dy, W)                   satmvs_conv3d_raw     (the data gradient of a stride-1 conv is the conv
+//                                                              with mirrored taps and swapped channel strides (mode 2); of a stride-2 conv
+//                                                              the transposed conv reading the SAME weight tensor (mode 3); of the
+//                                                              transposed conv the stride-2 conv reading the same weight tensor (mode 1))
+//                         dW = sum_o dy[o] x[s o + k - 1]      satmvs_conv3d_wgrad
+//
+// The data-path convolutions reuse the fp32 engines of the inference path (direct_conv.cuh, conv_engine.cuh); the weight gradient
+// is a contraction over all positions: every CTA walks output rows, keeps the nine (kz, ky) input rows of a few input channels and
+// the output-gradient row of all output channels in shared memory, accumulates (co, ci, kz, ky) x 3 kx partial filters in registers,
+// and a second kernel adds the per-CTA partials in a fixed order (deterministic, no float atomics).
+#include "conv_engine.cuh"
+#include "direct_conv.cuh"
+
+namespace satmvs {
+
+// ----------------------------------------------------------------------------------------------------------------------------
+// BatchNorm (training form) on [B][C][n] tensors
+// ----------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int B, int C, long long n, double* __restrict__ acc) {
+  const int c = blockIdx.y;
+  double s = 0.0, q = 0.0;
+  const long long n4 = n >> 2;
+  for (int b = 0; b < B; ++b) {
+    const float4* p = reinterpret_cast<const float4*>(y + ((long long)b * C + c) * n);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(p + i);
+      const float ls = (v.x + v.y) + (v.z + v.w);
+      const float lq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      s += ls; q += lq;
+    }
+  }
+  __shared__ double red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int i = 0; i < 8; ++i) { ts += red[0][i]; tq += red[1][i]; }
+    atomicAdd(acc + 2 * c, ts);
+    atomicAdd(acc + 2 * c + 1, tq);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double count, float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = acc[2 * c] / count;
+  double v = acc[2 * c + 1] / count - m * m;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)m;
+  var[c] = (float)v;      // biased, as used for normalisation; the caller derives the unbiased running_var update
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ y, int B, int C, long long n, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                                       const float* __restrict__ var, float eps, int relu,
+                                                       const float* __restrict__ post_add, float* __restrict__ z) {
+  const int c = blockIdx.y;
+  const float istd = rsqrtf(var[c] + eps);
+  const float g = (gamma ? gamma[c] : 1.0f) * istd, sh = (beta ? beta[c] : 0.0f) - mean[c] * g;
+  const long long n4 = n >> 2;
+  for (int b = 0; b < B; ++b) {
+    const long long base = ((long long)b * C + c) * n;
+    const float4* p = reinterpret_cast<const float4*>(y + base);
+    const float4* a = post_add ? reinterpret_cast<const float4*>(post_add + base) : nullptr;
+    float4* o = reinterpret_cast<float4*>(z + base);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      float4 v = __ldg(p + i);
+      v.x = fmaf(v.x, g, sh); v.y = fmaf(v.y, g, sh); v.z = fmaf(v.z, g, sh); v.w = fmaf(v.w, g, sh);
+      if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+      if (a) { const float4 s = __ldg(a + i); v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w; }
+      o[i] = v;
+    }
+  }
+}
+
+// sums of the masked output gradient and of (masked gradient x normalised activation) per channel
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ dz2, const float* __restrict__ y, int B, int C, long long n,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                                            int relu, double* __restrict__ acc) {
+  const int c = blockIdx.y;
+  const float istd = rsqrtf(var[c] + eps), m = mean[c];
+  const float g = (gamma ? gamma[c] : 1.0f) * istd, sh = (beta ? beta[c] : 0.0f) - m * g;
+  double s1 = 0.0, s2 = 0.0;
+  const long long n4 = n >> 2;
+  for (int b = 0; b < B; ++b) {
+    const long long base = ((long long)b * C + c) * n;
+    const float4* py = reinterpret_cast<const float4*>(y + base);
+    const float4* pd = reinterpret_cast<const float4*>(dz + base);
+    const float4* pe = dz2 ? reinterpret_cast<const float4*>(dz2 + base) : nullptr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(py + i);
+      float4 d = __ldg(pd + i);
+      if (pe) { const float4 e = __ldg(pe + i); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+      if (relu) {
+        if (fmaf(v.x, g, sh) <= 0.0f) d.x = 0.0f;
+        if (fmaf(v.y, g, sh) <= 0.0f) d.y = 0.0f;
+        if (fmaf(v.z, g, sh) <= 0.0f) d.z = 0.0f;
+        if (fmaf(v.w, g, sh) <= 0.0f) d.w = 0.0f;
+      }
+      const float l1 = (d.x + d.y) + (d.z + d.w);
+      const float l2 = (d.x * ((v.x - m) * istd) + d.y * ((v.y - m) * istd)) + (d.z * ((v.z - m) * istd) + d.w * ((v.w - m) * istd));
+      s1 += l1; s2 += l2;
+    }
+  }
+  __shared__ double red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b2 = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b2 += red[1][i]; }
+    atomicAdd(acc + 2 * c, a);
+    atomicAdd(acc + 2 * c + 1, b2);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ dz2, const float* __restrict__ y, int B, int C, long long n,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                                           int relu, const double* __restrict__ acc, double count, float* __restrict__ dy,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.y;
+  const float istd = rsqrtf(var[c] + eps), m = mean[c];
+  const float gm = gamma ? gamma[c] : 1.0f;
+  const float g = gm * istd, sh = (beta ? beta[c] : 0.0f) - m * g;
+  const float k1 = (float)(acc[2 * c] / count), k2 = (float)(acc[2 * c + 1] / count);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (dgamma) dgamma[c] = (float)acc[2 * c + 1];
+    if (dbeta) dbeta[c] = (float)acc[2 * c];
+  }
+  const long long n4 = n >> 2;
+  for (int b = 0; b < B; ++b) {
+    const long long base = ((long long)b * C + c) * n;
+    const float4* py = reinterpret_cast<const float4*>(y + base);
+    const float4* pd = reinterpret_cast<const float4*>(dz + base);
+    const float4* pe = dz2 ? reinterpret_cast<const float4*>(dz2 + base) : nullptr;
+    float4* po = reinterpret_cast<float4*>(dy + base);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(py + i);
+      float4 d = __ldg(pd + i);
+      if (pe) { const float4 e = __ldg(pe + i); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
+      if (relu) {
+        if (fmaf(v.x, g, sh) <= 0.0f) d.x = 0.0f;
+        if (fmaf(v.y, g, sh) <= 0.0f) d.y = 0.0f;
+        if (fmaf(v.z, g, sh) <= 0.0f) d.z = 0.0f;
+        if (fmaf(v.w, g, sh) <= 0.0f) d.w = 0.0f;
+      }
+      float4 r;
+      r.x = g * (d.x - k1 - (v.x - m) * istd * k2);
+      r.y = g * (d.y - k1 - (v.y - m) * istd * k2);
+      r.z = g * (d.z - k1 - (v.z - m) * istd * k2);
+      r.w = g * (d.w - k1 - (v.w - m) * istd * k2);
+      po[i] = r;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------------
+// weight gradient of a 3x3x3 (NZ 3) or 3x3 (NZ 1) convolution with padding 1 and stride S
+// ----------------------------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float* x;      // [Cin][Di][Hi][Wi]
+  const float* dy;     // [Cout][Do][Ho][Wo]
+  float* partial;      // [gridDim.x][Cout][Cin][NZ * 9]
+  int Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, NZ;
+  int ci_tile;         // input channels per CTA (grid.y = Cin / ci_tile, rounded up)
+  int rsx, rsy;        // shared-memory row strides (floats): rs / 4 odd, so that lanes on different rows hit different banks
+};
+
+constexpr int kWgThreads = 256;
+constexpr int kWgMaxItems = 18;   // (co, ci, kz, ky) items per thread: Cout 64 x 8 channels x 9 / 256
+
+template <int S>
+__global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int nkk = a.NZ * 3;
+  float* xs = smem;                                        // [ci_tile][nkk][rsx]; index p of a row <-> input column p - 1
+  float* dys = smem + (size_t)a.ci_tile * nkk * a.rsx;     // [Cout][rsy]
+  const int ci0 = blockIdx.y * a.ci_tile;
+  const int nci = min(a.ci_tile, a.Cin - ci0);
+  const int items = a.Cout * nci * nkk;
+  float acc[kWgMaxItems][3];
+#pragma unroll
+  for (int i = 0; i < kWgMaxItems; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.0f;
+  const int rows = a.Do * a.Ho;
+  const int wo4 = (a.Wo + 3) & ~3;
+  const long long in_cs = (long long)a.Di * a.Hi * a.Wi, out_cs = (long long)a.Do * a.Ho * a.Wo;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int oz = r / a.Ho, oy = r - oz * a.Ho;
+    __syncthreads();
+    // output-gradient row of every output channel, zero-padded to a multiple of 4
+    for (int i = threadIdx.x; i < a.Cout * a.rsy; i += kWgThreads) {
+      const int co = i / a.rsy, ox = i - co * a.rsy;
+      dys[i] = ox < a.Wo ? __ldg(a.dy + co * out_cs + ((long long)oz * a.Ho + oy) * a.Wo + ox) : 0.0f;
+    }
+    // the nkk input rows of the CTA's channels (zero outside the tensor)
+    for (int i = threadIdx.x; i < nci * nkk * a.rsx; i += kWgThreads) {
+      const int row = i / a.rsx, p = i - row * a.rsx;
+      const int cl = row / nkk, kk = row - cl * nkk;
+      const int kz = a.NZ == 3 ? kk / 3 : 1, ky = kk - (a.NZ == 3 ? kz * 3 : 0);
+      const int iz = a.NZ == 3 ? S * oz + kz - 1 : oz, iy = S * oy + ky - 1, ix = p - 1;
+      float v = 0.0f;
+      if (iz >= 0 && iz < a.Di && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
+        v = __ldg(a.x + (ci0 + cl) * in_cs + ((long long)iz * a.Hi + iy) * a.Wi + ix);
+      xs[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kWgMaxItems; ++it) {
+      const int id = threadIdx.x + it * kWgThreads;
+      if (id < items) {
+        const int co = id / (nci * nkk), rem = id - co * (nci * nkk);      // rem = ci_local * nkk + kk: the row of xs
+        const float* xr = xs + (size_t)rem * a.rsx;
+        const float* dr = dys + (size_t)co * a.rsy;
+        float a0 = acc[it][0], a1 = acc[it][1], a2 = acc[it][2];
+        for (int ox = 0; ox < wo4; ox += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(dr + ox);
+          if (S == 1) {
+            const float4 u = *reinterpret_cast<const float4*>(xr + ox);
+            const float2 v = *reinterpret_cast<const float2*>(xr + ox + 4);
+            a0 = fmaf(d.x, u.x, a0); a0 = fmaf(d.y, u.y, a0); a0 = fmaf(d.z, u.z, a0); a0 = fmaf(d.w, u.w, a0);
+            a1 = fmaf(d.x, u.y, a1); a1 = fmaf(d.y, u.z, a1); a1 = fmaf(d.z, u.w, a1); a1 = fmaf(d.w, v.x, a1);
+            a2 = fmaf(d.x, u.z, a2); a2 = fmaf(d.y, u.w, a2); a2 = fmaf(d.z, v.x, a2); a2 = fmaf(d.w, v.y, a2);
+          } else {
+            const float4 u = *reinterpret_cast<const float4*>(xr + 2 * ox);
+            const float4 v = *reinterpret_cast<const float4*>(xr + 2 * ox + 4);
+            const float w8 = xr[2 * ox + 8];
+            a0 = fmaf(d.x, u.x, a0); a0 = fmaf(d.y, u.z, a0); a0 = fmaf(d.z, v.x, a0); a0 = fmaf(d.w, v.z, a0);
+            a1 = fmaf(d.x, u.y, a1); a1 = fmaf(d.y, u.w, a1); a1 = fmaf(d.z, v.y, a1); a1 = fmaf(d.w, v.w, a1);
+            a2 = fmaf(d.x, u.z, a2); a2 = fmaf(d.y, v.x, a2); a2 = fmaf(d.z, v.z, a2); a2 = fmaf(d.w, w8, a2);
+          }
+        }
+        acc[it][0] = a0; acc[it][1] = a1; acc[it][2] = a2;
+      }
+    }
+  }
+  const int taps = a.NZ * 9;
+  float* out = a.partial + (size_t)blockIdx.x * a.Cout * a.Cin * taps;
+#pragma unroll
+  for (int it = 0; it < kWgMaxItems; ++it) {
+    const int id = threadIdx.x + it * kWgThreads;
+    if (id < items) {
+      const int co = id / (nci * nkk), rem = id - co * (nci * nkk);
+      const int cl = rem / nkk, kk = rem - cl * nkk;
+      float* o = out + ((size_t)co * a.Cin + ci0 + cl) * taps + kk * 3;
+      o[0] = acc[it][0]; o[1] = acc[it][1]; o[2] = acc[it][2];
+    }
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int Cout, int Cin, int taps, float* __restrict__ dw,
+                                    long long dw_co, long long dw_ci, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = Cout * Cin * taps;
+  if (i >= total) return;
+  float s = 0.0f;
+  for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * total + i];
+  const int co = i / (Cin * taps), rem = i - co * (Cin * taps), ci = rem / taps, t = rem - ci * taps;
+  float* o = dw + co * dw_co + ci * dw_ci + t;
+  *o = accumulate ? *o + s : s;
+}
+
+struct WgradPlan { int ci_tile, rsx, rsy, chunks, groups; size_t smem, ws_bytes; bool ok; };
+
+static WgradPlan wgrad_plan(int Cin, int Cout, int Wi, int Do, int Ho, int Wo, int NZ, int stride) {
+  WgradPlan p{};
+  const int wo4 = (Wo + 3) & ~3;
+  auto odd4 = [](int n) { n = (n + 3) & ~3; if (((n >> 2) & 1) == 0) n += 4; return n; };
+  p.rsy = odd4(wo4);
+  const int need = stride * wo4 + 12;                 // the furthest float the vector loads of the last group touch
+  p.rsx = odd4(need > Wi + 2 ? need : Wi + 2);
+  const int nkk = NZ * 3;
+  p.ok = false;
+  for (int t = 8; t >= 1; t >>= 1) {
+    const size_t sm = ((size_t)t * nkk * p.rsx + (size_t)Cout * p.rsy) * 4;
+    const int items = Cout * t * nkk;
+    if (sm <= 200 * 1024 && items <= kWgMaxItems * kWgThreads) { p.ci_tile = t; p.smem = sm; p.ok = true; break; }
+  }
+  if (!p.ok) return p;
+  p.groups = (Cin + p.ci_tile - 1) / p.ci_tile;
+  const int rows = Do * Ho;
+  int chunks = (2 * kNumSMs + p.groups - 1) / p.groups;
+  if (chunks > rows) chunks = rows;
+  if (chunks < 1) chunks = 1;
+  p.chunks = chunks;
+  p.ws_bytes = (size_t)chunks * Cout * Cin * NZ * 9 * 4;
+  return p;
+}
+
+}  // namespace satmvs
+
+using namespace satmvs;
+
+extern "C" {
+
+int satmvs_conv3d_raw(const float* in, int Cin, int Di, int Hi, int Wi, const float* w, long long w_co, long long w_ci,
+                      int NZ, int mode, float* out, int Cout, void* stream) {
+  SATMVS_CHECK_ASYNC();
+  SATMVS_REQUIRE(in && w && out && Cin >= 1 && Cout >= 1 && Di >= 1 && Hi >= 1 && Wi >= 1);
+  SATMVS_REQUIRE((NZ == 1 || NZ == 3) && mode >= 0 && mode <= 3);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool three = NZ == 3;
+  if (mode == 3) {   // ConvTranspose(k 3, stride 2, padding 1, output_padding 1): one problem per output parity class
+    ConvGroup g{};
+    int n = 0;
+    for (int pz = 0; pz < (three ? 2 : 1); ++pz)
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          ConvProblem p;
+          conv_problem_defaults(p);
+          p.in = in; p.w = w; p.out = out;
+          p.Cin = Cin; p.Cout = Cout;
+          p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.Do = three ? 2 * Di : Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
+          p.Qd = Di; p.Qh = Hi; p.Qw = Wi;
+          p.w_ci_stride = w_ci; p.w_co_stride = w_co;
+          if (three) { p.q2o_mul[0] = 2; p.q2o_add[0] = pz; }
+          p.q2o_mul[1] = 2; p.q2o_mul[2] = 2; p.q2o_add[1] = py; p.q2o_add[2] = px;
+          conv_taps_deconv_class(p, three, pz, py, px);
+          conv_finalize(p);
+          g.p[n++] = p;
+        }
+    g.n = n;
+    if (Cout >= 32) return conv_launch<Tile32>(g, st, "satmvs_conv3d_raw (transposed)");
+    if (Cout >= 16) return conv_launch<Tile16>(g, st, "satmvs_conv3d_raw (transposed)");
+    return conv_launch<Tile8>(g, st, "satmvs_conv3d_raw (transposed)");
+  }
+  const int stride = mode == 1 ? 2 : 1;
+  if (stride == 2) SATMVS_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0 && (!three || Di % 2 == 0));
+  const int Do = three ? Di / stride : Di, Ho = Hi / stride, Wo = Wi / stride;
+  {
+    DirectConv d{};
+    d.in = in; d.w = w; d.out = out;
+    d.Cin = Cin; d.Cout = Cout; d.Di = Di; d.Hi = Hi; d.Wi = Wi; d.Do = Do; d.Ho = Ho; d.Wo = Wo;
+    d.w_co = w_co; d.w_ci = w_ci; d.acc_scale = 1.0f; d.relu = 0; d.flip = mode == 2;
+    if (direct_conv_supported(d, NZ, stride)) return direct_conv_launch(d, NZ, stride, st, "satmvs_conv3d_raw (direct)");
+  }
+  ConvProblem p;
+  conv_problem_defaults(p);
+  p.in = in; p.w = w; p.out = out;
+  p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+  p.Qd = Do; p.Qh = Ho; p.Qw = Wo;
+  p.w_co_stride = w_co; p.w_ci_stride = w_ci;
+  for (int i = 0; i < 3; ++i) { p.q2i_mul[i] = stride; p.q2i_add[i] = -1; }
+  if (!three) { p.q2i_mul[0] = 1; p.q2i_add[0] = 0; }
+  conv_taps_dense(p, three);
+  if (mode == 2)
+    for (int t = 0; t < p.ntaps; ++t) p.tap_w[t] = (signed char)(p.ntaps - 1 - p.tap_w[t]);
+  conv_finalize(p);
+  ConvGroup g{};
+  g.p[0] = p; g.n = 1;
+  if (Cout >= 64) return conv_launch<Tile64>(g, st, "satmvs_conv3d_raw");
+  if (Cout >= 32) return conv_launch<Tile32>(g, st, "satmvs_conv3d_raw");
+  if (Cout >= 16) return conv_launch<Tile16>(g, st, "satmvs_conv3d_raw");
+  return conv_launch<Tile8>(g, st, "satmvs_conv3d_raw");
+}
+
+size_t satmvs_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int Di, int Hi, int Wi, int NZ, int stride) {
+  if (Cin < 1 || Cout < 1 || Di < 1 || Hi < 1 || Wi < 1 || (NZ != 1 && NZ != 3) || (stride != 1 && stride != 2)) return 0;
+  const WgradPlan p = wgrad_plan(Cin, Cout, Wi, NZ == 3 ? Di / stride : Di, Hi / stride, Wi / stride, NZ, stride);
+  return p.ok ? p.ws_bytes + 256 : 0;
+}
+
+int satmvs_conv3d_wgrad(const float* x, int Cin, int Di, int Hi, int Wi, const float* dy, int Cout, int NZ, int stride,
+                        float* dw, long long dw_co, long long dw_ci, int accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  SATMVS_CHECK_ASYNC();
+  SATMVS_REQUIRE(x && dy && dw && workspace && Cin >= 1 && Cout >= 1 && Di >= 1 && Hi >= 1 && Wi >= 1);
+  SATMVS_REQUIRE((NZ == 1 || NZ == 3) && (stride == 1 || stride == 2));
+  if (stride == 2) SATMVS_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0 && (NZ == 1 || Di % 2 == 0));
+  const int Do = NZ == 3 ? Di / stride : Di, Ho = Hi / stride, Wo = Wi / stride;
+  const WgradPlan p = wgrad_plan(Cin, Cout, Wi, Do, Ho, Wo, NZ, stride);
+  if (!p.ok) return fail_invalid("satmvs_conv3d_wgrad: a row of the tensors does not fit shared memory (Cout x Wo, Wi)");
+  SATMVS_REQUIRE(workspace_bytes >= p.ws_bytes);
+  SATMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  WgradArgs a{};
+  a.x = x; a.dy = dy; a.partial = static_cast<float*>(workspace);
+  a.Cin = Cin; a.Cout = Cout; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Do = Do; a.Ho = Ho; a.Wo = Wo; a.NZ = NZ;
+  a.ci_tile = p.ci_tile; a.rsx = p.rsx; a.rsy = p.rsy;
+  const dim3 grid(p.chunks, p.groups);
+  if (stride == 1) {
+    static const cudaError_t e1 = cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    (void)e1;
+    wgrad_kernel<1><<<grid, kWgThreads, p.smem, st>>>(a);
+  } else {
+    static const cudaError_t e2 = cudaFuncSetAttribute(wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    (void)e2;
+    wgrad_kernel<2><<<grid, kWgThreads, p.smem, st>>>(a);
+  }
+  int rc = check_launch("wgrad_kernel");
+  if (rc) return rc;
+  const int total = Cout * Cin * NZ * 9;
+  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a.partial, p.chunks, Cout, Cin, NZ * 9, dw, dw_co, dw_ci, accumulate);
+  return check_launch("wgrad_reduce_kernel");
+}
+
+// z = [relu](gamma (y - mean_batch) / sqrt(var_batch + eps) + beta) [+ post_add]; mean / var (biased) are outputs.
+// y, z, post_add: [B][C][n] with n a multiple of 4; acc: 2 C doubles of scratch.
+int satmvs_bn_train_fwd(const float* y, int B, int C, long long n, const float* gamma, const float* beta, float eps, int relu,
+                        const float* post_add, float* z, float* mean, float* var, double* acc, void* stream) {
+  SATMVS_CHECK_ASYNC();
+  SATMVS_REQUIRE(y && z && mean && var && acc && B >= 1 && C >= 1 && n >= 4 && n % 4 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(acc, 0, (size_t)C * 2 * sizeof(double), st);
+  int bx = (int)((n / 4 + 255) / 256);
+  const int cap = (8 * kNumSMs + C - 1) / C;
+  if (bx > cap) bx = cap;
+  bn_stats_kernel<<<dim3(bx, C), 256, 0, st>>>(y, B, C, n, acc);
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(acc, C, (double)B * (double)n, mean, var);
+  bn_apply_kernel<<<dim3(bx, C), 256, 0, st>>>(y, B, C, n, gamma, beta, mean, var, eps, relu, post_add, z);
+  return check_launch("satmvs_bn_train_fwd");
+}
+
+// dy (gradient at the conv output) from dz (+ dz2 when the block output feeds two consumers: the next block and a skip);
+// dgamma / dbeta [C] outputs (may be null).
+int satmvs_bn_train_bwd(const float* dz, const float* dz2, const float* y, int B, int C, long long n, const float* gamma, const float* beta,
+                        const float* mean, const float* var, float eps, int relu, float* dy, float* dgamma, float* dbeta,
+                        double* acc, void* stream) {
+  SATMVS_CHECK_ASYNC();
+  SATMVS_REQUIRE(dz && y && mean && var && dy && acc && B >= 1 && C >= 1 && n >= 4 && n % 4 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(acc, 0, (size_t)C * 2 * sizeof(double), st);
+  int bx = (int)((n / 4 + 255) / 256);
+  const int cap = (8 * kNumSMs + C - 1) / C;
+  if (bx > cap) bx = cap;
+  bn_bwd_reduce_kernel<<<dim3(bx, C), 256, 0, st>>>(dz, dz2, y, B, C, n, gamma, beta, mean, var, eps, relu, acc);
+  bn_bwd_apply_kernel<<<dim3(bx, C), 256, 0, st>>>(dz, dz2, y, B, C, n, gamma, beta, mean, var, eps, relu, acc, (double)B * (double)n, dy,
+                                                   dgamma, dbeta);
+  return check_launch("satmvs_bn_train_bwd");
+}
+
+}  // extern "C"

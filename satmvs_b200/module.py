@@ -258,7 +258,9 @@ class Deconv3d(nn.Module):
 
 class CostRegNet(nn.Module):
     """`CostRegNet` (`modules/module.py:546-577`): x [B,Cin,D,H,W] -> [B,1,D,H,W].
-    Inference-mode BatchNorm (running statistics); calling it in training mode raises."""
+    `.eval()`: BatchNorm on running statistics, folded into the convolutions (`satmvs_costreg_forward`).
+    `.train()`: BatchNorm on batch statistics (running statistics updated) and a backward to x and every parameter
+    (`satmvs_b200.training`, `csrc/train.cu`)."""
 
     _BLOCKS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11")
 
@@ -302,7 +304,9 @@ class CostRegNet(nn.Module):
 
     def forward(self, x):
         if self.training:
-            raise RuntimeError("satmvs_b200.CostRegNet implements inference-mode BatchNorm only; call .eval()")
+            # train.py:268 runs the network in train() mode: BatchNorm3d on batch statistics, backward to x and the parameters
+            from .training import costreg_train_forward
+            return costreg_train_forward(self, x)
         x = _lib.require_cuda(x, "x")
         B, Cc, D, H, W = x.shape
         if Cc != self.in_channels:

@@ -1,0 +1,132 @@
+"""Training form of CostRegNet (train.py:267-287: model.train(), loss.backward()) on the library's kernels against autograd of
+the CPU oracle: batch-statistics BatchNorm, running-stat updates, gradients to the input and to every parameter.
+Tolerance: 1e-3 of each tensor's largest magnitude (fp32 on both sides, different summation orders)."""
+import pytest
+import torch
+
+import satmvs_b200
+from oracle import regnets, regress
+from satmvs_b200 import synth, training
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("mode,cin,cout,D,H,W", [(0, 8, 16, 4, 8, 16), (1, 8, 16, 4, 8, 16), (3, 16, 8, 2, 4, 8), (0, 5, 3, 3, 5, 7),
+                                                  (1, 3, 5, 4, 6, 10), (3, 4, 6, 3, 5, 7)])
+def test_conv_primitives_match_autograd(mode, cin, cout, D, H, W):
+    """satmvs_conv3d_raw in its forward arrangement, the arrangement that is its data gradient, and satmvs_conv3d_wgrad."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(mode * 7 + cin)
+    x = torch.randn(1, cin, D, H, W, generator=g, requires_grad=True)
+    if mode == 3:
+        w = torch.randn(cin, cout, 3, 3, 3, generator=g, requires_grad=True)
+        y = F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1)
+    else:
+        w = torch.randn(cout, cin, 3, 3, 3, generator=g, requires_grad=True)
+        y = F.conv3d(x, w, stride=2 if mode == 1 else 1, padding=1)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    xd, wd, gyd = x.detach().to(DEV), w.detach().to(DEV), gy.to(DEV)
+    if mode == 3:
+        got = training.conv3d_raw(xd, wd, 3, cout, 27, cout * 27)
+        dx = training.conv3d_raw(gyd, wd, 1, cin, cout * 27, 27)
+        dw = training.conv3d_wgrad(gyd, xd, 2, torch.empty_like(wd), cout * 27, 27)
+    else:
+        got = training.conv3d_raw(xd, wd, mode, cout, cin * 27, 27)
+        dx = training.conv3d_raw(gyd, wd, 3 if mode == 1 else 2, cin, 27, cin * 27)
+        dw = training.conv3d_wgrad(xd, gyd, 2 if mode == 1 else 1, torch.empty_like(wd), cin * 27, 27)
+    assert rel(got, y) < 1e-5
+    assert rel(dx, x.grad) < 1e-5
+    assert rel(dw, w.grad) < 1e-4
+
+
+def test_batchnorm_train_matches_autograd():
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    y = (torch.randn(2, 6, 4, 6, 8, generator=g) * 3 + 1).requires_grad_(True)
+    gamma = torch.randn(6, generator=g).requires_grad_(True)
+    beta = torch.randn(6, generator=g).requires_grad_(True)
+    skip = torch.randn(2, 6, 4, 6, 8, generator=g)
+    z = F.relu(F.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-5)) + skip
+    gz, gz2 = torch.randn(z.shape, generator=g), torch.randn(z.shape, generator=g)
+    z.backward(gz + gz2)
+    zd, mean, var = training.bn_train_fwd(y.detach().to(DEV), gamma.detach().to(DEV), beta.detach().to(DEV), True, skip.to(DEV))
+    assert rel(zd, z) < 1e-5
+    assert rel(mean, y.detach().mean((0, 2, 3, 4))) < 1e-5
+    assert rel(var, y.detach().var((0, 2, 3, 4), unbiased=False)) < 1e-5
+    dy, dg, db = training.bn_train_bwd(gz.to(DEV), gz2.to(DEV), y.detach().to(DEV), gamma.detach().to(DEV), beta.detach().to(DEV),
+                                       mean, var, True)
+    assert rel(dy, y.grad) < 1e-4
+    assert rel(dg, gamma.grad) < 1e-4
+    assert rel(db, beta.grad) < 1e-4
+
+
+@pytest.mark.parametrize("C,B,D,H,W", [(8, 1, 8, 16, 32), (32, 1, 16, 32, 64), (16, 2, 8, 16, 32)])
+def test_costregnet_train_step_matches_oracle_autograd(C, B, D, H, W):
+    sd = synth.make_costregnet_weights(C, seed=3)
+    net = satmvs_b200.CostRegNet(C, 8)
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    x = synth.make_features(1, 1, B * C * D, H, W, seed=4)[0].view(B, C, D, H, W).abs()
+    gen = torch.Generator().manual_seed(9)
+    gout = torch.randn(B, 1, D, H, W, generator=gen)
+
+    ref = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    want = regnets.costregnet(xr, ref, training=True)
+    want.backward(gout)
+
+    xg = x.to(DEV).requires_grad_(True)
+    got = net(xg)
+    assert got.shape == want.shape and got.requires_grad
+    assert rel(got, want) < 1e-3
+    got.backward(gout.to(DEV))
+    assert rel(xg.grad, xr.grad) < 1e-3
+    worst = 0.0
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        r = rel(p.grad, ref[name].grad)
+        worst = max(worst, r)
+        assert r < 2e-3, (name, r)
+    # running statistics after one step: (1 - 0.1) * old + 0.1 * batch (unbiased variance), module.py:348 momentum
+    c0 = torch.nn.functional.conv3d(x, sd["conv0.conv.weight"], padding=1)
+    m = c0.mean((0, 2, 3, 4))
+    v = c0.var((0, 2, 3, 4), unbiased=True)
+    assert rel(net.conv0.bn.running_mean, 0.9 * sd["conv0.bn.running_mean"] + 0.1 * m) < 1e-4
+    assert rel(net.conv0.bn.running_var, 0.9 * sd["conv0.bn.running_var"] + 0.1 * v) < 1e-4
+    assert int(net.conv0.bn.num_batches_tracked) == int(sd.get("conv0.bn.num_batches_tracked", 0)) + 1
+
+
+def test_eval_after_train_uses_the_updated_running_statistics():
+    sd = synth.make_costregnet_weights(8, seed=3)
+    net = satmvs_b200.CostRegNet(8, 8)
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    x = synth.make_features(1, 1, 8 * 8, 16, 32, seed=4)[0].view(1, 8, 8, 16, 32).abs()
+    net(x.to(DEV))
+    net.eval()
+    with torch.no_grad():
+        got = net(x.to(DEV))
+    sd2 = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    want = regnets.costregnet(x, sd2)
+    assert rel(got, want) < 1e-3
+
+
+def test_softargmin_head_gradient():
+    gen = torch.Generator().manual_seed(2)
+    logits = torch.randn(2, 12, 9, 13, generator=gen).requires_grad_(True)
+    dv = (torch.linspace(400, 600, 12).view(1, 12, 1, 1) + torch.randn(2, 12, 9, 13, generator=gen)).contiguous()
+    want, _ = regress.softargmin_casmvs(logits, dv)
+    gd = torch.randn(2, 9, 13, generator=gen)
+    want.backward(gd)
+    lg = logits.detach().to(DEV).requires_grad_(True)
+    depth, conf = training.softargmin_casmvs_train(lg, dv.to(DEV))
+    assert rel(depth, want) < 1e-5 and not conf.requires_grad
+    depth.backward(gd.to(DEV))
+    assert rel(lg.grad, logits.grad) < 1e-4
