@@ -82,7 +82,7 @@ def lib():
 
 
 PROFILE_CLASSES = ("sweep", "conv_batched", "gru_gate_conv", "gru_output_conv", "gru_pointwise", "red_decoder",
-                   "costreg", "heads", "featurenet")
+                   "costreg", "heads", "featurenet", "train_conv", "train_wgrad", "train_norm")
 
 
 class profile:

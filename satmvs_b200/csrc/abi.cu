@@ -38,7 +38,7 @@ int async_error_poll() {
   return v;
 }
 ProfState& prof_state() {
-  static thread_local ProfState s;
+  static ProfState s;
   return s;
 }
 }  // namespace satmvs
@@ -46,7 +46,9 @@ ProfState& prof_state() {
 extern "C" {
 int satmvs_profile_begin(void) {
   satmvs::ProfState& s = satmvs::prof_state();
-  for (auto& v : s.ev) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }
+  std::lock_guard<std::mutex> lk(s.mu);
+  for (auto& v : s.ev) { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); v.clear(); }
+  ++s.generation;
   s.on = true;
   return SATMVS_OK;
 }
@@ -55,6 +57,11 @@ int satmvs_profile_end(float* ms_by_class, int* launches_by_class) {
   satmvs::ProfState& s = satmvs::prof_state();
   s.on = false;
   cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(s.mu);
+  ++s.generation;
+  for (int p = 0; p < satmvs::kProfCount; ++p)       // a scope still open on another thread: drop its unpaired start
+    for (size_t i = 0; i + 1 < s.ev[p].size(); i += 2)
+      if (s.ev[p][i + 1] == nullptr) { cudaEventDestroy(s.ev[p][i]); s.ev[p].erase(s.ev[p].begin() + i, s.ev[p].begin() + i + 2); i -= 2; }
   if (getenv("SATMVS_PROF_DUMP")) {   // timeline of every instrumented launch, relative to the first recorded event
     cudaEvent_t ref = nullptr;
     float best = 0.0f;

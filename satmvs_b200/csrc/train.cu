@@ -16,6 +16,7 @@
 // and a second kernel adds the per-CTA partials in a fixed order (deterministic, no float atomics).
 #include "conv_engine.cuh"
 #include "direct_conv.cuh"
+#include "prof.cuh"
 
 namespace satmvs {
 
@@ -174,73 +175,97 @@ struct WgradArgs {
   float* partial;      // [gridDim.x][Cout][Cin][NZ * 9]
   int Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, NZ;
   int ci_tile;         // input channels per CTA (grid.y = Cin / ci_tile, rounded up)
+  int rb;              // consecutive output rows per strip: their S * (rb - 1) + 3 input rows are staged once
   int rsx, rsy;        // shared-memory row strides (floats): rs / 4 odd, so that lanes on different rows hit different banks
 };
 
 constexpr int kWgThreads = 256;
-constexpr int kWgMaxItems = 18;   // (co, ci, kz, ky) items per thread: Cout 64 x 8 channels x 9 / 256
+constexpr int kWgMaxItems = 9;    // (co pair, ci, kz, ky) items per thread: Cout 64 / 2 x 8 channels x 9 / 256
 
 template <int S>
 __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int nkk = a.NZ * 3;
-  float* xs = smem;                                        // [ci_tile][nkk][rsx]; index p of a row <-> input column p - 1
-  float* dys = smem + (size_t)a.ci_tile * nkk * a.rsx;     // [Cout][rsy]
+  const int KZ = a.NZ == 3 ? 3 : 1, nkk = KZ * 3;
+  const int NR = S * (a.rb - 1) + 3;                        // input rows of a strip (per kz plane)
+  float* xs = smem;                                        // [ci_tile][KZ][NR][rsx]; index p of a row <-> input column p - 1
+  float* dys = smem + (size_t)a.ci_tile * KZ * NR * a.rsx;  // [Cout][rb][rsy]
   const int ci0 = blockIdx.y * a.ci_tile;
   const int nci = min(a.ci_tile, a.Cin - ci0);
-  const int items = a.Cout * nci * nkk;
-  float acc[kWgMaxItems][3];
+  const int cop = (a.Cout + 1) >> 1;                        // output-channel pairs: one staged input window feeds two filters
+  const int items = cop * nci * nkk;
+  float acc[kWgMaxItems][2][3];
 #pragma unroll
-  for (int i = 0; i < kWgMaxItems; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.0f;
-  const int rows = a.Do * a.Ho;
+  for (int i = 0; i < kWgMaxItems; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) acc[i][h][0] = acc[i][h][1] = acc[i][h][2] = 0.0f;
+  const int strips_y = (a.Ho + a.rb - 1) / a.rb;
+  const int strips = a.Do * strips_y;
   const int wo4 = (a.Wo + 3) & ~3;
   const long long in_cs = (long long)a.Di * a.Hi * a.Wi, out_cs = (long long)a.Do * a.Ho * a.Wo;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int oz = r / a.Ho, oy = r - oz * a.Ho;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
+    const int oz = sidx / strips_y, oy0 = (sidx - oz * strips_y) * a.rb;
     __syncthreads();
-    // output-gradient row of every output channel, zero-padded to a multiple of 4
-    for (int i = threadIdx.x; i < a.Cout * a.rsy; i += kWgThreads) {
-      const int co = i / a.rsy, ox = i - co * a.rsy;
-      dys[i] = ox < a.Wo ? __ldg(a.dy + co * out_cs + ((long long)oz * a.Ho + oy) * a.Wo + ox) : 0.0f;
+    // one warp per shared-memory row (row decode is warp-uniform, lanes walk the columns: no per-element divisions)
+    for (int row = warp; row < a.Cout * a.rb; row += nwarps) {   // output-gradient rows, zero-padded to a multiple of 4
+      const int co = row / a.rb, r = row - co * a.rb;
+      const bool live = oy0 + r < a.Ho;
+      const float* src = a.dy + co * out_cs + ((long long)oz * a.Ho + (live ? oy0 + r : 0)) * a.Wo;
+      float* dst = dys + (size_t)row * a.rsy;
+      for (int ox = lane; ox < a.rsy; ox += 32) dst[ox] = (live && ox < a.Wo) ? __ldg(src + ox) : 0.0f;
     }
-    // the nkk input rows of the CTA's channels (zero outside the tensor)
-    for (int i = threadIdx.x; i < nci * nkk * a.rsx; i += kWgThreads) {
-      const int row = i / a.rsx, p = i - row * a.rsx;
-      const int cl = row / nkk, kk = row - cl * nkk;
-      const int kz = a.NZ == 3 ? kk / 3 : 1, ky = kk - (a.NZ == 3 ? kz * 3 : 0);
-      const int iz = a.NZ == 3 ? S * oz + kz - 1 : oz, iy = S * oy + ky - 1, ix = p - 1;
-      float v = 0.0f;
-      if (iz >= 0 && iz < a.Di && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
-        v = __ldg(a.x + (ci0 + cl) * in_cs + ((long long)iz * a.Hi + iy) * a.Wi + ix);
-      xs[i] = v;
+    for (int row = warp; row < nci * KZ * NR; row += nwarps) {   // input rows (zero outside the tensor)
+      const int cl = row / (KZ * NR), rem = row - cl * (KZ * NR), kz = rem / NR, j = rem - kz * NR;
+      const int iz = a.NZ == 3 ? S * oz + kz - 1 : oz, iy = S * oy0 - 1 + j;
+      const bool live = iz >= 0 && iz < a.Di && iy >= 0 && iy < a.Hi;
+      const float* src = a.x + (ci0 + cl) * in_cs + ((long long)(live ? iz : 0) * a.Hi + (live ? iy : 0)) * a.Wi - 1;
+      float* dst = xs + (size_t)row * a.rsx;
+      for (int p = lane; p < a.rsx; p += 32) dst[p] = (live && p >= 1 && p <= a.Wi) ? __ldg(src + p) : 0.0f;
     }
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < kWgMaxItems; ++it) {
-      const int id = threadIdx.x + it * kWgThreads;
+      const int id = threadIdx.x + it * blockDim.x;
       if (id < items) {
-        const int co = id / (nci * nkk), rem = id - co * (nci * nkk);      // rem = ci_local * nkk + kk: the row of xs
-        const float* xr = xs + (size_t)rem * a.rsx;
-        const float* dr = dys + (size_t)co * a.rsy;
-        float a0 = acc[it][0], a1 = acc[it][1], a2 = acc[it][2];
-        for (int ox = 0; ox < wo4; ox += 4) {
-          const float4 d = *reinterpret_cast<const float4*>(dr + ox);
-          if (S == 1) {
-            const float4 u = *reinterpret_cast<const float4*>(xr + ox);
-            const float2 v = *reinterpret_cast<const float2*>(xr + ox + 4);
-            a0 = fmaf(d.x, u.x, a0); a0 = fmaf(d.y, u.y, a0); a0 = fmaf(d.z, u.z, a0); a0 = fmaf(d.w, u.w, a0);
-            a1 = fmaf(d.x, u.y, a1); a1 = fmaf(d.y, u.z, a1); a1 = fmaf(d.z, u.w, a1); a1 = fmaf(d.w, v.x, a1);
-            a2 = fmaf(d.x, u.z, a2); a2 = fmaf(d.y, u.w, a2); a2 = fmaf(d.z, v.x, a2); a2 = fmaf(d.w, v.y, a2);
-          } else {
-            const float4 u = *reinterpret_cast<const float4*>(xr + 2 * ox);
-            const float4 v = *reinterpret_cast<const float4*>(xr + 2 * ox + 4);
-            const float w8 = xr[2 * ox + 8];
-            a0 = fmaf(d.x, u.x, a0); a0 = fmaf(d.y, u.z, a0); a0 = fmaf(d.z, v.x, a0); a0 = fmaf(d.w, v.z, a0);
-            a1 = fmaf(d.x, u.y, a1); a1 = fmaf(d.y, u.w, a1); a1 = fmaf(d.z, v.y, a1); a1 = fmaf(d.w, v.w, a1);
-            a2 = fmaf(d.x, u.z, a2); a2 = fmaf(d.y, v.x, a2); a2 = fmaf(d.z, v.z, a2); a2 = fmaf(d.w, w8, a2);
+        const int cp = id / (nci * nkk), rem = id - cp * (nci * nkk);
+        const int cl = rem / nkk, kk = rem - cl * nkk, kz = kk / 3, ky = kk - kz * 3;
+        const int co0 = 2 * cp, co1 = min(2 * cp + 1, a.Cout - 1);       // an odd Cout computes its last filter twice (stored once)
+        float a0 = acc[it][0][0], a1 = acc[it][0][1], a2 = acc[it][0][2];
+        float b0 = acc[it][1][0], b1 = acc[it][1][1], b2 = acc[it][1][2];
+        for (int r = 0; r < a.rb; ++r) {
+          const float* xr = xs + (size_t)((cl * KZ + kz) * NR + S * r + ky) * a.rsx;
+          const float* dr = dys + (size_t)(co0 * a.rb + r) * a.rsy;
+          const float* er = dys + (size_t)(co1 * a.rb + r) * a.rsy;
+#pragma unroll 2
+          for (int ox = 0; ox < wo4; ox += 4) {
+            const float4 d = *reinterpret_cast<const float4*>(dr + ox);
+            const float4 e = *reinterpret_cast<const float4*>(er + ox);
+            float x0, x1, x2, x3, x4, x5, x6, x7, x8;
+            if (S == 1) {
+              const float4 u = *reinterpret_cast<const float4*>(xr + ox);
+              const float2 v = *reinterpret_cast<const float2*>(xr + ox + 4);
+              x0 = u.x; x1 = u.y; x2 = u.z; x3 = u.w; x4 = v.x; x5 = v.y; x6 = x7 = x8 = 0.0f;
+              a0 = fmaf(d.x, x0, a0); a0 = fmaf(d.y, x1, a0); a0 = fmaf(d.z, x2, a0); a0 = fmaf(d.w, x3, a0);
+              a1 = fmaf(d.x, x1, a1); a1 = fmaf(d.y, x2, a1); a1 = fmaf(d.z, x3, a1); a1 = fmaf(d.w, x4, a1);
+              a2 = fmaf(d.x, x2, a2); a2 = fmaf(d.y, x3, a2); a2 = fmaf(d.z, x4, a2); a2 = fmaf(d.w, x5, a2);
+              b0 = fmaf(e.x, x0, b0); b0 = fmaf(e.y, x1, b0); b0 = fmaf(e.z, x2, b0); b0 = fmaf(e.w, x3, b0);
+              b1 = fmaf(e.x, x1, b1); b1 = fmaf(e.y, x2, b1); b1 = fmaf(e.z, x3, b1); b1 = fmaf(e.w, x4, b1);
+              b2 = fmaf(e.x, x2, b2); b2 = fmaf(e.y, x3, b2); b2 = fmaf(e.z, x4, b2); b2 = fmaf(e.w, x5, b2);
+            } else {
+              const float4 u = *reinterpret_cast<const float4*>(xr + 2 * ox);
+              const float4 v = *reinterpret_cast<const float4*>(xr + 2 * ox + 4);
+              x0 = u.x; x1 = u.y; x2 = u.z; x3 = u.w; x4 = v.x; x5 = v.y; x6 = v.z; x7 = v.w; x8 = xr[2 * ox + 8];
+              a0 = fmaf(d.x, x0, a0); a0 = fmaf(d.y, x2, a0); a0 = fmaf(d.z, x4, a0); a0 = fmaf(d.w, x6, a0);
+              a1 = fmaf(d.x, x1, a1); a1 = fmaf(d.y, x3, a1); a1 = fmaf(d.z, x5, a1); a1 = fmaf(d.w, x7, a1);
+              a2 = fmaf(d.x, x2, a2); a2 = fmaf(d.y, x4, a2); a2 = fmaf(d.z, x6, a2); a2 = fmaf(d.w, x8, a2);
+              b0 = fmaf(e.x, x0, b0); b0 = fmaf(e.y, x2, b0); b0 = fmaf(e.z, x4, b0); b0 = fmaf(e.w, x6, b0);
+              b1 = fmaf(e.x, x1, b1); b1 = fmaf(e.y, x3, b1); b1 = fmaf(e.z, x5, b1); b1 = fmaf(e.w, x7, b1);
+              b2 = fmaf(e.x, x2, b2); b2 = fmaf(e.y, x4, b2); b2 = fmaf(e.z, x6, b2); b2 = fmaf(e.w, x8, b2);
+            }
           }
         }
-        acc[it][0] = a0; acc[it][1] = a1; acc[it][2] = a2;
+        acc[it][0][0] = a0; acc[it][0][1] = a1; acc[it][0][2] = a2;
+        acc[it][1][0] = b0; acc[it][1][1] = b1; acc[it][1][2] = b2;
       }
     }
   }
@@ -248,12 +273,18 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
   float* out = a.partial + (size_t)blockIdx.x * a.Cout * a.Cin * taps;
 #pragma unroll
   for (int it = 0; it < kWgMaxItems; ++it) {
-    const int id = threadIdx.x + it * kWgThreads;
+    const int id = threadIdx.x + it * blockDim.x;
     if (id < items) {
-      const int co = id / (nci * nkk), rem = id - co * (nci * nkk);
+      const int cp = id / (nci * nkk), rem = id - cp * (nci * nkk);
       const int cl = rem / nkk, kk = rem - cl * nkk;
-      float* o = out + ((size_t)co * a.Cin + ci0 + cl) * taps + kk * 3;
-      o[0] = acc[it][0]; o[1] = acc[it][1]; o[2] = acc[it][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int co = 2 * cp + h;
+        if (co < a.Cout) {
+          float* o = out + ((size_t)co * a.Cin + ci0 + cl) * taps + kk * 3;
+          o[0] = acc[it][h][0]; o[1] = acc[it][h][1]; o[2] = acc[it][h][2];
+        }
+      }
     }
   }
 }
@@ -270,7 +301,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunk
   *o = accumulate ? *o + s : s;
 }
 
-struct WgradPlan { int ci_tile, rsx, rsy, chunks, groups; size_t smem, ws_bytes; bool ok; };
+struct WgradPlan { int ci_tile, rb, rsx, rsy, chunks, groups, threads; size_t smem, ws_bytes; bool ok; };
 
 static WgradPlan wgrad_plan(int Cin, int Cout, int Wi, int Do, int Ho, int Wo, int NZ, int stride) {
   WgradPlan p{};
@@ -279,18 +310,34 @@ static WgradPlan wgrad_plan(int Cin, int Cout, int Wi, int Do, int Ho, int Wo, i
   p.rsy = odd4(wo4);
   const int need = stride * wo4 + 12;                 // the furthest float the vector loads of the last group touch
   p.rsx = odd4(need > Wi + 2 ? need : Wi + 2);
-  const int nkk = NZ * 3;
+  const int KZ = NZ == 3 ? 3 : 1, nkk = KZ * 3;
   p.ok = false;
-  for (int t = 8; t >= 1; t >>= 1) {
-    const size_t sm = ((size_t)t * nkk * p.rsx + (size_t)Cout * p.rsy) * 4;
-    const int items = Cout * t * nkk;
-    if (sm <= 200 * 1024 && items <= kWgMaxItems * kWgThreads) { p.ci_tile = t; p.smem = sm; p.ok = true; break; }
+  const int cand[8][2] = {{4, 8}, {4, 4}, {2, 8}, {2, 4}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};   // (rows per strip, channels per CTA)
+  static const int rb_cap = getenv("SATMVS_WGRAD_RB") ? atoi(getenv("SATMVS_WGRAD_RB")) : 2;
+  for (int c = 0; c < 8 && !p.ok; ++c) {
+    if (cand[c][0] > rb_cap) continue;
+    const int rb = cand[c][0] < Ho ? cand[c][0] : Ho, t = cand[c][1];
+    const int NR = stride * (rb - 1) + 3;
+    const size_t sm = ((size_t)t * KZ * NR * p.rsx + (size_t)Cout * rb * p.rsy) * 4;
+    const int items = (Cout + 1) / 2 * t * nkk;
+    if (sm <= 200 * 1024 && items <= kWgMaxItems * kWgThreads) { p.ci_tile = t; p.rb = rb; p.smem = sm; p.ok = true; }
   }
   if (!p.ok) return p;
+  {  // thread count with the fewest idle item slots (Cout 8 x 8 channels x 9 rows = 576 items: 192 threads x 3, not 256 x 2.25)
+    const int items = (Cout + 1) / 2 * (Cin < p.ci_tile ? Cin : p.ci_tile) * nkk;
+    double best = -1.0;
+    p.threads = kWgThreads;
+    for (int t = kWgThreads; t >= 128; t -= 32) {
+      const int passes = (items + t - 1) / t;
+      if (passes > kWgMaxItems) break;
+      const double eff = (double)items / ((double)passes * t) + 1e-3 * t / kWgThreads;
+      if (eff > best) { best = eff; p.threads = t; }
+    }
+  }
   p.groups = (Cin + p.ci_tile - 1) / p.ci_tile;
-  const int rows = Do * Ho;
+  const int strips = Do * ((Ho + p.rb - 1) / p.rb);
   int chunks = (2 * kNumSMs + p.groups - 1) / p.groups;
-  if (chunks > rows) chunks = rows;
+  if (chunks > strips) chunks = strips;
   if (chunks < 1) chunks = 1;
   p.chunks = chunks;
   p.ws_bytes = (size_t)chunks * Cout * Cin * NZ * 9 * 4;
@@ -309,6 +356,7 @@ int satmvs_conv3d_raw(const float* in, int Cin, int Di, int Hi, int Wi, const fl
   SATMVS_REQUIRE(in && w && out && Cin >= 1 && Cout >= 1 && Di >= 1 && Hi >= 1 && Wi >= 1);
   SATMVS_REQUIRE((NZ == 1 || NZ == 3) && mode >= 0 && mode <= 3);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(kProfTrainConv, st);
   const bool three = NZ == 3;
   if (mode == 3) {   // ConvTranspose(k 3, stride 2, padding 1, output_padding 1): one problem per output parity class
     ConvGroup g{};
@@ -383,19 +431,20 @@ int satmvs_conv3d_wgrad(const float* x, int Cin, int Di, int Hi, int Wi, const f
   SATMVS_REQUIRE(workspace_bytes >= p.ws_bytes);
   SATMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(kProfTrainWgrad, st);
   WgradArgs a{};
   a.x = x; a.dy = dy; a.partial = static_cast<float*>(workspace);
   a.Cin = Cin; a.Cout = Cout; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Do = Do; a.Ho = Ho; a.Wo = Wo; a.NZ = NZ;
-  a.ci_tile = p.ci_tile; a.rsx = p.rsx; a.rsy = p.rsy;
+  a.ci_tile = p.ci_tile; a.rb = p.rb; a.rsx = p.rsx; a.rsy = p.rsy;
   const dim3 grid(p.chunks, p.groups);
   if (stride == 1) {
     static const cudaError_t e1 = cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     (void)e1;
-    wgrad_kernel<1><<<grid, kWgThreads, p.smem, st>>>(a);
+    wgrad_kernel<1><<<grid, p.threads, p.smem, st>>>(a);
   } else {
     static const cudaError_t e2 = cudaFuncSetAttribute(wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     (void)e2;
-    wgrad_kernel<2><<<grid, kWgThreads, p.smem, st>>>(a);
+    wgrad_kernel<2><<<grid, p.threads, p.smem, st>>>(a);
   }
   int rc = check_launch("wgrad_kernel");
   if (rc) return rc;
@@ -411,6 +460,7 @@ int satmvs_bn_train_fwd(const float* y, int B, int C, long long n, const float* 
   SATMVS_CHECK_ASYNC();
   SATMVS_REQUIRE(y && z && mean && var && acc && B >= 1 && C >= 1 && n >= 4 && n % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(kProfTrainNorm, st);
   cudaMemsetAsync(acc, 0, (size_t)C * 2 * sizeof(double), st);
   int bx = (int)((n / 4 + 255) / 256);
   const int cap = (8 * kNumSMs + C - 1) / C;
@@ -429,6 +479,7 @@ int satmvs_bn_train_bwd(const float* dz, const float* dz2, const float* y, int B
   SATMVS_CHECK_ASYNC();
   SATMVS_REQUIRE(dz && y && mean && var && dy && acc && B >= 1 && C >= 1 && n >= 4 && n % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(kProfTrainNorm, st);
   cudaMemsetAsync(acc, 0, (size_t)C * 2 * sizeof(double), st);
   int bx = (int)((n / 4 + 255) / 256);
   const int cap = (8 * kNumSMs + C - 1) / C;

@@ -35,7 +35,11 @@ def stage_casmvs(features, cams, depth_values, regulariser, geo_model="rpc"):
     ref, srcs, ref_cam, src_cams = _split(features, cams)
     var = build_cost_volume(ref, srcs, ref_cam, src_cams, depth_values, geo_model)
     logits = regulariser(var).squeeze(1)
-    depth, conf = softargmin(logits, depth_values, "casmvs")
+    if logits.requires_grad:      # train(): the head carries a gradient to the logits (confidence has none, casmvs.py:69)
+        from .training import softargmin_casmvs_train
+        depth, conf = softargmin_casmvs_train(logits, depth_values)
+    else:
+        depth, conf = softargmin(logits, depth_values, "casmvs")
     return {"depth": depth, "photometric_confidence": conf}
 
 
