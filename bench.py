@@ -691,6 +691,26 @@ def sharded_block(args, dev, rank, world, barrier, flush):
             except Exception as ex:
                 out["modes"][mode] = {"unavailable": repr(ex)[:200]}
             barrier()
+        # the exchange-light consumer: regulariser-free soft-argmin, ranks exchange 3 fp64 sums per pixel
+        from satmvs_b200.regress import StreamingSoftArgmin
+
+        def reduced_single():
+            var = satmvs_b200.build_cost_volume(fe[0], fe[1:], cams[:, 0], [cams[:, v] for v in range(1, V)], dv, w["geo"])
+            head = StreamingSoftArgmin(w["B"], w["H"], w["W"], dev)
+            head.update_volume(var, dv, -1.0)
+            return head.finish()
+        try:
+            t1 = timed(reduced_single)
+            t = timed(lambda: sharded.sweep_depth_sharded(fe[0], fe[1:], cams[:, 0], [cams[:, v] for v in range(1, V)], dv, w["geo"]))
+            out["modes"]["reduced_exchange"] = {
+                "ms": t[0], "ms_best": t[1], "voxels_per_s": voxels / (t[0] * 1e-3), "single_gpu_ms": t1[0],
+                "speedup_vs_single_gpu": t1[0] / t[0], "exchanged_bytes_per_gpu": 24 * w["B"] * w["H"] * w["W"],
+                "what": "sweep of the rank's planes + matching cost (-mean_c var) folded into fp64 soft-argmin sums + all-reduce of "
+                        "(sum e, sum d*e, max e) + finish -> depth, confidence on every rank; single_gpu_ms = the same pipeline, all "
+                        "192 planes, one GPU"}
+        except Exception as ex:
+            out["modes"]["reduced_exchange"] = {"unavailable": repr(ex)[:200]}
+        barrier()
         out["ingress_bound_ms"] = ingress / 770e9 * 1e3
         out["note"] = ("every rank must receive (G-1)/G of the 1.81 GB fp32 volume: at 770 GB/s per direction that alone is "
                        f"{out['ingress_bound_ms']:.2f} ms, against {single[0]:.2f} ms to build the whole volume on one GPU -- gathering "

@@ -161,6 +161,10 @@ int satmvs_softargmin_stream_update(const float* reg, const float* depth_plane, 
  * accumulated in order with the per-plane arithmetic of satmvs_softargmin_stream_update. */
 int satmvs_softargmin_stream_update_planes(const float* reg, const float* depth, int depth_per_pixel, int K,
                                            int H, int W, double* state, void* stream);
+/* Plane sweep without a regulariser (the exchange-light consumer of a depth-sharded sweep): folds the K planes of a
+ * variance slab [C,K,H,W] into the same fp64 state with reg_k = scale * mean_c var[c,k] (scale < 0). */
+int satmvs_softargmin_stream_update_volume(const float* var, const float* depth, int depth_per_pixel, float scale, int C, int K,
+                                           int H, int W, double* state, void* stream);
 int satmvs_softargmin_stream_finish(const double* state, int H, int W,
                                     float* out_depth, float* out_conf, void* stream);
 

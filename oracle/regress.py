@@ -52,3 +52,29 @@ class StreamingSoftArgmin:
     def finish(self):
         tot = self.exp_sum + 1e-10
         return (self.depth_acc / tot).squeeze(1).float(), (self.max_e / tot).squeeze(1).float()
+
+
+class StreamingSoftArgminState(StreamingSoftArgmin):
+    """The streaming head with the product's packed state [B, 3, H, W] fp64 = (sum e, sum d*e, max e) and the regulariser-free
+    matching cost reg_k = scale * mean_c var[:, c, k] of a variance slab (what a depth-sharded sweep exchanges).
+    Stand-in for `satmvs_b200.regress.StreamingSoftArgmin` in the CPU (gloo) tests of `sharded.sweep_depth_sharded`."""
+
+    def __init__(self, B: int, H: int, W: int):
+        self.state = torch.zeros(B, 3, H, W, dtype=torch.float64)
+
+    def update_volume(self, var: torch.Tensor, depth_planes: torch.Tensor, scale: float = -1.0) -> None:
+        B, C, K, H, W = var.shape
+        for k in range(K):
+            s = torch.zeros(B, H, W, dtype=torch.float32)
+            for c in range(C):                       # channels in ascending order, fp32
+                s = s + var[:, c, k]
+            reg = (s * (1.0 / C)) * scale
+            e = reg.double().exp()
+            dp = depth_planes[:, k].double() if depth_planes.dim() == 4 else depth_planes[:, k].double().view(B, 1, 1)
+            self.state[:, 0] = self.state[:, 0] + e
+            self.state[:, 1] = dp * e + self.state[:, 1]
+            self.state[:, 2] = torch.where(self.state[:, 2] < e, e, self.state[:, 2])
+
+    def finish(self):
+        tot = self.state[:, 0] + 1e-10
+        return (self.state[:, 1] / tot).float(), (self.state[:, 2] / tot).float()

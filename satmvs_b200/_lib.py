@@ -37,6 +37,7 @@ _SIGNATURES = {
     "satmvs_softargmin_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "satmvs_softargmin_stream_update": ([_P, _P, _I, _I, _I, _P, _P], _I),
     "satmvs_softargmin_stream_update_planes": ([_P, _P, _I, _I, _I, _I, _P, _P], _I),
+    "satmvs_softargmin_stream_update_volume": ([_P, _P, _I, C.c_float, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_softargmin_stream_finish": ([_P, _I, _I, _P, _P, _P], _I),
     "satmvs_resize_bilinear": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_depth_hypotheses": ([_P, _I, _I, _P, _I, _I, C.c_float, _I, _I, _I, _I, _P, _P], _I),

@@ -84,6 +84,29 @@ __global__ void softargmin_stream_update_planes_kernel(const float* __restrict__
   state[pix] = es; state[HW + pix] = da; state[2 * (size_t)HW + pix] = me;
 }
 
+// Plane sweep without a regulariser: the matching cost of plane k is scale * mean_c var[c,k] (scale < 0: low variance = good match);
+// the planes of a [C,K,H,W] variance slab are folded into the fp64 running sums in their order, so a depth-sharded sweep only
+// has to exchange the three [H,W] sums.  The slab is read once, coalesced across pixels.
+__global__ void softargmin_stream_update_volume_kernel(const float* __restrict__ var, const float* __restrict__ depth,
+                                                       int depth_per_pixel, float scale, int C, int K, int HW,
+                                                       double* __restrict__ state) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  double es = state[pix], da = state[HW + pix], me = state[2 * (size_t)HW + pix];
+  const float inv_c = 1.0f / (float)C;
+  for (int k = 0; k < K; ++k) {
+    float s = 0.0f;
+    for (int c = 0; c < C; ++c) s += __ldg(var + ((size_t)c * K + k) * HW + pix);
+    const float reg = scale * (s * inv_c);
+    const double e = exp((double)reg);
+    const double dv = (double)(depth_per_pixel ? __ldg(depth + (size_t)k * HW + pix) : __ldg(depth + k));
+    es = es + e;
+    da = dv * e + da;
+    if (me < e) me = e;
+  }
+  state[pix] = es; state[HW + pix] = da; state[2 * (size_t)HW + pix] = me;
+}
+
 __global__ void softargmin_stream_finish_kernel(const double* __restrict__ state, int HW,
                                                 float* __restrict__ out_depth, float* __restrict__ out_conf) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,6 +169,16 @@ int satmvs_softargmin_stream_update_planes(const float* reg, const float* depth,
   const int HW = H * W;
   softargmin_stream_update_planes_kernel<<<ceil_div(HW, 128), 128, 0, (cudaStream_t)stream>>>(reg, depth, depth_per_pixel, K, HW, state);
   return check_launch("softargmin_stream_update_planes_kernel");
+}
+
+int satmvs_softargmin_stream_update_volume(const float* var, const float* depth, int depth_per_pixel, float scale, int C, int K,
+                                           int H, int W, double* state, void* stream) {
+  SATMVS_REQUIRE(var && depth && state && C >= 1 && K >= 1 && H >= 1 && W >= 1);
+  const int HW = H * W;
+  ProfScope prof(kProfHead, (cudaStream_t)stream);
+  softargmin_stream_update_volume_kernel<<<ceil_div(HW, 64), 64, 0, (cudaStream_t)stream>>>(var, depth, depth_per_pixel, scale, C, K,
+                                                                                            HW, state);
+  return check_launch("softargmin_stream_update_volume_kernel");
 }
 
 int satmvs_softargmin_stream_finish(const double* state, int H, int W,

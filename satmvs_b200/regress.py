@@ -100,6 +100,19 @@ class StreamingSoftArgmin:
                     reg[b].data_ptr(), dp[b].data_ptr(), per_pixel, K, self.H, self.W, self.state[b].data_ptr(), st),
                     "softargmin_stream_update_planes")
 
+    def update_volume(self, var: torch.Tensor, depth_planes: torch.Tensor, scale: float = -1.0) -> None:
+        """Plane sweep without a regulariser: reg_k = scale * mean_c var[:, c, k] folded plane by plane (var [B,C,K,H,W])."""
+        var = _lib.require_cuda(var, "var")
+        Cc, K = var.shape[1], var.shape[2]
+        dp = _lib.require_cuda(depth_planes, "depth_planes")
+        per_pixel = 1 if dp.dim() == 4 else 0
+        with torch.cuda.device(var.device):
+            st = _lib.stream_ptr(var.device)
+            for b in range(self.B):
+                _lib.check(_lib.lib().satmvs_softargmin_stream_update_volume(
+                    var[b].data_ptr(), dp[b].data_ptr(), per_pixel, float(scale), Cc, K, self.H, self.W,
+                    self.state[b].data_ptr(), st), "softargmin_stream_update_volume")
+
     def finish(self):
         depth = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.state.device)
         conf = torch.empty_like(depth)

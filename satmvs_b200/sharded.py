@@ -114,3 +114,38 @@ def build_cost_volume_sharded(ref_fea, src_feas, ref_cam, src_cams, depth_values
                        "cost_volume_fwd_sharded")
     hdl.barrier()                      # every rank's planes have landed everywhere
     return vol
+
+
+def combine_stream_states(state: torch.Tensor, group=None) -> torch.Tensor:
+    """All-reduce of the streaming soft-argmin state [B, 3, H, W] fp64 of depth-sharded planes: (sum e, sum d*e) add,
+    max e takes the maximum -- 24 bytes per pixel on the wire instead of 4 * C * D / G bytes per pixel of variance slab."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return state
+    sums = state[:, :2].contiguous()
+    mx = state[:, 2].contiguous()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    state[:, :2] = sums
+    state[:, 2] = mx
+    return state
+
+
+def sweep_depth_sharded(ref_fea, src_feas, ref_cam, src_cams, depth_values, geo_model="rpc", *, group=None, scale=-1.0,
+                        builder=None, head=None):
+    """Depth-sharded plane sweep WITHOUT a regulariser: every rank sweeps its planes, folds the matching cost
+    reg_k = scale * mean_c var[c, k] of its slab into the fp64 streaming soft-argmin sums (`casred.py:218-236` arithmetic) and
+    the ranks exchange only those sums.  Returns (depth [B,H,W], confidence [B,H,W]) on every rank.
+    `builder` / `head` replace the CUDA operators in the CPU (gloo) tests of the host logic."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    D = depth_values.shape[1]
+    d0, d1 = plane_range(D, rank, world)
+    shard = depth_values[:, d0:d1].contiguous()
+    slab = (builder or build_cost_volume)(ref_fea, src_feas, ref_cam, src_cams, shard, geo_model)
+    B, _, _, H, W = slab.shape
+    if head is None:
+        from .regress import StreamingSoftArgmin
+        head = StreamingSoftArgmin(B, H, W, slab.device)
+    head.update_volume(slab, shard, scale)
+    combine_stream_states(head.state, group)
+    return head.finish()

@@ -40,6 +40,14 @@ def _worker(rank, world, port, ret):
                 res[mode] = f"error: {ex!r}"[:300]
             if mode == "multimem" and isinstance(res[mode], str) and "NVLS multicast" in res[mode]:
                 res[mode] = "unsupported"     # no multicast mapping on this box: reported, not a failure
+        # regulariser-free sweep exchanging only the fp64 soft-argmin sums (24 B per pixel) against the same pipeline on one GPU
+        from satmvs_b200.regress import StreamingSoftArgmin
+        one = StreamingSoftArgmin(B, H, W, dev)
+        one.update_volume(want, dv, -1.5)
+        wd, wc = one.finish()
+        gd, gc = sharded.sweep_depth_sharded(fe[0], fe[1:], rp[:, 0], rp[:, 1:], dv, "rpc", scale=-1.5)
+        torch.cuda.synchronize()
+        res["reduced"] = bool(torch.allclose(gd, wd, rtol=1e-6, atol=0) and torch.allclose(gc, wc, rtol=1e-6, atol=0))
         ret[rank] = res
     finally:
         dist.destroy_process_group()
@@ -57,3 +65,26 @@ def test_sharded_build_matches_single_gpu(world):
         assert ret[r]["nccl"] is True, ret[r]
         assert ret[r]["fused"] is True, ret[r]
         assert ret[r]["multimem"] in (True, "unsupported"), ret[r]
+        assert ret[r]["reduced"] is True, ret[r]
+
+
+def test_regulariser_free_streaming_head_matches_oracle():
+    """satmvs_softargmin_stream_update_volume (matching cost = scale * channel mean of the variance, folded plane by plane into
+    the fp64 sums) against its CPU restatement; one GPU."""
+    import satmvs_b200
+    from oracle import regress, volume
+    from satmvs_b200 import synth
+    from satmvs_b200.regress import StreamingSoftArgmin
+    B, V, C, D, H, W = 1, 3, 8, 12, 24, 40
+    fe = synth.make_features(B, V, C, H, W, seed=5)
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv = synth.make_depth_planes(B, D, H, W)
+    var = volume.variance_cost_volume(fe, rp, dv, "rpc")
+    ref = regress.StreamingSoftArgminState(B, H, W)
+    ref.update_volume(var, dv, -2.0)
+    wd, wc = ref.finish()
+    head = StreamingSoftArgmin(B, H, W, "cuda:0")
+    head.update_volume(var.to("cuda:0"), dv.to("cuda:0"), -2.0)
+    assert torch.allclose(head.state.cpu(), ref.state, rtol=1e-12, atol=0)
+    gd, gc = head.finish()
+    assert torch.equal(gd.cpu(), wd) and torch.equal(gc.cpu(), wc)

@@ -63,6 +63,39 @@ def test_sharded_build_world2(D, mode):
     assert dict(ret) == {0: True, 1: True}
 
 
+def _worker_reduced(rank, world, port, D, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import regress, volume
+        B, V, C, H, W = 1, 3, 4, 10, 14
+        fe = synth.make_features(B, V, C, H, W, seed=3)
+        rp = synth.make_rpc_stack(B, V, H, W)
+        dv = synth.make_depth_planes(B, D, H, W)
+
+        def cpu_builder(ref, srcs, ref_cam, src_cams, depth, geo):
+            cams = torch.stack([ref_cam] + list(src_cams), 1)
+            return volume.variance_cost_volume([ref] + list(srcs), cams, depth, geo)
+
+        depth, conf = sharded.sweep_depth_sharded(fe[0], fe[1:], rp[:, 0], [rp[:, 1], rp[:, 2]], dv, "rpc", scale=-2.0,
+                                                  builder=cpu_builder, head=regress.StreamingSoftArgminState(B, H, W))
+        one = regress.StreamingSoftArgminState(B, H, W)
+        one.update_volume(volume.variance_cost_volume(fe, rp, dv, "rpc"), dv, -2.0)
+        wd, wc = one.finish()
+        # fp64 sums re-associated across ranks: equal to the last bits of the fp32 result
+        ret[rank] = bool(torch.allclose(depth, wd, rtol=1e-6, atol=0) and torch.allclose(conf, wc, rtol=1e-6, atol=0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("D", [8, 7])
+def test_sharded_sweep_exchanging_only_the_softargmin_sums_world2(D):
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_reduced, args=(world, _free_port(), D, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
 def test_gather_requires_even_split():
     # uneven D cannot use the single all-gather (documented); the caller pads or uses mode "none"
     with pytest.raises(Exception):
