@@ -46,6 +46,9 @@ WORKLOADS = {
     "cfg2_train": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="rpc", stage="casmvs_train",
                        desc="3-view 768x384, 64 planes, ONE TRAINING step of stage 1 with CostRegNet (train.py:267-287): forward in "
                             "train() mode (batch-statistics BatchNorm) + loss.backward() to the feature maps and every parameter"),
+    "cfg2_train_red": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="rpc", stage="red_train_bwd",
+                           desc="3-view 768x384, 64 planes, ONE TRAINING step of casred stage 1 (train.py:267-287): fused RPC cost volume "
+                                "+ RED regulariser + soft-argmin, forward + loss.backward() to the feature maps and every parameter"),
     "cfg5_build": dict(B=1, V=3, C=32, D=64, H=96, W=192, geo="pinhole", stage="build",
                        desc="pin-hole homography sweep 3-view 768x384, 64 planes, cost-volume build"),
     "cfg3_cascade": dict(B=1, V=3, C=32, D=48, H=96, W=192, geo="rpc", stage="cascade", img_hw=(384, 768), ndepths=(48, 32, 8),
@@ -210,20 +213,23 @@ def make_step(w, dev, args):
                 out = satmvs_b200.stage_casmvs(fe, cams, dv, reg, w["geo"])
             return out["depth"], out["photometric_confidence"]
         return step
-    if w["stage"] == "casmvs_train":
-        reg = satmvs_b200.CostRegNet(w["C"], 8)
-        reg.load_state_dict(synth.make_costregnet_weights(w["C"]))
+    if w["stage"] in ("casmvs_train", "red_train_bwd"):
+        red = w["stage"] == "red_train_bwd"
+        reg = satmvs_b200.RED_Regularization(w["C"], 8) if red else satmvs_b200.CostRegNet(w["C"], 8)
+        reg.load_state_dict(synth.make_red_weights(w["C"]) if red else synth.make_costregnet_weights(w["C"]))
         reg = reg.to(dev).train()
         gt = torch.full((w["B"], w["H"], w["W"]), 500.0, device=dev)
+        probe = reg.conv_gru1.gate_conv.weight if red else reg.conv0.conv.weight
+        stage = satmvs_b200.stage_train_red if red else satmvs_b200.stage_casmvs
 
         def step(fe, cams, dv):
             fe = [f.detach().requires_grad_(True) for f in fe]
             for p in reg.parameters():
                 p.grad = None
-            out = satmvs_b200.stage_casmvs(fe, cams, dv, reg, w["geo"])
+            out = stage(fe, cams, dv, reg, w["geo"])
             loss = torch.nn.functional.smooth_l1_loss(out["depth"], gt)      # train.py's loss, on the [B,H,W] depth map
             loss.backward()
-            return out["depth"].detach(), fe[0].grad, reg.conv0.conv.weight.grad
+            return out["depth"].detach(), fe[0].grad, probe.grad
         return step
     raise ValueError(w["stage"])
 
@@ -723,7 +729,7 @@ def sharded_block(args, dev, rank, world, barrier, flush):
 # ------------------------------------------------------------------------------------------------
 def red_on_device(var, sd, device, regnets):
     B, _, D, H, W = var.shape
-    states = [s.to(device) for s in regnets.red_initial_states(B, H, W)]
+    states = [s.to(device=device, dtype=var.dtype) for s in regnets.red_initial_states(B, H, W)]
     out = []
     for d in range(D):
         reg, *states = regnets.red_slice(var[:, :, d], *states, sd)
@@ -754,9 +760,10 @@ def oracle_step(w, planes, device="cpu", reg_dtype=torch.float32):
         def run():
             with torch.no_grad():
                 return stages.stage_casmvs(fe, cams, dv, sd, w["geo"])
-    elif w["stage"] == "casmvs_train":
+    elif w["stage"] in ("casmvs_train", "red_train_bwd"):
+        red = w["stage"] == "red_train_bwd"
         sd = {k: v.to(device).requires_grad_(v.is_floating_point() and "running" not in k)
-              for k, v in synth.make_costregnet_weights(w["C"]).items()}
+              for k, v in (synth.make_red_weights(w["C"]) if red else synth.make_costregnet_weights(w["C"])).items()}
         gt = torch.full((ws["B"], ws["H"], ws["W"]), 500.0, device=device)
         sdt = {k: (v.detach().to(reg_dtype) if v.is_floating_point() else v).requires_grad_(v.requires_grad) for k, v in sd.items()}
 
@@ -765,10 +772,14 @@ def oracle_step(w, planes, device="cpu", reg_dtype=torch.float32):
             for v in sdt.values():
                 v.grad = None
             var = volume.variance_cost_volume(fr, cams, dv, w["geo"]).to(reg_dtype)
-            logits = regnets.costregnet(var, sdt, training=True).squeeze(1)
-            depth, _ = regress.softargmin_casmvs(logits, dv.to(reg_dtype))
+            if red:
+                logits = red_on_device(var, sdt, device, regnets)
+                depth, _ = regress.softargmin_red(logits, dv.to(reg_dtype))
+            else:
+                logits = regnets.costregnet(var, sdt, training=True).squeeze(1)
+                depth, _ = regress.softargmin_casmvs(logits, dv.to(reg_dtype))
             torch.nn.functional.smooth_l1_loss(depth, gt.to(reg_dtype)).backward()
-            return depth.detach(), fr[0].grad, sdt["conv0.conv.weight"].grad
+            return depth.detach(), fr[0].grad, sdt["conv_gru1.gate_conv.weight" if red else "conv0.conv.weight"].grad
     else:
         def run():
             with torch.no_grad():
@@ -803,7 +814,7 @@ def gpu_eager_baseline(w, dev, fe, cams, dv):
         out["cost_volume_build"] = {"value": vox / (best * 1e-3), "unit": UNIT, "ms": best,
                                     "kind": "port of networks/casred.py:26-53 on CUDA tensors (ATen eager, best of 10)",
                                     "peak_alloc_bytes": torch.cuda.max_memory_allocated(dev)}
-        if w["stage"] in ("red_train", "casmvs", "casmvs_train"):
+        if w["stage"] in ("red_train", "casmvs", "casmvs_train", "red_train_bwd"):
             run, vox = oracle_step(w, w["D"], device=dev)
 
             def best_of(n):
@@ -883,22 +894,23 @@ def parity_block(w, dev, step, fe_h, cams, dv_h):
     from satmvs_b200 import synth
     try:
         with torch.no_grad():
-            got = None if w["stage"] == "casmvs_train" else step([f.to(dev) for f in fe_h], cams, dv_h.to(dev))
+            got = None if w["stage"] in ("casmvs_train", "red_train_bwd") else step([f.to(dev) for f in fe_h], cams, dv_h.to(dev))
             if w["stage"] == "red_train":
                 want = stages.stage_train_red(fe_h, cams, dv_h, synth.make_red_weights(w["C"]), w["geo"])["depth"]
             elif w["stage"] == "casmvs":
                 want = stages.stage_casmvs(fe_h, cams, dv_h, synth.make_costregnet_weights(w["C"]), w["geo"])["depth"]
             elif w["stage"] == "build":
                 want = volume.variance_cost_volume(fe_h, cams, dv_h, w["geo"])
-            elif w["stage"] != "casmvs_train":
+            elif w["stage"] not in ("casmvs_train", "red_train_bwd"):
                 return None
-        if w["stage"] == "casmvs_train":
+        if w["stage"] in ("casmvs_train", "red_train_bwd"):
             # fp32 training gradients carry cancellation noise of their own (batch-statistics BatchNorm backward): the yardstick is
             # the oracle with its regulariser evaluated in fp64; the fp32 oracle's distance to it is printed beside ours.
             got = step([f.to(dev) for f in fe_h], cams, dv_h.to(dev))
             want32 = oracle_step(w, w["D"], device="cpu")[0]()
             want64 = oracle_step(w, w["D"], device="cpu", reg_dtype=torch.float64)[0]()
-            names = ("depth map", "gradient to the reference feature map", "gradient to conv0.conv.weight")
+            names = ("depth map", "gradient to the reference feature map", "gradient to the first filter bank "
+                     "(conv_gru1.gate_conv.weight / conv0.conv.weight)")
             out = {"vs": "autograd of the oracle (CPU restatement of the reference in train() mode, regulariser + head in fp64) on "
                          "the same inputs; 'fp32_reference_rel_linf' = the same oracle in fp32 against that yardstick"}
             for nme, gg, w32, w64 in zip(names, got, want32, want64):

@@ -302,6 +302,42 @@ int satmvs_bn_train_bwd(const float* dz, const float* dz2, const float* y, int B
 int satmvs_softargmin_bwd(const float* logits, const float* depth_values, int per_pixel, int D, int H, int W,
                           const float* grad_depth, float* grad_logits, void* stream);
 
+/* ---- backward of the RED regulariser (RED_Regularization.forward, modules/module.py:614-649; train.py:284 loss.backward()) ----
+ * The forward (satmvs_red_forward) keeps, in its workspace, the hidden-state history S_l [ch_l][D+1][h_l][w_l] (slot 0 = initial
+ * state), the encoder outputs E_i [ch][D][h][w] and the decoder tensors U_l [ch_l][D+1][h_l][w_l]; satmvs_red_workspace_layout
+ * returns their byte offsets: offsets[0..3] = S_0..S_3, [4..6] = E_1..E_3, [7..9] = U_0..U_2.
+ * The host side (satmvs_b200/training.py) recomputes the gate / output pre-activations batched over planes, walks the planes
+ * backwards with satmvs_red_recurrence_bwd and finishes
+ * with batched data / weight gradients.  Tensors are [C][D][px] (channel stride D*px unless a stride argument says otherwise). */
+int satmvs_red_workspace_layout(int C, int D, int H, int W, size_t* offsets10);
+/* out = act(GroupNorm(1, ch)(pre + bias)) per plane and group (groups 2: reset | update halves; act 0 sigmoid, 1 tanh);
+ * stats [D][groups][2] = (mean, rstd) out; acc = D*groups*2 doubles of scratch. */
+int satmvs_gn_act_fwd(const float* pre, const float* bias, const float* gamma, const float* beta, int ch, int groups, int D, int px,
+                      float eps, int act, float* out, float* stats, double* acc, void* stream);
+/* out = scale * (a [+ b]) [* mul], zeroed where (m1 [- m2]) <= 0 when m1 is given; every operand with its own channel stride. */
+int satmvs_elementwise(const float* a, long long a_cs, const float* b, long long b_cs, const float* mul, long long mul_cs,
+                       const float* m1, long long m1_cs, const float* m2, long long m2_cs, float scale, float* out, long long out_cs,
+                       int C, long long n_per_c, void* stream);
+int satmvs_channel_sum(const float* t, int C, long long n_per_c, float* out, double* acc, void* stream);
+int satmvs_gn_param_grad(const float* dout, const float* pre, const float* bias, const float* stats, int ch, int groups, int D, int px,
+                         float* dgamma, float* dbeta, double* acc, void* stream);
+/* The sequential part: for each level (independent recurrences, one stream each between a fork from / join into `stream`) walk
+ * planes D-1 .. 0.  S: state history [ch][D+1][px]; ru [2ch][D][px] (reset | update gates), y, opre [ch][D][px], gpre [2ch][D][px]
+ * (conv results WITHOUT bias); ostat [D][2], gstat [D][2][2] (mean, rstd); dec [ch][D][px] = gradient reaching h'(d) from the
+ * decoder; wo_h / wg_h: the output / gate filters offset to their hidden input channels, w_ci = (cx + ch) * 9 their stride
+ * between output channels.  Outputs [.][D][px]: dyn, dgn (gradients at the GroupNorm outputs, for the affine gradients), dO, dG
+ * (gradients at the conv outputs).  scratch: 16 + 9 * ch * px floats. */
+typedef struct satmvs_gru_bwd_level {
+  const float* S; const float* ru; const float* y; const float* opre; const float* gpre;
+  const float* ob; const float* gb; const float* on_w; const float* rn_w; const float* un_w;
+  const float* ostat; const float* gstat; const float* dec;
+  const float* wo_h; const float* wg_h;
+  long long w_ci;
+  float* dyn; float* dgn; float* dO; float* dG; float* scratch;
+  int ch, h, w, D;
+} satmvs_gru_bwd_level;
+int satmvs_red_recurrence_bwd(const satmvs_gru_bwd_level* levels, int nlevels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

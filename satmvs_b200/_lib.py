@@ -58,6 +58,13 @@ _SIGNATURES = {
     "satmvs_bn_train_fwd": ([_P, _I, _I, C.c_longlong, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P, _P], _I),
     "satmvs_bn_train_bwd": ([_P, _P, _P, _I, _I, C.c_longlong, _P, _P, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P], _I),
     "satmvs_softargmin_bwd": ([_P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
+    "satmvs_red_workspace_layout": ([_I, _I, _I, _I, _P], _I),
+    "satmvs_gn_act_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _I, _P, _P, _P, _P], _I),
+    "satmvs_elementwise": ([_P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, C.c_float,
+                            _P, C.c_longlong, _I, C.c_longlong, _P], _I),
+    "satmvs_channel_sum": ([_P, _I, C.c_longlong, _P, _P, _P], _I),
+    "satmvs_gn_param_grad": ([_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),
+    "satmvs_red_recurrence_bwd": ([_P, _I, _P], _I),
 }
 
 

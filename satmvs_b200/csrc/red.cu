@@ -565,6 +565,16 @@ extern "C" {
 
 int satmvs_red_last_path(void) { return g_red_last_path; }
 
+int satmvs_red_workspace_layout(int C, int D, int H, int W, size_t* offsets10) {
+  SATMVS_REQUIRE(offsets10 && C >= 1 && D >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0);
+  char* base = nullptr;
+  const RedPlan p = red_plan(C, D, H, W, base);
+  for (int l = 0; l < 4; ++l) offsets10[l] = (size_t)(reinterpret_cast<char*>(p.lv[l].s) - base);
+  for (int i = 0; i < 3; ++i) offsets10[4 + i] = (size_t)(reinterpret_cast<char*>(p.e[i]) - base);
+  for (int i = 0; i < 3; ++i) offsets10[7 + i] = (size_t)(reinterpret_cast<char*>(p.u[i]) - base);
+  return SATMVS_OK;
+}
+
 size_t satmvs_red_workspace_bytes(int C, int D, int H, int W) {
   if (C < 1 || D < 1 || H < 8 || W < 8 || (H % 8) || (W % 8)) return 0;
   return red_plan(C, D, H, W, nullptr).bytes;

@@ -165,9 +165,13 @@ class _RedBase(nn.Module):
     def _run(self, volume: torch.Tensor, states_in, want_states: bool):
         """volume [B,C,D,H,W] -> logits [B,D,H,W] (+ final states)."""
         if torch.is_grad_enabled() and (volume.requires_grad or any(p.requires_grad for p in self.parameters())):
-            # inference only: no backward is implemented for the recurrence.  Failing here beats returning logits without
-            # a grad_fn, which would let `loss.backward()` (train.py:284) skip the regulariser and FeatureNet silently.
-            raise RuntimeError("satmvs_b200 RED regulariser is inference-only: call it under torch.no_grad() "
+            if states_in is None and not want_states:
+                # train.py:284 loss.backward(): the whole-volume form carries a backward through the recurrence (training.py)
+                from .training import red_train_forward
+                return red_train_forward(self, volume), None
+            # the per-slice form (predict path) has no backward.  Failing here beats returning logits without a grad_fn,
+            # which would let a loss skip the regulariser silently.
+            raise RuntimeError("satmvs_b200 slice_RED_Regularization is inference-only: call it under torch.no_grad() "
                                "(or with parameters and input that do not require grad)")
         vol = _lib.require_cuda(volume, "volume")
         B, Cc, D, H, W = vol.shape

@@ -26,7 +26,11 @@ def stage_train_red(features, cams, depth_values, regulariser, geo_model="rpc"):
     ref, srcs, ref_cam, src_cams = _split(features, cams)
     var = build_cost_volume(ref, srcs, ref_cam, src_cams, depth_values, geo_model)
     logits = regulariser(var)
-    depth, conf = softargmin(logits, depth_values, "red")
+    if logits.requires_grad:      # loss.backward() (train.py:284): head with a gradient to the logits
+        from .training import softargmin_train
+        depth, conf = softargmin_train(logits, depth_values, "red")
+    else:
+        depth, conf = softargmin(logits, depth_values, "red")
     return {"depth": depth, "photometric_confidence": conf}
 
 

@@ -183,12 +183,13 @@ def costreg_train_forward(net, x):
 
 
 class _SoftArgminDepthFn(torch.autograd.Function):
-    """depth = sum_d softmax(logits)_d * depth_values_d with its gradient to the logits (`casmvs.py:66-68`)."""
+    """depth = sum_d softmax(logits)_d * depth_values_d with its gradient to the logits (`casmvs.py:66-68`, `casred.py:58-61`);
+    the confidence map carries no gradient (`casmvs.py:69` computes it under `torch.no_grad()`)."""
 
     @staticmethod
-    def forward(ctx, logits, depth_values):
+    def forward(ctx, logits, depth_values, head):
         from .regress import softargmin
-        depth, conf = softargmin(logits.detach(), depth_values, head="casmvs")
+        depth, conf = softargmin(logits.detach(), depth_values, head=head)
         ctx.save_for_backward(logits.detach(), depth_values)
         ctx.mark_non_differentiable(conf)
         return depth, conf
@@ -205,10 +206,250 @@ class _SoftArgminDepthFn(torch.autograd.Function):
             for b in range(B):
                 _lib.check(_lib.lib().satmvs_softargmin_bwd(logits[b].data_ptr(), dv[b].data_ptr(), per_pixel, D, H, W,
                                                             gdepth[b].data_ptr(), out[b].data_ptr(), st), "softargmin_bwd")
-        return out, None
+        return out, None, None
+
+
+def softargmin_train(logits, depth_values, head="casmvs"):
+    """Soft-argmin head with a gradient to the logits: returns (depth [B,H,W], confidence [B,H,W] without gradient);
+    head "casmvs" (4-neighbour confidence) or "red" (max probability)."""
+    return _SoftArgminDepthFn.apply(logits.contiguous().float(), depth_values.contiguous().float(), head)
 
 
 def softargmin_casmvs_train(logits, depth_values):
-    """CasMVS head with a gradient to the logits: returns (depth [B,H,W], confidence [B,H,W] (no gradient, as in the reference's
-    `torch.no_grad()` block `casmvs.py:69`))."""
-    return _SoftArgminDepthFn.apply(logits.contiguous().float(), depth_values.contiguous().float())
+    return softargmin_train(logits, depth_values, "casmvs")
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# RED regulariser: backward through the recurrence (RED_Regularization.forward, modules/module.py:614-649)
+# ---------------------------------------------------------------------------------------------------------------------------
+_CH = (8, 16, 32, 64)
+_GN_EPS = 1e-5
+
+
+class _GruBwdLevel(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("S", "ru", "y", "opre", "gpre", "ob", "gb", "on_w", "rn_w", "un_w", "ostat", "gstat", "dec",
+                                          "wo_h", "wg_h")] + [("w_ci", C.c_longlong)] + \
+               [(n, C.c_void_p) for n in ("dyn", "dgn", "dO", "dG", "scratch")] + \
+               [("ch", C.c_int), ("h", C.c_int), ("w", C.c_int), ("D", C.c_int)]
+
+
+def _ew(a, out, b=None, mul=None, m1=None, m2=None, scale=1.0):
+    """out = scale * (a [+ b]) [* mul], zero where (m1 [- m2]) <= 0; operands [C, ...] views whose channels are contiguous."""
+    Cc, n = a.shape[0], a[0].numel()
+    for t in (a, out, b, mul, m1, m2):
+        assert t is None or (t.shape[0] == Cc and t[0].numel() == n and t[0].is_contiguous())
+    p = lambda t: (t.data_ptr(), t.stride(0)) if t is not None else (None, 0)
+    _lib.check(_lib.lib().satmvs_elementwise(*p(a), *p(b), *p(mul), *p(m1), *p(m2), float(scale), *p(out), Cc, n,
+                                             _lib.stream_ptr(a.device)), "elementwise")
+    return out
+
+
+def _conv2d(x, w_ptr_tensor, mode, cout, w_co, w_ci):
+    """Per-plane 3x3 conv of a [Cin, D, h, w] tensor (satmvs_conv3d_raw, NZ = 1)."""
+    return conv3d_raw(x.unsqueeze(0), w_ptr_tensor, mode, cout, w_co, w_ci, nz=1)[0]
+
+
+def _gn_act(pre, bias, gamma, beta, ch, groups, act):
+    Cc, D, h, w = pre.shape
+    out = torch.empty_like(pre)
+    stats = torch.empty((D, groups, 2), dtype=torch.float32, device=pre.device)
+    acc = torch.empty(D * groups * 2, dtype=torch.float64, device=pre.device)
+    _lib.check(_lib.lib().satmvs_gn_act_fwd(pre.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ch, groups, D, h * w,
+                                            _GN_EPS, act, out.data_ptr(), stats.data_ptr(), acc.data_ptr(),
+                                            _lib.stream_ptr(pre.device)), "gn_act_fwd")
+    return out, stats
+
+
+def _channel_sum(t):
+    Cc = t.shape[0]
+    out = torch.empty(Cc, dtype=torch.float32, device=t.device)
+    acc = torch.empty(2 * Cc, dtype=torch.float64, device=t.device)
+    _lib.check(_lib.lib().satmvs_channel_sum(t.data_ptr(), Cc, t[0].numel(), out.data_ptr(), acc.data_ptr(),
+                                             _lib.stream_ptr(t.device)), "channel_sum")
+    return out
+
+
+def _gn_param_grad(dout, pre, bias, stats, ch, groups):
+    Cc, D, h, w = pre.shape
+    dg = torch.empty(Cc, dtype=torch.float32, device=pre.device)
+    db = torch.empty(Cc, dtype=torch.float32, device=pre.device)
+    acc = torch.empty(2 * Cc, dtype=torch.float64, device=pre.device)
+    _lib.check(_lib.lib().satmvs_gn_param_grad(dout.data_ptr(), pre.data_ptr(), bias.data_ptr(), stats.data_ptr(), ch, groups, D,
+                                               h * w, dg.data_ptr(), db.data_ptr(), acc.data_ptr(), _lib.stream_ptr(pre.device)),
+               "gn_param_grad")
+    return dg, db
+
+
+def _wgrad2d(x, dy, stride, shape, co_stride):
+    dw = torch.empty(shape, dtype=torch.float32, device=x.device)
+    conv3d_wgrad(x.unsqueeze(0), dy.unsqueeze(0), stride, dw, co_stride, 9, nz=1)
+    return dw
+
+
+_RED_PARAM_NAMES = tuple(f"conv_gru{i + 1}.{n}" for i in range(4) for n in (
+    "gate_conv.weight", "gate_conv.bias", "output_conv.weight", "output_conv.bias", "reset_gate_norm.weight", "reset_gate_norm.bias",
+    "update_gate_norm.weight", "update_gate_norm.bias", "output_norm.weight", "output_norm.bias")) + (
+    "conv1.conv.weight", "conv2.conv.weight", "conv3.conv.weight", "upconv1.conv.weight", "upconv2.conv.weight",
+    "upconv3.conv.weight", "upconv2d.weight", "upconv2d.bias")
+
+
+def _red_backward_sample(P: dict, vol, ws, dlog):
+    """Gradients of one sample.  P: parameter name -> tensor; vol [C,D,H,W]; ws: the workspace the forward of THIS sample ran in;
+    dlog [D,H,W].  Returns (dvol [C,D,H,W], {name: grad})."""
+    dev = vol.device
+    Cin, D, H, W = vol.shape
+    offs = (C.c_size_t * 10)()
+    _lib.check(_lib.lib().satmvs_red_workspace_layout(Cin, D, H, W, offs), "red_workspace_layout")
+
+    def view(off, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        return ws[off:off + 4 * n].view(torch.float32).view(shape)
+
+    S = [view(offs[l], (_CH[l], D + 1, H >> l, W >> l)) for l in range(4)]
+    E = [None] + [view(offs[3 + l], (_CH[l], D, H >> l, W >> l)) for l in (1, 2, 3)]
+    U = [view(offs[7 + l], (_CH[l], D + 1, H >> l, W >> l)) for l in range(3)]
+    g = {}
+    X0 = _ew(vol, torch.empty_like(vol), scale=-1.0)                       # the network sees -cost (module.py:627, :640)
+    X = [X0, E[1], E[2], E[3]]
+
+    # ---- decoder, batched over planes (module.py:633-643) ----
+    dlog4 = dlog.reshape(1, D, H, W).contiguous()
+    w2d = P["upconv2d.weight"]
+    dU = _conv2d(dlog4, w2d, 0, 8, 9, 9)
+    U0c = _ew(U[0][:, 1:], torch.empty((8, D, H, W), dtype=torch.float32, device=dev))
+    g["upconv2d.weight"] = _wgrad2d(U0c, dlog4, 1, (1, 8, 3, 3), 72).flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    g["upconv2d.bias"] = _channel_sum(dlog4)
+    dec = [None] * 4
+    ups = ("upconv1.conv.weight", "upconv2.conv.weight", "upconv3.conv.weight")
+    for l in range(3):
+        dec[l] = dU
+        Hn = S[l][:, 1:]
+        dpre = _ew(dU, torch.empty_like(dU), m1=U[l][:, 1:], m2=Hn)                              # relu'(convT(.)) mask
+        src = U[l + 1][:, 1:] if l + 1 < 3 else S[3][:, 1:]                                     # the transposed conv's input
+        srcc = _ew(src, torch.empty((_CH[l + 1], D, H >> (l + 1), W >> (l + 1)), dtype=torch.float32, device=dev))
+        wt = P[ups[l]]                                                                          # [ch_{l+1}, ch_l, 3, 3]
+        g[ups[l]] = _wgrad2d(dpre, srcc, 2, tuple(wt.shape), _CH[l] * 9)
+        dU = _conv2d(dpre, wt, 1, _CH[l + 1], _CH[l] * 9, 9)
+    dec[3] = dU
+
+    # ---- per level: recompute the cell's pre-activations batched over planes ----
+    L = _lib.lib()
+    st = _lib.stream_ptr(dev)
+    lv = (_GruBwdLevel * 4)()
+    keep = []
+    for l in range(4):
+        ch, cx, h, w = _CH[l], (Cin if l == 0 else _CH[l]), H >> l, W >> l
+        nm = f"conv_gru{l + 1}."
+        Wg, bg, Wo, bo = P[nm + "gate_conv.weight"], P[nm + "gate_conv.bias"], P[nm + "output_conv.weight"], P[nm + "output_conv.bias"]
+        rn_w, un_w, on_w = P[nm + "reset_gate_norm.weight"], P[nm + "update_gate_norm.weight"], P[nm + "output_norm.weight"]
+        gam = torch.cat([rn_w, un_w]).contiguous()
+        bet = torch.cat([P[nm + "reset_gate_norm.bias"], P[nm + "update_gate_norm.bias"]]).contiguous()
+        Hp = S[l][:, :D]
+        XH = torch.empty((cx + ch, D, h, w), dtype=torch.float32, device=dev)
+        _ew(X[l], XH[:cx]); _ew(Hp, XH[cx:])
+        Gpre = _conv2d(XH, Wg, 0, 2 * ch, (cx + ch) * 9, 9)
+        RU, gstat = _gn_act(Gpre, bg, gam, bet, ch, 2, 0)
+        XRH = torch.empty_like(XH)
+        _ew(X[l], XRH[:cx]); _ew(RU[:ch], XRH[cx:], mul=Hp)
+        Opre = _conv2d(XRH, Wo, 0, ch, (cx + ch) * 9, 9)
+        Y, ostat = _gn_act(Opre, bo, on_w, P[nm + "output_norm.bias"], ch, 1, 1)
+        dGO = torch.empty((3 * ch, D, h, w), dtype=torch.float32, device=dev)     # [dG (2ch) | dO (ch)]
+        dGn = torch.empty((2 * ch, D, h, w), dtype=torch.float32, device=dev)
+        dYn = torch.empty((ch, D, h, w), dtype=torch.float32, device=dev)
+        scratch = torch.empty(16 + 9 * ch * h * w, dtype=torch.float32, device=dev)
+        Wo_h, Wg_h = Wo.reshape(-1)[cx * 9:], Wg.reshape(-1)[cx * 9:]
+        a = lv[l]
+        a.S, a.ru, a.y, a.opre, a.gpre = S[l].data_ptr(), RU.data_ptr(), Y.data_ptr(), Opre.data_ptr(), Gpre.data_ptr()
+        a.ob, a.gb, a.on_w, a.rn_w, a.un_w = bo.data_ptr(), bg.data_ptr(), on_w.data_ptr(), rn_w.data_ptr(), un_w.data_ptr()
+        a.ostat, a.gstat, a.dec = ostat.data_ptr(), gstat.data_ptr(), dec[l].data_ptr()
+        a.wo_h, a.wg_h, a.w_ci = Wo_h.data_ptr(), Wg_h.data_ptr(), (cx + ch) * 9
+        a.dyn, a.dgn, a.dG, a.dO, a.scratch = dYn.data_ptr(), dGn.data_ptr(), dGO.data_ptr(), dGO[2 * ch:].data_ptr(), scratch.data_ptr()
+        a.ch, a.h, a.w, a.D = ch, h, w, D
+        keep.append((XH, XRH, Gpre, Opre, RU, Y, gstat, ostat, dGO, dGn, dYn, scratch, Wg, bg, Wo, bo, cx))
+    # ---- sequential in depth: planes D-1 .. 0, the four levels on streams of their own (csrc/red_train.cu) ----
+    _lib.check(L.satmvs_red_recurrence_bwd(lv, 4, st), "red_recurrence_bwd")
+    # ---- batched: gradient to the cells' x inputs, filters, biases, GroupNorm affine parameters ----
+    dX = [None] * 4
+    for l in range(4):
+        XH, XRH, Gpre, Opre, RU, Y, gstat, ostat, dGO, dGn, dYn, scratch, Wg, bg, Wo, bo, cx = keep[l]
+        ch = _CH[l]
+        nm = f"conv_gru{l + 1}."
+        dG_all, dO_all = dGO[:2 * ch], dGO[2 * ch:]
+        Wcat = torch.cat([Wg, Wo], 0).contiguous()
+        dX[l] = _conv2d(dGO, Wcat, 2, cx, 9, (cx + ch) * 9)
+        g[nm + "gate_conv.weight"] = _wgrad2d(XH, dG_all, 1, tuple(Wg.shape), (cx + ch) * 9)
+        g[nm + "output_conv.weight"] = _wgrad2d(XRH, dO_all, 1, tuple(Wo.shape), (cx + ch) * 9)
+        g[nm + "gate_conv.bias"] = _channel_sum(dG_all)
+        g[nm + "output_conv.bias"] = _channel_sum(dO_all)
+        dgam, dbet = _gn_param_grad(dGn, Gpre, bg, gstat, ch, 2)
+        g[nm + "reset_gate_norm.weight"], g[nm + "update_gate_norm.weight"] = dgam[:ch].clone(), dgam[ch:].clone()
+        g[nm + "reset_gate_norm.bias"], g[nm + "update_gate_norm.bias"] = dbet[:ch].clone(), dbet[ch:].clone()
+        g[nm + "output_norm.weight"], g[nm + "output_norm.bias"] = _gn_param_grad(dYn, Opre, bo, ostat, ch, 1)
+
+    # ---- encoders conv3, conv2, conv1 (ConvReLU stride 2, module.py:627-629), batched ----
+    dE = dX[3]
+    for l in (3, 2, 1):
+        nm = f"conv{l}.conv.weight"
+        wc = P[nm]                                                     # [ch_l, cin, 3, 3]
+        cin = wc.shape[1]
+        dpre = _ew(dE, torch.empty_like(dE), m1=E[l])
+        g[nm] = _wgrad2d(X[l - 1], dpre, 2, tuple(wc.shape), cin * 9)
+        back = _conv2d(dpre, wc, 3, cin, 9, cin * 9)
+        dE = _ew(dX[l - 1], torch.empty_like(back), b=back, scale=(-1.0 if l == 1 else 1.0))
+    return dE, g
+
+
+class _RedTrainFn(torch.autograd.Function):
+    """RED_Regularization.forward with a backward: the forward is the library's fast path (tensor-core recurrence) run in a
+    workspace of its own per sample, which the backward reads the state history from."""
+
+    @staticmethod
+    def forward(ctx, net, volume, *params):
+        vol = _lib.require_cuda(volume.detach(), "volume").contiguous().float()
+        B, Cc, D, H, W = vol.shape
+        L = _lib.lib()
+        nbytes = L.satmvs_red_workspace_bytes(Cc, D, H, W)
+        if nbytes == 0:
+            raise ValueError("RED regulariser needs H and W to be multiples of 8")
+        w = net._weights()
+        logits = torch.empty((B, D, H, W), dtype=torch.float32, device=vol.device)
+        wss = []
+        with torch.cuda.device(vol.device):
+            st = _lib.stream_ptr(vol.device)
+            for b in range(B):
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=vol.device)
+                _lib.check(L.satmvs_red_forward(C.byref(w), vol[b].data_ptr(), Cc, D, H, W, None, None, logits[b].data_ptr(),
+                                                ws.data_ptr(), ws.numel(), st), "red_forward")
+                wss.append(ws)
+        ctx.save_for_backward(vol, *wss, *[p.detach() for p in params])
+        ctx.nb = B
+        return logits
+
+    @staticmethod
+    def backward(ctx, gl):
+        sv = ctx.saved_tensors
+        B = ctx.nb
+        vol, wss, params = sv[0], sv[1:1 + B], sv[1 + B:]
+        P = dict(zip(_RED_PARAM_NAMES, params))
+        gl = gl.contiguous().float()
+        dvol = torch.empty_like(vol)
+        total = None
+        with torch.cuda.device(vol.device):
+            for b in range(B):
+                dv, g = _red_backward_sample(P, vol[b], wss[b], gl[b])
+                dvol[b] = dv
+                if total is None:
+                    total = g
+                else:
+                    for k in total:
+                        total[k] = _ew(total[k].reshape(1, -1), torch.empty_like(total[k]).reshape(1, -1),
+                                       b=g[k].reshape(1, -1)).reshape(total[k].shape)
+        return (None, dvol, *[total[n] for n in _RED_PARAM_NAMES])
+
+
+def red_train_forward(net, volume):
+    """`RED_Regularization.forward` (`modules/module.py:614-649`) with gradients to the volume and to every parameter."""
+    sd = dict(net.named_parameters())
+    return _RedTrainFn.apply(net, volume, *[sd[n] for n in _RED_PARAM_NAMES])

@@ -15,21 +15,23 @@ DEV = "cuda:0"
 
 @pytest.fixture(autouse=True)
 def _inference_mode(request):
-    """The regulariser is inference-only and says so when gradients are on (test_requires_no_grad)."""
-    if "test_requires_no_grad" in request.node.name:
+    """Inference tests run under no_grad; the slice form says so when gradients are on (test_slice_form_requires_no_grad)."""
+    if "requires_no_grad" in request.node.name:
         yield
         return
     with torch.no_grad():
         yield
 
 
-def test_requires_no_grad():
-    m = satmvs_b200.RED_Regularization(8, 8).to(DEV)
-    x = torch.rand(1, 8, 2, 8, 8, device=DEV)
+def test_slice_form_requires_no_grad():
+    """The per-slice (predict) form has no backward and says so; the whole-volume form trains (tests/test_gpu_train.py)."""
+    m = satmvs_b200.slice_RED_Regularization(8, 8).to(DEV)
+    x = torch.rand(1, 8, 8, 8, device=DEV)
+    st = [torch.zeros(1, c, 8 >> l, 8 >> l, device=DEV) for l, c in enumerate((8, 16, 32, 64))]
     with pytest.raises(RuntimeError, match="inference-only"):
-        m(x)
+        m(x, *st)
     with torch.no_grad():
-        assert m(x).shape == (1, 2, 8, 8)
+        assert m(x, *st)[0].shape == (1, 1, 8, 8)
 
 
 def maxdiff(a, b):

@@ -118,15 +118,75 @@ def test_eval_after_train_uses_the_updated_running_statistics():
     assert rel(got, want) < 1e-3
 
 
-def test_softargmin_head_gradient():
+@pytest.mark.parametrize("head", ["casmvs", "red"])
+def test_softargmin_head_gradient(head):
     gen = torch.Generator().manual_seed(2)
     logits = torch.randn(2, 12, 9, 13, generator=gen).requires_grad_(True)
     dv = (torch.linspace(400, 600, 12).view(1, 12, 1, 1) + torch.randn(2, 12, 9, 13, generator=gen)).contiguous()
-    want, _ = regress.softargmin_casmvs(logits, dv)
+    want, _ = (regress.softargmin_casmvs if head == "casmvs" else regress.softargmin_red)(logits, dv)
     gd = torch.randn(2, 9, 13, generator=gen)
     want.backward(gd)
     lg = logits.detach().to(DEV).requires_grad_(True)
-    depth, conf = training.softargmin_casmvs_train(lg, dv.to(DEV))
+    depth, conf = training.softargmin_train(lg, dv.to(DEV), head)
     assert rel(depth, want) < 1e-5 and not conf.requires_grad
     depth.backward(gd.to(DEV))
     assert rel(lg.grad, logits.grad) < 1e-4
+
+
+@pytest.mark.parametrize("C,B,D,H,W", [(8, 1, 3, 16, 24), (32, 1, 4, 32, 32), (16, 2, 5, 16, 16)])
+def test_red_regulariser_backward_matches_oracle_autograd(C, B, D, H, W):
+    """loss.backward() through RED_Regularization (train.py:284): gradient to the volume and to all 48 parameters against autograd
+    of the oracle's restatement of modules/module.py:614-649."""
+    sd = synth.make_red_weights(C, seed=5)
+    net = satmvs_b200.RED_Regularization(C, 8)
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    x = synth.make_features(1, 1, B * C * D, H, W, seed=6)[0].view(B, C, D, H, W).abs()
+    gen = torch.Generator().manual_seed(10)
+    gout = torch.randn(B, D, H, W, generator=gen)
+
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    want = regnets.red_regularization(xr, ref)
+    want.backward(gout)
+
+    xg = x.to(DEV).requires_grad_(True)
+    got = net(xg)
+    assert got.requires_grad and rel(got, want) < 1e-4
+    got.backward(gout.to(DEV))
+    assert rel(xg.grad, xr.grad) < 1e-3
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        r = rel(p.grad, ref[name].grad)
+        assert r < 2e-3, (name, r)
+
+
+def test_red_training_stage_reaches_the_feature_maps():
+    """Fused sweep -> RED regulariser -> head, loss.backward(): gradients arrive at the feature maps and the parameters and match
+    autograd of the oracle stage."""
+    from oracle import volume
+    B, V, C, D, H, W = 1, 3, 8, 4, 16, 24
+    fe = synth.make_features(B, V, C, H, W, seed=2)
+    rp = synth.make_rpc_stack(B, V, H, W)
+    dv = synth.make_depth_planes(B, D, H, W)
+    sd = synth.make_red_weights(C)
+    gt = torch.full((B, H, W), float(dv.mean()))
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    fr = [f.clone().requires_grad_(True) for f in fe]
+    logits = regnets.red_regularization(volume.variance_cost_volume(fr, rp, dv, "rpc"), ref)
+    want, _ = regress.softargmin_red(logits, dv)
+    torch.nn.functional.smooth_l1_loss(want, gt).backward()
+
+    net = satmvs_b200.RED_Regularization(C, 8)
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    fg = [f.to(DEV).requires_grad_(True) for f in fe]
+    out = satmvs_b200.stage_train_red(fg, rp, dv.to(DEV), net, "rpc")
+    assert rel(out["depth"], want) < 1e-5
+    torch.nn.functional.smooth_l1_loss(out["depth"], gt.to(DEV)).backward()
+    for a, b in zip(fg, fr):
+        assert rel(a.grad, b.grad) < 2e-3
+    assert rel(net.conv_gru1.gate_conv.weight.grad, ref["conv_gru1.gate_conv.weight"].grad) < 2e-3
+    assert rel(net.upconv1.conv.weight.grad, ref["upconv1.conv.weight"].grad) < 2e-3
+    # (upconv2d.bias shifts every logit of a pixel alike: the soft-argmin is invariant, its exact gradient is zero)
+    assert net.upconv2d.bias.grad.abs().max().item() < 1e-4 * net.upconv2d.weight.grad.abs().max().item()
