@@ -325,11 +325,14 @@ def _red_backward_sample(P: dict, vol, ws, dlog):
     ups = ("upconv1.conv.weight", "upconv2.conv.weight", "upconv3.conv.weight")
     for l in range(3):
         dec[l] = dU
-        Hn = S[l][:, 1:]
-        dpre = _ew(dU, torch.empty_like(dU), m1=U[l][:, 1:], m2=Hn)                              # relu'(convT(.)) mask
         src = U[l + 1][:, 1:] if l + 1 < 3 else S[3][:, 1:]                                     # the transposed conv's input
         srcc = _ew(src, torch.empty((_CH[l + 1], D, H >> (l + 1), W >> (l + 1)), dtype=torch.float32, device=dev))
         wt = P[ups[l]]                                                                          # [ch_{l+1}, ch_l, 3, 3]
+        # ReLU mask from the recomputed transposed conv: U_l - S_l would lose activations smaller than an ulp of S_l, and a mask
+        # error is a 100 % error of that voxel's gradient
+        pre = _conv2d(srcc, wt, 3, _CH[l], 9, _CH[l] * 9)
+        dpre = _ew(dU, torch.empty_like(dU), m1=pre)
+        del pre
         g[ups[l]] = _wgrad2d(dpre, srcc, 2, tuple(wt.shape), _CH[l] * 9)
         dU = _conv2d(dpre, wt, 1, _CH[l + 1], _CH[l] * 9, 9)
     dec[3] = dU
