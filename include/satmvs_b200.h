@@ -294,6 +294,14 @@ size_t satmvs_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int Di, int Hi, in
 int satmvs_conv3d_wgrad(const float* x, int Cin, int Di, int Hi, int Wi, const float* dy, int Cout, int NZ, int stride,
                         float* dw, long long dw_co, long long dw_ci, int accumulate, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* Per-plane K x K (K = 1, 3, 5; padding K/2) forms of the two primitives above on [C][N][H][W] tensors (FeatureNet's layers,
+ * modules/module.py:442-543): same modes; satmvs_conv2d_wgrad: dw[co, ci, ky * K + kx]. */
+int satmvs_conv2d_raw(const float* in, int Cin, int N, int Hi, int Wi, const float* w, long long w_co, long long w_ci, int K, int mode,
+                      float* out, int Cout, void* stream);
+size_t satmvs_conv2d_wgrad_workspace_bytes(int Cin, int Cout, int N, int Hi, int Wi, int K, int stride);
+int satmvs_conv2d_wgrad(const float* x, int Cin, int N, int Hi, int Wi, const float* dy, int Cout, int K, int stride,
+                        float* dw, long long dw_co, long long dw_ci, int accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream);
 int satmvs_bn_train_fwd(const float* y, int B, int C, long long n, const float* gamma, const float* beta, float eps, int relu,
                         const float* post_add, float* z, float* mean, float* var, double* acc, void* stream);
 int satmvs_bn_train_bwd(const float* dz, const float* dz2, const float* y, int B, int C, long long n, const float* gamma, const float* beta,

@@ -106,12 +106,15 @@ def red_regularization(volume: torch.Tensor, sd: dict) -> torch.Tensor:
     return torch.stack(out, dim=1).squeeze(2)
 
 
-def featurenet(x: torch.Tensor, sd: dict) -> dict:
-    """`FeatureNet.forward` (`modules/module.py:506-543`), arch_mode "unet", three stages, eval-mode BatchNorm
-    (`Conv2d` / `Deconv2d` blocks `:78-159`, `DeConv2dFuse` `:303-321`).  x [B,3,H,W] -> {"stage1", "stage2", "stage3"}."""
+def featurenet(x: torch.Tensor, sd: dict, training: bool = False) -> dict:
+    """`FeatureNet.forward` (`modules/module.py:506-543`), arch_mode "unet", three stages; BatchNorm on running statistics, or on
+    batch statistics when `training` (`Conv2d` / `Deconv2d` blocks `:78-159`, `DeConv2dFuse` `:303-321`).
+    x [B,3,H,W] -> {"stage1", "stage2", "stage3"}."""
     import torch.nn.functional as F
 
     def bn(y, name):
+        if training:
+            return F.batch_norm(y, None, None, sd[name + ".bn.weight"], sd[name + ".bn.bias"], True, 0.1, 1e-5)
         return F.batch_norm(y, sd[name + ".bn.running_mean"], sd[name + ".bn.running_var"], sd[name + ".bn.weight"],
                             sd[name + ".bn.bias"], False, 0.1, 1e-5)
 

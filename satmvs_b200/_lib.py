@@ -55,6 +55,9 @@ _SIGNATURES = {
     "satmvs_conv3d_raw": ([_P, _I, _I, _I, _I, _P, C.c_longlong, C.c_longlong, _I, _I, _P, _I, _P], _I),
     "satmvs_conv3d_wgrad_workspace_bytes": ([_I, _I, _I, _I, _I, _I, _I], C.c_size_t),
     "satmvs_conv3d_wgrad": ([_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.c_longlong, C.c_longlong, _I, _P, C.c_size_t, _P], _I),
+    "satmvs_conv2d_raw": ([_P, _I, _I, _I, _I, _P, C.c_longlong, C.c_longlong, _I, _I, _P, _I, _P], _I),
+    "satmvs_conv2d_wgrad_workspace_bytes": ([_I, _I, _I, _I, _I, _I, _I], C.c_size_t),
+    "satmvs_conv2d_wgrad": ([_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, C.c_longlong, C.c_longlong, _I, _P, C.c_size_t, _P], _I),
     "satmvs_bn_train_fwd": ([_P, _I, _I, C.c_longlong, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P, _P], _I),
     "satmvs_bn_train_bwd": ([_P, _P, _P, _I, _I, C.c_longlong, _P, _P, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P], _I),
     "satmvs_softargmin_bwd": ([_P, _P, _I, _I, _I, _I, _P, _P, _P], _I),

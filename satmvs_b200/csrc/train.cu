@@ -344,6 +344,38 @@ static WgradPlan wgrad_plan(int Cin, int Cout, int Wi, int Do, int Ho, int Wo, i
   return p;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------------------
+// weight gradient of a K x K (K = 1 or 5) per-plane convolution with padding K/2 and stride S: the small layers of FeatureNet
+// (5x5 stride-2 and 1x1 convs, modules/module.py:456-470).  One thread per filter element and position chunk; partials as above.
+// ----------------------------------------------------------------------------------------------------------------------------
+struct WgradGenArgs {
+  const float* x; const float* dy; float* partial;
+  int Cin, Cout, N, Hi, Wi, Ho, Wo, K, S, chunk_len;
+};
+
+__global__ void __launch_bounds__(256) wgrad_generic_kernel(const WgradGenArgs a) {
+  const int taps = a.K * a.K, total = a.Cout * a.Cin * taps;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int co = e / (a.Cin * taps), rem = e - co * (a.Cin * taps), ci = rem / taps, t = rem - ci * taps;
+  const int ky = t / a.K, kx = t - ky * a.K, pad = a.K / 2;
+  const long long npos = (long long)a.N * a.Ho * a.Wo;
+  const long long o0 = (long long)blockIdx.y * a.chunk_len;
+  long long o1 = o0 + a.chunk_len;
+  if (o1 > npos) o1 = npos;
+  const float* dyc = a.dy + (long long)co * npos;
+  const float* xc = a.x + (long long)ci * a.N * a.Hi * a.Wi;
+  float acc = 0.0f;
+  for (long long o = o0; o < o1; ++o) {
+    const int n = (int)(o / (a.Ho * a.Wo)), r = (int)(o - (long long)n * a.Ho * a.Wo), oy = r / a.Wo, ox = r - oy * a.Wo;
+    const int iy = a.S * oy + ky - pad, ix = a.S * ox + kx - pad;
+    if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
+      acc = fmaf(__ldg(dyc + o), __ldg(xc + ((long long)n * a.Hi + iy) * a.Wi + ix), acc);
+  }
+  a.partial[(size_t)blockIdx.y * total + e] = acc;
+}
+
 }  // namespace satmvs
 
 using namespace satmvs;
@@ -450,6 +482,108 @@ int satmvs_conv3d_wgrad(const float* x, int Cin, int Di, int Hi, int Wi, const f
   if (rc) return rc;
   const int total = Cout * Cin * NZ * 9;
   wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a.partial, p.chunks, Cout, Cin, NZ * 9, dw, dw_co, dw_ci, accumulate);
+  return check_launch("wgrad_reduce_kernel");
+}
+
+// Per-plane K x K convolution (K = 1, 3, 5; padding K/2) of a [Cin][N][H][W] tensor in the arrangements of satmvs_conv3d_raw:
+// mode 0 stride 1, 1 stride 2, 2 stride 1 with mirrored taps, 3 transposed stride 2 (output_padding 1).  K = 3 is satmvs_conv3d_raw
+// with NZ = 1; the others (FeatureNet's 5x5 stride-2 and 1x1 layers and their data gradients) run on the implicit-GEMM engine.
+int satmvs_conv2d_raw(const float* in, int Cin, int N, int Hi, int Wi, const float* w, long long w_co, long long w_ci, int K, int mode,
+                      float* out, int Cout, void* stream) {
+  if (K == 3) return satmvs_conv3d_raw(in, Cin, N, Hi, Wi, w, w_co, w_ci, 1, mode, out, Cout, stream);
+  SATMVS_CHECK_ASYNC();
+  SATMVS_REQUIRE(in && w && out && Cin >= 1 && Cout >= 1 && N >= 1 && Hi >= 1 && Wi >= 1 && (K == 1 || K == 5) && mode >= 0 && mode <= 3);
+  SATMVS_REQUIRE(K * K <= kMaxTaps);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(kProfTrainConv, st);
+  const int pad = K / 2;
+  ConvGroup g{};
+  int n = 0;
+  if (mode == 3) {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        ConvProblem p;
+        conv_problem_defaults(p);
+        p.in = in; p.w = w; p.out = out; p.Cin = Cin; p.Cout = Cout;
+        p.Di = N; p.Hi = Hi; p.Wi = Wi; p.Do = N; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
+        p.Qd = N; p.Qh = Hi; p.Qw = Wi;
+        p.w_ci_stride = w_ci; p.w_co_stride = w_co;
+        p.q2o_mul[1] = 2; p.q2o_mul[2] = 2; p.q2o_add[1] = py; p.q2o_add[2] = px;
+        p.q2i_add[1] = -1; p.q2i_add[2] = -1;
+        int t = 0;
+        for (int ky = 0; ky < K; ++ky) {
+          if (((ky - py - pad) & 1) != 0) continue;              // i = 2 o - pad + k: k has the parity of i + pad
+          for (int kx = 0; kx < K; ++kx) {
+            if (((kx - px - pad) & 1) != 0) continue;
+            p.tap_dz[t] = 0; p.tap_dy[t] = (signed char)((py + pad - ky) / 2 + 1); p.tap_dx[t] = (signed char)((px + pad - kx) / 2 + 1);
+            p.tap_w[t] = (signed char)(ky * K + kx);
+            ++t;
+          }
+        }
+        if (t == 0) continue;
+        p.ntaps = t;
+        conv_finalize(p);
+        g.p[n++] = p;
+      }
+  } else {
+    const int stride = mode == 1 ? 2 : 1;
+    if (stride == 2) SATMVS_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0);
+    ConvProblem p;
+    conv_problem_defaults(p);
+    p.in = in; p.w = w; p.out = out; p.Cin = Cin; p.Cout = Cout;
+    p.Di = N; p.Hi = Hi; p.Wi = Wi; p.Do = N; p.Ho = Hi / stride; p.Wo = Wi / stride;
+    p.Qd = N; p.Qh = p.Ho; p.Qw = p.Wo;
+    p.w_co_stride = w_co; p.w_ci_stride = w_ci;
+    p.q2i_mul[1] = stride; p.q2i_mul[2] = stride; p.q2i_add[1] = -pad; p.q2i_add[2] = -pad;
+    int t = 0;
+    for (int ky = 0; ky < K; ++ky)
+      for (int kx = 0; kx < K; ++kx) {
+        p.tap_dz[t] = 0; p.tap_dy[t] = (signed char)ky; p.tap_dx[t] = (signed char)kx;
+        p.tap_w[t] = (signed char)(mode == 2 ? K * K - 1 - (ky * K + kx) : ky * K + kx);
+        ++t;
+      }
+    p.ntaps = t;
+    conv_finalize(p);
+    g.p[n++] = p;
+  }
+  g.n = n;
+  if (Cout >= 32) return conv_launch<Tile32>(g, st, "satmvs_conv2d_raw");
+  if (Cout >= 16) return conv_launch<Tile16>(g, st, "satmvs_conv2d_raw");
+  return conv_launch<Tile8>(g, st, "satmvs_conv2d_raw");
+}
+
+size_t satmvs_conv2d_wgrad_workspace_bytes(int Cin, int Cout, int N, int Hi, int Wi, int K, int stride) {
+  if (K == 3) return satmvs_conv3d_wgrad_workspace_bytes(Cin, Cout, N, Hi, Wi, 1, stride);
+  if (Cin < 1 || Cout < 1 || N < 1 || Hi < 1 || Wi < 1 || (K != 1 && K != 5) || (stride != 1 && stride != 2)) return 0;
+  return (size_t)256 * Cout * Cin * K * K * 4 + 256;
+}
+
+// dw[co * dw_co + ci * dw_ci + ky * K + kx] (+)= sum over planes and positions of dy[co, o] * x[ci, stride * o + k - K/2]
+int satmvs_conv2d_wgrad(const float* x, int Cin, int N, int Hi, int Wi, const float* dy, int Cout, int K, int stride,
+                        float* dw, long long dw_co, long long dw_ci, int accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  if (K == 3) return satmvs_conv3d_wgrad(x, Cin, N, Hi, Wi, dy, Cout, 1, stride, dw, dw_co, dw_ci, accumulate, workspace,
+                                         workspace_bytes, stream);
+  SATMVS_CHECK_ASYNC();
+  SATMVS_REQUIRE(x && dy && dw && workspace && Cin >= 1 && Cout >= 1 && N >= 1 && Hi >= 1 && Wi >= 1);
+  SATMVS_REQUIRE((K == 1 || K == 5) && (stride == 1 || stride == 2));
+  if (stride == 2) SATMVS_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(kProfTrainWgrad, st);
+  WgradGenArgs a{};
+  a.x = x; a.dy = dy; a.partial = static_cast<float*>(workspace);
+  a.Cin = Cin; a.Cout = Cout; a.N = N; a.Hi = Hi; a.Wi = Wi; a.Ho = Hi / stride; a.Wo = Wi / stride; a.K = K; a.S = stride;
+  const int total = Cout * Cin * K * K;
+  const long long npos = (long long)N * a.Ho * a.Wo;
+  int chunks = 256;
+  if (chunks > npos) chunks = (int)npos;
+  a.chunk_len = (int)((npos + chunks - 1) / chunks);
+  chunks = (int)((npos + a.chunk_len - 1) / a.chunk_len);
+  SATMVS_REQUIRE(workspace_bytes >= (size_t)chunks * total * 4);
+  wgrad_generic_kernel<<<dim3(ceil_div(total, 256), chunks), 256, 0, st>>>(a);
+  int rc = check_launch("wgrad_generic_kernel");
+  if (rc) return rc;
+  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a.partial, chunks, Cout, Cin, K * K, dw, dw_co, dw_ci, accumulate);
   return check_launch("wgrad_reduce_kernel");
 }
 

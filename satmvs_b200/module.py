@@ -419,9 +419,13 @@ class FeatureNet(nn.Module):
 
     def forward_views(self, images):
         if self.training:
-            raise RuntimeError("satmvs_b200.FeatureNet implements inference-mode BatchNorm only; call .eval()")
+            # train.py:268 model.train(): batch-statistics BatchNorm, one autograd node per block (training.py); the reference
+            # calls the net once per view (casred.py:116-119), so the statistics are per view here too
+            from .training import featurenet_train_forward
+            return [featurenet_train_forward(self, _lib.require_cuda(i, "image")) for i in images]
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("satmvs_b200.FeatureNet is inference-only: call it under torch.no_grad()")
+            raise RuntimeError("satmvs_b200.FeatureNet in eval() mode has no backward: call it under torch.no_grad() "
+                               "(a frozen extractor) or in train() mode")
         imgs = [_lib.require_cuda(i, "image") for i in images]
         B, c3, H, W = imgs[0].shape
         if c3 != 3 or any(i.shape != imgs[0].shape for i in imgs):

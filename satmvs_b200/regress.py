@@ -22,17 +22,8 @@ def resize_bilinear(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
     return out
 
 
-def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
-    """`depth_regression` (`modules/module.py:433-439`): sum_d p*d on given probabilities p [B,D,H,W];
-    depth_values [B,D] or [B,D,h,w] (resized bilinearly to p's grid like the reference)."""
-    p = _lib.require_cuda(p, "p")
+def _depth_regression_fwd(p, dv, per_pixel):
     B, D, H, W = p.shape
-    dv = _lib.require_cuda(depth_values, "depth_values")
-    per_pixel = 0
-    if dv.dim() > 2:
-        per_pixel = 1
-        if tuple(dv.shape[2:]) != (H, W):
-            dv = resize_bilinear(dv, H, W)
     depth = torch.empty((B, H, W), dtype=torch.float32, device=p.device)
     with torch.cuda.device(p.device):
         st = _lib.stream_ptr(p.device)
@@ -40,6 +31,46 @@ def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tenso
             _lib.check(_lib.lib().satmvs_softargmin_fwd(p[b].data_ptr(), dv[b].data_ptr(), per_pixel, 2, D, H, W,
                                                        depth[b].data_ptr(), None, st), "depth_regression")
     return depth
+
+
+class _DepthRegressionFn(torch.autograd.Function):
+    """sum_d p*d with its gradient to the probabilities, d depth / d p_d = depth_values_d (`casmvs.py:66-68` trains through it)."""
+
+    @staticmethod
+    def forward(ctx, p, dv, per_pixel):
+        ctx.save_for_backward(dv)
+        ctx.cfg = (per_pixel, tuple(p.shape))
+        return _depth_regression_fwd(p.detach(), dv, per_pixel)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dv,) = ctx.saved_tensors
+        per_pixel, (B, D, H, W) = ctx.cfg
+        g = g.contiguous().float()
+        out = torch.empty((B, D, H, W), dtype=torch.float32, device=g.device)
+        dvf = dv if per_pixel else dv.reshape(B, D, 1, 1).expand(B, D, H, W).contiguous()
+        with torch.cuda.device(g.device):
+            st = _lib.stream_ptr(g.device)
+            for b in range(B):     # out[d] = depth_values[d] * g  (g broadcast over the planes: channel stride 0)
+                _lib.check(_lib.lib().satmvs_elementwise(dvf[b].data_ptr(), H * W, None, 0, g[b].data_ptr(), 0, None, 0, None, 0, 1.0,
+                                                         out[b].data_ptr(), H * W, D, H * W, st), "depth_regression_bwd")
+        return out, None, None
+
+
+def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
+    """`depth_regression` (`modules/module.py:433-439`): sum_d p*d on given probabilities p [B,D,H,W];
+    depth_values [B,D] or [B,D,h,w] (resized bilinearly to p's grid like the reference).  Carries a gradient to p."""
+    p = _lib.require_cuda(p, "p")
+    B, D, H, W = p.shape
+    dv = _lib.require_cuda(depth_values.detach(), "depth_values")
+    per_pixel = 0
+    if dv.dim() > 2:
+        per_pixel = 1
+        if tuple(dv.shape[2:]) != (H, W):
+            dv = resize_bilinear(dv, H, W)
+    if torch.is_grad_enabled() and p.requires_grad:
+        return _DepthRegressionFn.apply(p, dv, per_pixel)
+    return _depth_regression_fwd(p, dv, per_pixel)
 
 
 def softargmin(logits: torch.Tensor, depth_values: torch.Tensor, head: str = "red"):

@@ -456,3 +456,126 @@ def red_train_forward(net, volume):
     """`RED_Regularization.forward` (`modules/module.py:614-649`) with gradients to the volume and to every parameter."""
     sd = dict(net.named_parameters())
     return _RedTrainFn.apply(net, volume, *[sd[n] for n in _RED_PARAM_NAMES])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# FeatureNet in train mode (modules/module.py:442-543): block-level autograd nodes on the 2-D primitives
+# ---------------------------------------------------------------------------------------------------------------------------
+def _conv2d_raw_b(x, w, K, mode, cout, w_co, w_ci):
+    """satmvs_conv2d_raw on a batch [B, Cin, H, W] -> [B, cout, H', W']."""
+    B, cin, H, W = x.shape
+    oh, ow = (H // 2, W // 2) if mode == 1 else ((2 * H, 2 * W) if mode == 3 else (H, W))
+    out = torch.empty((B, cout, oh, ow), dtype=torch.float32, device=x.device)
+    st = _lib.stream_ptr(x.device)
+    for b in range(B):
+        _lib.check(_lib.lib().satmvs_conv2d_raw(x[b].data_ptr(), cin, 1, H, W, w.data_ptr(), w_co, w_ci, K, mode,
+                                                out[b].data_ptr(), cout, st), "conv2d_raw")
+    return out
+
+
+def _conv2d_wgrad_b(x, dy, K, stride, shape, dw_co):
+    """dw (given shape) = sum over the batch of the weight gradient with x [B,Cin,H,W] as the conv input, dy [B,Cout,H',W']."""
+    B, cin, H, W = x.shape
+    cout = dy.shape[1]
+    L = _lib.lib()
+    nbytes = L.satmvs_conv2d_wgrad_workspace_bytes(cin, cout, 1, H, W, K, stride)
+    if nbytes == 0:
+        raise ValueError("conv2d_wgrad: shape not supported")
+    ws = _ws(nbytes, x.device)
+    dw = torch.empty(shape, dtype=torch.float32, device=x.device)
+    st = _lib.stream_ptr(x.device)
+    for b in range(B):
+        _lib.check(L.satmvs_conv2d_wgrad(x[b].data_ptr(), cin, 1, H, W, dy[b].data_ptr(), cout, K, stride, dw.data_ptr(), dw_co,
+                                         K * K, int(b > 0), ws.data_ptr(), ws.numel(), st), "conv2d_wgrad")
+    return dw
+
+
+class _Conv2dBlockFn(torch.autograd.Function):
+    """`Conv2d` / `Deconv2d` block of the reference (`modules/module.py:78-159`): conv (no bias) + BatchNorm2d on batch statistics +
+    ReLU.  kind 0: conv stride 1, 1: conv stride 2, 3: transposed conv stride 2 (output_padding 1)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, bn, K, kind):
+        x = _lib.require_cuda(x.detach(), "x").contiguous().float()
+        w_, g_, b_ = w.detach(), gamma.detach(), beta.detach()
+        taps = K * K
+        with torch.cuda.device(x.device):
+            if kind == 3:      # ConvTranspose2d weight [Cin, Cout, K, K]
+                cout = w_.shape[1]
+                y = _conv2d_raw_b(x, w_, K, 3, cout, taps, cout * taps)
+            else:              # Conv2d weight [Cout, Cin, K, K]
+                cout = w_.shape[0]
+                y = _conv2d_raw_b(x, w_, K, kind, cout, x.shape[1] * taps, taps)
+            z, mean, var = bn_train_fwd(y, g_, b_, True)
+        _update_running_stats(bn, mean, var, y.shape[0] * y[0, 0].numel())
+        ctx.save_for_backward(x, y, w_, g_, b_, mean, var)
+        ctx.cfg = (K, kind)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y, w, g, b, mean, var = ctx.saved_tensors
+        K, kind = ctx.cfg
+        taps = K * K
+        cin = x.shape[1]
+        dz = dz.contiguous().float()
+        with torch.cuda.device(x.device):
+            dy, dg, db = bn_train_bwd(dz, None, y, g, b, mean, var, True)
+            if kind == 3:
+                cout = w.shape[1]
+                dw = _conv2d_wgrad_b(dy, x, K, 2, tuple(w.shape), cout * taps)            # roles swapped (csrc/train.cu)
+                dx = _conv2d_raw_b(dy, w, K, 1, cin, cout * taps, taps) if ctx.needs_input_grad[0] else None
+            else:
+                dw = _conv2d_wgrad_b(x, dy, K, 2 if kind == 1 else 1, tuple(w.shape), cin * taps)
+                if not ctx.needs_input_grad[0]:
+                    dx = None
+                elif kind == 1:
+                    dx = _conv2d_raw_b(dy, w, K, 3, cin, taps, cin * taps)
+                else:
+                    dx = _conv2d_raw_b(dy, w, K, 2, cin, taps, cin * taps)
+        return dx, dw, dg, db, None, None, None
+
+
+class _Conv2dPlainFn(torch.autograd.Function):
+    """Bare `nn.Conv2d(bias=False)`, stride 1 (the 1x1 output heads `out1..3`, `modules/module.py:472-483`)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = _lib.require_cuda(x.detach(), "x").contiguous().float()
+        w_ = w.detach()
+        K = w_.shape[2]
+        with torch.cuda.device(x.device):
+            y = _conv2d_raw_b(x, w_, K, 0, w_.shape[0], x.shape[1] * K * K, K * K)
+        ctx.save_for_backward(x, w_)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        K, cin = w.shape[2], x.shape[1]
+        dy = dy.contiguous().float()
+        with torch.cuda.device(x.device):
+            dw = _conv2d_wgrad_b(x, dy, K, 1, tuple(w.shape), cin * K * K)
+            dx = _conv2d_raw_b(dy, w, K, 2, cin, K * K, cin * K * K) if ctx.needs_input_grad[0] else None
+        return dx, dw
+
+
+def _block2d(blk, x, kind):
+    K = blk.conv.weight.shape[2]
+    return _Conv2dBlockFn.apply(x, blk.conv.weight, blk.bn.weight, blk.bn.bias, blk.bn, K, kind)
+
+
+def featurenet_train_forward(net, x):
+    """`FeatureNet.forward` (`modules/module.py:506-543`, unet, three stages) in train mode: every block is an autograd node of its
+    own on the library's kernels; the concatenations of `DeConv2dFuse` (`:303-321`) are torch memory copies."""
+    if x.shape[2] % 4 or x.shape[3] % 4:
+        raise ValueError("FeatureNet needs H and W to be multiples of 4")
+    c0 = _block2d(net.conv0[1], _block2d(net.conv0[0], x, 0), 0)
+    c1 = _block2d(net.conv1[2], _block2d(net.conv1[1], _block2d(net.conv1[0], c0, 1), 0), 0)
+    c2 = _block2d(net.conv2[2], _block2d(net.conv2[1], _block2d(net.conv2[0], c1, 1), 0), 0)
+    out = {"stage1": _Conv2dPlainFn.apply(c2, net.out1.weight)}
+    f1 = _block2d(net.deconv1.conv, torch.cat((_block2d(net.deconv1.deconv, c2, 3), c1), dim=1), 0)
+    out["stage2"] = _Conv2dPlainFn.apply(f1, net.out2.weight)
+    f2 = _block2d(net.deconv2.conv, torch.cat((_block2d(net.deconv2.deconv, f1, 3), c0), dim=1), 0)
+    out["stage3"] = _Conv2dPlainFn.apply(f2, net.out3.weight)
+    return out

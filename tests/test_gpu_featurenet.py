@@ -58,7 +58,9 @@ def test_featurenet_checkpoint_keys_and_modes():
     assert set(have) == set(want) and all(have[k].shape == want[k].shape for k in want)
     assert m.out_channels == [32, 16, 8]
     m = m.to(DEV)
+    out = m(torch.rand(1, 3, 8, 8, device=DEV))            # training mode: batch statistics, autograd nodes (test_gpu_train.py)
+    assert out["stage3"].requires_grad and out["stage1"].shape == (1, 32, 2, 2)
     with pytest.raises(RuntimeError):
-        m(torch.rand(1, 3, 8, 8, device=DEV))              # training mode: batch statistics are not implemented
+        m.eval()(torch.rand(1, 3, 8, 8, device=DEV))       # eval mode with gradients enabled: no backward, says so
     with pytest.raises(NotImplementedError):
         satmvs_b200.FeatureNet(8, arch_mode="fpn")

@@ -190,3 +190,71 @@ def test_red_training_stage_reaches_the_feature_maps():
     assert rel(net.upconv1.conv.weight.grad, ref["upconv1.conv.weight"].grad) < 2e-3
     # (upconv2d.bias shifts every logit of a pixel alike: the soft-argmin is invariant, its exact gradient is zero)
     assert net.upconv2d.bias.grad.abs().max().item() < 1e-4 * net.upconv2d.weight.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("K,mode,cin,cout,H,W", [(5, 1, 8, 16, 16, 24), (5, 1, 3, 5, 12, 20), (1, 0, 32, 32, 8, 12), (1, 0, 5, 7, 9, 11),
+                                                  (3, 0, 8, 8, 16, 16), (3, 3, 16, 8, 8, 12)])
+def test_conv2d_primitives_match_autograd(K, mode, cin, cout, H, W):
+    """satmvs_conv2d_raw / satmvs_conv2d_wgrad for FeatureNet's layer shapes: 5x5 stride 2, 1x1, 3x3, transposed 3x3."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(K * 10 + mode)
+    x = torch.randn(2, cin, H, W, generator=g, requires_grad=True)
+    taps = K * K
+    if mode == 3:
+        w = torch.randn(cin, cout, K, K, generator=g, requires_grad=True)
+        y = F.conv_transpose2d(x, w, stride=2, padding=K // 2, output_padding=1)
+    else:
+        w = torch.randn(cout, cin, K, K, generator=g, requires_grad=True)
+        y = F.conv2d(x, w, stride=2 if mode == 1 else 1, padding=K // 2)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    xd, wd, gyd = x.detach().to(DEV), w.detach().to(DEV), gy.to(DEV)
+    if mode == 3:
+        got = training._conv2d_raw_b(xd, wd, K, 3, cout, taps, cout * taps)
+        dx = training._conv2d_raw_b(gyd, wd, K, 1, cin, cout * taps, taps)
+        dw = training._conv2d_wgrad_b(gyd, xd, K, 2, tuple(wd.shape), cout * taps)
+    else:
+        got = training._conv2d_raw_b(xd, wd, K, mode, cout, cin * taps, taps)
+        dx = training._conv2d_raw_b(gyd, wd, K, 3 if mode == 1 else 2, cin, taps, cin * taps)
+        dw = training._conv2d_wgrad_b(xd, gyd, K, 2 if mode == 1 else 1, tuple(wd.shape), cin * taps)
+    assert rel(got, y) < 1e-5
+    assert rel(dx, x.grad) < 1e-5
+    assert rel(dw, w.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 32, 48), (2, 16, 16)])
+def test_featurenet_train_step_matches_oracle_autograd(B, H, W):
+    sd = synth.make_featurenet_weights(8)
+    net = satmvs_b200.FeatureNet(8)
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    gen = torch.Generator().manual_seed(21)
+    x = torch.rand(B, 3, H, W, generator=gen)
+    ref = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    want = regnets.featurenet(x, ref, training=True)
+    gouts = {k: torch.randn(v.shape, generator=gen) for k, v in want.items()}
+    sum((want[k] * gouts[k]).sum() for k in want).backward()
+    got = net(x.to(DEV))
+    for k in want:
+        assert rel(got[k], want[k]) < 1e-4, k
+    sum((got[k] * gouts[k].to(DEV)).sum() for k in got).backward()
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        assert rel(p.grad, ref[name].grad) < 2e-3, (name, rel(p.grad, ref[name].grad))
+    assert int(net.conv0[0].bn.num_batches_tracked) == int(sd.get("conv0.0.bn.num_batches_tracked", 0)) + 1
+
+
+@pytest.mark.parametrize("per_pixel", [False, True])
+def test_depth_regression_gradient(per_pixel):
+    """The patched reference trains through `depth_regression(F.softmax(...), depth_values)` (casmvs.py:66-68)."""
+    gen = torch.Generator().manual_seed(4)
+    logits = torch.randn(2, 6, 10, 12, generator=gen, requires_grad=True)
+    dv = torch.rand(2, 6, 10, 12, generator=gen) * 100 if per_pixel else torch.rand(2, 6, generator=gen) * 100
+    want = regress.depth_regression(torch.softmax(logits, 1), dv)
+    gd = torch.randn(2, 10, 12, generator=gen)
+    want.backward(gd)
+    lg = logits.detach().to(DEV).requires_grad_(True)
+    got = satmvs_b200.depth_regression(torch.softmax(lg, 1), dv.to(DEV))
+    assert rel(got, want) < 1e-5
+    got.backward(gd.to(DEV))
+    assert rel(lg.grad, logits.grad) < 1e-5
