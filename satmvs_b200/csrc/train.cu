@@ -172,18 +172,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 struct WgradArgs {
   const float* x;      // [Cin][Di][Hi][Wi]
   const float* dy;     // [Cout][Do][Ho][Wo]
-  float* partial;      // [gridDim.x][Cout][Cin][NZ * 9]
+  float* partial;      // [gridDim.x * split][Cout][Cin][NZ * 9]
   int Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, NZ;
   int ci_tile;         // input channels per CTA (grid.y = Cin / ci_tile, rounded up)
   int rb;              // consecutive output rows per strip: their S * (rb - 1) + 3 input rows are staged once
   int rsx, rsy;        // shared-memory row strides (floats): rs / 4 odd, so that lanes on different rows hit different banks
+  int split;           // threads sharing one (co pair, ci, kz, ky) item, each on its own range of output columns
+  int groups_per_split;  // 4-column groups per such range
 };
 
-constexpr int kWgThreads = 256;
-constexpr int kWgMaxItems = 9;    // (co pair, ci, kz, ky) items per thread: Cout 64 / 2 x 8 channels x 9 / 256
+constexpr int kWgThreads = 512;
+constexpr int kWgMaxItems = 4;    // work units (item x column range) per thread
+
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  const int bytes = valid ? 4 : 0;                                     // src-size 0: the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
 
 template <int S>
-__global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
+__global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int KZ = a.NZ == 3 ? 3 : 1, nkk = KZ * 3;
   const int NR = S * (a.rb - 1) + 3;                        // input rows of a strip (per kz plane)
@@ -193,6 +201,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
   const int nci = min(a.ci_tile, a.Cin - ci0);
   const int cop = (a.Cout + 1) >> 1;                        // output-channel pairs: one staged input window feeds two filters
   const int items = cop * nci * nkk;
+  const int units = items * a.split;
   float acc[kWgMaxItems][2][3];
 #pragma unroll
   for (int i = 0; i < kWgMaxItems; ++i)
@@ -206,30 +215,34 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
   for (int sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
     const int oz = sidx / strips_y, oy0 = (sidx - oz * strips_y) * a.rb;
     __syncthreads();
-    // one warp per shared-memory row (row decode is warp-uniform, lanes walk the columns: no per-element divisions)
+    // staging by asynchronous 4-byte copies (every element of the strip in flight at once; zero fill outside the tensors):
+    // one warp per shared-memory row, the row decode is warp-uniform, lanes walk the columns
     for (int row = warp; row < a.Cout * a.rb; row += nwarps) {   // output-gradient rows, zero-padded to a multiple of 4
       const int co = row / a.rb, r = row - co * a.rb;
       const bool live = oy0 + r < a.Ho;
       const float* src = a.dy + co * out_cs + ((long long)oz * a.Ho + (live ? oy0 + r : 0)) * a.Wo;
       float* dst = dys + (size_t)row * a.rsy;
-      for (int ox = lane; ox < a.rsy; ox += 32) dst[ox] = (live && ox < a.Wo) ? __ldg(src + ox) : 0.0f;
+      for (int ox = lane; ox < a.rsy; ox += 32) { const bool ok = live && ox < a.Wo; cp_async4(dst + ox, ok ? src + ox : a.dy, ok); }
     }
-    for (int row = warp; row < nci * KZ * NR; row += nwarps) {   // input rows (zero outside the tensor)
+    for (int row = warp; row < nci * KZ * NR; row += nwarps) {   // input rows
       const int cl = row / (KZ * NR), rem = row - cl * (KZ * NR), kz = rem / NR, j = rem - kz * NR;
       const int iz = a.NZ == 3 ? S * oz + kz - 1 : oz, iy = S * oy0 - 1 + j;
       const bool live = iz >= 0 && iz < a.Di && iy >= 0 && iy < a.Hi;
       const float* src = a.x + (ci0 + cl) * in_cs + ((long long)(live ? iz : 0) * a.Hi + (live ? iy : 0)) * a.Wi - 1;
       float* dst = xs + (size_t)row * a.rsx;
-      for (int p = lane; p < a.rsx; p += 32) dst[p] = (live && p >= 1 && p <= a.Wi) ? __ldg(src + p) : 0.0f;
+      for (int p = lane; p < a.rsx; p += 32) { const bool ok = live && p >= 1 && p <= a.Wi; cp_async4(dst + p, ok ? src + p : a.x, ok); }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < kWgMaxItems; ++it) {
-      const int id = threadIdx.x + it * blockDim.x;
-      if (id < items) {
+      const int unit = threadIdx.x + it * blockDim.x;
+      if (unit < units) {
+        const int id = unit / a.split, sp = unit - id * a.split;
         const int cp = id / (nci * nkk), rem = id - cp * (nci * nkk);
         const int cl = rem / nkk, kk = rem - cl * nkk, kz = kk / 3, ky = kk - kz * 3;
         const int co0 = 2 * cp, co1 = min(2 * cp + 1, a.Cout - 1);       // an odd Cout computes its last filter twice (stored once)
+        const int ox_lo = sp * a.groups_per_split * 4, ox_hi = min(wo4, ox_lo + a.groups_per_split * 4);
         float a0 = acc[it][0][0], a1 = acc[it][0][1], a2 = acc[it][0][2];
         float b0 = acc[it][1][0], b1 = acc[it][1][1], b2 = acc[it][1][2];
         for (int r = 0; r < a.rb; ++r) {
@@ -237,7 +250,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
           const float* dr = dys + (size_t)(co0 * a.rb + r) * a.rsy;
           const float* er = dys + (size_t)(co1 * a.rb + r) * a.rsy;
 #pragma unroll 2
-          for (int ox = 0; ox < wo4; ox += 4) {
+          for (int ox = ox_lo; ox < ox_hi; ox += 4) {
             const float4 d = *reinterpret_cast<const float4*>(dr + ox);
             const float4 e = *reinterpret_cast<const float4*>(er + ox);
             float x0, x1, x2, x3, x4, x5, x6, x7, x8;
@@ -270,13 +283,14 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradArgs a) {
     }
   }
   const int taps = a.NZ * 9;
-  float* out = a.partial + (size_t)blockIdx.x * a.Cout * a.Cin * taps;
 #pragma unroll
   for (int it = 0; it < kWgMaxItems; ++it) {
-    const int id = threadIdx.x + it * blockDim.x;
-    if (id < items) {
+    const int unit = threadIdx.x + it * blockDim.x;
+    if (unit < units) {
+      const int id = unit / a.split, sp = unit - id * a.split;
       const int cp = id / (nci * nkk), rem = id - cp * (nci * nkk);
       const int cl = rem / nkk, kk = rem - cl * nkk;
+      float* out = a.partial + ((size_t)blockIdx.x * a.split + sp) * a.Cout * a.Cin * taps;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int co = 2 * cp + h;
@@ -301,7 +315,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunk
   *o = accumulate ? *o + s : s;
 }
 
-struct WgradPlan { int ci_tile, rb, rsx, rsy, chunks, groups, threads; size_t smem, ws_bytes; bool ok; };
+struct WgradPlan { int ci_tile, rb, rsx, rsy, chunks, groups, threads, split, groups_per_split; size_t smem, ws_bytes; bool ok; };
 
 static WgradPlan wgrad_plan(int Cin, int Cout, int Wi, int Do, int Ho, int Wo, int NZ, int stride) {
   WgradPlan p{};
@@ -314,25 +328,31 @@ static WgradPlan wgrad_plan(int Cin, int Cout, int Wi, int Do, int Ho, int Wo, i
   p.ok = false;
   const int cand[8][2] = {{4, 8}, {4, 4}, {2, 8}, {2, 4}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};   // (rows per strip, channels per CTA)
   static const int rb_cap = getenv("SATMVS_WGRAD_RB") ? atoi(getenv("SATMVS_WGRAD_RB")) : 2;
+  static const int ci_cap = getenv("SATMVS_WGRAD_CI") ? atoi(getenv("SATMVS_WGRAD_CI")) : 8;
   for (int c = 0; c < 8 && !p.ok; ++c) {
-    if (cand[c][0] > rb_cap) continue;
+    if (cand[c][0] > rb_cap || cand[c][1] > ci_cap) continue;
     const int rb = cand[c][0] < Ho ? cand[c][0] : Ho, t = cand[c][1];
     const int NR = stride * (rb - 1) + 3;
     const size_t sm = ((size_t)t * KZ * NR * p.rsx + (size_t)Cout * rb * p.rsy) * 4;
     const int items = (Cout + 1) / 2 * t * nkk;
-    if (sm <= 200 * 1024 && items <= kWgMaxItems * kWgThreads) { p.ci_tile = t; p.rb = rb; p.smem = sm; p.ok = true; }
+    if (sm <= 100 * 1024 && items <= kWgMaxItems * kWgThreads) { p.ci_tile = t; p.rb = rb; p.smem = sm; p.ok = true; }
   }
   if (!p.ok) return p;
-  {  // thread count with the fewest idle item slots (Cout 8 x 8 channels x 9 rows = 576 items: 192 threads x 3, not 256 x 2.25)
+  {  // threads: every (co pair, ci, kz, ky) item is shared by `split` threads on disjoint column ranges until the CTA has ~512
+     // work units: the staged strip is the same, the thread-level parallelism is what hides the shared-memory latency
     const int items = (Cout + 1) / 2 * (Cin < p.ci_tile ? Cin : p.ci_tile) * nkk;
-    double best = -1.0;
-    p.threads = kWgThreads;
-    for (int t = kWgThreads; t >= 128; t -= 32) {
-      const int passes = (items + t - 1) / t;
-      if (passes > kWgMaxItems) break;
-      const double eff = (double)items / ((double)passes * t) + 1e-3 * t / kWgThreads;
-      if (eff > best) { best = eff; p.threads = t; }
-    }
+    const int groups4 = wo4 / 4;
+    static const int target = getenv("SATMVS_WGRAD_UNITS") ? atoi(getenv("SATMVS_WGRAD_UNITS")) : 512;
+    int split = 1;
+    while (items * split * 2 <= target && split * 2 <= groups4) split *= 2;
+    p.split = split;
+    p.groups_per_split = (groups4 + split - 1) / split;
+    const int units = items * split;
+    int threads = units < kWgThreads ? (units + 31) / 32 * 32 : kWgThreads;
+    const int passes = (units + threads - 1) / threads;
+    threads = ((units + passes - 1) / passes + 31) / 32 * 32;          // even out the passes
+    p.threads = threads;
+    if (passes > kWgMaxItems) { p.ok = false; return p; }
   }
   p.groups = (Cin + p.ci_tile - 1) / p.ci_tile;
   const int strips = Do * ((Ho + p.rb - 1) / p.rb);
@@ -340,10 +360,9 @@ static WgradPlan wgrad_plan(int Cin, int Cout, int Wi, int Do, int Ho, int Wo, i
   if (chunks > strips) chunks = strips;
   if (chunks < 1) chunks = 1;
   p.chunks = chunks;
-  p.ws_bytes = (size_t)chunks * Cout * Cin * NZ * 9 * 4;
+  p.ws_bytes = (size_t)chunks * p.split * Cout * Cin * NZ * 9 * 4;
   return p;
 }
-
 
 // ----------------------------------------------------------------------------------------------------------------------------
 // weight gradient of a K x K (K = 1 or 5) per-plane convolution with padding K/2 and stride S: the small layers of FeatureNet
@@ -467,7 +486,7 @@ int satmvs_conv3d_wgrad(const float* x, int Cin, int Di, int Hi, int Wi, const f
   WgradArgs a{};
   a.x = x; a.dy = dy; a.partial = static_cast<float*>(workspace);
   a.Cin = Cin; a.Cout = Cout; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Do = Do; a.Ho = Ho; a.Wo = Wo; a.NZ = NZ;
-  a.ci_tile = p.ci_tile; a.rb = p.rb; a.rsx = p.rsx; a.rsy = p.rsy;
+  a.ci_tile = p.ci_tile; a.rb = p.rb; a.rsx = p.rsx; a.rsy = p.rsy; a.split = p.split; a.groups_per_split = p.groups_per_split;
   const dim3 grid(p.chunks, p.groups);
   if (stride == 1) {
     static const cudaError_t e1 = cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -481,7 +500,7 @@ int satmvs_conv3d_wgrad(const float* x, int Cin, int Di, int Hi, int Wi, const f
   int rc = check_launch("wgrad_kernel");
   if (rc) return rc;
   const int total = Cout * Cin * NZ * 9;
-  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a.partial, p.chunks, Cout, Cin, NZ * 9, dw, dw_co, dw_ci, accumulate);
+  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a.partial, p.chunks * p.split, Cout, Cin, NZ * 9, dw, dw_co, dw_ci, accumulate);
   return check_launch("wgrad_reduce_kernel");
 }
 

@@ -18,7 +18,7 @@ _OPS = {
     "depth_regression": module.depth_regression,             # modules/module.py:433
     "get_depth_range_samples": depth_range.get_depth_range_samples,   # modules/depth_range.py:23
     "CostRegNet": module.CostRegNet,                         # modules/module.py:546
-    "FeatureNet": module.FeatureNet,                         # modules/module.py:442 (inference mode)
+    "FeatureNet": module.FeatureNet,                         # modules/module.py:442
     "RED_Regularization": module.RED_Regularization,         # modules/module.py:595
     "slice_RED_Regularization": module.slice_RED_Regularization,      # modules/module.py:653
 }

@@ -258,3 +258,83 @@ def test_depth_regression_gradient(per_pixel):
     assert rel(got, want) < 1e-5
     got.backward(gd.to(DEV))
     assert rel(lg.grad, logits.grad) < 1e-5
+
+
+def test_depth_range_samples_gradient():
+    """casred.py:132-154 keeps the previous depth attached: d samples / d cur_depth = 1 per plane."""
+    from oracle import hypotheses
+    gen = torch.Generator().manual_seed(8)
+    cur = (torch.rand(2, 12, 16, generator=gen) * 50 + 400).requires_grad_(True)
+    nd, interval = 8, 2.5
+    lo = cur - nd / 2 * interval
+    want = lo.unsqueeze(1) + torch.arange(nd).view(1, -1, 1, 1) * (((cur + nd / 2 * interval) - lo) / (nd - 1)).unsqueeze(1)
+    gd = torch.randn(2, nd, 12, 16, generator=gen)
+    want.backward(gd)
+    c = cur.detach().to(DEV).requires_grad_(True)
+    got = satmvs_b200.get_depth_range_samples(c, nd, interval, shape=(2, 12, 16))
+    assert rel(got, want) < 1e-6
+    got.backward(gd.to(DEV))
+    assert rel(c.grad, cur.grad) < 1e-5
+
+
+def test_whole_casmvs_network_training_step():
+    """Images -> FeatureNet (train) per view -> three CasMVS stages (fused sweep, train-mode CostRegNet, head; depth detached between
+    stages as `casmvs.py:145-146`) -> sum of stage losses -> backward: gradients at the first FeatureNet filter and at every stage's
+    regulariser against autograd of the oracle network."""
+    from oracle import hypotheses, volume
+    B, V, Himg, Wimg = 1, 3, 128, 128      # large enough that every BatchNorm sees >= 32 voxels per channel
+    nds, ratios, scales = (16, 16, 8), (4, 2, 1), (4, 2, 1)
+    gen = torch.Generator().manual_seed(31)
+    imgs = [torch.rand(B, 3, Himg, Wimg, generator=gen) for _ in range(V)]
+    fsd = synth.make_featurenet_weights(8)
+    rsd = [synth.make_costregnet_weights(c, seed=40 + i) for i, c in enumerate((32, 16, 8))]
+    cams = [synth.make_rpc_stack(B, V, Himg // s, Wimg // s) for s in scales]
+    rng = torch.tensor([[400.0, 600.0]])
+    gt = torch.full((B, Himg, Wimg), 500.0)
+
+    # oracle network with autograd
+    fref = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in fsd.items()}
+    rref = [{k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()} for sd in rsd]
+    feats = [regnets.featurenet(i, fref, training=True) for i in imgs]
+    depth, loss_ref = None, 0.0
+    for s in range(3):
+        h, w = Himg // scales[s], Wimg // scales[s]
+        dv = hypotheses.stage_hypotheses(None if depth is None else depth.detach(), rng, nds[s], ratios[s] * 2.5, (Himg, Wimg), scales[s])
+        var = volume.variance_cost_volume([f[f"stage{s + 1}"] for f in feats], cams[s], dv, "rpc")
+        logits = regnets.costregnet(var, rref[s], training=True).squeeze(1)
+        depth, _ = regress.softargmin_casmvs(logits, dv)
+        loss_ref = loss_ref + torch.nn.functional.smooth_l1_loss(depth, gt[:, :h, :w])
+    loss_ref.backward()
+
+    fnet = satmvs_b200.FeatureNet(8)
+    fnet.load_state_dict(fsd)
+    fnet = fnet.to(DEV).train()
+    regs = []
+    for sd, c in zip(rsd, (32, 16, 8)):
+        r = satmvs_b200.CostRegNet(c, 8)
+        r.load_state_dict(sd)
+        regs.append(r.to(DEV).train())
+    fg = fnet.forward_views([i.to(DEV) for i in imgs])
+    out = satmvs_b200.cascade([[f[f"stage{s + 1}"] for f in fg] for s in range(3)], cams, rng.to(DEV), regs, img_hw=(Himg, Wimg),
+                              ndepths=nds, depth_interals_ratio=ratios, min_interval=2.5, scales=scales, geo_model="rpc", head="casmvs")
+    loss = 0.0
+    for s in range(3):
+        h, w = Himg // scales[s], Wimg // scales[s]
+        loss = loss + torch.nn.functional.smooth_l1_loss(out[f"stage{s + 1}"]["depth"], gt[:, :h, :w].to(DEV))
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * abs(loss_ref.item())
+    loss.backward()
+    # a deep fp32 network with batch-statistics BatchNorm amplifies rounding differences: direction and size of each gradient
+    errs = {}
+    def close(a, b, what):
+        a, b = a.detach().cpu().double().flatten(), b.double().flatten()
+        cos = torch.dot(a, b).item() / (a.norm().item() * b.norm().item() + 1e-300)
+        errs[what] = (round(1.0 - cos, 6), round(a.norm().item() / b.norm().item(), 4))
+    close(fnet.conv0[0].conv.weight.grad, fref["conv0.0.conv.weight"].grad, "featurenet conv0.0")
+    close(fnet.conv2[2].conv.weight.grad, fref["conv2.2.conv.weight"].grad, "featurenet conv2.2")
+    close(fnet.out3.weight.grad, fref["out3.weight"].grad, "featurenet out3")
+    for s in range(3):
+        close(regs[s].conv0.conv.weight.grad, rref[s]["conv0.conv.weight"].grad, f"stage {s + 1} conv0")
+        close(regs[s].prob.weight.grad, rref[s]["prob.weight"].grad, f"stage {s + 1} prob")
+    print("whole-network training step: (1 - cosine, norm ratio) per gradient:", errs)
+    for what, (c, r) in errs.items():
+        assert c < 1e-3 and abs(r - 1.0) < 2e-2, (what, errs)
