@@ -525,14 +525,15 @@ static int launch_plane_conv(const ConvProblem& p, int stride, cudaStream_t st, 
   return launch_by_cout(p, st, what);
 }
 
-// Side streams of the overlapped flow (per host thread and device; created once, live as long as the library): `rec` runs the
-// recurrence (highest priority: its 64 CTAs must become resident before the producers fill the machine), `lv[1..3]` run the
-// batched convs of levels 1..3 (level 0 stays on the caller's stream) so that chunk c of level l overlaps chunk c+1 of level l-1.
+// Side streams of the overlapped flow (per host thread and device; created once, live as long as the library): `rec` and
+// `lv[1..3]` run the recurrences of levels 0 and 1..3 (highest priority: their 16-CTA clusters must become resident before the
+// producers fill the machine); every level has a stream of its own so that it starts as soon as ITS producers are done -- the
+// levels' producers form a chain (level l reads the encoder output of level l-1), and level 0, the slowest recurrence, is ready first.
 constexpr int kRedMaxChunks = 32;
 struct RedSideStream {
   cudaStream_t rec = nullptr, lv[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t chunk[3][kRedMaxChunks];
+  cudaEvent_t chunk[8][kRedMaxChunks];     // [0..3]: producers of level l, chunk c done; [4..7]: recurrence of level l over chunk c done
   int dev = -1; bool ok = false;
 };
 static RedSideStream& red_side_stream() {
@@ -546,8 +547,8 @@ static RedSideStream& red_side_stream() {
     bool ok = cudaStreamCreateWithPriority(&r.rec, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&r.join[i], cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 1; i < 4 && ok; ++i) ok = cudaStreamCreateWithPriority(&r.lv[i], cudaStreamNonBlocking, lo) == cudaSuccess;
-    for (int i = 0; i < 3 && ok; ++i)
+    for (int i = 1; i < 4 && ok; ++i) ok = cudaStreamCreateWithPriority(&r.lv[i], cudaStreamNonBlocking, hi) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i)
       for (int c = 0; c < kRedMaxChunks && ok; ++c) ok = cudaEventCreateWithFlags(&r.chunk[i][c], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) cudaGetLastError();
     r.ok = ok; r.dev = dev;
@@ -852,7 +853,8 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
     // the side stream runs the recurrence over chunk c as soon as the producers of chunk c are done (state carried through
     // the history slots), i.e. concurrently with the producers of chunk c + 1 on the 84 SMs the recurrence leaves free.
     // Chunk schedule: the producers of a chunk cost ~125 us of launch latencies + ~7.5 us per plane, the recurrence ~21 us per
-    // plane + ~30 us per launch, so two chunks of 16 planes get the consumer going and one big chunk finishes the volume
+    // plane + ~30 us per launch; with one recurrence stream per level (below) equal chunks of 16 planes are best: a big last chunk
+    // makes the deepest level wait for the very last producer launch
     // (measured at cfg-2, profiles/r02_red_overlap_notes.md: [8]x8 1.99 ms, [16]x4 1.95 ms per forward against 2.03 sequential)
     static const int kChunk = getenv("SATMVS_RED_CHUNK") ? atoi(getenv("SATMVS_RED_CHUNK")) : 16;
     static const bool chunked_decoder = getenv("SATMVS_RED_NO_CHUNKED_DECODER") == nullptr;
@@ -871,7 +873,7 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
     } else if (kChunk > 0 && D >= 2 * kChunk) {
       while (cstart[nchunks] < D && nchunks < kRedMaxChunks) {
         const int left = D - cstart[nchunks];
-        const int take = (nchunks >= 2 || left < 2 * kChunk) ? left : kChunk;
+        const int take = (left < 2 * kChunk || nchunks == kRedMaxChunks - 1) ? left : kChunk;
         cstart[nchunks + 1] = cstart[nchunks] + take;
         ++nchunks;
       }
@@ -881,35 +883,48 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
         for (int l = 0; l < 4; ++l)
           for (int i = 0; i < xp[l].n; ++i) umma_conv_pack(xp[l].u[i], st);
       xpacked = true;
+      cudaStream_t rs[4] = {side.rec, side.lv[1], side.lv[2], side.lv[3]};
+      static const bool per_level = getenv("SATMVS_RED_ONE_LAUNCH") == nullptr;   // off: the four levels in one 64-CTA grid
       cudaEventRecord(side.fork, st);
-      cudaStreamWaitEvent(side.rec, side.fork, 0);
+      for (int l = 0; l < (per_level ? 4 : 1); ++l) cudaStreamWaitEvent(rs[l], side.fork, 0);
       TcArgs ta = tc_args(false);
       for (int c = 0; c < nchunks; ++c) {
         const int d0 = cstart[c], np = cstart[c + 1] - cstart[c];
         if (c == 0 || persistent) {
-          for (int l = 0; l < 4; ++l) RUN(run_xhalf(l, d0, np, false, nullptr, st));
-          cudaEventRecord(side.chunk[0][c], st);
-          cudaStreamWaitEvent(side.rec, side.chunk[0][c], 0);
           ta.d_begin = d0; ta.d_end = d0 + np;
           bool ran = false;
-          ProfScope prof(kProfGruGate, side.rec);
-          RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, side.rec, &ran, c == 0 && do_pack));
+          if (per_level) {
+            for (int l = 0; l < 4; ++l) {
+              RUN(run_xhalf(l, d0, np, false, nullptr, st));
+              cudaEventRecord(side.chunk[l][c], st);
+              cudaStreamWaitEvent(rs[l], side.chunk[l][c], 0);
+              ProfScope prof(kProfGruGate, rs[l]);
+              RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, rs[l], &ran, c == 0 && do_pack, l));
+              if (!ran) break;
+              cudaEventRecord(side.chunk[4 + l][c], rs[l]);
+            }
+          } else {
+            for (int l = 0; l < 4; ++l) RUN(run_xhalf(l, d0, np, false, nullptr, st));
+            cudaEventRecord(side.chunk[0][c], st);
+            cudaStreamWaitEvent(side.rec, side.chunk[0][c], 0);
+            ProfScope prof(kProfGruGate, side.rec);
+            RUN(red_tc_launch(ta, gwh, owh, wco, P.tcpack, P.umma_err, dbg, side.rec, &ran, c == 0 && do_pack));
+            if (ran) cudaEventRecord(side.chunk[4][c], side.rec);
+          }
           if (c == 0) persistent = ran;
           if (!ran) break;                                                 // shape not taken: the sequential flow below finishes the job
-          cudaEventRecord(side.chunk[1][c], side.rec);
         }
       }
       if (persistent && chunked_decoder) {
-        // the decoder of chunk c follows the producers of all chunks on the caller's stream and starts when the recurrence has
+        // the decoder of chunk c follows the producers of all chunks on the caller's stream and starts when the recurrences have
         // left chunk c behind: only the last chunk's decoder stays on the critical path
         for (int c = 0; c < nchunks; ++c) {
-          cudaStreamWaitEvent(st, side.chunk[1][c], 0);
+          for (int l = 0; l < (per_level ? 4 : 1); ++l) cudaStreamWaitEvent(st, side.chunk[4 + l][c], 0);
           RUN(run_decoder(cstart[c], cstart[c + 1] - cstart[c], st));
         }
         decoded = true;
       }
-      cudaEventRecord(side.join[0], side.rec);
-      cudaStreamWaitEvent(st, side.join[0], 0);
+      for (int l = 0; l < (per_level ? 4 : 1); ++l) { cudaEventRecord(side.join[l], rs[l]); cudaStreamWaitEvent(st, side.join[l], 0); }
       if (persistent) { g_red_last_path = 3; xhalf_done = true; tc_report(); }
     }
   }

@@ -48,7 +48,7 @@ struct TcLevel {
   int R, MT, PWa, NPP;                        // rows per strip, 128-position tiles, window positions, positions padded to 32
   const int* ready; int expected;             // optional: ready[d] reaches `expected` when the x-halves of plane d are in memory
 };                                            // (their producers run concurrently on the SMs this kernel leaves free)
-struct TcArgs { TcLevel l[4]; int d_begin, d_end; int* err; long long* dbg; };   // planes [d_begin, d_end): state read from history slot d_begin
+struct TcArgs { TcLevel l[4]; int d_begin, d_end; int* err; long long* dbg; int level0; };   // planes [d_begin, d_end): state read from history slot d_begin; level0: level of cluster 0 of the grid
 
 struct TcGeom { int R, MT, PWa, NPP; size_t smem; };
 // geometry + dynamic shared memory of one level (host and device agree on the carve-up through this function)
@@ -664,7 +664,7 @@ __device__ __forceinline__ void tc_level_run(const TcLevel& L, const int d_begin
   if (!alive && tid == 0) *reinterpret_cast<volatile int*>(err) = 1;
   if (dbg != nullptr && tid == 0 && (rank == 0))
 #pragma unroll
-    for (int i = 0; i < 20; ++i) dbg[(blockIdx.x / kTcCluster) * 20 + i] = sh.t_acc[i];
+    for (int i = 0; i < 20; ++i) dbg[(CH == 8 ? 0 : CH == 16 ? 1 : CH == 32 ? 2 : 3) * 20 + i] = sh.t_acc[i];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   tc_cluster_sync();                                                       // no CTA leaves while a peer may still write into its shared memory
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 red_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   __shared__ TcShared sh;
-  const int lv = blockIdx.x / kTcCluster;
+  const int lv = a.level0 + blockIdx.x / kTcCluster;
 #ifndef TC_ONLY
 #define TC_ONLY -1
 #endif
@@ -690,7 +690,8 @@ inline size_t tc_pack_bytes(int ch) { return (size_t)216 * ch * ch; }     // KG 
 // of 4 pixels, more tiles per CTA than a thread can hold, shared memory), and the caller then uses the FFMA cluster kernel
 // or the per-plane chain.  `wpack[l]` = tc_pack_bytes(ch_l) bytes of scratch per level.
 inline int red_tc_launch(TcArgs& a, const float* const* gate_w_h, const float* const* out_w_h, const long long* w_co,
-                         char* const* wpack, int* err_flag, long long* dbg, cudaStream_t st, bool* launched, bool pack = true) {
+                         char* const* wpack, int* err_flag, long long* dbg, cudaStream_t st, bool* launched, bool pack = true,
+                         int only_level = -1) {   // only_level >= 0: a one-cluster grid running that level alone
   *launched = false;
   static const bool verbose = getenv("SATMVS_RED_DEBUG") != nullptr;
   int dev = 0, optin = 0;
@@ -727,16 +728,17 @@ inline int red_tc_launch(TcArgs& a, const float* const* gate_w_h, const float* c
   if ((e = cudaFuncSetAttribute(red_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
     return declined("dynamic shared memory", e);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(4 * kTcCluster); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((only_level < 0 ? 4 : 1) * kTcCluster); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kTcCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int nclusters = 0;
+  a.level0 = only_level < 0 ? 0 : only_level;
   if ((e = cudaOccupancyMaxActiveClusters(&nclusters, red_tc_kernel, &cfg)) != cudaSuccess || nclusters < 4)
     return declined("fewer than 4 co-resident clusters", e);
   for (int l = 0; l < 4; ++l) {
-    if (pack) {
+    if (pack && (only_level < 0 || only_level == l)) {
       TcPack p{gate_w_h[l], out_w_h[l], w_co[l], a.l[l].ch, kTcKG[l], reinterpret_cast<float4*>(wpack[l])};
       const int total = (int)(tc_pack_bytes(a.l[l].ch) / 16);
       tc_pack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(p);

@@ -6,8 +6,8 @@ R=${1:-r02}
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3
 timeout 400 python bench.py > gpurun_out/${R}_bench_stage1.json 2> gpurun_out/${R}_err.txt
-for wl in cfg3_cascade cfg1_pred cfg2_casmvs cfg2_build cfg5_build; do
-  timeout 300 python bench.py --workload $wl --no-sharded > gpurun_out/${R}_bench_$wl.json 2>> gpurun_out/${R}_err.txt
+for wl in cfg3_cascade cfg1_pred cfg2_casmvs cfg2_build cfg5_build cfg2_train cfg2_train_red; do
+  timeout 500 python bench.py --workload $wl --no-sharded > gpurun_out/${R}_bench_$wl.json 2>> gpurun_out/${R}_err.txt
 done
 timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/${R}_err.txt
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_stage1.csv \
@@ -18,7 +18,8 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
   python tools/run_featurenet_once.py > /dev/null 2>&1
 python - <<PY
 import json
-for n in ("bench_stage1", "bench_cfg3_cascade", "bench_cfg1_pred", "bench_cfg2_casmvs", "bench_cfg2_build", "bench_cfg5_build", "bench_reference"):
+for n in ("bench_stage1", "bench_cfg3_cascade", "bench_cfg1_pred", "bench_cfg2_casmvs", "bench_cfg2_build", "bench_cfg5_build", "bench_cfg2_train",
+          "bench_cfg2_train_red", "bench_reference"):
     try:
         j = json.load(open(f"gpurun_out/${R}_{n}.json"))
         print(n, j.get("ms_per_step"), j.get("value"), j.get("e2e", {}).get("value"),
