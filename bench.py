@@ -332,9 +332,9 @@ def run_cascade(args, w):
     if rank == 0:
         hbm, _, peak_src = peaks()
         ms = total_ms / args.steps
-        tot_prof = sum(prof.ms.values()) or 1.0
-        kernels = [{"class": n, "launches_per_step": prof.launches[n] / prof_steps, "ms_per_step": prof.ms[n] / prof_steps,
-                    "share": prof.ms[n] / tot_prof} for n in _lib.PROFILE_CLASSES if prof.launches[n]]
+        tot_prof = sum(prof.busy_ms.values()) or 1.0
+        kernels = [{"class": n, "launches_per_step": prof.launches[n] / prof_steps, "ms_per_step": prof.busy_ms[n] / prof_steps,
+                    "share": prof.busy_ms[n] / tot_prof} for n in _lib.PROFILE_CLASSES if prof.launches[n]]
         kernels.sort(key=lambda k: -k["share"])
         sweep_bytes = sum(d * (img_hw[0] // sc) * (img_hw[1] // sc) * sweep_bytes_per_cell(dict(C=c, V=V, D=d))
                           for d, sc, c in zip(ndepths, scales, chans))
@@ -534,13 +534,15 @@ def run_ours(args, w):
         }
         # per kernel class: share of the step, achieved rate against the bound that applies
         flops = red_flops(w) if w["stage"] == "red_train" else {}
-        kernels, tot_prof = [], sum(prof.ms.values()) or 1.0
+        # launches of one class may run concurrently (the four levels of the recurrence on four streams): the class is charged the
+        # time during which at least one of its launches was running (busy), avg_launch_us is the mean duration of a launch
+        kernels, tot_prof = [], sum(prof.busy_ms.values()) or 1.0
         for name in _lib.PROFILE_CLASSES:
-            n, t_ms = prof.launches[name], prof.ms[name]
+            n, t_sum, t_ms = prof.launches[name], prof.ms[name], prof.busy_ms[name]
             if n == 0:
                 continue
             k = {"class": name, "launches_per_step": n / prof_steps, "ms_per_step": t_ms / prof_steps,
-                 "share": t_ms / tot_prof, "avg_launch_us": 1e3 * t_ms / n}
+                 "share": t_ms / tot_prof, "avg_launch_us": 1e3 * t_sum / n, "concurrency": t_sum / t_ms if t_ms > 0 else 1.0}
             if name == "sweep":
                 planes = w["D"] / world if sharded_run else w["D"]
                 bpc = sweep_bytes_per_cell(dict(w, D=planes))
@@ -559,7 +561,8 @@ def run_ours(args, w):
                     fl += flops["gru_output_conv"]
                     if red_path >= 2:
                         k["kernel"] = ("red_tc_kernel (whole depth recurrence on tcgen05: 4 clusters x 16 CTAs = 64 of 148 SMs"
-                                       + (", launched per chunk of planes, overlapped with the batched convs)" if red_path == 3 else ")"))
+                                       + (", one launch per level and chunk of 16 planes on four streams, overlapped with the batched "
+                                          "convs; rate = flops of the step / time with a recurrence launch running)" if red_path == 3 else ")"))
                         k["bound_note"] = ("sequential-in-depth recurrence: per plane two dependent convolutions (A-operand shared-memory "
                                            "reads bound the small-N MMAs of levels 0/1), two cluster-wide GroupNorm reductions and two halo "
                                            "exchanges; useful flops (1 MAC = 2 flop; the 3xTF32 split issues 3x as many) against the dense bf16 "

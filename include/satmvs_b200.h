@@ -48,6 +48,8 @@ const char* satmvs_last_error(void);
 #define SATMVS_PROFILE_CLASSES 8
 int satmvs_profile_begin(void);
 int satmvs_profile_end(float* ms_by_class, int* launches_by_class);
+/* the same, plus per class the time during which at least one of its launches was running (launches of concurrent streams overlap) */
+int satmvs_profile_end_ex(float* ms_by_class, int* launches_by_class, float* busy_ms_by_class);
 
 /* ---- fused plane sweep: per-hypothesis geometry + bilinear gather + variance over views ----
  * Replaces networks/casred.py:26-53 (== networks/casmvs.py:30-59; per-plane form casred.py:191-212)
@@ -285,7 +287,7 @@ int satmvs_costreg_forward(const satmvs_costreg_weights* w, const float* x, int 
  * satmvs_conv3d_wgrad: dw[co * dw_co + ci * dw_ci + tap] (+)= sum_o dy[co, o] x[ci, stride * o + k - 1]  (padding 1);
  *   for a transposed block call it with x = the output gradient (large tensor) and dy = the block input (small tensor), stride 2.
  * satmvs_bn_train_fwd / _bwd: BatchNorm3d on batch statistics (+ ReLU, + skip tensor added after the ReLU, module.py:573-575)
- *   on [B,C,n] tensors (n % 4 == 0); mean / var (biased) are outputs of _fwd and inputs of _bwd; acc = 2 C doubles of scratch;
+ *   on [B,C,n] tensors; mean / var (biased) are outputs of _fwd and inputs of _bwd; acc = 2 C doubles of scratch;
  *   dz2 (may be null) is a second gradient added to dz (a block output that also feeds a skip connection).
  * satmvs_softargmin_bwd: gradient of depth = sum_d softmax(logits)_d * depth_d to the logits [D,H,W] (casmvs.py:66-68). */
 int satmvs_conv3d_raw(const float* in, int Cin, int Di, int Hi, int Wi, const float* w, long long w_co, long long w_ci,

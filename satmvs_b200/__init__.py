@@ -10,5 +10,6 @@ from .rpc_tensor import RPCModelParameter  # noqa: F401
 from .module import RED_Regularization, slice_RED_Regularization, CostRegNet, FeatureNet, depth_regression, conv_block  # noqa: F401
 from .stages import stage_train_red, stage_pred_red, stage_casmvs, cascade
 from .depth_range import get_depth_range_samples, stage_depth_hypotheses  # noqa: F401
+from . import training  # noqa: F401  (train() mode and loss.backward() of the patched operators, train.py:267-287)
 from . import data_io  # noqa: F401  (PFM / RPC text formats)
 from . import rpc_filter  # noqa: F401  (geometric-consistency filter, tools/rpc_filter.py)

@@ -21,6 +21,7 @@ _SIGNATURES = {
     "satmvs_async_error": ([], _I),
     "satmvs_profile_begin": ([], _I),
     "satmvs_profile_end": ([_P, _P], _I),
+    "satmvs_profile_end_ex": ([_P, _P, _P], _I),
     "satmvs_cost_volume_rpc_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_cost_volume_homo_fwd": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "satmvs_cost_volume_rpc_fwd_sharded": ([_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, C.c_size_t, _P], _I),
@@ -97,7 +98,7 @@ PROFILE_CLASSES = ("sweep", "conv_batched", "gru_gate_conv", "gru_output_conv", 
 
 
 class profile:
-    """Context manager around satmvs_profile_begin/end: per-kernel-class device time inside the library."""
+    """Context manager around satmvs_profile_begin/end_ex: per-kernel-class device time inside the library."""
 
     def __enter__(self):
         lib().satmvs_profile_begin()
@@ -106,8 +107,10 @@ class profile:
     def __exit__(self, *a):
         ms = (C.c_float * len(PROFILE_CLASSES))()
         n = (C.c_int * len(PROFILE_CLASSES))()
-        lib().satmvs_profile_end(ms, n)
-        self.ms = dict(zip(PROFILE_CLASSES, list(ms)))
+        busy = (C.c_float * len(PROFILE_CLASSES))()
+        lib().satmvs_profile_end_ex(ms, n, busy)
+        self.ms = dict(zip(PROFILE_CLASSES, list(ms)))              # sum of the launch durations
+        self.busy_ms = dict(zip(PROFILE_CLASSES, list(busy)))       # time with at least one launch of the class running
         self.launches = dict(zip(PROFILE_CLASSES, list(n)))
 
 

@@ -1,7 +1,10 @@
 // abi.cu — version and thread-local error text of libsatmvs_b200.so
 #include "common.cuh"
 #include "prof.cuh"
+#include <algorithm>
 #include <cstring>
+#include <utility>
+#include <vector>
 #include <cstdlib>
 
 namespace satmvs {
@@ -53,7 +56,7 @@ int satmvs_profile_begin(void) {
   return SATMVS_OK;
 }
 
-int satmvs_profile_end(float* ms_by_class, int* launches_by_class) {
+int satmvs_profile_end_ex(float* ms_by_class, int* launches_by_class, float* busy_ms_by_class) {
   satmvs::ProfState& s = satmvs::prof_state();
   s.on = false;
   cudaDeviceSynchronize();
@@ -79,19 +82,47 @@ int satmvs_profile_end(float* ms_by_class, int* launches_by_class) {
         fprintf(stderr, "prof class %d launch %zu: %.1f .. %.1f us\n", p, i / 2, (a - best) * 1e3f, (b - best) * 1e3f);
       }
   }
+  cudaEvent_t ref0 = nullptr;
+  for (int p = 0; p < satmvs::kProfCount && !ref0; ++p)
+    if (!s.ev[p].empty()) ref0 = s.ev[p][0];
   for (int p = 0; p < satmvs::kProfCount; ++p) {
     float tot = 0.0f;
+    std::vector<std::pair<float, float>> iv;
     for (size_t i = 0; i + 1 < s.ev[p].size(); i += 2) {
       float ms = 0.0f;
       cudaEventElapsedTime(&ms, s.ev[p][i], s.ev[p][i + 1]);
       tot += ms;
+      if (busy_ms_by_class) {
+        float a = 0.0f, b = 0.0f;
+        cudaEventElapsedTime(&a, ref0, s.ev[p][i]);
+        cudaEventElapsedTime(&b, ref0, s.ev[p][i + 1]);
+        iv.emplace_back(a, b);
+      }
+    }
+    if (busy_ms_by_class) {       // time during which at least one launch of the class was running (launches on concurrent streams overlap)
+      std::sort(iv.begin(), iv.end());
+      float busy = 0.0f, lo = 0.0f, hi = 0.0f;
+      bool open = false;
+      for (const auto& x : iv) {
+        if (!open) { lo = x.first; hi = x.second; open = true; }
+        else if (x.first <= hi) { if (x.second > hi) hi = x.second; }
+        else { busy += hi - lo; lo = x.first; hi = x.second; }
+      }
+      if (open) busy += hi - lo;
+      busy_ms_by_class[p] = busy;
     }
     if (ms_by_class) ms_by_class[p] = tot;
     if (launches_by_class) launches_by_class[p] = (int)(s.ev[p].size() / 2);
+  }
+  for (int p = 0; p < satmvs::kProfCount; ++p) {     // after every class has been measured against the common reference event
     for (cudaEvent_t e : s.ev[p]) cudaEventDestroy(e);
     s.ev[p].clear();
   }
   return SATMVS_OK;
+}
+
+int satmvs_profile_end(float* ms_by_class, int* launches_by_class) {
+  return satmvs_profile_end_ex(ms_by_class, launches_by_class, nullptr);
 }
 
 int satmvs_async_error(void) { return satmvs::async_error_poll(); }

@@ -26,14 +26,19 @@ namespace satmvs {
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int B, int C, long long n, double* __restrict__ acc) {
   const int c = blockIdx.y;
   double s = 0.0, q = 0.0;
-  const long long n4 = n >> 2;
+  const long long n4 = (n & 3) ? 0 : (n >> 2);          // rows of a multiple of 4 floats are read as float4; anything else scalar
   for (int b = 0; b < B; ++b) {
-    const float4* p = reinterpret_cast<const float4*>(y + ((long long)b * C + c) * n);
+    const float* pb = y + ((long long)b * C + c) * n;
+    const float4* p = reinterpret_cast<const float4*>(pb);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
       const float4 v = __ldg(p + i);
       const float ls = (v.x + v.y) + (v.z + v.w);
       const float lq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
       s += ls; q += lq;
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const float v = __ldg(pb + i);
+      s += v; q += v * v;
     }
   }
   __shared__ double red[2][8];
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   const int c = blockIdx.y;
   const float istd = rsqrtf(var[c] + eps);
   const float g = (gamma ? gamma[c] : 1.0f) * istd, sh = (beta ? beta[c] : 0.0f) - mean[c] * g;
-  const long long n4 = n >> 2;
+  const long long n4 = (n & 3) ? 0 : (n >> 2);
   for (int b = 0; b < B; ++b) {
     const long long base = ((long long)b * C + c) * n;
     const float4* p = reinterpret_cast<const float4*>(y + base);
@@ -78,6 +83,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
       if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
       if (a) { const float4 s = __ldg(a + i); v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w; }
       o[i] = v;
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      float v = fmaf(__ldg(y + base + i), g, sh);
+      if (relu) v = fmaxf(v, 0.0f);
+      if (post_add) v += __ldg(post_add + base + i);
+      z[base + i] = v;
     }
   }
 }
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
   const float istd = rsqrtf(var[c] + eps), m = mean[c];
   const float g = (gamma ? gamma[c] : 1.0f) * istd, sh = (beta ? beta[c] : 0.0f) - m * g;
   double s1 = 0.0, s2 = 0.0;
-  const long long n4 = n >> 2;
+  const long long n4 = (n & 3) ? 0 : (n >> 2);
   for (int b = 0; b < B; ++b) {
     const long long base = ((long long)b * C + c) * n;
     const float4* py = reinterpret_cast<const float4*>(y + base);
@@ -110,6 +121,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
       const float l1 = (d.x + d.y) + (d.z + d.w);
       const float l2 = (d.x * ((v.x - m) * istd) + d.y * ((v.y - m) * istd)) + (d.z * ((v.z - m) * istd) + d.w * ((v.w - m) * istd));
       s1 += l1; s2 += l2;
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const float v = __ldg(y + base + i);
+      float d = __ldg(dz + base + i) + (dz2 ? __ldg(dz2 + base + i) : 0.0f);
+      if (relu && fmaf(v, g, sh) <= 0.0f) d = 0.0f;
+      s1 += d; s2 += d * ((v - m) * istd);
     }
   }
   __shared__ double red[2][8];
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     if (dgamma) dgamma[c] = (float)acc[2 * c + 1];
     if (dbeta) dbeta[c] = (float)acc[2 * c];
   }
-  const long long n4 = n >> 2;
+  const long long n4 = (n & 3) ? 0 : (n >> 2);
   for (int b = 0; b < B; ++b) {
     const long long base = ((long long)b * C + c) * n;
     const float4* py = reinterpret_cast<const float4*>(y + base);
@@ -162,6 +179,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       r.z = g * (d.z - k1 - (v.z - m) * istd * k2);
       r.w = g * (d.w - k1 - (v.w - m) * istd * k2);
       po[i] = r;
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const float v = __ldg(y + base + i);
+      float d = __ldg(dz + base + i) + (dz2 ? __ldg(dz2 + base + i) : 0.0f);
+      if (relu && fmaf(v, g, sh) <= 0.0f) d = 0.0f;
+      dy[base + i] = g * (d - k1 - (v - m) * istd * k2);
     }
   }
 }
@@ -611,11 +634,11 @@ int satmvs_conv2d_wgrad(const float* x, int Cin, int N, int Hi, int Wi, const fl
 int satmvs_bn_train_fwd(const float* y, int B, int C, long long n, const float* gamma, const float* beta, float eps, int relu,
                         const float* post_add, float* z, float* mean, float* var, double* acc, void* stream) {
   SATMVS_CHECK_ASYNC();
-  SATMVS_REQUIRE(y && z && mean && var && acc && B >= 1 && C >= 1 && n >= 4 && n % 4 == 0);
+  SATMVS_REQUIRE(y && z && mean && var && acc && B >= 1 && C >= 1 && n >= 1);
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(kProfTrainNorm, st);
   cudaMemsetAsync(acc, 0, (size_t)C * 2 * sizeof(double), st);
-  int bx = (int)((n / 4 + 255) / 256);
+  int bx = (int)(((n + 3) / 4 + 255) / 256);
   const int cap = (8 * kNumSMs + C - 1) / C;
   if (bx > cap) bx = cap;
   bn_stats_kernel<<<dim3(bx, C), 256, 0, st>>>(y, B, C, n, acc);
@@ -630,11 +653,11 @@ int satmvs_bn_train_bwd(const float* dz, const float* dz2, const float* y, int B
                         const float* mean, const float* var, float eps, int relu, float* dy, float* dgamma, float* dbeta,
                         double* acc, void* stream) {
   SATMVS_CHECK_ASYNC();
-  SATMVS_REQUIRE(dz && y && mean && var && dy && acc && B >= 1 && C >= 1 && n >= 4 && n % 4 == 0);
+  SATMVS_REQUIRE(dz && y && mean && var && dy && acc && B >= 1 && C >= 1 && n >= 1);
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(kProfTrainNorm, st);
   cudaMemsetAsync(acc, 0, (size_t)C * 2 * sizeof(double), st);
-  int bx = (int)((n / 4 + 255) / 256);
+  int bx = (int)(((n + 3) / 4 + 255) / 256);
   const int cap = (8 * kNumSMs + C - 1) / C;
   if (bx > cap) bx = cap;
   bn_bwd_reduce_kernel<<<dim3(bx, C), 256, 0, st>>>(dz, dz2, y, B, C, n, gamma, beta, mean, var, eps, relu, acc);

@@ -177,8 +177,6 @@ def costreg_train_forward(net, x):
         raise ValueError(f"expected {net.in_channels} channels, got {Cc}")
     if D % 8 or H % 8 or W % 8:
         raise ValueError("CostRegNet needs D, H and W to be multiples of 8")
-    if (D * H * W // 512) % 4:
-        raise ValueError("training form: the coarsest level must hold a multiple of 4 voxels per channel (D*H*W % 2048 == 0)")
     return _CostRegTrainFn.apply(net, x.contiguous().float(), *params)
 
 

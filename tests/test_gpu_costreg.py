@@ -40,10 +40,14 @@ def test_vs_oracle(C, D, H, W):
     assert maxdiff(got, want) < 2e-4 * max(1.0, want.abs().max().item())
 
 
-def test_training_mode_is_refused():
+def test_training_mode_runs_on_batch_statistics():
+    """train() is the mode train.py:268 uses: batch-statistics BatchNorm and a backward (tests/test_gpu_train.py has the parity)."""
     m = make(8).train()
-    with pytest.raises(RuntimeError, match="inference-mode"):
-        m(torch.zeros(1, 8, 8, 8, 8, device=DEV))
+    x = torch.rand(2, 8, 8, 16, 24, device=DEV)          # coarsest level: 1 x 2 x 3 voxels per sample (a ragged BatchNorm row)
+    y = m(x)
+    assert y.shape == (2, 1, 8, 16, 24) and y.requires_grad
+    want = regnets.costregnet(x.cpu(), {k: v.detach().cpu() for k, v in m.state_dict().items()}, training=True)
+    assert maxdiff(y, want) < 1e-3 * max(1.0, want.abs().max().item())
 
 
 def test_casmvs_stage_vs_oracle():
