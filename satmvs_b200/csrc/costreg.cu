@@ -58,6 +58,13 @@ static int run_by_cout(const ConvProblem& p, cudaStream_t st, const char* what) 
 // ConvTranspose3d(k=3, stride 2, padding 1, output_padding 1): 8 parity classes in one launch
 static int run_deconv3d(const float* in, int Cin, int Di, int Hi, int Wi, const float* w, const float* scale,
                         const float* shift, const float* skip, float* out, int Cout, cudaStream_t st) {
+  {  // register-tiled direct kernel (direct_conv.cuh) when rows are 16-byte aligned; the implicit-GEMM engine otherwise
+    DirectDeconv3d d{};
+    d.in = in; d.w = w; d.w_ci = (long long)Cout * 27; d.w_co = 27; d.scale = scale; d.shift = shift; d.post_add = skip; d.out = out;
+    d.Cin = Cin; d.Cout = Cout; d.Di = Di; d.Hi = Hi; d.Wi = Wi; d.relu = 1;
+    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+    if (!no_direct && direct_deconv3d_supported(d)) return direct_deconv3d_launch(d, st, "costreg deconv (direct)");
+  }
   ConvGroup g{};
   int n = 0;
   for (int pz = 0; pz < 2; ++pz)

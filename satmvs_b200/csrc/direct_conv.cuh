@@ -355,3 +355,148 @@ inline int direct_deconv_launch(const DirectDeconv& p, cudaStream_t st, const ch
 }
 
 }  // namespace satmvs
+
+// ---------------------------------------------------------------------------------------------
+// 3-D transposed convolution, k 3, stride 2, padding 1, output_padding 1 (CostRegNet's Deconv3d blocks, modules/module.py:369-410,
+// and the data gradient of its stride-2 convs): the 2-D scheme above with the plane axis added.  One thread = 2 output channels
+// x 4 input voxels of a row = a 2 x 2 x 8 output block; per axis an even output uses tap 1 of the same input index, an odd
+// output tap 0 of the next index and tap 2 of the same one, so no multiplication touches a structural zero.
+// Weight element (ci, co, tap) at w[ci * w_ci + co * w_co + tap].  Epilogue: scale / shift (folded BatchNorm), ReLU, + skip.
+// ---------------------------------------------------------------------------------------------
+namespace satmvs {
+
+struct DirectDeconv3d {
+  const float* in;        // [Cin][Di][Hi][Wi]
+  const float* w; long long w_ci, w_co;
+  const float* scale; const float* shift; const float* post_add;
+  float* out;             // [Cout][2Di][2Hi][2Wi]
+  int Cin, Cout, Di, Hi, Wi;
+  int relu;
+};
+
+constexpr int kD3Co = 2, kD3Px = 4, kD3Threads = 128, kD3CiChunk = 16;
+
+template <int kUnused>
+__global__ void __launch_bounds__(kD3Threads, 3)
+direct_deconv3d_kernel(const __grid_constant__ DirectDeconv3d a) {
+  __shared__ __align__(8) float wsm[kD3CiChunk * 27 * kD3Co];       // [ci][tap][co]
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.y * kD3Co;
+  const int npx = a.Hi * a.Wi;
+  const long long g0 = ((long long)blockIdx.x * kD3Threads + tid) * kD3Px;
+  const bool ok = g0 < (long long)npx * a.Di;
+  const int z = ok ? (int)(g0 / npx) : 0;
+  const int p0 = ok ? (int)(g0 - (long long)z * npx) : 0;
+  const int q = p0 / a.Wi, x0 = p0 - q * a.Wi;
+  const bool zn = ok && (z + 1 < a.Di), yn = ok && (q + 1 < a.Hi), xn = x0 + kD3Px < a.Wi;
+  const long long in_cs = (long long)a.Di * npx;
+  const float* in0 = a.in + (long long)z * npx + p0;
+
+  float acc[kD3Co][2][2][2 * kD3Px];
+#pragma unroll
+  for (int i = 0; i < kD3Co; ++i)
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int j = 0; j < 2 * kD3Px; ++j) acc[i][pz][py][j] = 0.0f;
+
+  for (int c0 = 0; c0 < a.Cin; c0 += kD3CiChunk) {
+    const int nci = min(kD3CiChunk, a.Cin - c0);
+    __syncthreads();
+    for (int e = tid; e < kD3CiChunk * 27 * kD3Co; e += kD3Threads) {
+      const int ci = e / (27 * kD3Co), rr = e - ci * (27 * kD3Co), tp = rr / kD3Co, co = rr - tp * kD3Co;
+      wsm[e] = (ci < nci && co0 + co < a.Cout) ? __ldg(a.w + (long long)(c0 + ci) * a.w_ci + (long long)(co0 + co) * a.w_co + tp) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < nci; ++c) {
+      // I[dz][dy][0..4]: the voxel rows (z + dz, q + dy), columns x0 .. x0 + 4 (zero beyond the tensor)
+      float I[2][2][kD3Px + 1];
+      const float* rp = in0 + (long long)(c0 + c) * in_cs;
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+          float e = 0.f;
+          if (ok && (dz == 0 || zn) && (dy == 0 || yn)) {
+            const float* r = rp + (long long)dz * npx + dy * a.Wi;
+            m = __ldg(reinterpret_cast<const float4*>(r));
+            if (xn) e = __ldg(r + kD3Px);
+          }
+          I[dz][dy][0] = m.x; I[dz][dy][1] = m.y; I[dz][dy][2] = m.z; I[dz][dy][3] = m.w; I[dz][dy][4] = e;
+        }
+      const float* wc = wsm + c * 27 * kD3Co;
+      // parity p of an output coordinate: terms (tap k, input offset d): p = 0 -> (1, 0); p = 1 -> (0, 1), (2, 0)
+#pragma unroll
+      for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+        for (int tz = 0; tz <= pz; ++tz) {
+          const int kz = pz == 0 ? 1 : (tz == 0 ? 0 : 2), dz = (pz == 1 && tz == 0) ? 1 : 0;
+#pragma unroll
+          for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int ty = 0; ty <= py; ++ty) {
+              const int ky = py == 0 ? 1 : (ty == 0 ? 0 : 2), dy = (py == 1 && ty == 0) ? 1 : 0;
+#pragma unroll
+              for (int px = 0; px < 2; ++px)
+#pragma unroll
+                for (int tx = 0; tx <= px; ++tx) {
+                  const int kx = px == 0 ? 1 : (tx == 0 ? 0 : 2), dx = (px == 1 && tx == 0) ? 1 : 0;
+                  const int tap = (kz * 3 + ky) * 3 + kx;
+                  const float2 w2 = *reinterpret_cast<const float2*>(wc + tap * kD3Co);
+                  const float w0 = w2.x, w1 = w2.y;
+#pragma unroll
+                  for (int j = 0; j < kD3Px; ++j) {
+                    const float v = I[dz][dy][j + dx];
+                    acc[0][pz][py][2 * j + px] = fmaf(v, w0, acc[0][pz][py][2 * j + px]);
+                    acc[1][pz][py][2 * j + px] = fmaf(v, w1, acc[1][pz][py][2 * j + px]);
+                  }
+                }
+            }
+        }
+    }
+  }
+  if (!ok) return;
+  const int Wo = 2 * a.Wi, Ho = 2 * a.Hi;
+  const long long oplane = (long long)Ho * Wo, out_cs = 2LL * a.Di * oplane;
+#pragma unroll
+  for (int i = 0; i < kD3Co; ++i) {
+    if (co0 + i >= a.Cout) break;
+    const float sc = a.scale ? __ldg(a.scale + co0 + i) : 1.0f, sh = a.shift ? __ldg(a.shift + co0 + i) : 0.0f;
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const long long idx = (long long)(co0 + i) * out_cs + (long long)(2 * z + pz) * oplane + (long long)(2 * q + py) * Wo + 2 * x0;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = acc[i][pz][py][j] * sc + sh;
+          if (a.relu) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (a.post_add) {
+          const float4 p0v = __ldg(reinterpret_cast<const float4*>(a.post_add + idx));
+          const float4 p1v = __ldg(reinterpret_cast<const float4*>(a.post_add + idx + 4));
+          v[0] += p0v.x; v[1] += p0v.y; v[2] += p0v.z; v[3] += p0v.w; v[4] += p1v.x; v[5] += p1v.y; v[6] += p1v.z; v[7] += p1v.w;
+        }
+        *reinterpret_cast<float4*>(a.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(a.out + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+  }
+}
+
+inline bool direct_deconv3d_supported(const DirectDeconv3d& p) {
+  return p.Wi % 4 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
+         (p.post_add == nullptr || reinterpret_cast<uintptr_t>(p.post_add) % 16 == 0);
+}
+
+inline int direct_deconv3d_launch(const DirectDeconv3d& p, cudaStream_t st, const char* what) {
+  dim3 grid(ceil_div((long long)p.Di * p.Hi * p.Wi, kD3Threads * kD3Px), ceil_div(p.Cout, kD3Co), 1);
+  direct_deconv3d_kernel<0><<<grid, kD3Threads, 0, st>>>(p);
+  return check_launch(what);
+}
+
+}  // namespace satmvs

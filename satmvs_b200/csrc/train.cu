@@ -432,6 +432,11 @@ int satmvs_conv3d_raw(const float* in, int Cin, int Di, int Hi, int Wi, const fl
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(kProfTrainConv, st);
   const bool three = NZ == 3;
+  if (mode == 3 && three) {   // register-tiled direct kernel when rows are 16-byte aligned
+    DirectDeconv3d d{};
+    d.in = in; d.w = w; d.w_ci = w_ci; d.w_co = w_co; d.out = out; d.Cin = Cin; d.Cout = Cout; d.Di = Di; d.Hi = Hi; d.Wi = Wi;
+    if (direct_deconv3d_supported(d)) return direct_deconv3d_launch(d, st, "satmvs_conv3d_raw (transposed, direct)");
+  }
   if (mode == 3) {   // ConvTranspose(k 3, stride 2, padding 1, output_padding 1): one problem per output parity class
     ConvGroup g{};
     int n = 0;
