@@ -39,7 +39,7 @@ static int run_conv(ConvProblem p, cudaStream_t st, const char* what) {
   return conv_launch<T>(g, st, what);
 }
 
-static int run_by_cout(const ConvProblem& p, cudaStream_t st, const char* what) {
+static int run_by_cout(const ConvProblem& p, cudaStream_t st, const char* what, float* ksplit_buf = nullptr, size_t ksplit_floats = 0) {
   {  // dense 3x3x3 layers: register-tiled direct kernel when rows are 16-byte aligned
     DirectConv d{};
     d.in = p.in; d.w = p.w; d.scale = p.scale; d.shift = p.shift; d.post_add = p.post_add; d.out = p.out;
@@ -47,7 +47,15 @@ static int run_by_cout(const ConvProblem& p, cudaStream_t st, const char* what) 
     d.w_co = p.w_co_stride; d.w_ci = p.w_ci_stride; d.acc_scale = p.acc_scale; d.relu = p.relu;
     const int stride = p.q2i_mul[0];
     static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
-    if (!no_direct && p.ntaps == 27 && direct_conv_supported(d, 3, stride)) return direct_conv_launch(d, 3, stride, st, what);
+    if (!no_direct && p.ntaps == 27 && stride == 1 && direct_conv3d_c1_supported(d)) return direct_conv3d_c1_launch(d, st, what);
+    if (!no_direct && p.ntaps == 27 && direct_conv_supported(d, 3, stride)) {
+      // small deep layers (conv5 / conv6: 40 output tiles of 8 channels x 512 voxels): split the input channels over grid.z
+      const long long tiles = (long long)ceil_div((long long)p.Do * p.Ho * p.Wo, kDcWarps * 32 * kDcPx) * ceil_div(p.Cout, kDcCo);
+      int ks = 1;
+      while (ks < 4 && tiles * ks < kNumSMs && p.Cin / (2 * ks) >= kDcCiChunk) ks *= 2;
+      if (ks > 1 && ksplit_buf && (size_t)ks * p.Cout * p.Do * p.Ho * p.Wo <= ksplit_floats) { d.ksplit = ks; d.partial = ksplit_buf; }
+      return direct_conv_launch(d, 3, stride, st, what);
+    }
   }
   if (p.Cout >= 64) return run_conv<Tile64>(p, st, what);
   if (p.Cout >= 32) return run_conv<Tile32>(p, st, what);
@@ -92,6 +100,7 @@ static int run_deconv3d(const float* in, int Cin, int Di, int Hi, int Wi, const 
 
 struct CostRegPlan {
   float* c[7]; float* x7; float* x9; float* x11;
+  float* ksplit; size_t ksplit_floats;         // partial sums of the layers whose input channels are split over CTAs
   char* wpack[5]; size_t wpack_bytes[5];       // packed (raw, lo) weights of the tensor-core layers: conv0, conv2, conv4, conv6, prob
   int* umma_err;
   size_t bytes;
@@ -107,6 +116,7 @@ static CostRegPlan costreg_plan(int base, int D, int H, int W, char* mem) {
   p.c[3] = take(4 * base * v2); p.c[4] = take(4 * base * v2);
   p.c[5] = take(8 * base * v3); p.c[6] = take(8 * base * v3);
   p.x7 = take(4 * base * v2); p.x9 = take(2 * base * v1); p.x11 = take(base * v0);
+  p.ksplit_floats = 4 * 8 * base * v3; p.ksplit = take(p.ksplit_floats);
   // (Cin / 8) x 3 planes x (raw, lo) x 9 taps x 2 quads x N (padded to 16) float4; conv0's Cin is bounded by 64 here
   const int wcin[5] = {64, 2 * base, 4 * base, 8 * base, base}, wn[5] = {base, 2 * base, 4 * base, 8 * base, 1};
   for (int i = 0; i < 5; ++i) {
@@ -181,7 +191,7 @@ int satmvs_costreg_forward(const satmvs_costreg_weights* wt, const float* x, int
     }
     ConvProblem p = conv3d_problem(cur, cin[i], d, h, w, wt->conv_w[i], P.c[i], cout[i], stride[i]);
     p.scale = wt->bn_scale[i]; p.shift = wt->bn_shift[i];
-    RUN(run_by_cout(p, st, "costreg conv"));
+    RUN(run_by_cout(p, st, "costreg conv", P.ksplit, P.ksplit_floats));
     cur = P.c[i];
     d /= stride[i]; h /= stride[i]; w /= stride[i];
   }

@@ -28,6 +28,8 @@ struct DirectConv {
   float acc_scale;
   int relu;
   int flip;               // 1: taps mirrored (tap -> TAPS-1-tap): a stride-1 transposed conv as a correlation
+  int ksplit;             // > 1: grid.z CTAs share the input channels (small deep layers: too few output tiles to fill the GPU);
+  float* partial;         //      raw sums go to partial[z][Cout][Do*Ho*Wo], direct_conv_finish_kernel adds them and applies the epilogue
 };
 
 constexpr int kDcWarps = 4, kDcCo = 8, kDcPx = 4, kDcCiChunk = 16;
@@ -116,8 +118,10 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
     }
   };
 
-  for (int c0 = 0; c0 < a.Cin; c0 += kDcCiChunk) {
-    const int nci = min(kDcCiChunk, a.Cin - c0);
+  const int c_per = a.ksplit > 1 ? (a.Cin / a.ksplit + kDcCiChunk - 1) / kDcCiChunk * kDcCiChunk : a.Cin;
+  const int c_begin = a.ksplit > 1 ? (int)blockIdx.z * c_per : 0, c_end = min(a.Cin, c_begin + c_per);
+  for (int c0 = c_begin; c0 < c_end; c0 += kDcCiChunk) {
+    const int nci = min(kDcCiChunk, c_end - c0);
     __syncthreads();                                   // previous chunk's weights no longer in use
     {  // stage this chunk's weights: [co][ci][tap] in global -> [ci][tap][co] in smem, loads batched
       constexpr int kPer = (kDcCiChunk * TAPS * kDcCo + kDcWarps * 32 - 1) / (kDcWarps * 32);
@@ -158,6 +162,19 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
 
   if (!ok) return;
   const long long out_plane = (long long)a.Ho * a.Wo;
+  if (a.ksplit > 1) {        // raw partial sums; the epilogue runs in direct_conv_finish_kernel
+    float* pp = a.partial + (long long)blockIdx.z * a.Cout * a.Do * out_plane;
+#pragma unroll
+    for (int i = 0; i < kDcCo; ++i) {
+      const int co = co0 + i;
+      if (co >= a.Cout) break;
+      float v[kDcPx];
+#pragma unroll
+      for (int j = 0; j < kDcPx; ++j) { float alo, ahi; upk(acc[i >> 1][j], alo, ahi); v[j] = (i & 1) ? ahi : alo; }
+      *reinterpret_cast<float4*>(pp + ((long long)co * a.Do + oz) * out_plane + p0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < kDcCo; ++i) {
     const int co = co0 + i;
@@ -181,6 +198,21 @@ direct_conv_kernel(const __grid_constant__ DirectConv a) {
 }
 
 // true if the layer shape is one the direct kernel handles (16-byte aligned rows)
+// out = epilogue(sum over the ksplit partial tensors, in their order): scale / shift, ReLU, + post_add
+template <int kUnused>     // template only so the header can be included from several translation units
+__global__ void __launch_bounds__(256) direct_conv_finish_kernel(const DirectConv a) {
+  const long long per_c = (long long)a.Do * a.Ho * a.Wo, total = per_c * a.Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / per_c);
+    float v = 0.0f;
+    for (int z = 0; z < a.ksplit; ++z) v += a.partial[(long long)z * total + i];
+    v = v * a.acc_scale * (a.scale ? __ldg(a.scale + co) : 1.0f) + (a.shift ? __ldg(a.shift + co) : 0.0f);
+    if (a.relu) v = fmaxf(v, 0.0f);
+    if (a.post_add) v += __ldg(a.post_add + i);
+    a.out[i] = v;
+  }
+}
+
 inline bool direct_conv_supported(const DirectConv& p, int NZ, int S) {
   if (p.Wi % 4 || p.Wo % 4) return false;
   if (S == 2 && (p.Wi != 2 * p.Wo || p.Hi != 2 * p.Ho)) return false;
@@ -199,11 +231,15 @@ inline int direct_conv_launch_cs(DirectConv p, long long in_cs, cudaStream_t st,
 }
 
 inline int direct_conv_launch(const DirectConv& p, int NZ, int S, cudaStream_t st, const char* what) {
-  dim3 grid(ceil_div((long long)p.Ho * p.Wo * p.Do, kDcWarps * 32 * kDcPx), ceil_div(p.Cout, kDcCo), 1);
+  dim3 grid(ceil_div((long long)p.Ho * p.Wo * p.Do, kDcWarps * 32 * kDcPx), ceil_div(p.Cout, kDcCo), p.ksplit > 1 ? p.ksplit : 1);
   if (NZ == 1 && S == 1) direct_conv_kernel<1, 1><<<grid, kDcWarps * 32, 0, st>>>(p);
   else if (NZ == 1 && S == 2) direct_conv_kernel<1, 2><<<grid, kDcWarps * 32, 0, st>>>(p);
   else if (NZ == 3 && S == 1) direct_conv_kernel<3, 1><<<grid, kDcWarps * 32, 0, st>>>(p);
   else direct_conv_kernel<3, 2><<<grid, kDcWarps * 32, 0, st>>>(p);
+  if (p.ksplit > 1) {
+    const long long total = (long long)p.Cout * p.Do * p.Ho * p.Wo;
+    direct_conv_finish_kernel<0><<<(int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs), 256, 0, st>>>(p);
+  }
   return check_launch(what);
 }
 
@@ -496,6 +532,83 @@ inline bool direct_deconv3d_supported(const DirectDeconv3d& p) {
 inline int direct_deconv3d_launch(const DirectDeconv3d& p, cudaStream_t st, const char* what) {
   dim3 grid(ceil_div((long long)p.Di * p.Hi * p.Wi, kD3Threads * kD3Px), ceil_div(p.Cout, kD3Co), 1);
   direct_deconv3d_kernel<0><<<grid, kD3Threads, 0, st>>>(p);
+  return check_launch(what);
+}
+
+}  // namespace satmvs
+
+// ---------------------------------------------------------------------------------------------
+// 3x3x3 stride-1 convolution to ONE output channel (CostRegNet's `prob` head, modules/module.py:566): direct_conv_kernel computes
+// 8 output channels per thread, 7 of them on zero filters here.  One thread = 8 consecutive output voxels of a row x 1 channel.
+// ---------------------------------------------------------------------------------------------
+namespace satmvs {
+
+constexpr int kC1Px = 8, kC1Threads = 128, kC1MaxCin = 64;
+
+template <int kUnused>
+__global__ void __launch_bounds__(kC1Threads)
+direct_conv3d_c1_kernel(const __grid_constant__ DirectConv a) {
+  __shared__ float wsm[kC1MaxCin * 27];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < a.Cin * 27; e += kC1Threads) {
+    const int ci = e / 27, tp = e - ci * 27;
+    wsm[e] = __ldg(a.w + (long long)ci * a.w_ci + (a.flip ? 26 - tp : tp));
+  }
+  __syncthreads();
+  const int npx = a.Hi * a.Wi;
+  const long long g0 = ((long long)blockIdx.x * kC1Threads + tid) * kC1Px;
+  if (g0 >= (long long)npx * a.Di) return;
+  const int oz = (int)(g0 / npx), p0 = (int)(g0 - (long long)oz * npx), oy = p0 / a.Wi, ox = p0 - oy * a.Wi;
+  const long long in_cs = (long long)a.Di * npx;
+  const bool lok = ox > 0, rok = ox + kC1Px < a.Wi;
+  float acc[kC1Px];
+#pragma unroll
+  for (int j = 0; j < kC1Px; ++j) acc[j] = 0.0f;
+#pragma unroll 1
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    const float* wc = wsm + ci * 27;
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz) {
+      const int iz = oz - 1 + kz;
+      if ((unsigned)iz >= (unsigned)a.Di) continue;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy - 1 + ky;
+        if ((unsigned)iy >= (unsigned)a.Hi) continue;
+        const float* rp = a.in + ci * in_cs + ((long long)iz * a.Hi + iy) * a.Wi + ox;
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(rp)), m1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+        const float r[kC1Px + 2] = {lok ? __ldg(rp - 1) : 0.0f, m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, rok ? __ldg(rp + kC1Px) : 0.0f};
+        const float w0 = wc[(kz * 3 + ky) * 3], w1 = wc[(kz * 3 + ky) * 3 + 1], w2 = wc[(kz * 3 + ky) * 3 + 2];
+#pragma unroll
+        for (int j = 0; j < kC1Px; ++j) acc[j] = fmaf(r[j], w0, fmaf(r[j + 1], w1, fmaf(r[j + 2], w2, acc[j])));
+      }
+    }
+  }
+  const float sc = (a.scale ? __ldg(a.scale) : 1.0f) * a.acc_scale, sh = a.shift ? __ldg(a.shift) : 0.0f;
+  float v[kC1Px];
+#pragma unroll
+  for (int j = 0; j < kC1Px; ++j) {
+    v[j] = acc[j] * sc + sh;
+    if (a.relu) v[j] = fmaxf(v[j], 0.0f);
+  }
+  float* op = a.out + (long long)oz * npx + p0;
+  if (a.post_add) {
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.post_add + (long long)oz * npx + p0));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.post_add + (long long)oz * npx + p0 + 4));
+    v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
+  }
+  *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+inline bool direct_conv3d_c1_supported(const DirectConv& p) {
+  return p.Cout == 1 && p.Cin <= kC1MaxCin && p.Wi % kC1Px == 0 && p.Wo == p.Wi && p.Ho == p.Hi && p.Do == p.Di && p.in_cs == 0 &&
+         reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
+         (p.post_add == nullptr || reinterpret_cast<uintptr_t>(p.post_add) % 16 == 0);
+}
+
+inline int direct_conv3d_c1_launch(const DirectConv& p, cudaStream_t st, const char* what) {
+  direct_conv3d_c1_kernel<0><<<ceil_div((long long)p.Di * p.Hi * p.Wi, kC1Threads * kC1Px), kC1Threads, 0, st>>>(p);
   return check_launch(what);
 }
 

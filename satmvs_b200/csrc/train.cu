@@ -469,6 +469,7 @@ int satmvs_conv3d_raw(const float* in, int Cin, int Di, int Hi, int Wi, const fl
     d.in = in; d.w = w; d.out = out;
     d.Cin = Cin; d.Cout = Cout; d.Di = Di; d.Hi = Hi; d.Wi = Wi; d.Do = Do; d.Ho = Ho; d.Wo = Wo;
     d.w_co = w_co; d.w_ci = w_ci; d.acc_scale = 1.0f; d.relu = 0; d.flip = mode == 2;
+    if (NZ == 3 && stride == 1 && direct_conv3d_c1_supported(d)) return direct_conv3d_c1_launch(d, st, "satmvs_conv3d_raw (direct, 1 channel)");
     if (direct_conv_supported(d, NZ, stride)) return direct_conv_launch(d, NZ, stride, st, "satmvs_conv3d_raw (direct)");
   }
   ConvProblem p;
