@@ -259,6 +259,7 @@ namespace satmvs {
 struct DirectDeconv {
   const float* in;   long long in_cs;    // [Cin] channels of Dn planes of Hi x Wi; channel stride in elements
   const float* w;                        // [Cin][Cout][9]
+  const float* scale; const float* shift;   // [Cout] folded BatchNorm applied before the ReLU, or null
   const float* post_add;                 // like out, or null
   float* out;        long long out_cs;   // [Cout] channels of Dn planes of 2Hi x 2Wi
   int Cin, Cout, Dn, Hi, Wi;
@@ -366,8 +367,9 @@ direct_deconv2x_kernel(const __grid_constant__ DirectDeconv a) {
     for (int r = 0; r < 2; ++r) {
       const long long idx = (long long)(co0 + i) * a.out_cs + (long long)z * oplane + (long long)(2 * q + r) * Wo + 2 * x0;
       float v[8];
+      const float sc = a.scale ? __ldg(a.scale + co0 + i) : 1.0f, sh = a.shift ? __ldg(a.shift + co0 + i) : 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = a.relu ? fmaxf(acc[i][r][j], 0.0f) : acc[i][r][j];
+      for (int j = 0; j < 8; ++j) { const float t = fmaf(acc[i][r][j], sc, sh); v[j] = a.relu ? fmaxf(t, 0.0f) : t; }
       if (a.post_add) {
         const float4 p0v = __ldg(reinterpret_cast<const float4*>(a.post_add + idx));
         const float4 p1v = __ldg(reinterpret_cast<const float4*>(a.post_add + idx + 4));
@@ -609,6 +611,57 @@ inline bool direct_conv3d_c1_supported(const DirectConv& p) {
 
 inline int direct_conv3d_c1_launch(const DirectConv& p, cudaStream_t st, const char* what) {
   direct_conv3d_c1_kernel<0><<<ceil_div((long long)p.Di * p.Hi * p.Wi, kC1Threads * kC1Px), kC1Threads, 0, st>>>(p);
+  return check_launch(what);
+}
+
+}  // namespace satmvs
+
+// ---------------------------------------------------------------------------------------------
+// 1x1 convolution (FeatureNet's output heads, modules/module.py:469-483): out[co][p] = sum_ci w[co][ci] in[ci][p].  Memory-bound;
+// one thread = 8 output channels x 4 consecutive positions, the filters in shared memory.
+// ---------------------------------------------------------------------------------------------
+namespace satmvs {
+
+struct Conv1x1 { const float* in; const float* w; float* out; long long n; int Cin, Cout; };   // in [Cin][n], out [Cout][n], n % 4 == 0
+
+constexpr int kP1Co = 8, kP1MaxCin = 64;
+
+template <int kUnused>
+__global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1 a) {
+  __shared__ float wsm[kP1MaxCin * kP1Co];          // [ci][co]
+  const int co0 = blockIdx.y * kP1Co;
+  for (int e = threadIdx.x; e < a.Cin * kP1Co; e += blockDim.x) {
+    const int ci = e / kP1Co, co = e - ci * kP1Co;
+    wsm[e] = co0 + co < a.Cout ? __ldg(a.w + (long long)(co0 + co) * a.Cin + ci) : 0.0f;
+  }
+  __syncthreads();
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= a.n) return;
+  float4 acc[kP1Co];
+#pragma unroll
+  for (int c = 0; c < kP1Co; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.in + (long long)ci * a.n + i));
+    const float4 w0 = *reinterpret_cast<const float4*>(&wsm[ci * kP1Co]), w1 = *reinterpret_cast<const float4*>(&wsm[ci * kP1Co + 4]);
+    const float wv[kP1Co] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int c = 0; c < kP1Co; ++c) {
+      acc[c].x = fmaf(v.x, wv[c], acc[c].x); acc[c].y = fmaf(v.y, wv[c], acc[c].y);
+      acc[c].z = fmaf(v.z, wv[c], acc[c].z); acc[c].w = fmaf(v.w, wv[c], acc[c].w);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kP1Co; ++c)
+    if (co0 + c < a.Cout) *reinterpret_cast<float4*>(a.out + (long long)(co0 + c) * a.n + i) = acc[c];
+}
+
+inline bool conv1x1_supported(const Conv1x1& p) {
+  return p.Cin <= kP1MaxCin && p.n % 4 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0;
+}
+
+inline int conv1x1_launch(const Conv1x1& p, cudaStream_t st, const char* what) {
+  conv1x1_kernel<0><<<dim3(ceil_div(p.n / 4, 256), ceil_div(p.Cout, kP1Co)), 256, 0, st>>>(p);
   return check_launch(what);
 }
 

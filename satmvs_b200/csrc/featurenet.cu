@@ -8,9 +8,10 @@
 // scale / shift.  The two concatenations never happen: the skip tensors (conv0, conv1 outputs) are produced directly in the
 // upper channel halves of the concatenation buffers and the transposed convs write the lower halves.
 // Kernels: the 3x3 stride-1 layers with >= 8 input channels (7 of the 15 layers, 60 % of the FLOPs) run on the tensor cores
-// (umma_conv.cuh: tcgen05 kind::tf32, 3-way split, fp32-faithful); the 3-channel first layer, the 5x5 stride-2 convs, the
-// transposed convs and the 1x1 heads on the fp32 implicit-GEMM engine (conv_engine.cuh).
+// (umma_conv.cuh: tcgen05 kind::tf32, 3-way split, fp32-faithful); the 3-channel first layer, the transposed convs and the 1x1
+// heads on register-tiled fp32 kernels (direct_conv.cuh), the 5x5 stride-2 convs on the fp32 implicit-GEMM engine (conv_engine.cuh).
 #include "conv_engine.cuh"
+#include "direct_conv.cuh"
 #include "umma_conv.cuh"
 #include "prof.cuh"
 #include <cstdlib>
@@ -64,6 +65,14 @@ ConvProblem fn_conv(const FnTensor& in, int in_off, int Cin, const float* w, con
 // output-parity problems in one grouped launch; weight layout [Cin][Cout][3][3]
 int fn_deconv(const FnTensor& in, int Cin, const float* w, const float* scale, const float* shift, const FnTensor& out, int out_off,
               int Cout, int V, cudaStream_t st, const char* what) {
+  {  // register-tiled direct kernel (direct_conv.cuh) when rows are 16-byte aligned
+    DirectDeconv d{};
+    const long long ics = (long long)V * in.h * in.w, ocs = (long long)V * out.h * out.w;
+    d.in = in.p; d.in_cs = ics; d.w = w; d.scale = scale; d.shift = shift; d.out = out.p + (size_t)out_off * ocs; d.out_cs = ocs;
+    d.Cin = Cin; d.Cout = Cout; d.Dn = V; d.Hi = in.h; d.Wi = in.w; d.relu = 1;
+    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+    if (!no_direct && direct_deconv_supported(d)) return direct_deconv_launch(d, st, what);
+  }
   ConvGroup g{};
   int n = 0;
   for (int py = 0; py < 2; ++py)
@@ -146,7 +155,23 @@ int satmvs_featurenet_forward(const satmvs_featurenet_weights* wt, const float* 
         return umma_conv_launch(up, tc_err, st, what);
       }
     }
+    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+    if (k == 3 && s == 1 && !no_direct) {        // the 3-channel first layer: register-tiled direct kernel
+      const long long ics = (long long)V * in.h * in.w, ocs = (long long)V * out.h * out.w;
+      DirectConv d{};
+      d.in = in.p + (size_t)in_off * ics; d.w = L[i].w; d.scale = L[i].scale; d.shift = L[i].shift; d.out = out.p + (size_t)out_off * ocs;
+      d.Cin = Cin; d.Cout = Cout; d.Di = V; d.Hi = in.h; d.Wi = in.w; d.Do = V; d.Ho = out.h; d.Wo = out.w;
+      d.w_co = (long long)Cin * 9; d.w_ci = 9; d.acc_scale = 1.0f; d.relu = 1;
+      if (direct_conv_supported(d, 1, 1)) return direct_conv_launch(d, 1, 1, st, what);
+    }
     ConvProblem p = fn_conv(in, in_off, Cin, L[i].w, L[i].scale, L[i].shift, 1, out, out_off, Cout, k, s, V);
+    return fn_launch(p, st, what);
+  };
+  auto head = [&](const FnTensor& in, int Cin, const float* w, const FnTensor& out, const char* what) {   // bare 1x1 conv, no bias
+    Conv1x1 c{in.p, w, out.p, (long long)V * in.h * in.w, Cin, Cin};
+    static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
+    if (!no_direct && conv1x1_supported(c)) return conv1x1_launch(c, st, what);
+    ConvProblem p = fn_conv(in, 0, Cin, w, nullptr, nullptr, 0, out, 0, Cin, 1, 1, V);
     return fn_launch(p, st, what);
   };
   // conv0 (module.py:452-455); its output is the skip tensor of deconv2: upper half of cat2
@@ -160,24 +185,15 @@ int satmvs_featurenet_forward(const satmvs_featurenet_weights* wt, const float* 
   RUN(conv(5, cat1, 2 * b, 2 * b, t2a, 0, 4 * b, 5, 2, "featurenet conv2.0"));
   RUN(conv(6, t2a, 0, 4 * b, t2b, 0, 4 * b, 3, 1, "featurenet conv2.1"));
   RUN(conv(7, t2b, 0, 4 * b, t2c, 0, 4 * b, 3, 1, "featurenet conv2.2"));
-  {  // out1: bare 1x1 conv, no bias (:469, :511-512)
-    ConvProblem p = fn_conv(t2c, 0, 4 * b, wt->out_w[0], nullptr, nullptr, 0, o1, 0, 4 * b, 1, 1, V);
-    RUN(fn_launch(p, st, "featurenet out1"));
-  }
+  RUN(head(t2c, 4 * b, wt->out_w[0], o1, "featurenet out1"));       // out1: bare 1x1 conv, no bias (:469, :511-512)
   // deconv1 = DeConv2dFuse(4b -> 2b) (:474, :515): transposed conv into the lower half of cat1, 3x3 conv over both halves
   RUN(fn_deconv(t2c, 4 * b, L[8].w, L[8].scale, L[8].shift, cat1, 0, 2 * b, V, st, "featurenet deconv1.deconv"));
   RUN(conv(9, cat1, 0, 4 * b, f1, 0, 2 * b, 3, 1, "featurenet deconv1.conv"));
-  {
-    ConvProblem p = fn_conv(f1, 0, 2 * b, wt->out_w[1], nullptr, nullptr, 0, o2, 0, 2 * b, 1, 1, V);
-    RUN(fn_launch(p, st, "featurenet out2"));
-  }
+  RUN(head(f1, 2 * b, wt->out_w[1], o2, "featurenet out2"));
   // deconv2 = DeConv2dFuse(2b -> b) (:475, :519)
   RUN(fn_deconv(f1, 2 * b, L[10].w, L[10].scale, L[10].shift, cat2, 0, b, V, st, "featurenet deconv2.deconv"));
   RUN(conv(11, cat2, 0, 2 * b, f2, 0, b, 3, 1, "featurenet deconv2.conv"));
-  {
-    ConvProblem p = fn_conv(f2, 0, b, wt->out_w[2], nullptr, nullptr, 0, o3, 0, b, 1, 1, V);
-    RUN(fn_launch(p, st, "featurenet out3"));
-  }
+  RUN(head(f2, b, wt->out_w[2], o3, "featurenet out3"));
 #undef RUN
   return check_launch("satmvs_featurenet_forward");
 }
