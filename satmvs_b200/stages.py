@@ -47,7 +47,7 @@ def stage_casmvs(features, cams, depth_values, regulariser, geo_model="rpc"):
     return {"depth": depth, "photometric_confidence": conf}
 
 
-def stage_pred_red(features, cams, depth_values, regulariser, geo_model="rpc", chunk=16):
+def stage_pred_red(features, cams, depth_values, regulariser, geo_model="rpc", chunk=None):
     """Plane-streaming stage of the inference net (`compute_depth_when_pred`, `networks/casred.py:161-238`): sweep, one
     recurrent regulariser step per plane (states carried), streaming fp64 soft-argmin -- in chunks of `chunk` planes: ONE
     fused sweep builds the chunk's variance planes, ONE library call runs the recurrence over them (tensor-core cluster
@@ -59,6 +59,10 @@ def stage_pred_red(features, cams, depth_values, regulariser, geo_model="rpc", c
     states = [torch.zeros((B, c, H >> l, W >> l), dtype=torch.float32, device=dev) for l, c in enumerate((8, 16, 32, 64))]
     head = StreamingSoftArgmin(B, H, W, dev)
     D = depth_values.shape[1]
+    if chunk is None:      # planes per library call: SATMVS_PRED_CHUNK, default 32 (>= 32 planes per call
+        # let the library overlap the batched convs with the recurrence inside the call: 2.36 -> 2.07 ms on the 256x128 cascade)
+        import os
+        chunk = int(os.environ.get("SATMVS_PRED_CHUNK", "32"))
     chunk = max(1, int(chunk))
     for d0 in range(0, D, chunk):
         planes = depth_values[:, d0:d0 + chunk].contiguous()
