@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgradArgs a)
     for (int it = 0; it < kWgMaxItems; ++it) {
       const int unit = threadIdx.x + it * blockDim.x;
       if (unit < units) {
-        const int id = unit / a.split, sp = unit - id * a.split;
+        const int sp = unit / items, id = unit - sp * items;      // items fastest: the lanes of a warp read different rows (fewer bank conflicts)
         const int cp = id / (nci * nkk), rem = id - cp * (nci * nkk);
         const int cl = rem / nkk, kk = rem - cl * nkk, kz = kk / 3, ky = kk - kz * 3;
         const int co0 = 2 * cp, co1 = min(2 * cp + 1, a.Cout - 1);       // an odd Cout computes its last filter twice (stored once)
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgradArgs a)
   for (int it = 0; it < kWgMaxItems; ++it) {
     const int unit = threadIdx.x + it * blockDim.x;
     if (unit < units) {
-      const int id = unit / a.split, sp = unit - id * a.split;
+      const int sp = unit / items, id = unit - sp * items;      // items fastest: the lanes of a warp read different rows (fewer bank conflicts)
       const int cp = id / (nci * nkk), rem = id - cp * (nci * nkk);
       const int cl = rem / nkk, kk = rem - cl * nkk;
       float* out = a.partial + ((size_t)blockIdx.x * a.split + sp) * a.Cout * a.Cin * taps;
