@@ -228,6 +228,55 @@ def golden_cascade(ref):
         save(f"cascade_{tag}", **arrays)
 
 
+
+def golden_training(ref):
+    """train() mode + loss.backward() of the UNMODIFIED reference modules (`train.py:267-287`): outputs, gradients to the input
+    and to a few parameters, running statistics after the step -- pins the oracle's (and the library's) training form."""
+    import contextlib
+    rng = np.random.default_rng(41)
+    # CostRegNet: batch-statistics BatchNorm3d
+    C, D, H, W = 8, 8, 16, 32
+    x = torch.from_numpy(rng.standard_normal((2, C, D, H, W), dtype=np.float32)).abs_().requires_grad_(True)
+    m = ref.module.CostRegNet(C, 8)
+    m.load_state_dict(synth.make_costregnet_weights(C, seed=3))
+    m.train()
+    y = m(x)
+    gy = torch.from_numpy(rng.standard_normal(tuple(y.shape), dtype=np.float32))
+    y.backward(gy)
+    save("train_costregnet", x=x, gy=gy, y=y, dx=x.grad,
+         d_conv0_w=m.conv0.conv.weight.grad, d_conv6_w=m.conv6.conv.weight.grad, d_conv7_w=m.conv7.conv.weight.grad,
+         d_conv7_bn_w=m.conv7.bn.weight.grad, d_conv7_bn_b=m.conv7.bn.bias.grad, d_prob_w=m.prob.weight.grad,
+         rm_conv0=m.conv0.bn.running_mean, rv_conv0=m.conv0.bn.running_var, rm_conv11=m.conv11.bn.running_mean,
+         rv_conv11=m.conv11.bn.running_var)
+    # RED regulariser: backward through the recurrence
+    C, D, H, W = 8, 4, 16, 24
+    v = torch.from_numpy(rng.standard_normal((1, C, D, H, W), dtype=np.float32)).abs_().requires_grad_(True)
+    r = ref.module.RED_Regularization(C, 8)
+    r.load_state_dict(synth.make_red_weights(C, seed=5))
+    r.train()
+    lg = r(v)
+    gl = torch.from_numpy(rng.standard_normal(tuple(lg.shape), dtype=np.float32))
+    lg.backward(gl)
+    save("train_red", volume=v, gl=gl, logits=lg, dvolume=v.grad,
+         d_gru1_gate_w=r.conv_gru1.gate_conv.weight.grad, d_gru1_gate_b=r.conv_gru1.gate_conv.bias.grad,
+         d_gru4_out_w=r.conv_gru4.output_conv.weight.grad, d_gru2_rn_w=r.conv_gru2.reset_gate_norm.weight.grad,
+         d_gru3_on_b=r.conv_gru3.output_norm.bias.grad, d_conv2_w=r.conv2.conv.weight.grad, d_upconv2_w=r.upconv2.conv.weight.grad,
+         d_upconv2d_w=r.upconv2d.weight.grad)
+    # FeatureNet: batch-statistics BatchNorm2d, three output heads
+    with open(os.devnull, "w") as devnull, contextlib.redirect_stdout(devnull):
+        f = ref.module.FeatureNet(base_channels=8, stride=4, num_stage=3, arch_mode="unet")
+    f.load_state_dict(synth.make_featurenet_weights(8))
+    f.train()
+    img = torch.from_numpy(rng.random((2, 3, 32, 48), dtype=np.float32))
+    out = f(img)
+    gs = {k: torch.from_numpy(rng.standard_normal(tuple(o.shape), dtype=np.float32)) for k, o in out.items()}
+    sum((out[k] * gs[k]).sum() for k in out).backward()
+    save("train_featurenet", img=img, **{f"g_{k}": g for k, g in gs.items()}, **{k: o for k, o in out.items()},
+         d_conv0_0_w=f.conv0[0].conv.weight.grad, d_conv1_0_w=f.conv1[0].conv.weight.grad, d_deconv1_deconv_w=f.deconv1.deconv.conv.weight.grad,
+         d_deconv2_conv_bn_w=f.deconv2.conv.bn.weight.grad, d_out1_w=f.out1.weight.grad, d_out3_w=f.out3.weight.grad,
+         rm_conv0_0=f.conv0[0].bn.running_mean, rv_conv0_0=f.conv0[0].bn.running_var)
+
+
 def main_featurenet_only():
     golden_featurenet(reference_loader.load())
 
@@ -244,10 +293,13 @@ def main():
     golden_hypotheses(ref)
     golden_cascade(ref)
     golden_featurenet(ref)
+    golden_training(ref)
 
 
 if __name__ == "__main__":
     if "--featurenet" in sys.argv:
         main_featurenet_only()
+    elif "--training" in sys.argv:
+        golden_training(reference_loader.load())
     else:
         main()

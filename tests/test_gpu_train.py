@@ -338,3 +338,53 @@ def test_whole_casmvs_network_training_step():
     print("whole-network training step: (1 - cosine, norm ratio) per gradient:", errs)
     for what, (c, r) in errs.items():
         assert c < 1e-3 and abs(r - 1.0) < 2e-2, (what, errs)
+
+
+def test_training_goldens_from_the_unmodified_reference(golden):
+    """CUDA train() + backward against outputs / gradients / running statistics the UNMODIFIED reference modules produced in
+    train() mode (oracle/make_golden.py --training): CostRegNet, RED_Regularization, FeatureNet."""
+    def todev(t):
+        return t.to(DEV)
+
+    g = golden("train_costregnet")
+    net = satmvs_b200.CostRegNet(8, 8)
+    net.load_state_dict(synth.make_costregnet_weights(8, seed=3))
+    net = net.to(DEV).train()
+    x = todev(g["x"]).requires_grad_(True)
+    y = net(x)
+    y.backward(todev(g["gy"]))
+    assert rel(y, g["y"]) < 1e-3 and rel(x.grad, g["dx"]) < 1e-3
+    for key, p in (("d_conv0_w", net.conv0.conv.weight), ("d_conv6_w", net.conv6.conv.weight), ("d_conv7_w", net.conv7.conv.weight),
+                   ("d_conv7_bn_w", net.conv7.bn.weight), ("d_conv7_bn_b", net.conv7.bn.bias), ("d_prob_w", net.prob.weight)):
+        assert rel(p.grad, g[key]) < 2e-3, key
+    for key, buf in (("rm_conv0", net.conv0.bn.running_mean), ("rv_conv0", net.conv0.bn.running_var),
+                     ("rm_conv11", net.conv11.bn.running_mean), ("rv_conv11", net.conv11.bn.running_var)):
+        assert rel(buf, g[key]) < 1e-4, key
+
+    g = golden("train_red")
+    red = satmvs_b200.RED_Regularization(8, 8)
+    red.load_state_dict(synth.make_red_weights(8, seed=5))
+    red = red.to(DEV).train()
+    v = todev(g["volume"]).requires_grad_(True)
+    lg = red(v)
+    lg.backward(todev(g["gl"]))
+    assert rel(lg, g["logits"]) < 1e-4 and rel(v.grad, g["dvolume"]) < 1e-3
+    for key, p in (("d_gru1_gate_w", red.conv_gru1.gate_conv.weight), ("d_gru1_gate_b", red.conv_gru1.gate_conv.bias),
+                   ("d_gru4_out_w", red.conv_gru4.output_conv.weight), ("d_gru2_rn_w", red.conv_gru2.reset_gate_norm.weight),
+                   ("d_gru3_on_b", red.conv_gru3.output_norm.bias), ("d_conv2_w", red.conv2.conv.weight),
+                   ("d_upconv2_w", red.upconv2.conv.weight), ("d_upconv2d_w", red.upconv2d.weight)):
+        assert rel(p.grad, g[key]) < 2e-3, key
+
+    g = golden("train_featurenet")
+    fnet = satmvs_b200.FeatureNet(8)
+    fnet.load_state_dict(synth.make_featurenet_weights(8))
+    fnet = fnet.to(DEV).train()
+    out = fnet(todev(g["img"]))
+    sum((out[k] * todev(g[f"g_{k}"])).sum() for k in out).backward()
+    for k in out:
+        assert rel(out[k], g[k]) < 1e-4, k
+    for key, p in (("d_conv0_0_w", fnet.conv0[0].conv.weight), ("d_conv1_0_w", fnet.conv1[0].conv.weight),
+                   ("d_deconv1_deconv_w", fnet.deconv1.deconv.conv.weight), ("d_deconv2_conv_bn_w", fnet.deconv2.conv.bn.weight),
+                   ("d_out1_w", fnet.out1.weight), ("d_out3_w", fnet.out3.weight)):
+        assert rel(p.grad, g[key]) < 2e-3, key
+    assert rel(fnet.conv0[0].bn.running_mean, g["rm_conv0_0"]) < 1e-4 and rel(fnet.conv0[0].bn.running_var, g["rv_conv0_0"]) < 1e-4

@@ -151,3 +151,46 @@ def test_featurenet_restatement_equals_reference(golden):
             out = regnets.featurenet(g[f"img{v}"], sd)
             for k in ("stage1", "stage2", "stage3"):
                 assert maxdiff(out[k], g[f"{k}_v{v}"]) == 0.0
+
+
+def _rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def test_training_form_of_the_oracle_equals_reference(golden):
+    """The oracle's train-mode restatements (batch-statistics BatchNorm, autograd through the recurrence) against outputs and
+    gradients of the UNMODIFIED reference modules in train() mode (`train.py:267-287`; oracle/make_golden.py --training)."""
+    g = golden("train_costregnet")
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k)
+          for k, v in synth.make_costregnet_weights(8, seed=3).items()}
+    x = g["x"].clone().requires_grad_(True)
+    y = regnets.costregnet(x, sd, training=True)
+    y.backward(g["gy"])
+    assert _rel(y, g["y"]) < 1e-5 and _rel(x.grad, g["dx"]) < 1e-4
+    for key, name in (("d_conv0_w", "conv0.conv.weight"), ("d_conv6_w", "conv6.conv.weight"), ("d_conv7_w", "conv7.conv.weight"),
+                      ("d_conv7_bn_w", "conv7.bn.weight"), ("d_conv7_bn_b", "conv7.bn.bias"), ("d_prob_w", "prob.weight")):
+        assert _rel(sd[name].grad, g[key]) < 1e-4, name
+
+    g = golden("train_red")
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.make_red_weights(8, seed=5).items()}
+    v = g["volume"].clone().requires_grad_(True)
+    lg = regnets.red_regularization(v, sd)
+    lg.backward(g["gl"])
+    assert _rel(lg, g["logits"]) < 1e-5 and _rel(v.grad, g["dvolume"]) < 1e-4
+    for key, name in (("d_gru1_gate_w", "conv_gru1.gate_conv.weight"), ("d_gru1_gate_b", "conv_gru1.gate_conv.bias"),
+                      ("d_gru4_out_w", "conv_gru4.output_conv.weight"), ("d_gru2_rn_w", "conv_gru2.reset_gate_norm.weight"),
+                      ("d_gru3_on_b", "conv_gru3.output_norm.bias"), ("d_conv2_w", "conv2.conv.weight"),
+                      ("d_upconv2_w", "upconv2.conv.weight"), ("d_upconv2d_w", "upconv2d.weight")):
+        assert _rel(sd[name].grad, g[key]) < 1e-4, name
+
+    g = golden("train_featurenet")
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in synth.make_featurenet_weights(8).items()}
+    out = regnets.featurenet(g["img"], sd, training=True)
+    sum((out[k] * g[f"g_{k}"]).sum() for k in out).backward()
+    for k in out:
+        assert _rel(out[k], g[k]) < 1e-5, k
+    for key, name in (("d_conv0_0_w", "conv0.0.conv.weight"), ("d_conv1_0_w", "conv1.0.conv.weight"),
+                      ("d_deconv1_deconv_w", "deconv1.deconv.conv.weight"), ("d_deconv2_conv_bn_w", "deconv2.conv.bn.weight"),
+                      ("d_out1_w", "out1.weight"), ("d_out3_w", "out3.weight")):
+        assert _rel(sd[name].grad, g[key]) < 1e-4, name
