@@ -650,7 +650,7 @@ def featurenet_block(dev, flush, V=3, H=384, W=768):
     ms = sorted(ts)[len(ts) // 2]
     return {"views": V, "image_hw": [H, W], "ms": ms, "ms_best": min(ts), "megapixels_per_s": V * px / (ms * 1e-3) / 1e6,
             "approx_tflops_fp32": flop / (ms * 1e-3) / 1e12,
-            "note": "3x3 stride-1 layers on tcgen05 (3xTF32), first layer / transposed convs / 1x1 heads on register-tiled fp32 kernels, the 5x5 stride-2 convs on the implicit-GEMM engine; includes the [B,3,V,H,W] stacking copy and the per-view output copies"}
+            "note": "3x3 stride-1 layers on tcgen05 (3xTF32), first layer / 5x5 stride-2 convs / transposed convs / 1x1 heads on register-tiled fp32 kernels; includes the [B,3,V,H,W] stacking copy and the per-view output copies"}
 
 
 def sharded_block(args, dev, rank, world, barrier, flush):

@@ -666,3 +666,116 @@ inline int conv1x1_launch(const Conv1x1& p, cudaStream_t st, const char* what) {
 }
 
 }  // namespace satmvs
+
+// ---------------------------------------------------------------------------------------------
+// 5x5 stride-2 convolution, padding 2, per plane (FeatureNet conv1.0 / conv2.0, modules/module.py:456-466): one thread = 8 output
+// channels x 4 consecutive output pixels; the five input rows of a channel (11 values each) sit in registers, weights broadcast
+// from shared memory as (co, co+1) pairs, accumulation in FFMA2.  Epilogue: scale / shift (folded BatchNorm) + ReLU.
+// ---------------------------------------------------------------------------------------------
+namespace satmvs {
+
+struct DirectConv5 {
+  const float* in; long long in_cs;      // [Cin] channels of N planes of Hi x Wi
+  const float* w;                        // [Cout][Cin][25]
+  const float* scale; const float* shift;
+  float* out; long long out_cs;          // [Cout] channels of N planes of Hi/2 x Wi/2
+  int Cin, Cout, N, Hi, Wi, relu;
+};
+
+constexpr int kC5Co = 8, kC5Px = 4, kC5Threads = 128, kC5CiChunk = 8;
+
+template <int kUnused>
+__global__ void __launch_bounds__(kC5Threads, 3)
+direct_conv5x5s2_kernel(const __grid_constant__ DirectConv5 a) {
+  __shared__ __align__(16) float wsm[kC5CiChunk * 25 * kC5Co];      // [ci][tap][co]
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.y * kC5Co;
+  const int Ho = a.Hi >> 1, Wo = a.Wi >> 1, npx = Ho * Wo;
+  const long long g0 = ((long long)blockIdx.x * kC5Threads + tid) * kC5Px;
+  const bool ok = g0 < (long long)npx * a.N;
+  const int z = ok ? (int)(g0 / npx) : 0;
+  const int p0 = ok ? (int)(g0 - (long long)z * npx) : 0;
+  const int oy = p0 / Wo, ox = p0 - oy * Wo;
+  const int iy0 = 2 * oy - 2, ix0 = 2 * ox;                        // first input row; first ALIGNED input column (tap 2 of pixel 0)
+  const bool lok = ix0 >= 4, rok = ix0 + 8 < a.Wi;
+  const float* in0 = a.in + (long long)z * a.Hi * a.Wi + (long long)iy0 * a.Wi + ix0;
+
+  u64 acc[kC5Co / 2][kC5Px];
+#pragma unroll
+  for (int i = 0; i < kC5Co / 2; ++i)
+#pragma unroll
+    for (int j = 0; j < kC5Px; ++j) acc[i][j] = 0ULL;
+
+  for (int c0 = 0; c0 < a.Cin; c0 += kC5CiChunk) {
+    const int nci = min(kC5CiChunk, a.Cin - c0);
+    __syncthreads();
+    for (int e = tid; e < kC5CiChunk * 25 * kC5Co; e += kC5Threads) {
+      const int ci = e / (25 * kC5Co), rr = e - ci * (25 * kC5Co), tp = rr / kC5Co, co = rr - tp * kC5Co;
+      wsm[e] = (ci < nci && co0 + co < a.Cout) ? __ldg(a.w + ((long long)(co0 + co) * a.Cin + c0 + ci) * 25 + tp) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < nci; ++c) {
+      const float* cp = in0 + (long long)(c0 + c) * a.in_cs;
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) {
+        // r[0..10] = in[iy0 + ky][ix0 - 2 .. ix0 + 8]  (zero outside the plane)
+        float r[11];
+        const bool yok = ok && (unsigned)(iy0 + ky) < (unsigned)a.Hi;
+        const float* rp = cp + (long long)ky * a.Wi;
+        float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
+        float2 l2 = make_float2(0.f, 0.f);
+        float e8 = 0.f;
+        if (yok) {
+          m0 = __ldg(reinterpret_cast<const float4*>(rp));
+          m1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+          if (lok) l2 = __ldg(reinterpret_cast<const float2*>(rp - 2));
+          if (rok) e8 = __ldg(rp + 8);
+        }
+        r[0] = l2.x; r[1] = l2.y; r[2] = m0.x; r[3] = m0.y; r[4] = m0.z; r[5] = m0.w; r[6] = m1.x; r[7] = m1.y; r[8] = m1.z; r[9] = m1.w; r[10] = e8;
+        u64 rr2[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) rr2[k] = pk(r[k], r[k]);
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const float* wp = &wsm[(c * 25 + ky * 5 + kx) * kC5Co];
+          const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wp), w1 = *reinterpret_cast<const ulonglong2*>(wp + 4);
+          const u64 wv[kC5Co / 2] = {w0.x, w0.y, w1.x, w1.y};
+#pragma unroll
+          for (int i = 0; i < kC5Co / 2; ++i)
+#pragma unroll
+            for (int j = 0; j < kC5Px; ++j) acc[i][j] = ffma2(wv[i], rr2[2 * j + kx], acc[i][j]);
+        }
+      }
+    }
+  }
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < kC5Co; ++i) {
+    const int co = co0 + i;
+    if (co >= a.Cout) break;
+    const float sc = a.scale ? __ldg(a.scale + co) : 1.0f, sh = a.shift ? __ldg(a.shift + co) : 0.0f;
+    float v[kC5Px];
+#pragma unroll
+    for (int j = 0; j < kC5Px; ++j) {
+      float alo, ahi;
+      upk(acc[i >> 1][j], alo, ahi);
+      v[j] = fmaf((i & 1) ? ahi : alo, sc, sh);
+      if (a.relu) v[j] = fmaxf(v[j], 0.0f);
+    }
+    *reinterpret_cast<float4*>(a.out + (long long)co * a.out_cs + (long long)z * npx + p0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+inline bool direct_conv5_supported(const DirectConv5& p) {
+  return p.Wi % 8 == 0 && p.Hi % 2 == 0 && p.in_cs % 4 == 0 && p.out_cs % 4 == 0 &&
+         reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0;
+}
+
+inline int direct_conv5_launch(const DirectConv5& p, cudaStream_t st, const char* what) {
+  dim3 grid(ceil_div((long long)p.N * (p.Hi / 2) * (p.Wi / 2), kC5Threads * kC5Px), ceil_div(p.Cout, kC5Co), 1);
+  direct_conv5x5s2_kernel<0><<<grid, kC5Threads, 0, st>>>(p);
+  return check_launch(what);
+}
+
+}  // namespace satmvs

@@ -8,8 +8,9 @@
 // scale / shift.  The two concatenations never happen: the skip tensors (conv0, conv1 outputs) are produced directly in the
 // upper channel halves of the concatenation buffers and the transposed convs write the lower halves.
 // Kernels: the 3x3 stride-1 layers with >= 8 input channels (7 of the 15 layers, 60 % of the FLOPs) run on the tensor cores
-// (umma_conv.cuh: tcgen05 kind::tf32, 3-way split, fp32-faithful); the 3-channel first layer, the transposed convs and the 1x1
-// heads on register-tiled fp32 kernels (direct_conv.cuh), the 5x5 stride-2 convs on the fp32 implicit-GEMM engine (conv_engine.cuh).
+// (umma_conv.cuh: tcgen05 kind::tf32, 3-way split, fp32-faithful); the 3-channel first layer, the 5x5 stride-2 convs, the transposed
+// convs and the 1x1 heads on register-tiled fp32 kernels (direct_conv.cuh); the implicit-GEMM engine (conv_engine.cuh) is the
+// fallback for unaligned widths.
 #include "conv_engine.cuh"
 #include "direct_conv.cuh"
 #include "umma_conv.cuh"
@@ -163,6 +164,13 @@ int satmvs_featurenet_forward(const satmvs_featurenet_weights* wt, const float* 
       d.Cin = Cin; d.Cout = Cout; d.Di = V; d.Hi = in.h; d.Wi = in.w; d.Do = V; d.Ho = out.h; d.Wo = out.w;
       d.w_co = (long long)Cin * 9; d.w_ci = 9; d.acc_scale = 1.0f; d.relu = 1;
       if (direct_conv_supported(d, 1, 1)) return direct_conv_launch(d, 1, 1, st, what);
+    }
+    if (k == 5 && s == 2 && !no_direct) {        // the two down-sampling layers: register-tiled direct kernel
+      DirectConv5 d{};
+      const long long ics = (long long)V * in.h * in.w, ocs = (long long)V * out.h * out.w;
+      d.in = in.p + (size_t)in_off * ics; d.in_cs = ics; d.w = L[i].w; d.scale = L[i].scale; d.shift = L[i].shift;
+      d.out = out.p + (size_t)out_off * ocs; d.out_cs = ocs; d.Cin = Cin; d.Cout = Cout; d.N = V; d.Hi = in.h; d.Wi = in.w; d.relu = 1;
+      if (direct_conv5_supported(d)) return direct_conv5_launch(d, st, what);
     }
     ConvProblem p = fn_conv(in, in_off, Cin, L[i].w, L[i].scale, L[i].shift, 1, out, out_off, Cout, k, s, V);
     return fn_launch(p, st, what);
