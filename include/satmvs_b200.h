@@ -238,8 +238,8 @@ int satmvs_red_last_path(void);
  *     8 deconv1.deconv [4b,2b,3,3] (ConvTranspose2d, stride 2)   9 deconv1.conv [2b,4b,3,3]
  *    10 deconv2.deconv [2b,b,3,3]                               11 deconv2.conv [b,2b,3,3]
  *   out_w[k]: the bare 1x1 heads out1 [4b,4b], out2 [2b,2b], out3 [b,b] (no bias).
- *   images [3,V,H,W] (channel-major, the V views as planes); out1 [4b,V,H/4,W/4], out2 [2b,V,H/2,W/2], out3 [b,V,H,W]
- *   = outputs["stage1".."stage3"] of every view.  H and W multiples of 4. */
+ *   images [3,V,H,W] (channel-major, the V views as planes); out1 [V,4b,H/4,W/4], out2 [V,2b,H/2,W/2], out3 [V,b,H,W]
+ *   (view-major: every view's outputs["stage1".."stage3"] is a contiguous [C,h,w] tensor).  H and W multiples of 4. */
 typedef struct satmvs_conv_bn { const float* w; const float* scale; const float* shift; } satmvs_conv_bn;
 typedef struct satmvs_featurenet_weights { satmvs_conv_bn block[12]; const float* out_w[3]; } satmvs_featurenet_weights;
 size_t satmvs_featurenet_workspace_bytes(int base_channels, int V, int H, int W);

@@ -622,7 +622,9 @@ inline int direct_conv3d_c1_launch(const DirectConv& p, cudaStream_t st, const c
 // ---------------------------------------------------------------------------------------------
 namespace satmvs {
 
-struct Conv1x1 { const float* in; const float* w; float* out; long long n; int Cin, Cout; };   // in [Cin][n], out [Cout][n], n % 4 == 0
+struct Conv1x1 {           // in [Cin][n], n % 4 == 0; out [Cout][n], or per view [n / view_n][Cout][view_n] when view_n > 0 (view_n % 4 == 0)
+  const float* in; const float* w; float* out; long long n; int Cin, Cout; long long view_n;
+};
 
 constexpr int kP1Co = 8, kP1MaxCin = 64;
 
@@ -651,13 +653,16 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const Conv1x1 a) {
       acc[c].z = fmaf(v.z, wv[c], acc[c].z); acc[c].w = fmaf(v.w, wv[c], acc[c].w);
     }
   }
+  long long obase = i, ocs = a.n;
+  if (a.view_n > 0) { const long long v = i / a.view_n; obase = v * a.Cout * a.view_n + (i - v * a.view_n); ocs = a.view_n; }
 #pragma unroll
   for (int c = 0; c < kP1Co; ++c)
-    if (co0 + c < a.Cout) *reinterpret_cast<float4*>(a.out + (long long)(co0 + c) * a.n + i) = acc[c];
+    if (co0 + c < a.Cout) *reinterpret_cast<float4*>(a.out + (long long)(co0 + c) * ocs + obase) = acc[c];
 }
 
 inline bool conv1x1_supported(const Conv1x1& p) {
-  return p.Cin <= kP1MaxCin && p.n % 4 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0;
+  return p.Cin <= kP1MaxCin && p.n % 4 == 0 && p.view_n % 4 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0 &&
+         reinterpret_cast<uintptr_t>(p.out) % 16 == 0;
 }
 
 inline int conv1x1_launch(const Conv1x1& p, cudaStream_t st, const char* what) {

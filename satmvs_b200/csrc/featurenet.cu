@@ -175,12 +175,20 @@ int satmvs_featurenet_forward(const satmvs_featurenet_weights* wt, const float* 
     ConvProblem p = fn_conv(in, in_off, Cin, L[i].w, L[i].scale, L[i].shift, 1, out, out_off, Cout, k, s, V);
     return fn_launch(p, st, what);
   };
-  auto head = [&](const FnTensor& in, int Cin, const float* w, const FnTensor& out, const char* what) {   // bare 1x1 conv, no bias
-    Conv1x1 c{in.p, w, out.p, (long long)V * in.h * in.w, Cin, Cin};
+  // bare 1x1 conv, no bias; output VIEW-major [V][C][h][w]: every view's feature map is a contiguous [C][h][w] tensor
+  auto head = [&](const FnTensor& in, int Cin, const float* w, const FnTensor& out, const char* what) {
+    const long long hw = (long long)in.h * in.w;
+    Conv1x1 c{in.p, w, out.p, (long long)V * hw, Cin, Cin, hw};
     static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
     if (!no_direct && conv1x1_supported(c)) return conv1x1_launch(c, st, what);
-    ConvProblem p = fn_conv(in, 0, Cin, w, nullptr, nullptr, 0, out, 0, Cin, 1, 1, V);
-    return fn_launch(p, st, what);
+    for (int v = 0; v < V; ++v) {      // implicit-GEMM engine: one launch per view, the input plane pinned
+      const FnTensor ov{out.p + (size_t)v * Cin * hw, Cin, in.h, in.w};
+      ConvProblem p = fn_conv(in, 0, Cin, w, nullptr, nullptr, 0, ov, 0, Cin, 1, 1, V);
+      p.Do = 1; p.Qd = 1; p.q2i_add[0] = v;
+      const int r = fn_launch(p, st, what);
+      if (r) return r;
+    }
+    return (int)SATMVS_OK;
   };
   // conv0 (module.py:452-455); its output is the skip tensor of deconv2: upper half of cat2
   RUN(conv(0, img, 0, 3, t0a, 0, b, 3, 1, "featurenet conv0.0"));

@@ -437,9 +437,9 @@ class FeatureNet(nn.Module):
         ws = _workspace(nbytes, imgs[0].device)
         x = torch.stack(imgs, dim=2).contiguous()                        # [B, 3, V, H, W]: the views ride the plane axis
         dev = x.device
-        o1 = torch.empty((B, 4 * b, V, H // 4, W // 4), dtype=torch.float32, device=dev)
-        o2 = torch.empty((B, 2 * b, V, H // 2, W // 2), dtype=torch.float32, device=dev)
-        o3 = torch.empty((B, b, V, H, W), dtype=torch.float32, device=dev)
+        o1 = torch.empty((B, V, 4 * b, H // 4, W // 4), dtype=torch.float32, device=dev)      # view-major per sample
+        o2 = torch.empty((B, V, 2 * b, H // 2, W // 2), dtype=torch.float32, device=dev)
+        o3 = torch.empty((B, V, b, H, W), dtype=torch.float32, device=dev)
         w = self._weights()
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
@@ -447,8 +447,8 @@ class FeatureNet(nn.Module):
                 _lib.check(_lib.lib().satmvs_featurenet_forward(C.byref(w), x[bi].data_ptr(), b, V, H, W, o1[bi].data_ptr(),
                                                                o2[bi].data_ptr(), o3[bi].data_ptr(), ws.data_ptr(), ws.numel(), st),
                            "featurenet_forward")
-        return [{"stage1": o1[:, :, v].contiguous(), "stage2": o2[:, :, v].contiguous(), "stage3": o3[:, :, v].contiguous()}
-                for v in range(V)]
+        # batch 1 (the reference's recipes): every view's [1,C,h,w] map is a contiguous slice, no copy
+        return [{"stage1": o1[:, v].contiguous(), "stage2": o2[:, v].contiguous(), "stage3": o3[:, v].contiguous()} for v in range(V)]
 
     def forward(self, x):
         return self.forward_views([x])[0]
