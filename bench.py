@@ -61,6 +61,9 @@ WORKLOADS = {
                            "hypothesis swept, one recurrent regulariser step, fp64 online soft-argmin per plane)"),
     "cfg4_sharded192": dict(B=1, V=5, C=32, D=192, H=192, W=384, geo="rpc", stage="sharded",
                             desc="5-view 1536x768, 192 planes single-stage, cost-volume build depth-sharded across ranks"),
+    "cfg4_stress": dict(B=1, V=5, C=8, D=192, H=768, W=1536, geo="rpc", stage="sharded",
+                        desc="stress reading of configs[3] (SURVEY 8 size table): 768x1536 FEATURE map, C 8, 5 views, 192 planes, "
+                             "7.25 GB fp32 volume, depth-sharded across ranks"),
 }
 
 
@@ -733,6 +736,38 @@ def sharded_block(args, dev, rank, world, barrier, flush):
         out["note"] = ("every rank must receive (G-1)/G of the 1.81 GB fp32 volume: at 770 GB/s per direction that alone is "
                        f"{out['ingress_bound_ms']:.2f} ms, against {single[0]:.2f} ms to build the whole volume on one GPU -- gathering "
                        "the raw volume cannot scale; the build itself (mode none) does")
+        # the same two communication-free / communication-light modes with 16x the work per rank (stress reading of configs[3])
+        del fe, dv
+        torch.cuda.empty_cache()
+        try:
+            ws_ = WORKLOADS["cfg4_stress"]
+            fh, cs, dh = make_inputs(ws_, seed=0)
+            f2, d2 = [f.to(dev) for f in fh], dh.to(dev)
+            vox2 = ws_["B"] * ws_["V"] * ws_["D"] * ws_["H"] * ws_["W"]
+            iters = 5
+            src2 = [cs[:, v] for v in range(1, ws_["V"])]
+
+            def stress_single():
+                var = satmvs_b200.build_cost_volume(f2[0], f2[1:], cs[:, 0], src2, d2, ws_["geo"])
+                head = StreamingSoftArgmin(ws_["B"], ws_["H"], ws_["W"], dev)
+                head.update_volume(var, d2, -1.0)
+                return head.finish()
+            b1 = timed(lambda: satmvs_b200.build_cost_volume(f2[0], f2[1:], cs[:, 0], src2, d2, ws_["geo"]))
+            bn = timed(lambda: sharded.build_cost_volume_sharded(f2[0], f2[1:], cs[:, 0], src2, d2, ws_["geo"], mode="none"))
+            r1 = timed(stress_single)
+            rn = timed(lambda: sharded.sweep_depth_sharded(f2[0], f2[1:], cs[:, 0], src2, d2, ws_["geo"]))
+            out["stress"] = {"workload": ws_["desc"], "config": {k: ws_[k] for k in ("B", "V", "C", "D", "H", "W")},
+                             "volume_bytes": ws_["B"] * ws_["C"] * ws_["D"] * ws_["H"] * ws_["W"] * 4,
+                             "build_single_gpu_ms": b1[0], "build_sharded_ms": bn[0], "build_speedup": b1[0] / bn[0],
+                             "build_voxels_per_s": vox2 / (bn[0] * 1e-3),
+                             "reduced_exchange_single_gpu_ms": r1[0], "reduced_exchange_ms": rn[0],
+                             "reduced_exchange_speedup": r1[0] / rn[0], "reduced_exchange_voxels_per_s": vox2 / (rn[0] * 1e-3),
+                             "timing": "mean of 5 iterations, max over ranks, CUDA events, L2 flushed"}
+            del f2, d2
+        except Exception as ex:
+            out["stress"] = {"unavailable": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+        barrier()
     return out
 
 
