@@ -336,7 +336,7 @@ int satmvs_gn_param_grad(const float* dout, const float* pre, const float* bias,
  * (conv results WITHOUT bias); ostat [D][2], gstat [D][2][2] (mean, rstd); dec [ch][D][px] = gradient reaching h'(d) from the
  * decoder; wo_h / wg_h: the output / gate filters offset to their hidden input channels, w_ci = (cx + ch) * 9 their stride
  * between output channels.  Outputs [.][D][px]: dyn, dgn (gradients at the GroupNorm outputs, for the affine gradients), dO, dG
- * (gradients at the conv outputs).  scratch: 16 + 9 * ch * px floats. */
+ * (gradients at the conv outputs).  scratch: 12 * D + 4 + 14 * ch * px floats. */
 typedef struct satmvs_gru_bwd_level {
   const float* S; const float* ru; const float* y; const float* opre; const float* gpre;
   const float* ob; const float* gb; const float* on_w; const float* rn_w; const float* un_w;

@@ -14,8 +14,9 @@
 //     (2) gn_bwd_apply:  dO = GN_o'(dYn)                    -> conv^T with the h-half of the output filters -> dRH
 //     (3) gru_bwd_reset: dRn = dRH h r (1-r);  carry += dRH r;                                 sums for GN_r'
 //     (4) gn_bwd_apply:  dG = [GN_r'(dRn), GN_u'(dUn)]      -> conv^T with the h-half of the gate filters   -> dHg
-//     (5) gru_bwd_carry: dh'(d-1) = carry + dHg + (gradient reaching h'(d-1) from the decoder)
+//     (5) folded into step (1) of plane d-1: dh'(d-1) = carry + dHg + (gradient reaching h'(d-1) from the decoder)
 #include "common.cuh"
+#include "direct_conv.cuh"
 #include "prof.cuh"
 
 namespace satmvs {
@@ -136,7 +137,7 @@ __global__ void acc_to_float_kernel(const double* __restrict__ acc, int n, int s
 // ---- sequential part, one plane of one level per launch ----
 struct GruBwdArgs {
   // per-plane views (already offset to plane d); cs = channel stride of the [C][D][px] tensors
-  const float* dh;      // [ch][px] contiguous: gradient at h'(d)
+  const float* dh;      // null at the last plane (only the decoder reaches h'(D-1)), any non-null value below it
   const float* h;       // state before the cell, channel stride s_cs
   const float* ru;      // [2ch] r then u, channel stride cs
   const float* y;       // [ch], cs
@@ -154,9 +155,8 @@ struct GruBwdArgs {
   const float* dRH;     // [ch][px] contiguous: conv^T(dO) restricted to the hidden channels
   const float* dHg;     // [ch][px] contiguous: conv^T(dG) restricted to the hidden channels
   float* carry;         // [ch][px] contiguous
-  const float* dec;     // gradient reaching h'(d-1) from the decoder, channel stride dec_cs, or null at d = 0
-  float* dh_next;       // [ch][px] contiguous: gradient at h'(d-1)
-  double* red;          // [6] zeroed: (a1, a2) output norm, (b1, b2) update norm, (c1, c2) reset norm
+  const float* dec;     // gradient reaching h'(d) from the decoder, channel stride dec_cs
+  double* red;          // [6] of this plane, zeroed: (a1, a2) output norm, (b1, b2) update norm, (c1, c2) reset norm
   long long cs, s_cs, dec_cs;
   int ch, px;
 };
@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(256) gru_bwd_out_kernel(const GruBwdArgs a) {
   double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int c = i / a.px, p = i - c * a.px;
-    const float dh = a.dh[i], h = __ldg(a.h + c * a.s_cs + p), u = __ldg(a.ru + (a.ch + c) * a.cs + p), y = __ldg(a.y + c * a.cs + p);
+    // gradient at h'(d): from the decoder, plus (below the last plane) what plane d+1 left in carry and its gate-conv gradient
+    const float dh = __ldg(a.dec + c * a.dec_cs + p) + (a.dh ? a.carry[i] + __ldg(a.dHg + i) : 0.0f);
+    const float h = __ldg(a.h + c * a.s_cs + p), u = __ldg(a.ru + (a.ch + c) * a.cs + p), y = __ldg(a.y + c * a.cs + p);
     const float dyn = dh * (1.0f - u) * (1.0f - y * y);
     const float dun = dh * (h - y) * u * (1.0f - u);
     a.dyn[c * a.cs + p] = dyn;
@@ -228,20 +230,30 @@ __global__ void __launch_bounds__(256) gru_bwd_dG_kernel(const GruBwdArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256) gru_bwd_carry_kernel(const GruBwdArgs a) {
-  const int n = a.ch * a.px;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = i / a.px, p = i - c * a.px;
-    float v = a.carry[i] + __ldg(a.dHg + i);
-    if (a.dec) v += __ldg(a.dec + c * a.dec_cs + p);
-    a.dh_next[i] = v;
-  }
-}
-
 static inline int grid_for(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = 4LL * kNumSMs;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// conv^T restricted to the hidden input channels, one plane: a 3x3 conv with mirrored taps over `cin` gradient channels.  The deep
+// levels are tiny (288 pixels x 64 channels at level 3 of a 96x192 plane): their input channels are split over CTAs (ksplit) so the
+// per-plane latency is a few microseconds instead of one long serial loop on 8 CTAs.
+constexpr int kMaxKsplit = 8;
+static int hidden_dgrad(const float* in, int cin, const satmvs_gru_bwd_level& L, const float* w_h, float* out, float* partial,
+                        cudaStream_t st) {
+  DirectConv d{};
+  d.in = in; d.w = w_h; d.out = out;
+  d.Cin = cin; d.Cout = L.ch; d.Di = 1; d.Hi = L.h; d.Wi = L.w; d.Do = 1; d.Ho = L.h; d.Wo = L.w;
+  d.w_co = 9; d.w_ci = L.w_ci; d.acc_scale = 1.0f; d.flip = 1;
+  if (!direct_conv_supported(d, 1, 1))
+    return satmvs_conv3d_raw(in, cin, 1, L.h, L.w, w_h, 9, L.w_ci, 1, 2, out, L.ch, st);
+  const long long tiles = (long long)ceil_div((long long)L.h * L.w, kDcWarps * 32 * kDcPx) * ceil_div(L.ch, kDcCo);
+  int ks = 1;
+  while (ks < kMaxKsplit && tiles * ks < kNumSMs && cin / (2 * ks) >= kDcCiChunk) ks *= 2;
+  if (ks > 1) { d.ksplit = ks; d.partial = partial; }
+  ProfScope prof(kProfTrainConv, st);
+  return direct_conv_launch(d, 1, 1, st, "satmvs_red_recurrence_bwd (conv^T)");
 }
 
 }  // namespace satmvs
@@ -343,7 +355,7 @@ int satmvs_red_recurrence_bwd(const satmvs_gru_bwd_level* lv, int nlevels, void*
     for (int l = 0; l < nlevels; ++l) cudaStreamWaitEvent(ls[l], ts.fork, 0);
   }
   GruBwdArgs a[4];
-  float* dh[4][2]; float* dRH[4]; float* dHg[4];
+  float* dRH[4]; float* dHg[4]; float* ksp[4]; double* red[4];
   int Dmax = 0;
   for (int l = 0; l < nlevels; ++l) {
     const satmvs_gru_bwd_level& L = lv[l];
@@ -355,19 +367,15 @@ int satmvs_red_recurrence_bwd(const satmvs_gru_bwd_level* lv, int nlevels, void*
     g = GruBwdArgs{};
     g.ob = L.ob; g.gb = L.gb; g.on_w = L.on_w; g.rn_w = L.rn_w; g.un_w = L.un_w;
     float* sc = L.scratch;
-    g.red = reinterpret_cast<double*>(sc); sc += 16;          // 6 doubles (64 bytes reserved)
+    red[l] = reinterpret_cast<double*>(sc); sc += 12 * (size_t)L.D + 4;      // 6 doubles per plane, zeroed once
     g.dO_p = sc; sc += n;
     g.dG_p = sc; sc += 2 * n;
     g.carry = sc; sc += n;
-    dh[l][0] = sc; sc += n;
-    dh[l][1] = sc; sc += n;
     dRH[l] = sc; sc += n;
     dHg[l] = sc; sc += n;
+    ksp[l] = sc; sc += kMaxKsplit * n;
     g.cs = (long long)L.D * px; g.s_cs = (long long)(L.D + 1) * px; g.dec_cs = g.cs; g.ch = L.ch; g.px = px;
-    // gradient at h'(D-1): only the decoder reaches it
-    EwArgs e{};
-    e.a = L.dec + (size_t)(L.D - 1) * px; e.a_cs = g.cs; e.out = dh[l][0]; e.out_cs = px; e.n_per_c = px; e.C = L.ch; e.scale = 1.0f;
-    ew_kernel<<<dim3(grid_for(px), L.ch), 256, 0, ls[l]>>>(e);
+    cudaMemsetAsync(red[l], 0, (size_t)L.D * 6 * sizeof(double), ls[l]);
     if (L.D > Dmax) Dmax = L.D;
   }
   int rc = check_launch("satmvs_red_recurrence_bwd (init)");
@@ -378,25 +386,24 @@ int satmvs_red_recurrence_bwd(const satmvs_gru_bwd_level* lv, int nlevels, void*
       const int d = L.D - 1 - step;
       if (d < 0) continue;
       GruBwdArgs& g = a[l];
-      const int px = g.px, cur = step & 1;
+      const int px = g.px;
       const size_t o = (size_t)d * px;
-      g.dh = dh[l][cur]; g.dh_next = dh[l][1 - cur];
+      g.dh = step == 0 ? nullptr : dHg[l];       // flag: below the last plane the carry / gate-conv gradient of plane d+1 are added
       g.h = L.S + o; g.ru = L.ru + o; g.y = L.y + o; g.opre = L.opre + o; g.gpre = L.gpre + o;
       g.ostat = L.ostat + (size_t)d * 2; g.gstat = L.gstat + (size_t)d * 4;
       g.dyn = L.dyn + o; g.dgn = L.dgn + o; g.dO = L.dO + o; g.dG = L.dG + o;
       g.dRH = dRH[l]; g.dHg = dHg[l];
-      g.dec = d > 0 ? L.dec + (size_t)(d - 1) * px : nullptr;
+      g.dec = L.dec + o;
+      g.red = red[l] + (size_t)d * 6;
       const int n = g.ch * px, bx = grid_for(n);
-      cudaMemsetAsync(g.red, 0, 6 * sizeof(double), ls[l]);
       gru_bwd_out_kernel<<<bx, 256, 0, ls[l]>>>(g);
       gru_bwd_dO_kernel<<<bx, 256, 0, ls[l]>>>(g);
-      rc = satmvs_conv3d_raw(g.dO_p, g.ch, 1, L.h, L.w, L.wo_h, 9, L.w_ci, 1, 2, dRH[l], g.ch, ls[l]);
+      rc = hidden_dgrad(g.dO_p, g.ch, L, L.wo_h, dRH[l], ksp[l], ls[l]);
       if (rc) return rc;
       gru_bwd_reset_kernel<<<bx, 256, 0, ls[l]>>>(g);
       gru_bwd_dG_kernel<<<grid_for(2LL * n), 256, 0, ls[l]>>>(g);
-      rc = satmvs_conv3d_raw(g.dG_p, 2 * g.ch, 1, L.h, L.w, L.wg_h, 9, L.w_ci, 1, 2, dHg[l], g.ch, ls[l]);
+      rc = hidden_dgrad(g.dG_p, 2 * g.ch, L, L.wg_h, dHg[l], ksp[l], ls[l]);
       if (rc) return rc;
-      gru_bwd_carry_kernel<<<bx, 256, 0, ls[l]>>>(g);
     }
   }
   if (ts.ok)

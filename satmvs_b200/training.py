@@ -359,7 +359,7 @@ def _red_backward_sample(P: dict, vol, ws, dlog):
         dGO = torch.empty((3 * ch, D, h, w), dtype=torch.float32, device=dev)     # [dG (2ch) | dO (ch)]
         dGn = torch.empty((2 * ch, D, h, w), dtype=torch.float32, device=dev)
         dYn = torch.empty((ch, D, h, w), dtype=torch.float32, device=dev)
-        scratch = torch.empty(16 + 9 * ch * h * w, dtype=torch.float32, device=dev)
+        scratch = torch.empty(12 * D + 4 + 14 * ch * h * w, dtype=torch.float32, device=dev)
         Wo_h, Wg_h = Wo.reshape(-1)[cx * 9:], Wg.reshape(-1)[cx * 9:]
         a = lv[l]
         a.S, a.ru, a.y, a.opre, a.gpre = S[l].data_ptr(), RU.data_ptr(), Y.data_ptr(), Opre.data_ptr(), Gpre.data_ptr()
