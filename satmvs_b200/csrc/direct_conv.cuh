@@ -540,38 +540,40 @@ inline int direct_deconv3d_launch(const DirectDeconv3d& p, cudaStream_t st, cons
 }  // namespace satmvs
 
 // ---------------------------------------------------------------------------------------------
-// 3x3x3 stride-1 convolution to ONE output channel (CostRegNet's `prob` head, modules/module.py:566): direct_conv_kernel computes
+// 3x3x3 (NZ 3) or per-plane 3x3 (NZ 1) stride-1 convolution to ONE output channel (CostRegNet's `prob` head, modules/module.py:566;
+// RED's final upconv2d, :610): direct_conv_kernel computes
 // 8 output channels per thread, 7 of them on zero filters here.  One thread = 8 consecutive output voxels of a row x 1 channel.
 // ---------------------------------------------------------------------------------------------
 namespace satmvs {
 
 constexpr int kC1Px = 8, kC1Threads = 128, kC1MaxCin = 64;
 
-template <int kUnused>
+template <int NZ>
 __global__ void __launch_bounds__(kC1Threads)
-direct_conv3d_c1_kernel(const __grid_constant__ DirectConv a) {
-  __shared__ float wsm[kC1MaxCin * 27];
+direct_conv_c1_kernel(const __grid_constant__ DirectConv a) {
+  constexpr int TAPS = NZ * 9;
+  __shared__ float wsm[kC1MaxCin * TAPS];
   const int tid = threadIdx.x;
-  for (int e = tid; e < a.Cin * 27; e += kC1Threads) {
-    const int ci = e / 27, tp = e - ci * 27;
-    wsm[e] = __ldg(a.w + (long long)ci * a.w_ci + (a.flip ? 26 - tp : tp));
+  for (int e = tid; e < a.Cin * TAPS; e += kC1Threads) {
+    const int ci = e / TAPS, tp = e - ci * TAPS;
+    wsm[e] = __ldg(a.w + (long long)ci * a.w_ci + (a.flip ? TAPS - 1 - tp : tp));
   }
   __syncthreads();
   const int npx = a.Hi * a.Wi;
   const long long g0 = ((long long)blockIdx.x * kC1Threads + tid) * kC1Px;
   if (g0 >= (long long)npx * a.Di) return;
   const int oz = (int)(g0 / npx), p0 = (int)(g0 - (long long)oz * npx), oy = p0 / a.Wi, ox = p0 - oy * a.Wi;
-  const long long in_cs = (long long)a.Di * npx;
+  const long long in_cs = a.in_cs ? a.in_cs : (long long)a.Di * npx;
   const bool lok = ox > 0, rok = ox + kC1Px < a.Wi;
   float acc[kC1Px];
 #pragma unroll
   for (int j = 0; j < kC1Px; ++j) acc[j] = 0.0f;
 #pragma unroll 1
   for (int ci = 0; ci < a.Cin; ++ci) {
-    const float* wc = wsm + ci * 27;
+    const float* wc = wsm + ci * TAPS;
 #pragma unroll
-    for (int kz = 0; kz < 3; ++kz) {
-      const int iz = oz - 1 + kz;
+    for (int kz = 0; kz < NZ; ++kz) {
+      const int iz = NZ == 1 ? oz : oz - 1 + kz;
       if ((unsigned)iz >= (unsigned)a.Di) continue;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -604,13 +606,15 @@ direct_conv3d_c1_kernel(const __grid_constant__ DirectConv a) {
 }
 
 inline bool direct_conv3d_c1_supported(const DirectConv& p) {
-  return p.Cout == 1 && p.Cin <= kC1MaxCin && p.Wi % kC1Px == 0 && p.Wo == p.Wi && p.Ho == p.Hi && p.Do == p.Di && p.in_cs == 0 &&
+  return p.Cout == 1 && p.Cin <= kC1MaxCin && p.Wi % kC1Px == 0 && p.Wo == p.Wi && p.Ho == p.Hi && p.Do == p.Di && p.in_cs % 4 == 0 &&
          reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
          (p.post_add == nullptr || reinterpret_cast<uintptr_t>(p.post_add) % 16 == 0);
 }
 
-inline int direct_conv3d_c1_launch(const DirectConv& p, cudaStream_t st, const char* what) {
-  direct_conv3d_c1_kernel<0><<<ceil_div((long long)p.Di * p.Hi * p.Wi, kC1Threads * kC1Px), kC1Threads, 0, st>>>(p);
+inline int direct_conv3d_c1_launch(const DirectConv& p, cudaStream_t st, const char* what, int NZ = 3) {
+  const int grid = ceil_div((long long)p.Di * p.Hi * p.Wi, kC1Threads * kC1Px);
+  if (NZ == 3) direct_conv_c1_kernel<3><<<grid, kC1Threads, 0, st>>>(p);
+  else direct_conv_c1_kernel<1><<<grid, kC1Threads, 0, st>>>(p);
   return check_launch(what);
 }
 

@@ -836,8 +836,10 @@ int satmvs_red_forward_packed(const satmvs_red_weights* wt, const float* volume,
     dc.w_co = 9; dc.w_ci = 9; dc.acc_scale = 1.0f; dc.relu = 0; dc.flip = 1;
     static const bool no_direct = getenv("SATMVS_NO_DIRECT_CONV") != nullptr;
     ProfScope prof(kProfDecoder, st);
-    if (!no_direct && direct_conv_supported(dc, 1, 1)) {
-      // the input tensor has D+1 planes per channel: express it as Di = D with the channel stride of D+1 planes
+    dc.in_cs = (long long)(D + 1) * H * W;      // the input tensor has D+1 planes per channel
+    if (!no_direct && direct_conv3d_c1_supported(dc)) {
+      RUN(direct_conv3d_c1_launch(dc, st, "red upconv2d (direct, 1 channel)", 1));
+    } else if (!no_direct && direct_conv_supported(dc, 1, 1)) {
       RUN(direct_conv_launch_cs(dc, (long long)(D + 1) * H * W, st, "red upconv2d (direct)"));
     } else {
       RUN(launch_one<Tile8>(p, st, "red upconv2d"));
