@@ -116,7 +116,8 @@ static CostRegPlan costreg_plan(int base, int D, int H, int W, char* mem) {
   p.c[3] = take(4 * base * v2); p.c[4] = take(4 * base * v2);
   p.c[5] = take(8 * base * v3); p.c[6] = take(8 * base * v3);
   p.x7 = take(4 * base * v2); p.x9 = take(2 * base * v1); p.x11 = take(base * v0);
-  p.ksplit_floats = 4 * 8 * base * v3; p.ksplit = take(p.ksplit_floats);
+  p.ksplit_floats = 4 * 8 * base * v3 > 2 * 4 * base * v2 ? 4 * 8 * base * v3 : 2 * 4 * base * v2;   // conv5 / conv6 (x4), conv4 (x2)
+  p.ksplit = take(p.ksplit_floats);
   // (Cin / 8) x 3 planes x (raw, lo) x 9 taps x 2 quads x N (padded to 16) float4; conv0's Cin is bounded by 64 here
   const int wcin[5] = {64, 2 * base, 4 * base, 8 * base, base}, wn[5] = {base, 2 * base, 4 * base, 8 * base, 1};
   for (int i = 0; i < 5; ++i) {
