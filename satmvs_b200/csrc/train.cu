@@ -235,25 +235,40 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgradArgs a)
   const int wo4 = (a.Wo + 3) & ~3;
   const long long in_cs = (long long)a.Di * a.Hi * a.Wi, out_cs = (long long)a.Do * a.Ho * a.Wo;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // the zero padding of every staged row (column -1 and everything from the row's end on) is written once: the copies below only
+  // touch the interior
+  for (int row = warp; row < a.Cout * a.rb; row += nwarps)
+    for (int ox = a.Wo + lane; ox < a.rsy; ox += 32) dys[(size_t)row * a.rsy + ox] = 0.0f;
+  for (int row = warp; row < nci * KZ * NR; row += nwarps) {
+    float* dst = xs + (size_t)row * a.rsx;
+    if (lane == 0) dst[0] = 0.0f;
+    for (int p = a.Wi + 1 + lane; p < a.rsx; p += 32) dst[p] = 0.0f;
+  }
   for (int sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
     const int oz = sidx / strips_y, oy0 = (sidx - oz * strips_y) * a.rb;
     __syncthreads();
-    // staging by asynchronous 4-byte copies (every element of the strip in flight at once; zero fill outside the tensors):
-    // one warp per shared-memory row, the row decode is warp-uniform, lanes walk the columns
-    for (int row = warp; row < a.Cout * a.rb; row += nwarps) {   // output-gradient rows, zero-padded to a multiple of 4
+    // staging by asynchronous 4-byte copies (every element of the strip in flight at once): one warp per shared-memory row, the row
+    // decode is warp-uniform, lanes walk the columns; rows outside the tensors are zero-filled with plain stores
+    for (int row = warp; row < a.Cout * a.rb; row += nwarps) {   // output-gradient rows
       const int co = row / a.rb, r = row - co * a.rb;
-      const bool live = oy0 + r < a.Ho;
-      const float* src = a.dy + co * out_cs + ((long long)oz * a.Ho + (live ? oy0 + r : 0)) * a.Wo;
       float* dst = dys + (size_t)row * a.rsy;
-      for (int ox = lane; ox < a.rsy; ox += 32) { const bool ok = live && ox < a.Wo; cp_async4(dst + ox, ok ? src + ox : a.dy, ok); }
+      if (oy0 + r < a.Ho) {
+        const float* src = a.dy + co * out_cs + ((long long)oz * a.Ho + oy0 + r) * a.Wo;
+        for (int ox = lane; ox < a.Wo; ox += 32) cp_async4(dst + ox, src + ox, true);
+      } else {
+        for (int ox = lane; ox < a.Wo; ox += 32) dst[ox] = 0.0f;
+      }
     }
     for (int row = warp; row < nci * KZ * NR; row += nwarps) {   // input rows
       const int cl = row / (KZ * NR), rem = row - cl * (KZ * NR), kz = rem / NR, j = rem - kz * NR;
       const int iz = a.NZ == 3 ? S * oz + kz - 1 : oz, iy = S * oy0 - 1 + j;
-      const bool live = iz >= 0 && iz < a.Di && iy >= 0 && iy < a.Hi;
-      const float* src = a.x + (ci0 + cl) * in_cs + ((long long)(live ? iz : 0) * a.Hi + (live ? iy : 0)) * a.Wi - 1;
-      float* dst = xs + (size_t)row * a.rsx;
-      for (int p = lane; p < a.rsx; p += 32) { const bool ok = live && p >= 1 && p <= a.Wi; cp_async4(dst + p, ok ? src + p : a.x, ok); }
+      float* dst = xs + (size_t)row * a.rsx + 1;
+      if (iz >= 0 && iz < a.Di && iy >= 0 && iy < a.Hi) {
+        const float* src = a.x + (ci0 + cl) * in_cs + ((long long)iz * a.Hi + iy) * a.Wi;
+        for (int p = lane; p < a.Wi; p += 32) cp_async4(dst + p, src + p, true);
+      } else {
+        for (int p = lane; p < a.Wi; p += 32) dst[p] = 0.0f;
+      }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
