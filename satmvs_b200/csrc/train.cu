@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgradArgs a)
           const float* xr = xs + (size_t)((cl * KZ + kz) * NR + S * r + ky) * a.rsx;
           const float* dr = dys + (size_t)(co0 * a.rb + r) * a.rsy;
           const float* er = dys + (size_t)(co1 * a.rb + r) * a.rsy;
-#pragma unroll 2
+#pragma unroll 4
           for (int ox = ox_lo; ox < ox_hi; ox += 4) {
             const float4 d = *reinterpret_cast<const float4*>(dr + ox);
             const float4 e = *reinterpret_cast<const float4*>(er + ox);
